@@ -1,0 +1,393 @@
+#!/usr/bin/env python
+"""bench.py -- gate-applications/s of the dense-statevector hot path (BASELINE.json metric).
+
+  python bench.py --gpus 1 --steps K --warmup W          our arm, 30-qubit brickwork depth 100, ComplexF64
+  torchrun ... bench.py --gpus N ...                      our arm, 34-qubit circuit sharded over N GPUs
+  python bench.py --impl reference ...                    the reference's CPU path (oracle port) on the host cores
+
+One JSON line on stdout (rank 0).  A "step" is one application of the whole circuit to the resident state.
+`value` is measured with inputs resident in HBM; `e2e` goes through the public host-buffer call
+(`apply(psi::Array, circuit)` -> qcb_apply_brickwork_host) with pinned host buffers, H2D and D2H inside
+the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md, used only if MEASURED_PEAKS.json is absent
+NOMINAL_FP64_TFLOPS = 37.0  # 148 SMs x 64 DFMA/clk x 1.965 GHz x 2 (datasheet-level figure; measured one preferred)
+
+
+def parse_args():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=3)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--nqubits", type=int, default=None)
+    p.add_argument("--layers", type=int, default=100)
+    p.add_argument("--dtype", default="c128", choices=["c128", "c64"])
+    p.add_argument("--tile-bits", type=int, default=None)
+    p.add_argument("--low-bits", type=int, default=None)
+    p.add_argument("--max-gates-per-pass", type=int, default=None)
+    p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--cpu-seconds", type=float, default=12.0, help="time budget of the bounded CPU sample")
+    p.add_argument("--seed", type=int, default=20261019)
+    return p.parse_args()
+
+
+def workload(args):
+    n = args.nqubits if args.nqubits is not None else (30 if args.gpus == 1 else 34)
+    return n, args.layers
+
+
+def make_angles(n, layers, seed):
+    """angles ~ U[0, 2pi) (examples/hpc/barren_plateau_trial.jl:14-15), Philox counter RNG, 15 x G column-major."""
+    from oracle import oracle_np as onp
+
+    G = onp.brickwork_num_gates(n, layers)
+    rng = np.random.Generator(np.random.Philox(seed))
+    return np.asfortranarray(rng.uniform(0, 2 * np.pi, (15, G))), G
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.lines, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(power)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the reference's execution shape (oracle/qc_oracle.c), bounded sample
+# ------------------------------------------------------------------------------------------------
+def cpu_sample(n, layers, angles, dtype, budget_s, threads=0):
+    """Applies the first gates of the SAME circuit with the oracle (reference CPU path restated in C + OpenMP:
+    zero fill + one work-item per output amplitude, src/apply.jl:62-84,135) for about budget_s seconds.
+    Returns (gate_apps_per_s at n qubits, description)."""
+    import oracle
+
+    oracle.build()
+    oracle.set_threads(threads)
+    cores = oracle.max_threads() if threads == 0 else threads
+    npdt = np.complex128 if dtype == "c128" else np.complex64
+    n_run = n
+    try:
+        import psutil
+
+        avail = psutil.virtual_memory().available
+    except Exception:
+        avail = 64 << 30
+    while 2 * (np.dtype(npdt).itemsize << n_run) > 0.6 * avail and n_run > 20:
+        n_run -= 1
+    ang = angles
+    if n_run != n:
+        ang, _ = make_angles(n_run, layers, 1)
+    psi = np.zeros(1 << n_run, dtype=npdt)
+    psi[0] = 1
+    G = ang.shape[1]
+    # one gate to size the sample, then as many as fit the budget
+    t0 = time.perf_counter()
+    oracle.apply_brickwork(psi, n_run, layers, ang, 0, 1, inplace=True)
+    t1 = time.perf_counter() - t0
+    g = int(max(1, min(G - 1, budget_s / max(t1, 1e-6))))
+    t0 = time.perf_counter()
+    oracle.apply_brickwork(psi, n_run, layers, ang, 1, 1 + g, inplace=True)
+    dt = time.perf_counter() - t0
+    rate = g / dt  # gate-apps/s at n_run qubits
+    scale = 2.0 ** (n_run - n)
+    desc = (f"first {g} gates of the {n_run}-qubit circuit in {dt:.2f} s with {cores} OpenMP threads "
+            f"(C restatement of the reference CPU path, not Julia)")
+    if n_run != n:
+        desc += f"; host RAM too small for {n} qubits, per-amplitude rate scaled by 2^{n_run - n}"
+    return rate * scale, cores, desc
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n, layers = workload(args)
+    angles, G = make_angles(n, layers, args.seed)
+    per_step = max(2.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
+    for _ in range(args.warmup):
+        cpu_sample(n, layers, angles, args.dtype, per_step / 2)
+    rates, cores, desc = [], 0, ""
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        r, cores, desc = cpu_sample(n, layers, angles, args.dtype, per_step)
+        rates.append(r)
+    wall = time.perf_counter() - t0
+    value = float(np.mean(rates)) if rates else 0.0
+    line = {
+        "impl": "reference", "metric": "gate_apps_per_sec", "value": value, "unit": "gate-apps/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(1, args.steps), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64" if args.dtype == "c128" else "f32", "data": "synthetic",
+        "config": {"workload": f"{n}-qubit brickwork circuit, {layers} half-layers ({G} gates), Complex{'F64' if args.dtype == 'c128' else 'F32'}",
+                   "step": "bounded sample: leading gates of the circuit, gate-apps/s = gates / time"},
+        "cpu_baseline": {"value": value, "unit": "gate-apps/s", "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": value, "unit": "gate-apps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def profile_note(name):
+    path = os.path.join(ROOT, "profiles", name)
+    if os.path.exists(path):
+        try:
+            with open(path) as f:
+                return json.load(f)
+        except Exception:
+            return None
+    return None
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import qcb200 as qc
+    from qcb200 import _lib
+    import ctypes as C
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}; launch with torch.distributed.run --nproc-per-node {args.gpus}")
+    torch.cuda.set_device(local_rank)
+    qc.init(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if args.tile_bits is not None:
+        qc.set_option("tile_bits", args.tile_bits)
+    if args.low_bits is not None:
+        qc.set_option("low_bits", args.low_bits)
+    if args.max_gates_per_pass is not None:
+        qc.set_option("max_gates_per_pass", args.max_gates_per_pass)
+
+    n, layers = workload(args)
+    angles, G = make_angles(n, layers, args.seed)
+    circuit = qc.GenericBrickworkCircuit(n, layers, gate_angles=angles)
+    npdt = np.complex128 if args.dtype == "c128" else np.complex64
+    amp_bytes = np.dtype(npdt).itemsize
+
+    if world == 1:
+        state = qc.B200State(n, npdt)  # |0...0> resident in HBM
+        step = lambda: qc.apply_(state, state, circuit)  # noqa: E731
+        nloc = n
+    else:
+        from qcb200 import dist as qdist
+
+        qdist.init_from_torch()
+        state = qdist.ShardedState(n, npdt)
+        step = lambda: state.apply_circuit(circuit)  # noqa: E731
+        nloc = state.local_qubits
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    passes = qc.get_stat("passes")
+    stages = qc.get_stat("stages")
+    launches0 = qc.get_stat("launches_total")
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = qc.get_stat("launches_total") - launches0
+    if world > 1:
+        t = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+        lt = torch.tensor([launches], device="cuda", dtype=torch.float64)
+        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+        launches = float(lt.item())
+    ms_step = ms_total / args.steps
+    gate_apps = G / (ms_step * 1e-3)
+    # whole-job value in 2^30-amplitude gate applications per second (== gate-apps/s for the 30-qubit config)
+    value = gate_apps * (2.0 ** (n - 30)) if world > 1 else gate_apps
+
+    # ---- roofline of the dominant kernel (tile_pass_kernel): HBM bytes per launch / average launch duration
+    bytes_pass = 2.0 * amp_bytes * (2.0 ** nloc)
+    launch_ms = ms_step / max(passes, 1.0) if world == 1 else None
+    peak, peak_src = measured_peaks()
+    traffic = profile_note("r01_tile_pass_traffic.json")
+    fp64 = profile_note("r01_fp64_peak.json")
+    roofline = None
+    if launch_ms:
+        achieved = bytes_pass / (launch_ms * 1e-3) / 1e9
+        flops = 32.0 * (2.0 ** n) * G / (ms_step * 1e-3) / 1e12  # 16 FMA per amplitude per gate
+        peak_fl = (fp64 or {}).get("dfma_tflops" if args.dtype == "c128" else "ffma_tflops")
+        roofline = {
+            "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": (traffic or {}).get("dram_bytes_per_launch"), "peak_source": peak_src,
+            "kernel": f"tile_pass_kernel<{'double' if args.dtype == 'c128' else 'float'}, TB={int(min(qc_opt('tile_bits', 11), nloc))}>",
+            "launches_per_step": passes, "stages_per_step": stages, "gates_per_launch": G / max(passes, 1.0),
+            "algorithmic_bytes_per_launch": bytes_pass, "avg_launch_ms": launch_ms,
+            "fma_roof": {"achieved_tflops": flops, "peak_tflops": peak_fl if peak_fl else NOMINAL_FP64_TFLOPS * (1 if args.dtype == "c128" else 2),
+                         "peak_source": "measured tools/fp64_peak (profiles/r01_fp64_peak.json)" if peak_fl else "nominal",
+                         "note": "with this many gates fused per HBM pass the kernel is bound by FP FMA issue, not HBM; "
+                                 "--max-gates-per-pass 4 gives the HBM-bound regime"},
+        }
+
+    # ---- end to end through the host-buffer API
+    e2e = None
+    if not args.no_e2e and world == 1:
+        nelem = 1 << n
+        tdt = torch.complex128 if args.dtype == "c128" else torch.complex64
+        h_in = torch.zeros(nelem, dtype=tdt, pin_memory=True)
+        h_out = torch.empty(nelem, dtype=tdt, pin_memory=True)
+        h_in[0] = 1
+        a_in, a_out = h_in.numpy(), h_out.numpy()
+        qc.apply_circuit_host(a_in, circuit, out=a_out)  # warm-up (allocates the device staging state)
+        torch.cuda.synchronize()
+        k = max(1, min(args.steps, 3))
+        l0 = qc.get_stat("launches_total")
+        t0 = time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            qc.apply_circuit_host(a_in, circuit, out=a_out)
+        e1.record()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        ms = max(e0.elapsed_time(e1), wall * 1e3) / k
+        launches += qc.get_stat("launches_total") - l0
+        nrm = float(np.vdot(a_out[: 1 << 20], a_out[: 1 << 20]).real)
+        e2e = {"value": G / (ms * 1e-3), "unit": "gate-apps/s", "h2d_bytes_per_step": int(nelem * amp_bytes + angles.nbytes),
+               "d2h_bytes_per_step": int(nelem * amp_bytes), "ms_per_step": ms, "steps": k,
+               "api": "apply(psi::Array, circuit) -> qcb_apply_brickwork_host, pinned host buffers",
+               "check_norm2_first_2^20": nrm}
+        del h_in, h_out
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, cores, desc = cpu_sample(n, layers, angles, args.dtype, args.cpu_seconds)
+        cpu = {"value": v, "unit": "gate-apps/s", "cores": cores, "kind": "port", "sample": desc}
+
+    if rank == 0:
+        cname = "ComplexF64" if args.dtype == "c128" else "ComplexF32"
+        line = {
+            "metric": "gate_apps_per_sec", "value": value,
+            "unit": "gate-apps/s" if world == 1 else "gate-apps/s in 2^30-amplitude units (n-qubit gate-app counts 2^(n-30))",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64" if args.dtype == "c128" else "f32", "data": "synthetic",
+            "config": {"workload": f"{n}-qubit brickwork circuit, {layers} half-layers ({G} gates), {cname}, psi0=|0...0>, angles U[0,2pi)",
+                       "state_bytes_per_gpu": int(amp_bytes * 2 ** nloc), "l2_policy": "state (>= 16 GiB) is far larger than the 126 MB L2",
+                       "sharding": "none" if world == 1 else f"top {n - nloc} qubits over {world} ranks, qubit swaps via NCCL all-to-all",
+                       "gate_apps_per_sec_raw": gate_apps, "tile_bits": int(qc_opt("tile_bits", 11)), "low_bits": int(qc_opt("low_bits", 3))},
+            "gpu_launches": int(launches), "clocks": clocks,
+        }
+        if roofline:
+            line["roofline"] = roofline
+        if cpu:
+            line["cpu_baseline"] = cpu
+        if e2e:
+            line["e2e"] = e2e
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+_OPTS = {}
+
+
+def qc_opt(key, default):
+    return _OPTS.get(key, default)
+
+
+def main():
+    args = parse_args()
+    if args.tile_bits is not None:
+        _OPTS["tile_bits"] = args.tile_bits
+    if args.low_bits is not None:
+        _OPTS["low_bits"] = args.low_bits
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,113 @@
+"""apply / apply! entry points of the reference (src/apply.jl, src/circuits.jl:19-42).
+
+Julia's `apply!` is spelled `apply_` here.  The (psi', psi) ping-pong signature is kept: kernels
+run in place on a copy made into psi', and psi' is returned, so callers that swap buffers keep
+working (SURVEY.md 8b "In-place vs out-of-place").  Host NumPy arrays are accepted wherever
+the reference accepts an `Array`: they are uploaded, processed on the GPU and downloaded -- there is
+no CPU arithmetic path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .circuits import GenericBrickworkCircuit
+from .gates import AbstractGate, Abstract2SpinGate, Localised1SpinGate, Localised2SpinAdjGate, gate_abi_block
+from .state import B200State
+
+
+class B200ApplyCache:
+    """Stands where CPUApplyCache / GPUApplyCache stand (src/apply.jl:89-104).  Stateless: gate
+    matrices travel as kernel parameters, so there is no staging array to cache."""
+
+
+def construct_apply_cache(psi):
+    _lib.init()
+    return B200ApplyCache()
+
+
+def _check_pair(psi_out, psi):
+    if not isinstance(psi_out, B200State) or not isinstance(psi, B200State):
+        raise AssertionError("The backend of each array must be the same")  # src/apply.jl:107
+    if psi_out.nqubits != psi.nqubits or psi_out.dtype != psi.dtype:
+        raise ValueError("ψ′ must be the same size as ψ.")  # src/apply.jl:108
+
+
+def _apply_list_inplace(state, gates):
+    if not gates:
+        return
+    G = len(gates)
+    K = np.empty(G, dtype=np.int32)
+    ar = np.empty(G, dtype=np.int32)
+    mats = np.empty((G, 16), dtype=np.complex128)
+    for i, g in enumerate(gates):
+        if not isinstance(g, (Localised1SpinGate, Localised2SpinAdjGate)):
+            raise TypeError("gates must be Localised1SpinGate or Localised2SpinAdjGate")
+        ar[i], K[i], mats[i] = gate_abi_block(g)
+    _lib.check(_lib.lib().qcb_apply_gates(state._handle, C.c_int(G), K.ctypes.data_as(C.c_void_p),
+                                          ar.ctypes.data_as(C.c_void_p), mats.ctypes.data_as(C.c_void_p)))
+
+
+def _apply_circuit_inplace(state, circuit, first=0, last=None, adjoint=False):
+    last = circuit.ngates if last is None else last
+    a = circuit.angles_abi()
+    _lib.check(_lib.lib().qcb_apply_brickwork_range(state._handle, C.c_int(circuit.nbits), C.c_int(circuit.nlayers),
+                                                    a.ctypes.data_as(C.c_void_p), C.c_int(first), C.c_int(last),
+                                                    C.c_int(1 if adjoint else 0)))
+
+
+def apply_(*args):
+    """apply!(psi', psi, gate) | apply!(cache, psi', psi, gate) | apply!(cache, psi', psi, circuit)
+
+    src/apply.jl:20,39,117,121 and src/circuits.jl:19.  Returns the state that holds the result (psi')."""
+    if isinstance(args[0], B200ApplyCache):
+        args = args[1:]
+    psi_out, psi, op = args
+    _check_pair(psi_out, psi)
+    if psi_out is not psi:
+        psi_out.assign(psi)
+    if isinstance(op, GenericBrickworkCircuit):
+        _apply_circuit_inplace(psi_out, op)
+    else:
+        _apply_list_inplace(psi_out, [op])
+    return psi_out
+
+
+def apply(psi, op):
+    """apply(psi, gate) | apply(psi, gates) | apply(psi, circuit) -- src/apply.jl:1-18, src/circuits.jl:37-42.
+
+    The input is not modified.  NumPy in -> NumPy out (same shape), B200State in -> B200State out."""
+    host = not isinstance(psi, B200State)
+    if host and isinstance(op, GenericBrickworkCircuit):
+        return apply_circuit_host(psi, op)
+    st = B200State(psi)
+    if isinstance(op, GenericBrickworkCircuit):
+        _apply_circuit_inplace(st, op)
+    elif isinstance(op, AbstractGate):
+        _apply_list_inplace(st, [op])
+    else:
+        _apply_list_inplace(st, list(op))
+    if host:
+        out = st.to_numpy()
+        return out.reshape(np.shape(psi), order="F") if np.ndim(psi) > 1 else out
+    return st
+
+
+def apply_circuit_host(psi, circuit, out=None):
+    """apply(psi::Array, circuit) through the one-shot host-buffer entry point (H2D, circuit, D2H)."""
+    _lib.init()
+    src = np.asarray(psi)
+    flat = src.reshape(-1, order="F") if src.ndim > 1 else src
+    flat = np.ascontiguousarray(flat)
+    if flat.dtype not in (np.complex64, np.complex128):
+        flat = flat.astype(np.complex128)
+    if flat.size != 1 << circuit.nbits:
+        raise ValueError("state size does not match the circuit")
+    res = np.empty_like(flat) if out is None else out
+    a = circuit.angles_abi()
+    _lib.check(_lib.lib().qcb_apply_brickwork_host(C.c_int(1 if flat.dtype == np.complex128 else 0), C.c_int(circuit.nbits),
+                                                   C.c_int(circuit.nlayers), a.ctypes.data_as(C.c_void_p),
+                                                   flat.ctypes.data_as(C.c_void_p), res.ctypes.data_as(C.c_void_p)))
+    return res.reshape(src.shape, order="F") if src.ndim > 1 else res

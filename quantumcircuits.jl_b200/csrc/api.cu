@@ -1,0 +1,642 @@
+// api.cu -- the extern "C" surface of libqcb200.so (include/qcb200.h) and the host drivers
+// behind it.  Each entry point replaces the reference interface named in the header.
+#include <cmath>
+#include <cstring>
+
+#include "gates_host.hpp"
+#include "kernels.cuh"
+#include "qcb_internal.hpp"
+
+namespace qcb {
+
+static thread_local char g_err[1024] = "";
+
+Ctx &ctx()
+{
+    static Ctx c;
+    return c;
+}
+
+int set_error(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int ensure_scratch(int slot, size_t bytes)
+{
+    Ctx &c = ctx();
+    if (c.scratch_bytes[slot] >= bytes) return QCB_OK;
+    if (c.scratch[slot]) { cudaFree(c.scratch[slot]); c.scratch[slot] = nullptr; c.scratch_bytes[slot] = 0; }
+    QCB_CUDA(cudaMalloc(&c.scratch[slot], bytes));
+    c.scratch_bytes[slot] = bytes;
+    return QCB_OK;
+}
+int ensure_partial(size_t doubles)
+{
+    Ctx &c = ctx();
+    if (c.partial_cap >= doubles) return QCB_OK;
+    if (c.d_partial) cudaFree(c.d_partial);
+    c.d_partial = nullptr; c.partial_cap = 0;
+    QCB_CUDA(cudaMalloc(&c.d_partial, doubles * sizeof(double)));
+    c.partial_cap = doubles;
+    return QCB_OK;
+}
+int ensure_out(size_t doubles)
+{
+    Ctx &c = ctx();
+    if (c.out_cap >= doubles) return QCB_OK;
+    if (c.d_out) cudaFree(c.d_out);
+    if (c.h_out) cudaFreeHost(c.h_out);
+    c.d_out = nullptr; c.h_out = nullptr; c.out_cap = 0;
+    QCB_CUDA(cudaMalloc(&c.d_out, doubles * sizeof(double)));
+    QCB_CUDA(cudaMallocHost(&c.h_out, doubles * sizeof(double)));
+    c.out_cap = doubles;
+    return QCB_OK;
+}
+
+static unsigned grid_for(unsigned long long items, int threads, int per_sm)
+{
+    const unsigned long long want = (items + threads - 1) / threads;
+    const unsigned long long cap = (unsigned long long)ctx().sm_count * per_sm;
+    return (unsigned)std::max<unsigned long long>(1, std::min(want, cap));
+}
+
+static int check_state(const qcb_state *s)
+{
+    if (!s || !s->d) return set_error(QCB_EINVAL, "null state handle");
+    return QCB_OK;
+}
+
+// ---- measure ------------------------------------------------------------------------
+static int measure_impl(const qcb_state *s, int kind, double p0, double p1, double p2, double *out2)
+{
+    QCB_REQUIRE_INIT();
+    QCB_TRY(check_state(s));
+    if (s->sharded) return set_error(QCB_EUNSUPPORTED, "measure on a sharded state: use qcb_state_download_shard or gather first");
+    Ctx &c = ctx();
+    const unsigned long long namps = 1ull << s->nloc;
+    const unsigned blocks = grid_for(namps, kRedThreads, 8);
+    QCB_TRY(ensure_partial((size_t)blocks * 2));
+    QCB_TRY(ensure_out(64));
+    HamEval H{kind, s->n, p0, p1, p2};
+    if (s->dtype == QCB_C128)
+        k_measure<double><<<blocks, kRedThreads, 0, c.stream>>>((const double2 *)s->d, namps, H, (double2 *)c.d_partial);
+    else
+        k_measure<float><<<blocks, kRedThreads, 0, c.stream>>>((const float2 *)s->d, namps, H, (double2 *)c.d_partial);
+    QCB_CUDA(cudaGetLastError());
+    k_final_sum<<<2, 256, 0, c.stream>>>(c.d_partial, (int)blocks, 2, c.d_out);
+    QCB_CUDA(cudaGetLastError());
+    count_launch(2);
+    QCB_CUDA(cudaMemcpyAsync(c.h_out, c.d_out, 2 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    QCB_CUDA(cudaStreamSynchronize(c.stream));
+    out2[0] = c.h_out[0];
+    out2[1] = c.h_out[1];
+    return QCB_OK;
+}
+
+// ---- brickwork helpers ----------------------------------------------------------------
+static int brickwork_gates(int nbits, int nlayers, const double *angles, int first, int last, bool reverse,
+                           std::vector<GateOp> &gates, std::vector<double> &mats)
+{
+    if (nbits < 2) return set_error(QCB_EINVAL, "a brickwork circuit needs at least 2 qubits");
+    const std::vector<int> pos = brickwork_positions(nbits, nlayers);
+    const int G = (int)pos.size();
+    if (first < 0 || last > G || first > last) return set_error(QCB_EINVAL, "gate range [%d, %d) outside [0, %d)", first, last, G);
+    const int m = last - first;
+    gates.resize(m);
+    mats.resize((size_t)32 * m);
+    for (int i = 0; i < m; i++) {
+        const int g = reverse ? (last - 1 - i) : (first + i);
+        to_doubles(general_unitary(angles + 15 * (size_t)g), mats.data() + 32 * (size_t)i);
+        gates[i] = GateOp{pos[g], i};
+    }
+    return QCB_OK;
+}
+
+static int copy_state_raw(void *dst, const void *src, size_t bytes)
+{
+    QCB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, ctx().stream));
+    return QCB_OK;
+}
+
+// adjoint-method gradient; numbers equal the reference's shift sweep.
+static int gradients_impl(const qcb_state *psi0, int nbits, int nlayers, const double *angles, int ham_kind, const double *hp,
+                          int want_energy, double *out_E, double *out_grads)
+{
+    QCB_REQUIRE_INIT();
+    QCB_TRY(check_state(psi0));
+    if (psi0->sharded) return set_error(QCB_EUNSUPPORTED, "gradients on sharded states are not supported");
+    if (psi0->n != nbits) return set_error(QCB_EINVAL, "circuit has %d qubits, state has %d", nbits, psi0->n);
+    if (ham_kind != QCB_HAM_TFIM && ham_kind != QCB_HAM_EAST) return set_error(QCB_EINVAL, "unknown Hamiltonian kind %d", ham_kind);
+    Ctx &c = ctx();
+    const std::vector<int> pos = brickwork_positions(nbits, nlayers);
+    const int G = (int)pos.size();
+    QCB_TRY(ensure_scratch(0, psi0->bytes));
+    QCB_TRY(ensure_scratch(1, psi0->bytes));
+    qcb_state A = *psi0, B = *psi0;
+    A.d = c.scratch[0]; A.owned = false;
+    B.d = c.scratch[1]; B.owned = false;
+    QCB_TRY(copy_state_raw(A.d, psi0->d, psi0->bytes)); // psi .= psi0   gradients.jl:90
+    std::vector<GateOp> gates;
+    std::vector<double> mats;
+    QCB_TRY(brickwork_gates(nbits, nlayers, angles, 0, G, false, gates, mats));
+    QCB_TRY(run_gate_list(&A, gates, mats.data(), false)); // forward pass  gradients.jl:92-101
+    const double fw_passes = c.st_passes, fw_stages = c.st_stages, fw_launches = c.st_launches;
+    if (want_energy) {
+        double E2[2];
+        QCB_TRY(measure_impl(&A, ham_kind, hp[0], hp[1], hp[2], E2)); // gradients.jl:104
+        *out_E = E2[0];
+    }
+    if (G == 0) return QCB_OK;
+    // lambda = H psi_G
+    const unsigned long long namps = 1ull << nbits;
+    HamEval H{ham_kind, nbits, hp[0], hp[1], hp[2]};
+    {
+        const unsigned blocks = grid_for(namps, 256, 16);
+        if (psi0->dtype == QCB_C128)
+            k_apply_ham<double><<<blocks, 256, 0, c.stream>>>((double2 *)B.d, (const double2 *)A.d, namps, H);
+        else
+            k_apply_ham<float><<<blocks, 256, 0, c.stream>>>((float2 *)B.d, (const float2 *)A.d, namps, H);
+        QCB_CUDA(cudaGetLastError());
+        count_launch();
+    }
+    // backward sweep: un-apply gate g on psi and lambda, reduce the 4x4 environment
+    const unsigned long long nquads = namps >> 2;
+    const unsigned blocks = grid_for(nquads, kRedThreads, 4);
+    QCB_TRY(ensure_partial((size_t)blocks * 32));
+    QCB_TRY(ensure_out((size_t)32 * G));
+    for (int g = G - 1; g >= 0; g--) {
+        const double *m = mats.data() + 32 * (size_t)g;
+        if (psi0->dtype == QCB_C128) {
+            GateMat<double> Ud;
+            for (int r = 0; r < 4; r++)
+                for (int cc = 0; cc < 4; cc++) { Ud.v[2 * (r + 4 * cc)] = m[2 * (cc + 4 * r)]; Ud.v[2 * (r + 4 * cc) + 1] = -m[2 * (cc + 4 * r) + 1]; }
+            k_adjoint_step<double><<<blocks, kRedThreads, 0, c.stream>>>((double2 *)A.d, (double2 *)B.d, nquads, pos[g], Ud, c.d_partial);
+        } else {
+            GateMat<float> Ud;
+            for (int r = 0; r < 4; r++)
+                for (int cc = 0; cc < 4; cc++) { Ud.v[2 * (r + 4 * cc)] = (float)m[2 * (cc + 4 * r)]; Ud.v[2 * (r + 4 * cc) + 1] = (float)-m[2 * (cc + 4 * r) + 1]; }
+            k_adjoint_step<float><<<blocks, kRedThreads, 0, c.stream>>>((float2 *)A.d, (float2 *)B.d, nquads, pos[g], Ud, c.d_partial);
+        }
+        QCB_CUDA(cudaGetLastError());
+        k_final_sum<<<32, 128, 0, c.stream>>>(c.d_partial, (int)blocks, 32, c.d_out + 32 * (size_t)g);
+        QCB_CUDA(cudaGetLastError());
+        count_launch(2);
+    }
+    QCB_CUDA(cudaMemcpyAsync(c.h_out, c.d_out, sizeof(double) * 32 * (size_t)G, cudaMemcpyDeviceToHost, c.stream));
+    QCB_CUDA(cudaStreamSynchronize(c.stream));
+    // grads[k, g] = 2 Re sum_{r,c} env_g[r,c] dU_g/dtheta_k [r,c]
+    for (int g = 0; g < G; g++) {
+        const double *env = c.h_out + 32 * (size_t)g;
+        for (int k = 0; k < 15; k++) {
+            const M4 dU = general_unitary(angles + 15 * (size_t)g, k);
+            double s = 0;
+            for (int i = 0; i < 16; i++) s += env[2 * i] * dU.m[i].real() - env[2 * i + 1] * dU.m[i].imag();
+            out_grads[k + 15 * (size_t)g] = 2 * s;
+        }
+    }
+    c.st_passes += fw_passes + G; c.st_stages += fw_stages; c.st_launches += fw_launches; c.st_gates = 4.0 * G;
+    return QCB_OK;
+}
+
+} // namespace qcb
+
+using namespace qcb;
+
+extern "C" {
+
+const char *qcb_last_error(void) { return g_err; }
+const char *qcb_version(void) { return "qcb200 0.1.0 (sm_100a)"; }
+
+int qcb_device_count(int *out)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { *out = 0; return set_error(QCB_ECUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e)); }
+    *out = n;
+    return QCB_OK;
+}
+
+int qcb_init(int device)
+{
+    Ctx &c = ctx();
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return set_error(QCB_ECUDA, "no CUDA device available (%s); this backend has no CPU fallback",
+                         e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    if (device < 0 || device >= n) return set_error(QCB_EINVAL, "device %d out of range [0, %d)", device, n);
+    if (c.inited && c.device == device) return QCB_OK;
+    if (c.inited) qcb_finalize();
+    QCB_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    QCB_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return set_error(QCB_ECUDA, "device %d is sm_%d%d; libqcb200 is built for sm_100a (B200) only", device, prop.major, prop.minor);
+    c.sm_count = prop.multiProcessorCount;
+    c.stream = nullptr; // the CUDA default stream, shared with the host framework unless qcb_set_stream is called
+    QCB_CUDA(cudaEventCreate(&c.ev0));
+    QCB_CUDA(cudaEventCreate(&c.ev1));
+    c.device = device;
+    c.inited = true;
+    return QCB_OK;
+}
+
+int qcb_finalize(void)
+{
+    Ctx &c = ctx();
+    if (!c.inited) return QCB_OK;
+    cudaStreamSynchronize(c.stream);
+    for (int i = 0; i < 3; i++) { if (c.scratch[i]) cudaFree(c.scratch[i]); c.scratch[i] = nullptr; c.scratch_bytes[i] = 0; }
+    if (c.d_partial) cudaFree(c.d_partial);
+    if (c.d_out) cudaFree(c.d_out);
+    if (c.h_out) cudaFreeHost(c.h_out);
+    c.d_partial = c.d_out = c.h_out = nullptr;
+    c.partial_cap = c.out_cap = 0;
+    cudaEventDestroy(c.ev0); cudaEventDestroy(c.ev1);
+    c.stream = nullptr;
+    c.plan_cache.clear();
+    c.inited = false;
+    return QCB_OK;
+}
+
+int qcb_sync(void)
+{
+    QCB_REQUIRE_INIT();
+    QCB_CUDA(cudaStreamSynchronize(ctx().stream));
+    return QCB_OK;
+}
+
+int qcb_set_stream(void *cuda_stream)
+{
+    QCB_REQUIRE_INIT();
+    Ctx &c = ctx();
+    QCB_CUDA(cudaStreamSynchronize(c.stream));
+    c.stream = (cudaStream_t)cuda_stream; // NULL = the CUDA default stream
+    return QCB_OK;
+}
+
+int qcb_timer_start(void)
+{
+    QCB_REQUIRE_INIT();
+    QCB_CUDA(cudaEventRecord(ctx().ev0, ctx().stream));
+    return QCB_OK;
+}
+int qcb_timer_stop(float *out_ms)
+{
+    QCB_REQUIRE_INIT();
+    QCB_CUDA(cudaEventRecord(ctx().ev1, ctx().stream));
+    QCB_CUDA(cudaEventSynchronize(ctx().ev1));
+    QCB_CUDA(cudaEventElapsedTime(out_ms, ctx().ev0, ctx().ev1));
+    return QCB_OK;
+}
+
+int qcb_set_option(const char *key, long value)
+{
+    Ctx &c = ctx();
+    const std::string k(key ? key : "");
+    if (k == "tile_bits") {
+        if (value < kMinTB || value > kMaxTB) return set_error(QCB_EINVAL, "tile_bits must be in [%d, %d]", kMinTB, kMaxTB);
+        c.tile_bits = value;
+    } else if (k == "low_bits") {
+        if (value < 0 || value > 6) return set_error(QCB_EINVAL, "low_bits must be in [0, 6]");
+        c.low_bits = value;
+    } else if (k == "max_gates_per_pass") {
+        if (value < 1) return set_error(QCB_EINVAL, "max_gates_per_pass must be >= 1");
+        c.max_gates_per_pass = value;
+    } else if (k == "force_simple") {
+        c.force_simple = value ? 1 : 0;
+    } else
+        return set_error(QCB_EINVAL, "unknown option '%s'", k.c_str());
+    c.plan_cache.clear();
+    return QCB_OK;
+}
+
+int qcb_get_stat(const char *key, double *out)
+{
+    Ctx &c = ctx();
+    const std::string k(key ? key : "");
+    if (k == "passes") *out = c.st_passes;
+    else if (k == "stages") *out = c.st_stages;
+    else if (k == "launches") *out = c.st_launches;
+    else if (k == "gates") *out = c.st_gates;
+    else if (k == "launches_total") *out = c.st_launches_total;
+    else if (k == "sm_count") *out = c.sm_count;
+    else return set_error(QCB_EINVAL, "unknown stat '%s'", k.c_str());
+    return QCB_OK;
+}
+
+// ---- states -----------------------------------------------------------------------------
+static int new_state(int nqubits, int dtype, void *wrap, bool sharded, qcb_state **out)
+{
+    QCB_REQUIRE_INIT();
+    if (!out) return set_error(QCB_EINVAL, "null output pointer");
+    if (dtype != QCB_C64 && dtype != QCB_C128) return set_error(QCB_EINVAL, "dtype must be QCB_C64 (0) or QCB_C128 (1)");
+    Ctx &c = ctx();
+    int gbits = 0;
+    if (sharded) {
+        if (c.nranks < 2 || !c.nccl_comm) return set_error(QCB_EINVAL, "qcb_dist_init must be called before creating sharded states");
+        while ((1 << gbits) < c.nranks) gbits++;
+    }
+    if (nqubits < 1 || nqubits - gbits > 40 || nqubits - gbits < 1) return set_error(QCB_EINVAL, "nqubits = %d not supported", nqubits);
+    if (sharded && nqubits - gbits < kMaxTB + gbits) return set_error(QCB_EINVAL, "sharded states need at least %d local qubits", kMaxTB + gbits);
+    qcb_state *s = new qcb_state;
+    s->n = nqubits;
+    s->nloc = nqubits - gbits;
+    s->dtype = dtype;
+    s->sharded = sharded;
+    s->bytes = amp_bytes(dtype) << s->nloc;
+    s->phys.resize(nqubits);
+    for (int q = 0; q < nqubits; q++) s->phys[q] = q;
+    if (wrap) {
+        s->d = wrap;
+        s->owned = false;
+    } else {
+        cudaError_t e = cudaMalloc(&s->d, s->bytes);
+        if (e != cudaSuccess) {
+            delete s;
+            return set_error(e == cudaErrorMemoryAllocation ? QCB_ENOMEM : QCB_ECUDA, "cudaMalloc(%zu bytes): %s", (size_t)(amp_bytes(dtype) << (nqubits - gbits)), cudaGetErrorString(e));
+        }
+        s->owned = true;
+    }
+    *out = s;
+    return QCB_OK;
+}
+
+int qcb_state_create(int nqubits, int dtype, qcb_state **out) { return new_state(nqubits, dtype, nullptr, false, out); }
+int qcb_state_wrap(int nqubits, int dtype, void *device_ptr, qcb_state **out)
+{
+    if (!device_ptr) return set_error(QCB_EINVAL, "null device pointer");
+    return new_state(nqubits, dtype, device_ptr, false, out);
+}
+int qcb_state_create_sharded(int nqubits, int dtype, qcb_state **out) { return new_state(nqubits, dtype, nullptr, true, out); }
+
+int qcb_state_destroy(qcb_state *s)
+{
+    if (!s) return QCB_OK;
+    if (s->owned && s->d) {
+        if (ctx().inited) cudaStreamSynchronize(ctx().stream);
+        cudaFree(s->d);
+    }
+    delete s;
+    return QCB_OK;
+}
+int qcb_state_nqubits(const qcb_state *s, int *out) { QCB_TRY(check_state(s)); *out = s->n; return QCB_OK; }
+int qcb_state_local_qubits(const qcb_state *s, int *out) { QCB_TRY(check_state(s)); *out = s->nloc; return QCB_OK; }
+int qcb_state_dtype(const qcb_state *s, int *out) { QCB_TRY(check_state(s)); *out = s->dtype; return QCB_OK; }
+int qcb_state_device_ptr(const qcb_state *s, void **out) { QCB_TRY(check_state(s)); *out = s->d; return QCB_OK; }
+
+int qcb_state_set_zero_state(qcb_state *s)
+{
+    QCB_REQUIRE_INIT();
+    QCB_TRY(check_state(s));
+    const unsigned long long namps = 1ull << s->nloc;
+    const int set_one = (!s->sharded || ctx().rank == 0) ? 1 : 0;
+    const unsigned blocks = grid_for(namps, 256, 16);
+    if (s->dtype == QCB_C128) k_set_zero_state<double><<<blocks, 256, 0, ctx().stream>>>((double2 *)s->d, namps, set_one);
+    else k_set_zero_state<float><<<blocks, 256, 0, ctx().stream>>>((float2 *)s->d, namps, set_one);
+    QCB_CUDA(cudaGetLastError());
+    count_launch();
+    for (int q = 0; q < s->n; q++) s->phys[q] = q;
+    return QCB_OK;
+}
+
+int qcb_state_upload(qcb_state *s, const void *host)
+{
+    QCB_REQUIRE_INIT();
+    QCB_TRY(check_state(s));
+    if (!host) return set_error(QCB_EINVAL, "null host pointer");
+    if (s->sharded) return set_error(QCB_EINVAL, "use qcb_state_upload_shard for sharded states");
+    QCB_CUDA(cudaMemcpyAsync(s->d, host, s->bytes, cudaMemcpyHostToDevice, ctx().stream));
+    QCB_CUDA(cudaStreamSynchronize(ctx().stream));
+    return QCB_OK;
+}
+int qcb_state_download(const qcb_state *s, void *host)
+{
+    QCB_REQUIRE_INIT();
+    QCB_TRY(check_state(s));
+    if (!host) return set_error(QCB_EINVAL, "null host pointer");
+    if (s->sharded) return set_error(QCB_EINVAL, "use qcb_state_download_shard for sharded states");
+    QCB_CUDA(cudaMemcpyAsync(host, s->d, s->bytes, cudaMemcpyDeviceToHost, ctx().stream));
+    QCB_CUDA(cudaStreamSynchronize(ctx().stream));
+    return QCB_OK;
+}
+int qcb_state_upload_shard(qcb_state *s, const void *host)
+{
+    QCB_REQUIRE_INIT();
+    QCB_TRY(check_state(s));
+    if (!host) return set_error(QCB_EINVAL, "null host pointer");
+    QCB_CUDA(cudaMemcpyAsync(s->d, host, s->bytes, cudaMemcpyHostToDevice, ctx().stream));
+    QCB_CUDA(cudaStreamSynchronize(ctx().stream));
+    for (int q = 0; q < s->n; q++) s->phys[q] = q;
+    return QCB_OK;
+}
+int qcb_state_download_shard(qcb_state *s, void *host)
+{
+    QCB_REQUIRE_INIT();
+    QCB_TRY(check_state(s));
+    if (!host) return set_error(QCB_EINVAL, "null host pointer");
+    if (s->sharded) QCB_TRY(dist_state_canonicalize(s));
+    QCB_CUDA(cudaMemcpyAsync(host, s->d, s->bytes, cudaMemcpyDeviceToHost, ctx().stream));
+    QCB_CUDA(cudaStreamSynchronize(ctx().stream));
+    return QCB_OK;
+}
+
+int qcb_state_copy(qcb_state *dst, const qcb_state *src)
+{
+    QCB_REQUIRE_INIT();
+    QCB_TRY(check_state(dst));
+    QCB_TRY(check_state(src));
+    if (dst->n != src->n || dst->dtype != src->dtype || dst->nloc != src->nloc)
+        return set_error(QCB_EINVAL, "ψ′ must be the same size as ψ."); // src/apply.jl:108
+    QCB_TRY(copy_state_raw(dst->d, src->d, src->bytes));
+    dst->phys = src->phys;
+    return QCB_OK;
+}
+
+int qcb_state_norm2(const qcb_state *s, double *out)
+{
+    QCB_REQUIRE_INIT();
+    QCB_TRY(check_state(s));
+    Ctx &c = ctx();
+    const unsigned long long namps = 1ull << s->nloc;
+    const unsigned blocks = grid_for(namps, kRedThreads, 8);
+    QCB_TRY(ensure_partial(blocks));
+    QCB_TRY(ensure_out(64));
+    if (s->dtype == QCB_C128) k_norm2<double><<<blocks, kRedThreads, 0, c.stream>>>((const double2 *)s->d, namps, c.d_partial);
+    else k_norm2<float><<<blocks, kRedThreads, 0, c.stream>>>((const float2 *)s->d, namps, c.d_partial);
+    QCB_CUDA(cudaGetLastError());
+    k_final_sum<<<1, 256, 0, c.stream>>>(c.d_partial, (int)blocks, 1, c.d_out);
+    QCB_CUDA(cudaGetLastError());
+    count_launch(2);
+    QCB_CUDA(cudaMemcpyAsync(c.h_out, c.d_out, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    QCB_CUDA(cudaStreamSynchronize(c.stream));
+    *out = c.h_out[0]; // local shard only for sharded states
+    return QCB_OK;
+}
+
+// ---- host gate algebra --------------------------------------------------------------------
+int qcb_build_general_unitary_gate(const double *angles15, double *out_u32)
+{
+    if (!angles15 || !out_u32) return set_error(QCB_EINVAL, "null pointer");
+    to_doubles(general_unitary(angles15), out_u32);
+    return QCB_OK;
+}
+int qcb_general_unitary_gate_derivative(const double *angles15, int k, double *out_u32)
+{
+    if (!angles15 || !out_u32 || k < 0 || k > 14) return set_error(QCB_EINVAL, "bad arguments");
+    to_doubles(general_unitary(angles15, k), out_u32);
+    return QCB_OK;
+}
+int qcb_brickwork_num_gates(int nbits, int nlayers) { return (int)brickwork_positions(nbits, nlayers).size(); }
+
+// ---- gate application ---------------------------------------------------------------------
+int qcb_apply_gates(qcb_state *s, int ngates, const int *K, const int *arity, const double *mats_in)
+{
+    QCB_REQUIRE_INIT();
+    QCB_TRY(check_state(s));
+    if (ngates < 0 || (ngates > 0 && (!K || !arity || !mats_in))) return set_error(QCB_EINVAL, "bad gate list");
+    const int n = s->n;
+    // a lone 1-qubit state has no pair to embed into: dedicated kernel
+    if (n == 1) {
+        for (int g = 0; g < ngates; g++) {
+            if (arity[g] != 1 || K[g] != 1) return set_error(QCB_EINVAL, "The gate cannot be applied as it sits outside the qubit space.");
+            const double *u = mats_in + 32 * (size_t)g;
+            if (s->dtype == QCB_C128) {
+                Gate1<double> U; for (int i = 0; i < 8; i++) U.v[i] = u[i];
+                k_apply_1q_simple<double><<<1, 32, 0, ctx().stream>>>((double2 *)s->d, 1ull, 0, U);
+            } else {
+                Gate1<float> U; for (int i = 0; i < 8; i++) U.v[i] = (float)u[i];
+                k_apply_1q_simple<float><<<1, 32, 0, ctx().stream>>>((float2 *)s->d, 1ull, 0, U);
+            }
+            QCB_CUDA(cudaGetLastError());
+            count_launch();
+        }
+        return QCB_OK;
+    }
+    std::vector<GateOp> gates(ngates);
+    std::vector<double> mats((size_t)32 * ngates);
+    for (int g = 0; g < ngates; g++) {
+        const double *u = mats_in + 32 * (size_t)g;
+        if (arity[g] == 2) {
+            if (!(K[g] > 0 && K[g] < n)) // src/apply.jl:112
+                return set_error(QCB_EINVAL, "The gate cannot be applied as it sits outside the qubit space.");
+            std::memcpy(mats.data() + 32 * (size_t)g, u, 32 * sizeof(double));
+            gates[g] = GateOp{K[g] - 1, g};
+        } else if (arity[g] == 1) {
+            if (!(K[g] >= 1 && K[g] <= n)) // src/apply.jl:27
+                return set_error(QCB_EINVAL, "The gate cannot be applied as it sits outside the qubit space.");
+            const bool on_low = K[g] < n; // pair (K, K+1) unless K is the last qubit
+            embed_1q(u, on_low, mats.data() + 32 * (size_t)g);
+            gates[g] = GateOp{on_low ? K[g] - 1 : K[g] - 2, g};
+        } else
+            return set_error(QCB_EINVAL, "gate %d: arity must be 1 or 2", g);
+    }
+    return run_gate_list(s, gates, mats.data(), false);
+}
+
+int qcb_apply_1q(qcb_state *s, const double *u8, int K)
+{
+    if (!u8) return set_error(QCB_EINVAL, "null gate");
+    double m[32] = {0};
+    std::memcpy(m, u8, 8 * sizeof(double));
+    const int ar = 1;
+    return qcb_apply_gates(s, 1, &K, &ar, m);
+}
+int qcb_apply_2q(qcb_state *s, const double *u32, int K)
+{
+    if (!u32) return set_error(QCB_EINVAL, "null gate");
+    const int ar = 2;
+    return qcb_apply_gates(s, 1, &K, &ar, u32);
+}
+
+int qcb_apply_brickwork_range(qcb_state *s, int nbits, int nlayers, const double *angles, int first_gate, int last_gate, int adjoint)
+{
+    QCB_REQUIRE_INIT();
+    QCB_TRY(check_state(s));
+    if (s->n != nbits) return set_error(QCB_EINVAL, "circuit has %d qubits, state has %d", nbits, s->n);
+    if (!angles && last_gate > first_gate) return set_error(QCB_EINVAL, "null angles");
+    std::vector<GateOp> gates;
+    std::vector<double> mats;
+    QCB_TRY(brickwork_gates(nbits, nlayers, angles, first_gate, last_gate, adjoint != 0, gates, mats));
+    return run_gate_list(s, gates, mats.data(), adjoint != 0);
+}
+int qcb_apply_brickwork(qcb_state *s, int nbits, int nlayers, const double *angles)
+{
+    return qcb_apply_brickwork_range(s, nbits, nlayers, angles, 0, qcb_brickwork_num_gates(nbits, nlayers), 0);
+}
+
+int qcb_apply_brickwork_host(int dtype, int nbits, int nlayers, const double *angles, const void *psi_in_host, void *psi_out_host)
+{
+    QCB_REQUIRE_INIT();
+    if (!psi_out_host) return set_error(QCB_EINVAL, "null output buffer");
+    if (dtype != QCB_C64 && dtype != QCB_C128) return set_error(QCB_EINVAL, "bad dtype");
+    if (nbits < 1 || nbits > 40) return set_error(QCB_EINVAL, "bad qubit count");
+    Ctx &c = ctx();
+    const size_t bytes = amp_bytes(dtype) << nbits;
+    QCB_TRY(ensure_scratch(2, bytes));
+    qcb_state s;
+    s.n = s.nloc = nbits; s.dtype = dtype; s.d = c.scratch[2]; s.bytes = bytes;
+    s.phys.resize(nbits);
+    for (int q = 0; q < nbits; q++) s.phys[q] = q;
+    if (psi_in_host) QCB_CUDA(cudaMemcpyAsync(s.d, psi_in_host, bytes, cudaMemcpyHostToDevice, c.stream));
+    else QCB_TRY(qcb_state_set_zero_state(&s));
+    QCB_TRY(qcb_apply_brickwork(&s, nbits, nlayers, angles));
+    QCB_CUDA(cudaMemcpyAsync(psi_out_host, s.d, bytes, cudaMemcpyDeviceToHost, c.stream));
+    QCB_CUDA(cudaStreamSynchronize(c.stream));
+    return QCB_OK;
+}
+
+// ---- expectation values ---------------------------------------------------------------------
+int qcb_measure_tfim(const qcb_state *s, double J, double h, double g, double *out_E2)
+{
+    if (!out_E2) return set_error(QCB_EINVAL, "null output");
+    return measure_impl(s, QCB_HAM_TFIM, J, h, g, out_E2);
+}
+int qcb_measure_east(const qcb_state *s, double c, double A, double B, double *out_E2)
+{
+    if (!out_E2) return set_error(QCB_EINVAL, "null output");
+    return measure_impl(s, QCB_HAM_EAST, c, A, B, out_E2);
+}
+
+// ---- gradients / optimisation -----------------------------------------------------------------
+int qcb_gradients_brickwork(const qcb_state *psi0, int nbits, int nlayers, const double *angles, int ham_kind,
+                            const double *ham_params3, int want_energy, double *out_E, double *out_grads)
+{
+    if (!angles || !ham_params3 || !out_grads || (want_energy && !out_E)) return set_error(QCB_EINVAL, "null pointer");
+    return gradients_impl(psi0, nbits, nlayers, angles, ham_kind, ham_params3, want_energy, out_E, out_grads);
+}
+
+int qcb_optimise_brickwork(const qcb_state *psi0, int nbits, int nlayers, double *angles, int ham_kind, const double *hp,
+                           int epochs, double lr, double *energies)
+{
+    QCB_REQUIRE_INIT();
+    if (!angles || !hp || !energies || epochs < 0) return set_error(QCB_EINVAL, "bad arguments");
+    const int G = qcb_brickwork_num_gates(nbits, nlayers);
+    std::vector<double> grads((size_t)15 * std::max(G, 1));
+    energies[0] = 0.0; // never written by the reference (src/gradients.jl:5,11)
+    for (int e = 1; e <= epochs; e++) {
+        double E = 0;
+        QCB_TRY(gradients_impl(psi0, nbits, nlayers, angles, ham_kind, hp, 1, &E, grads.data()));
+        energies[e] = E;                                                          // :11
+        for (size_t i = 0; i < (size_t)15 * G; i++) angles[i] -= lr * grads[i];  // :13
+    }
+    // energies[end] = measure(H, psi0, circuit)   :15
+    Ctx &c = ctx();
+    QCB_TRY(check_state(psi0));
+    QCB_TRY(ensure_scratch(0, psi0->bytes));
+    qcb_state A = *psi0;
+    A.d = c.scratch[0]; A.owned = false;
+    QCB_TRY(copy_state_raw(A.d, psi0->d, psi0->bytes));
+    QCB_TRY(qcb_apply_brickwork(&A, nbits, nlayers, angles));
+    double E2[2];
+    QCB_TRY(measure_impl(&A, ham_kind, hp[0], hp[1], hp[2], E2));
+    energies[epochs] = E2[0];
+    return QCB_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,253 @@
+// kernels.cuh -- the non-tiled device kernels of the backend:
+//   * single-gate in-place kernels (small states, `force_simple` cross-check path),
+//   * fused sweep-and-reduce expectation values for the kernel Hamiltonians
+//     (replaces _tfim_measure! src/hamiltonians/tfim.jl:17-54 and _eastmodel_measure!
+//     src/hamiltonians/east_model.jl:30-52 *plus* the separate sum(psi') pass of
+//     src/hamiltonians/hamiltonians.jl:41 -- no scratch state is written),
+//   * lambda = H psi and the 4x4 environment reduction of the adjoint gradient sweep
+//     (replaces the O(G^2) shift sweep of src/gradients.jl:88-152).
+// Reductions are deterministic: warp shuffles -> one partial per CTA -> fixed-order final sum.
+#pragma once
+#include "tile.cuh"
+
+namespace qcb {
+
+constexpr int kRedThreads = 256;
+
+template <typename R> struct HamParams {
+    int kind;       // 0 TFIM (p0 = J, p1 = h, p2 = g); 1 East (p0 = c, p1 = A, p2 = B)
+    double p0, p1, p2;
+};
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// sums NV doubles per thread over the CTA; result valid in thread 0 (written to out[0..NV)).
+template <int NV> __device__ __forceinline__ void block_sum(double (&v)[NV], double *out)
+{
+    __shared__ double red[kRedThreads / 32][NV];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; i++) {
+        const double s = warp_sum(v[i]);
+        if (lane == 0) red[warp][i] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < NV) {
+        double s = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) s += red[w][threadIdx.x];
+        out[threadIdx.x] = s;
+    }
+    __syncthreads();
+}
+
+// ---- in-place single gates --------------------------------------------------------
+template <typename R>
+__global__ void __launch_bounds__(256) k_apply_2q_simple(typename Vec2<R>::type *psi, unsigned long long nquads, int kb,
+                                                         const __grid_constant__ GateMat<R> U)
+{
+    using V = typename Vec2<R>::type;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    const unsigned long long low = (1ull << kb) - 1ull;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < nquads; i += stride) {
+        const unsigned long long base = ((i >> kb) << (kb + 2)) | (i & low);
+        V x0 = psi[base], x1 = psi[base | (1ull << kb)], x2 = psi[base | (2ull << kb)], x3 = psi[base | (3ull << kb)];
+        apply_quad<R, V>(x0, x1, x2, x3, U);
+        psi[base] = x0; psi[base | (1ull << kb)] = x1; psi[base | (2ull << kb)] = x2; psi[base | (3ull << kb)] = x3;
+    }
+}
+
+// 1-qubit gate on bit kb: u[out + 2 in] as 8 reals
+template <typename R> struct Gate1 { R v[8]; };
+template <typename R>
+__global__ void __launch_bounds__(256) k_apply_1q_simple(typename Vec2<R>::type *psi, unsigned long long npairs, int kb,
+                                                         const __grid_constant__ Gate1<R> U)
+{
+    using V = typename Vec2<R>::type;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    const unsigned long long low = (1ull << kb) - 1ull;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < npairs; i += stride) {
+        const unsigned long long base = ((i >> kb) << (kb + 1)) | (i & low);
+        const V a = psi[base], b = psi[base | (1ull << kb)];
+        V o0, o1;
+        o0.x = U.v[0] * a.x - U.v[1] * a.y + U.v[4] * b.x - U.v[5] * b.y;
+        o0.y = U.v[0] * a.y + U.v[1] * a.x + U.v[4] * b.y + U.v[5] * b.x;
+        o1.x = U.v[2] * a.x - U.v[3] * a.y + U.v[6] * b.x - U.v[7] * b.y;
+        o1.y = U.v[2] * a.y + U.v[3] * a.x + U.v[6] * b.y + U.v[7] * b.x;
+        psi[base] = o0; psi[base | (1ull << kb)] = o1;
+    }
+}
+
+template <typename R>
+__global__ void __launch_bounds__(256) k_set_zero_state(typename Vec2<R>::type *psi, unsigned long long n, int set_one)
+{
+    using V = typename Vec2<R>::type;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        V z; z.x = (i == 0 && set_one) ? (R)1 : (R)0; z.y = (R)0;
+        psi[i] = z;
+    }
+}
+
+// ---- Hamiltonian diagonal / off-diagonal pieces -----------------------------------
+// C is the full logical configuration.  diag(C): coefficient of |psi[C]|^2 ; the off-diagonal
+// part is coef * sum_i w_i(C) psi[C ^ 2^i].
+struct HamEval {
+    int kind, n;
+    double p0, p1, p2;
+    __device__ __forceinline__ double diag(unsigned long long C) const
+    {
+        if (kind == 0) { // -J (zz + h z)        tfim.jl:25-32,48-52
+            const unsigned long long pairmask = (n >= 2) ? ((1ull << (n - 1)) - 1ull) : 0ull;
+            const int eq = __popcll(~(C ^ (C >> 1)) & pairmask);
+            const int zz = 2 * eq - (n - 1);
+            const int z = n - 2 * __popcll(C);
+            return -p0 * ((double)zz + p1 * (double)z);
+        }
+        // East: B * (n_0 + sum_{i>=1} n_{i-1} n_i + c n_{i-1}) + c       east_model.jl:38-50
+        const unsigned long long all = (n >= 64) ? ~0ull : ((1ull << n) - 1ull);
+        const unsigned long long zero = ~C & all; // bit i set iff n_i = 1
+        const unsigned long long prev = zero & ((n >= 2) ? ((1ull << (n - 1)) - 1ull) : 0ull); // n_{i-1}, i = 1..n-1
+        const int nn = __popcll(prev & (zero >> 1));
+        const int np = __popcll(prev);
+        return p2 * ((double)(zero & 1ull) + (double)nn + p0 * (double)np) + p0;
+    }
+    __device__ __forceinline__ double offdiag_coef() const { return kind == 0 ? -p0 * p2 : p1; }
+    // weight of the flip of bit i at configuration C
+    __device__ __forceinline__ bool flip_on(unsigned long long C, int i) const
+    {
+        if (kind == 0 || i == 0) return true;
+        return ((C >> (i - 1)) & 1ull) == 0ull; // n_{i-1}
+    }
+};
+
+// E = sum_C conj(psi[C]) (H psi)[C], accumulated in double; one pass, no scratch state.
+// `base` / `perm` support sharded states: logical C = base | deposit(local index).
+template <typename R>
+__global__ void __launch_bounds__(kRedThreads) k_measure(const typename Vec2<R>::type *__restrict__ psi,
+                                                         unsigned long long namps, HamEval H, double2 *partial)
+{
+    using V = typename Vec2<R>::type;
+    double acc[2] = {0.0, 0.0};
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    const double oc = H.offdiag_coef();
+    for (unsigned long long C = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; C < namps; C += stride) {
+        const V p = psi[C];
+        const double pr = (double)p.x, pi = (double)p.y;
+        double xr = 0, xi = 0;
+        for (int i = 0; i < H.n; i++) {
+            if (!H.flip_on(C, i)) continue;
+            const V o = psi[C ^ (1ull << i)];
+            xr += (double)o.x;
+            xi += (double)o.y;
+        }
+        // conj(x) * p  (tfim.jl:39-46: x = sum conj(psi_other); tf = x * psi)
+        acc[0] += H.diag(C) * (pr * pr + pi * pi) + oc * (xr * pr + xi * pi);
+        acc[1] += oc * (xr * pi - xi * pr);
+    }
+    __shared__ double out[2];
+    block_sum<2>(acc, out);
+    if (threadIdx.x == 0) partial[blockIdx.x] = make_double2(out[0], out[1]);
+}
+
+// lambda = H psi (out of place)
+template <typename R>
+__global__ void __launch_bounds__(256) k_apply_ham(typename Vec2<R>::type *__restrict__ lam,
+                                                   const typename Vec2<R>::type *__restrict__ psi, unsigned long long namps,
+                                                   HamEval H)
+{
+    using V = typename Vec2<R>::type;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    const double oc = H.offdiag_coef();
+    for (unsigned long long C = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; C < namps; C += stride) {
+        const V p = psi[C];
+        double xr = 0, xi = 0;
+        for (int i = 0; i < H.n; i++) {
+            if (!H.flip_on(C, i)) continue;
+            const V o = psi[C ^ (1ull << i)];
+            xr += (double)o.x;
+            xi += (double)o.y;
+        }
+        const double d = H.diag(C);
+        V r;
+        r.x = (R)(d * (double)p.x + oc * xr);
+        r.y = (R)(d * (double)p.y + oc * xi);
+        lam[C] = r;
+    }
+}
+
+// generic fixed-order final reduction: out[v] = sum_b partial[b * nv + v]
+static __global__ void k_final_sum(const double *__restrict__ partial, int nblocks, int nv, double *out)
+{
+    const int v = blockIdx.x;
+    double s = 0;
+    for (int b = threadIdx.x; b < nblocks; b += blockDim.x) s += partial[(size_t)b * nv + v];
+    __shared__ double red[32];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += red[w];
+        out[v] = t;
+    }
+}
+
+// sum |amp|^2
+template <typename R>
+__global__ void __launch_bounds__(kRedThreads) k_norm2(const typename Vec2<R>::type *__restrict__ psi, unsigned long long namps,
+                                                       double *partial)
+{
+    double acc[1] = {0.0};
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long C = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; C < namps; C += stride) {
+        const auto p = psi[C];
+        acc[0] += (double)p.x * (double)p.x + (double)p.y * (double)p.y;
+    }
+    __shared__ double out[1];
+    block_sum<1>(acc, out);
+    if (threadIdx.x == 0) partial[blockIdx.x] = out[0];
+}
+
+// ---- adjoint sweep, unfused step for one gate on bits (kb, kb+1) ---------------------
+//   psi <- U^dagger psi ;  env[r + 4c] += conj(lam[r]) psi[c] ;  lam <- U^dagger lam
+// Ud holds U^dagger.  partial: [gridDim.x][32] doubles.
+template <typename R>
+__global__ void __launch_bounds__(kRedThreads) k_adjoint_step(typename Vec2<R>::type *psi, typename Vec2<R>::type *lam,
+                                                              unsigned long long nquads, int kb,
+                                                              const __grid_constant__ GateMat<R> Ud, double *partial)
+{
+    using V = typename Vec2<R>::type;
+    double acc[32];
+#pragma unroll
+    for (int i = 0; i < 32; i++) acc[i] = 0.0;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    const unsigned long long low = (1ull << kb) - 1ull;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < nquads; i += stride) {
+        const unsigned long long base = ((i >> kb) << (kb + 2)) | (i & low);
+        V x[4], l[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) { x[j] = psi[base | ((unsigned long long)j << kb)]; l[j] = lam[base | ((unsigned long long)j << kb)]; }
+        apply_quad<R, V>(x[0], x[1], x[2], x[3], Ud);
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                const double lr = (double)l[r].x, li = (double)l[r].y, xr = (double)x[c].x, xi = (double)x[c].y;
+                acc[2 * (r + 4 * c)] += lr * xr + li * xi;     // Re conj(l) x
+                acc[2 * (r + 4 * c) + 1] += lr * xi - li * xr; // Im conj(l) x
+            }
+        apply_quad<R, V>(l[0], l[1], l[2], l[3], Ud);
+#pragma unroll
+        for (int j = 0; j < 4; j++) { psi[base | ((unsigned long long)j << kb)] = x[j]; lam[base | ((unsigned long long)j << kb)] = l[j]; }
+    }
+    __shared__ double out[32];
+    block_sum<32>(acc, out);
+    if (threadIdx.x < 32) partial[(size_t)blockIdx.x * 32 + threadIdx.x] = out[threadIdx.x];
+}
+
+} // namespace qcb

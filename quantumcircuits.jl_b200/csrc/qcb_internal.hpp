@@ -1,0 +1,91 @@
+// qcb_internal.hpp -- process-wide context and state handle shared by the translation units
+// of libqcb200.so.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/qcb200.h"
+#include "schedule.hpp"
+
+struct qcb_state {
+    int n = 0;        // logical qubits
+    int nloc = 0;     // local index bits held by this process (n unless sharded)
+    int dtype = QCB_C128;
+    void *d = nullptr;
+    bool owned = false;
+    bool sharded = false;
+    size_t bytes = 0;
+    std::vector<int> phys; // logical qubit -> physical index bit (>= nloc: rank bit nloc + k)
+};
+
+namespace qcb {
+
+struct Ctx {
+    bool inited = false;
+    int device = -1;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // options
+    long tile_bits = 11, low_bits = 3, max_gates_per_pass = 1 << 30, force_simple = 0;
+    // stats
+    double st_passes = 0, st_stages = 0, st_launches = 0, st_gates = 0, st_launches_total = 0;
+    // scratch
+    double *d_partial = nullptr; // reduction partials
+    size_t partial_cap = 0;      // in doubles
+    double *d_out = nullptr;     // small device result buffer
+    size_t out_cap = 0;
+    double *h_out = nullptr;     // pinned mirror
+    void *scratch[3] = {nullptr, nullptr, nullptr};
+    size_t scratch_bytes[3] = {0, 0, 0};
+    std::map<std::string, std::vector<PassPlan>> plan_cache;
+    // distributed
+    int rank = 0, nranks = 1;
+    void *nccl_comm = nullptr;
+};
+
+Ctx &ctx();
+int set_error(int code, const char *fmt, ...);
+
+#define QCB_CUDA(call)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t e__ = (call);                                                                        \
+        if (e__ != cudaSuccess)                                                                          \
+            return qcb::set_error(e__ == cudaErrorMemoryAllocation ? QCB_ENOMEM : QCB_ECUDA, "%s: %s (%s:%d)", #call, \
+                                  cudaGetErrorString(e__), __FILE__, __LINE__);                         \
+    } while (0)
+
+#define QCB_REQUIRE_INIT()                                                                               \
+    do {                                                                                                 \
+        if (!qcb::ctx().inited) return qcb::set_error(QCB_ECUDA, "qcb_init has not been called (no CUDA device bound; there is no CPU fallback)"); \
+    } while (0)
+
+#define QCB_TRY(expr)                  \
+    do {                               \
+        int rc__ = (expr);             \
+        if (rc__ != QCB_OK) return rc__; \
+    } while (0)
+
+inline size_t amp_bytes(int dtype) { return dtype == QCB_C128 ? 16 : 8; }
+
+int ensure_scratch(int slot, size_t bytes);
+int ensure_partial(size_t doubles);
+int ensure_out(size_t doubles);
+inline void count_launch(int k = 1)
+{
+    ctx().st_launches += k;
+    ctx().st_launches_total += k;
+}
+
+// gate-list execution (passes.cu)
+int run_gate_list(qcb_state *s, const std::vector<GateOp> &gates, const double *mats, bool adjoint);
+
+// distributed (dist.cu)
+int dist_state_canonicalize(qcb_state *s);
+
+} // namespace qcb

@@ -1,0 +1,231 @@
+// tile.cuh -- the fused gate pass: one sweep over HBM applies a whole trapezoid of
+// 2-qubit gates to shared-memory tiles of the statevector.
+//
+// Replaces the reference's one-launch-per-gate KernelAbstractions kernel
+// (_apply_2spin!, src/apply.jl:62-84, launched from src/apply.jl:134-142 after a full
+// zero fill) -- same arithmetic per gate, psi'[i,j] = sum_{a,b} u[i,j,a,b] psi[a,b],
+// but in place and with many gates per pass.
+//
+// Data layout in HBM: the reference's -- 2^n interleaved complex amplitudes, qubit q
+// (1-based) = bit q-1 of the linear index.  A pass picks TB "tile bits" of the index
+// (always including the lowest physical bits so every global access is a >= 128 B run);
+// each CTA owns the 2^TB amplitudes that share the remaining n-TB bits, stages them in
+// shared memory, and runs `nstages` register stages on them:
+//
+//   stage: every thread pulls the 16 amplitudes spanned by 4 consecutive local bits
+//          [p0, p0+4) into registers and applies up to 4 gates on the bit pairs
+//          C=(1,2), A=(0,1), B=(2,3), C=(1,2) of that window (a brickwork diamond),
+//          64 real FMAs per amplitude quad per gate; gate matrices are kernel
+//          parameters, so ptxas feeds them to DFMA/FFMA from uniform registers.
+//
+// Shared memory is XOR-swizzled (low SWB bits of the 16 B / 8 B chunk index ^= xor of
+// the higher SWB-bit groups) so that every stage window and the load/store phases are
+// bank-conflict free; the host scheduler (schedule.hpp) orders the thread bits so that
+// the lanes of a quarter warp land on distinct bank groups.
+//
+// All functions are __host__ __device__: tests/emu/ replays the identical code on the
+// CPU, thread by thread, to check the index algebra and the scheduler without a GPU.
+#pragma once
+#include <stdint.h>
+#include <math.h>
+
+#if defined(__CUDACC__)
+#include <cuda_runtime.h>
+#define QCB_HD __host__ __device__ __forceinline__
+#else
+#define QCB_HD inline
+struct double2 { double x, y; };
+struct float2 { float x, y; };
+#endif
+
+namespace qcb {
+
+constexpr int kRegBits = 4;    // qubits of the per-thread register window
+constexpr int kRegAmps = 16;   // 2^kRegBits amplitudes per thread
+constexpr int kSlots = 4;      // gate slots per stage (C A B C)
+constexpr int kMaxStages = 12; // register stages per pass (bounds the kernel-parameter block)
+constexpr int kMaxSeg = 8;
+constexpr int kMinTB = 9;
+constexpr int kMaxTB = 13;
+
+template <typename R> struct Vec2;
+template <> struct Vec2<double> { using type = double2; static constexpr int SWB = 3; };
+template <> struct Vec2<float> { using type = float2; static constexpr int SWB = 4; };
+
+// local bit pair (lo, lo+1) of each slot inside the 4-bit register window
+QCB_HD constexpr int slot_lo(int slot) { return slot == 1 ? 0 : (slot == 2 ? 2 : 1); }
+
+// XOR swizzle of a tile-local element index (modifies only the low SWB bits).
+template <int SWB> QCB_HD uint32_t swz(uint32_t e)
+{
+    if (SWB == 3) return e ^ (((e >> 3) ^ (e >> 6) ^ (e >> 9) ^ (e >> 12)) & 7u);
+    return e ^ (((e >> 4) ^ (e >> 8) ^ (e >> 12)) & 15u);
+}
+
+template <typename R> struct GateMat { R v[32]; }; // v[2*(r+4c)] = Re, v[2*(r+4c)+1] = Im ; r = out, c = in
+
+struct StageDesc {
+    uint8_t p0;                        // first local bit of the register window
+    uint8_t mask;                      // active slots, bit s = slot s
+    uint8_t tpos[kMaxTB - kRegBits];   // thread bit k -> local bit position (outside the window)
+    uint8_t pad;
+    uint16_t roff[kRegAmps];           // swizzled offset of register element r:  swz(r << p0)
+};
+
+template <typename R> struct PassParams {
+    GateMat<R> U[kMaxStages * kSlots];
+    StageDesc stage[kMaxStages];
+    int32_t nstages;
+    int32_t nseg;                      // the CTA index is deposited into the non-tile bits, segment by segment
+    uint8_t seg_start[kMaxSeg], seg_len[kMaxSeg];
+    uint8_t ld_phys[kMaxTB];           // memory-order bit k (thread bits first) -> physical index bit
+    uint8_t ld_lpos[kMaxTB];           // memory-order bit k -> tile-local bit when loading
+    uint8_t st_lpos[kMaxTB];           // ... when storing (differs only for bit-permuting passes)
+    unsigned long long ld_goff[kRegAmps]; // global element offset of per-thread element i (top 4 memory-order bits)
+    uint16_t ld_eoff[kRegAmps];        // swizzled local offset of element i when loading
+    uint16_t st_eoff[kRegAmps];        // ... when storing
+};
+
+// ---------------------------------------------------------------------------------
+// one gate on one amplitude quad held in registers
+// ---------------------------------------------------------------------------------
+template <typename R, typename V> QCB_HD void apply_quad(V &x0, V &x1, V &x2, V &x3, const GateMat<R> &U)
+{
+    const V in[4] = {x0, x1, x2, x3};
+    V out[4];
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        R re = U.v[2 * r] * in[0].x;
+        R im = U.v[2 * r] * in[0].y;
+        re = fma(-U.v[2 * r + 1], in[0].y, re);
+        im = fma(U.v[2 * r + 1], in[0].x, im);
+#pragma unroll
+        for (int c = 1; c < 4; c++) {
+            const R ur = U.v[2 * (r + 4 * c)], ui = U.v[2 * (r + 4 * c) + 1];
+            re = fma(ur, in[c].x, re);
+            im = fma(ur, in[c].y, im);
+            re = fma(-ui, in[c].y, re);
+            im = fma(ui, in[c].x, im);
+        }
+        out[r].x = re;
+        out[r].y = im;
+    }
+    x0 = out[0]; x1 = out[1]; x2 = out[2]; x3 = out[3];
+}
+
+// gate on register-window bits (LO, LO+1): 4 quads per thread
+template <int LO, typename R, typename V> QCB_HD void apply_window_gate(V (&a)[kRegAmps], const GateMat<R> &U)
+{
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        // spread the two bits of q over the window bits other than LO, LO+1
+        int other = 0, qq = q;
+#pragma unroll
+        for (int b = 0; b < 4; b++)
+            if (b != LO && b != LO + 1) { other |= (qq & 1) << b; qq >>= 1; }
+        apply_quad<R, V>(a[other], a[other | (1 << LO)], a[other | (2 << LO)], a[other | (3 << LO)], U);
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// phases of a pass (each is followed by a CTA barrier in the kernel)
+// ---------------------------------------------------------------------------------
+template <typename R> QCB_HD unsigned long long cta_base(const PassParams<R> &P, unsigned long long b)
+{
+    unsigned long long base = 0;
+    for (int s = 0; s < P.nseg; s++) {
+        const int len = P.seg_len[s];
+        base |= (b & ((1ull << len) - 1ull)) << P.seg_start[s];
+        b >>= len;
+    }
+    return base;
+}
+
+template <typename R, int TB>
+QCB_HD void tile_load(const typename Vec2<R>::type *__restrict__ src, const PassParams<R> &P,
+                      typename Vec2<R>::type *sm, uint32_t tid, unsigned long long bid)
+{
+    using V = typename Vec2<R>::type;
+    constexpr int SWB = Vec2<R>::SWB;
+    constexpr int TBITS = TB - kRegBits;
+    unsigned long long g = cta_base(P, bid);
+    uint32_t e = 0;
+#pragma unroll
+    for (int k = 0; k < TBITS; k++) {
+        const uint32_t bit = (tid >> k) & 1u;
+        g |= (unsigned long long)bit << P.ld_phys[k];
+        e |= bit << P.ld_lpos[k];
+    }
+    e = swz<SWB>(e);
+    V tmp[kRegAmps];
+#pragma unroll
+    for (int i = 0; i < kRegAmps; i++) tmp[i] = src[g | P.ld_goff[i]];
+#pragma unroll
+    for (int i = 0; i < kRegAmps; i++) sm[e ^ P.ld_eoff[i]] = tmp[i];
+}
+
+template <typename R, int TB>
+QCB_HD void tile_store(typename Vec2<R>::type *__restrict__ dst, const PassParams<R> &P,
+                       const typename Vec2<R>::type *sm, uint32_t tid, unsigned long long bid)
+{
+    constexpr int SWB = Vec2<R>::SWB;
+    constexpr int TBITS = TB - kRegBits;
+    unsigned long long g = cta_base(P, bid);
+    uint32_t e = 0;
+#pragma unroll
+    for (int k = 0; k < TBITS; k++) {
+        const uint32_t bit = (tid >> k) & 1u;
+        g |= (unsigned long long)bit << P.ld_phys[k];
+        e |= bit << P.st_lpos[k];
+    }
+    e = swz<SWB>(e);
+#pragma unroll
+    for (int i = 0; i < kRegAmps; i++) dst[g | P.ld_goff[i]] = sm[e ^ P.st_eoff[i]];
+}
+
+template <typename R, int TB>
+QCB_HD void tile_stage(const PassParams<R> &P, int s, typename Vec2<R>::type *sm, uint32_t tid)
+{
+    using V = typename Vec2<R>::type;
+    constexpr int SWB = Vec2<R>::SWB;
+    constexpr int TBITS = TB - kRegBits;
+    const StageDesc &S = P.stage[s];
+    uint32_t e = 0;
+#pragma unroll
+    for (int k = 0; k < TBITS; k++) e |= ((tid >> k) & 1u) << S.tpos[k];
+    e = swz<SWB>(e);
+    V a[kRegAmps];
+#pragma unroll
+    for (int r = 0; r < kRegAmps; r++) a[r] = sm[e ^ S.roff[r]];
+    const uint32_t mask = S.mask;
+    if (mask & 1u) apply_window_gate<1, R, V>(a, P.U[s * kSlots + 0]);
+    if (mask & 2u) apply_window_gate<0, R, V>(a, P.U[s * kSlots + 1]);
+    if (mask & 4u) apply_window_gate<2, R, V>(a, P.U[s * kSlots + 2]);
+    if (mask & 8u) apply_window_gate<1, R, V>(a, P.U[s * kSlots + 3]);
+#pragma unroll
+    for (int r = 0; r < kRegAmps; r++) sm[e ^ S.roff[r]] = a[r];
+}
+
+#if defined(__CUDACC__)
+template <typename R, int TB, int MINB>
+__global__ void __launch_bounds__(1 << (TB - kRegBits), MINB)
+tile_pass_kernel(const typename Vec2<R>::type *src, typename Vec2<R>::type *dst,
+                 const __grid_constant__ PassParams<R> P)
+{
+    using V = typename Vec2<R>::type;
+    extern __shared__ __align__(16) unsigned char qcb_smem_raw[];
+    V *sm = reinterpret_cast<V *>(qcb_smem_raw);
+    const uint32_t tid = threadIdx.x;
+    const unsigned long long bid = blockIdx.x;
+    tile_load<R, TB>(src, P, sm, tid, bid);
+    __syncthreads();
+#pragma unroll 1
+    for (int s = 0; s < P.nstages; s++) {
+        tile_stage<R, TB>(P, s, sm, tid);
+        __syncthreads();
+    }
+    tile_store<R, TB>(dst, P, sm, tid, bid);
+}
+#endif
+
+} // namespace qcb

@@ -1,0 +1,53 @@
+"""ctypes access to tests/emu/libqcb_emu.so -- CPU replay of the device tile-pass code."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu")
+_SO = os.path.join(_HERE, "libqcb_emu.so")
+_CSRC = os.path.join(os.path.dirname(_HERE), "..", "quantumcircuits.jl_b200", "csrc")
+_lib = None
+
+
+def build(force=False):
+    srcs = [os.path.join(_HERE, "emu_tile.cu"), os.path.join(_CSRC, "tile.cuh"), os.path.join(_CSRC, "schedule.hpp")]
+    if force or not os.path.exists(_SO) or any(os.path.getmtime(_SO) < os.path.getmtime(s) for s in srcs):
+        subprocess.check_call(["nvcc", "-O2", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler",
+                               "-fPIC", "-shared", "-o", _SO, srcs[0]], cwd=_HERE)
+    return _SO
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_SO)
+    return _lib
+
+
+def apply_gates(psi, q0, mats, tile_bits, low_bits, phys=None, nloc=None, max_gates=0, adjoint=False):
+    """psi: flat complex array (modified copy returned); q0: 0-based logical low qubits; mats: (G,4,4)."""
+    psi = np.ascontiguousarray(psi).copy()
+    n = int(psi.size).bit_length() - 1
+    nloc = n if nloc is None else nloc
+    phys = np.arange(n, dtype=np.int32) if phys is None else np.ascontiguousarray(phys, dtype=np.int32)
+    q0 = np.ascontiguousarray(q0, dtype=np.int32)
+    m = np.ascontiguousarray(np.stack([np.asarray(M, dtype=np.complex128).reshape(-1, order="F") for M in mats]))
+    stats = np.zeros(4, dtype=np.int32)
+    rc = lib().emu_apply_gates(C.c_int(1 if psi.dtype == np.complex128 else 0), C.c_int(nloc), C.c_int(len(phys)),
+                               phys.ctypes.data_as(C.c_void_p), psi.ctypes.data_as(C.c_void_p), C.c_int(len(q0)),
+                               q0.ctypes.data_as(C.c_void_p), m.ctypes.data_as(C.c_void_p), C.c_int(tile_bits),
+                               C.c_int(low_bits), C.c_int(max_gates), C.c_int(1 if adjoint else 0),
+                               stats.ctypes.data_as(C.c_void_p))
+    if rc:
+        raise RuntimeError(f"emu_apply_gates rc={rc}")
+    return psi, (int(stats[0]), int(stats[1]))
+
+
+def plan_brickwork(nbits, nlayers, tile_bits, low_bits, max_gates=0):
+    stats = np.zeros(4, dtype=np.int32)
+    lib().emu_plan_brickwork(C.c_int(nbits), C.c_int(nlayers), C.c_int(tile_bits), C.c_int(low_bits), C.c_int(max_gates),
+                             stats.ctypes.data_as(C.c_void_p))
+    return dict(passes=int(stats[0]), stages=int(stats[1]), gates=int(stats[2]))

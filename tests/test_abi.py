@@ -1,0 +1,86 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol the header
+declares, fails loudly without a GPU, and its host-side gate algebra matches the oracle."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import qcb200
+from qcb200 import _lib
+from oracle import oracle_np as onp
+
+
+def test_library_exports_every_declared_symbol():
+    L = _lib.lib()
+    names = _lib.declared_symbols()
+    assert len(names) >= 35
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, missing
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(_lib.QCBError) as ei:
+        qcb200.B200State(4)
+    assert ei.value.code == _lib.QCB_ECUDA
+    with pytest.raises(_lib.QCBError):
+        qcb200.apply(onp.zero_state(4), qcb200.GenericBrickworkCircuit(4, 2))
+    with pytest.raises(_lib.QCBError):
+        qcb200.measure(qcb200.TFIMHamiltonian(1.0, 0.1, 0.5), onp.zero_state(4))
+
+
+def test_general_unitary_gate_matches_oracle(oracle):
+    rng = np.random.default_rng(0)
+    for _ in range(25):
+        a = rng.uniform(-np.pi, 2 * np.pi, 15)
+        u = qcb200.build_general_unitary_gate(a).mat().reshape(4, 4, order="F")
+        np.testing.assert_allclose(u, oracle.build_general_unitary_gate(a), atol=2e-16 * 8)
+        np.testing.assert_allclose(u, onp.build_general_unitary_gate(a), atol=1e-15)
+
+
+def test_general_unitary_gate_derivative():
+    L = _lib.lib()
+    rng = np.random.default_rng(1)
+    a = rng.uniform(0, 2 * np.pi, 15)
+    eps = 1e-6
+    for k in range(15):
+        d = np.empty(16, dtype=np.complex128)
+        _lib.check(L.qcb_general_unitary_gate_derivative(a.ctypes.data_as(C.c_void_p), C.c_int(k), d.ctypes.data_as(C.c_void_p)))
+        ap, am = a.copy(), a.copy()
+        ap[k] += eps
+        am[k] -= eps
+        fd = (onp.build_general_unitary_gate(ap) - onp.build_general_unitary_gate(am)) / (2 * eps)
+        np.testing.assert_allclose(d.reshape(4, 4, order="F"), fd, atol=1e-9)
+
+
+def test_gate_types_match_reference_tables():
+    # src/gates.jl:10-16 and the 4x4 forms verified in SURVEY.md 8a a3
+    assert np.array_equal(qcb200.CNOTGate().mat().reshape(4, 4, order="F"), onp.CNOT4)
+    assert np.array_equal(qcb200.ReverseCNOTGate().mat().reshape(4, 4, order="F"), onp.RCNOT4)
+    np.testing.assert_allclose(qcb200.HadamardGate().mat(), onp.HADAMARD)
+    np.testing.assert_allclose(qcb200.RZGate(0.3).mat(), onp.rz(0.3))
+    np.testing.assert_allclose(qcb200.RYGate(0.3).mat(), onp.ry(0.3))
+    np.testing.assert_allclose(qcb200.RXGate(0.3).mat(), onp.rx(0.3))
+    np.testing.assert_allclose(qcb200.RotationGate(0.3, 0.4, 0.5).mat(), onp.rotation(0.3, 0.4, 0.5))
+    g = qcb200.Generic2SpinGate(np.arange(16).reshape(2, 2, 2, 2, order="F") * (1 + 1j))
+    np.testing.assert_allclose(qcb200.adjoint(g).mat().reshape(4, 4, order="F"), g.mat().reshape(4, 4, order="F").conj().T)
+
+
+def test_circuit_geometry():
+    assert list(qcb200.circuit_layer_starts(1, 5)) == [1, 3] and list(qcb200.circuit_layer_starts(2, 5)) == [2, 4]
+    for n, L, G in [(12, 20, 110), (20, 4, 38), (28, 4, 54), (30, 100, 1450), (34, 100, 1650)]:
+        assert qcb200.brickwork_num_gates(n, L) == G
+        assert qcb200.GenericBrickworkCircuit(n, L).gate_angles.shape == (15, G)
+    c = qcb200.GenericBrickworkCircuit(4, 2)
+    c2 = qcb200.reconstruct(c, 16, 0.5)  # 0-based linear index -> angle [1, 1]
+    assert c2.gate_angles[1, 1] == 0.5 and c.gate_angles[1, 1] == 0.0
+
+
+def test_zero_state_constructors():
+    t = qcb200.zero_state_tensor(3)
+    assert t.shape == (2, 2, 2) and t[0, 0, 0] == 1 and abs(t).sum() == 1
+    v = qcb200.zero_state_vec(np.complex64, 3)
+    assert v.dtype == np.complex64 and v[0] == 1

@@ -1,0 +1,119 @@
+"""CPU replay of the fused tile pass + scheduler (the same __host__ __device__ code the GPU runs)
+against the oracle.  Needs nvcc (host compile only), no GPU."""
+import shutil
+
+import numpy as np
+import pytest
+
+from oracle import oracle_np as onp
+
+pytestmark = pytest.mark.skipif(shutil.which("nvcc") is None, reason="nvcc not available")
+
+
+@pytest.fixture(scope="module")
+def emu():
+    import emu_helper
+
+    emu_helper.build()
+    return emu_helper
+
+
+def rand_state(rng, n, dtype=np.complex128):
+    v = rng.standard_normal(2 ** n) + 1j * rng.standard_normal(2 ** n)
+    return (v / np.linalg.norm(v)).astype(dtype)
+
+
+def rel(a, b):
+    return np.linalg.norm(a - b) / np.linalg.norm(b)
+
+
+@pytest.mark.parametrize("n,layers,tb,c", [(9, 6, 9, 3), (12, 20, 12, 3), (13, 9, 9, 3), (14, 12, 11, 3), (14, 7, 10, 4),
+                                           (15, 10, 11, 3), (13, 8, 13, 3), (16, 5, 12, 4)])
+def test_emu_brickwork_vs_oracle(emu, oracle, n, layers, tb, c):
+    rng = np.random.default_rng(n * 100 + layers)
+    G = onp.brickwork_num_gates(n, layers)
+    angles = rng.uniform(0, 2 * np.pi, (15, G))
+    q0 = np.array(onp.brickwork_gate_positions(n, layers)) - 1
+    mats = [oracle.build_general_unitary_gate(angles[:, g]) for g in range(G)]
+    psi0 = rand_state(rng, n)
+    ref = oracle.apply_brickwork(psi0, n, layers, angles)
+    out, (npass, nst) = emu.apply_gates(psi0, q0, mats, tb, c)
+    assert rel(out, ref) < 1e-13
+    assert npass < G and nst < G  # fused: fewer sweeps than gates
+
+
+def test_emu_c64(emu, oracle):
+    rng = np.random.default_rng(64)
+    n, layers = 13, 10
+    G = onp.brickwork_num_gates(n, layers)
+    angles = rng.uniform(0, 2 * np.pi, (15, G))
+    q0 = np.array(onp.brickwork_gate_positions(n, layers)) - 1
+    mats = [oracle.build_general_unitary_gate(angles[:, g]) for g in range(G)]
+    psi0 = rand_state(rng, n, np.complex64)
+    ref = oracle.apply_brickwork(psi0.astype(np.complex128), n, layers, angles)
+    out, _ = emu.apply_gates(psi0, q0, mats, 11, 4)
+    assert out.dtype == np.complex64
+    assert rel(out.astype(np.complex128), ref) < 1e-5
+
+
+def test_emu_random_nonunitary_gate_list(emu, oracle):
+    # test/correctness_tests.jl:86-124 style matrices, random (non-brickwork) positions
+    rng = np.random.default_rng(7)
+    n, G = 13, 60
+    q0 = rng.integers(0, n - 1, size=G)
+    mats = []
+    for _ in range(G):
+        u = rng.standard_normal((4, 4)) + 1j * rng.standard_normal((4, 4))
+        mats.append(u / np.linalg.det(u) ** 0.25)
+    psi0 = rand_state(rng, n)
+    ref = psi0
+    for q, M in zip(q0, mats):
+        ref = oracle.apply_2q(ref, M, int(q) + 1)
+    for tb, c in [(9, 3), (11, 3), (13, 4)]:
+        out, _ = emu.apply_gates(psi0, q0, mats, tb, c)
+        assert rel(out, ref) < 1e-12
+
+
+def test_emu_adjoint_undoes_circuit(emu, oracle):
+    rng = np.random.default_rng(5)
+    n, layers = 12, 6
+    G = onp.brickwork_num_gates(n, layers)
+    angles = rng.uniform(0, 2 * np.pi, (15, G))
+    q0 = np.array(onp.brickwork_gate_positions(n, layers)) - 1
+    mats = [oracle.build_general_unitary_gate(angles[:, g]) for g in range(G)]
+    psi0 = rand_state(rng, n)
+    fwd, _ = emu.apply_gates(psi0, q0, mats, 10, 3)
+    back, _ = emu.apply_gates(fwd, q0[::-1], mats[::-1], 10, 3, adjoint=True)
+    assert rel(back, psi0) < 1e-13
+
+
+def test_emu_permuted_layout(emu, oracle):
+    """logical -> physical bit permutation (what the sharded path uses after a qubit swap)."""
+    rng = np.random.default_rng(11)
+    n, layers = 12, 5
+    G = onp.brickwork_num_gates(n, layers)
+    angles = rng.uniform(0, 2 * np.pi, (15, G))
+    q0 = np.array(onp.brickwork_gate_positions(n, layers)) - 1
+    mats = [oracle.build_general_unitary_gate(angles[:, g]) for g in range(G)]
+    psi0 = rand_state(rng, n)
+    ref = oracle.apply_brickwork(psi0, n, layers, angles)
+    for trial in range(3):
+        phys = rng.permutation(n)
+        # physical-layout copy of the logical state: bit phys[q] of the physical index = bit q of the logical index
+        idx = np.arange(2 ** n)
+        pidx = np.zeros_like(idx)
+        for q in range(n):
+            pidx |= ((idx >> q) & 1) << phys[q]
+        psi_phys = np.empty_like(psi0)
+        psi_phys[pidx] = psi0
+        out_phys, _ = emu.apply_gates(psi_phys, q0, mats, 9, 3, phys=phys)
+        assert rel(out_phys[pidx], ref) < 1e-13
+
+
+def test_schedule_statistics(emu):
+    # 30 qubits x 100 half-layers (BASELINE config C3): the pass count bounds HBM traffic
+    st = emu.plan_brickwork(30, 100, 11, 3)
+    assert st["gates"] == 1450
+    assert st["passes"] <= 100 and st["stages"] <= 520
+    st4 = emu.plan_brickwork(30, 100, 11, 3, max_gates=4)
+    assert st4["gates"] == 1450 and st4["passes"] >= 1450 // 4

@@ -1,0 +1,113 @@
+// fp64_peak.cu -- measures the FP64 / FP32 FMA issue roofs of this GPU, and whether FP64 tensor
+// (DMMA m8n8k4) work runs concurrently with the FP64 FMA pipe.  SURVEY.md section 8d asks for a measured
+// FMA-bound microkernel before any compute-roof fraction is quoted for the fused gate passes.
+// Usage: fp64_peak [iters]   -> one JSON line.
+#include <cstdio>
+#include <cstdlib>
+#include <cuda_runtime.h>
+
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("{\"error\": \"%s\"}\n", cudaGetErrorString(e)); return 1; } } while (0)
+
+template <typename T, int ILP> __global__ void __launch_bounds__(256) k_fma(T *out, int iters, T a, T b)
+{
+    T acc[ILP];
+#pragma unroll
+    for (int i = 0; i < ILP; i++) acc[i] = (T)(threadIdx.x + i);
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < ILP; i++) acc[i] = fma(acc[i], a, b);
+    }
+    T s = 0;
+#pragma unroll
+    for (int i = 0; i < ILP; i++) s += acc[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// DMMA m8n8k4: D(8x8) += A(8x4) B(4x8), one instruction = 256 FMA per warp
+template <int ILP> __global__ void __launch_bounds__(256) k_dmma(double *out, int iters, double a, double b)
+{
+    double c0[ILP], c1[ILP];
+#pragma unroll
+    for (int i = 0; i < ILP; i++) { c0[i] = threadIdx.x; c1[i] = i; }
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < ILP; i++)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                         : "+d"(c0[i]), "+d"(c1[i]) : "d"(a), "d"(b));
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < ILP; i++) s += c0[i] + c1[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// half of the warps do DFMA, the other half DMMA
+template <int ILP> __global__ void __launch_bounds__(256) k_mixed(double *out, int iters, double a, double b)
+{
+    const int warp = threadIdx.x >> 5;
+    double s = 0;
+    if (warp & 1) {
+        double c0[ILP], c1[ILP];
+#pragma unroll
+        for (int i = 0; i < ILP; i++) { c0[i] = threadIdx.x; c1[i] = i; }
+        for (int it = 0; it < iters; it++) {
+#pragma unroll
+            for (int i = 0; i < ILP; i++)
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                             : "+d"(c0[i]), "+d"(c1[i]) : "d"(a), "d"(b));
+        }
+#pragma unroll
+        for (int i = 0; i < ILP; i++) s += c0[i] + c1[i];
+    } else {
+        double acc[ILP];
+#pragma unroll
+        for (int i = 0; i < ILP; i++) acc[i] = (double)(threadIdx.x + i);
+        for (int it = 0; it < iters; it++) {
+#pragma unroll
+            for (int i = 0; i < ILP; i++) acc[i] = fma(acc[i], a, b);
+        }
+#pragma unroll
+        for (int i = 0; i < ILP; i++) s += acc[i];
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+template <typename F> static float time_ms(F f)
+{
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    f(); cudaDeviceSynchronize();
+    cudaEventRecord(e0);
+    f();
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    return ms;
+}
+
+int main(int argc, char **argv)
+{
+    const int iters = argc > 1 ? atoi(argv[1]) : 4096;
+    cudaDeviceProp p;
+    CK(cudaGetDeviceProperties(&p, 0));
+    const int sms = p.multiProcessorCount, blocks = sms * 8, threads = 256;
+    double *out;
+    CK(cudaMalloc(&out, sizeof(double) * blocks * threads));
+    constexpr int ILP = 16;
+    const double nthreads = (double)blocks * threads;
+    float ms_d = time_ms([&] { k_fma<double, ILP><<<blocks, threads>>>(out, iters, 1.0000001, 1e-9); });
+    float ms_f = time_ms([&] { k_fma<float, ILP><<<blocks, threads>>>((float *)out, iters, 1.0000001f, 1e-9f); });
+    float ms_m = time_ms([&] { k_dmma<ILP><<<blocks, threads>>>(out, iters, 1.0000001, 1e-9); });
+    float ms_x = time_ms([&] { k_mixed<ILP><<<blocks, threads>>>(out, iters, 1.0000001, 1e-9); });
+    CK(cudaGetLastError());
+    const double fma_d = nthreads * iters * ILP / (ms_d * 1e-3);
+    const double fma_f = nthreads * iters * ILP / (ms_f * 1e-3);
+    const double fma_m = (nthreads / 32) * iters * ILP * 256.0 / (ms_m * 1e-3);
+    const double fma_x = ((nthreads / 2) * iters * ILP + (nthreads / 64) * iters * ILP * 256.0) / (ms_x * 1e-3);
+    printf("{\"gpu\": \"%s\", \"sms\": %d, \"dfma_tflops\": %.2f, \"ffma_tflops\": %.2f, \"dmma_tflops\": %.2f, "
+           "\"mixed_dfma_dmma_tflops\": %.2f, \"dfma_per_clk_per_sm_at_max_clock\": %.1f, \"ms\": [%.3f, %.3f, %.3f, %.3f]}\n",
+           p.name, sms, 2 * fma_d / 1e12, 2 * fma_f / 1e12, 2 * fma_m / 1e12, 2 * fma_x / 1e12,
+           fma_d / sms / (p.clockRate * 1e3), ms_d, ms_f, ms_m, ms_x);
+    return 0;
+}
