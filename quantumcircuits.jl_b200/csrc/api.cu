@@ -325,6 +325,7 @@ int qcb_get_stat(const char *key, double *out)
     else if (k == "launches") *out = c.st_launches;
     else if (k == "gates") *out = c.st_gates;
     else if (k == "launches_total") *out = c.st_launches_total;
+    else if (k == "swaps") *out = c.st_swaps;
     else if (k == "sm_count") *out = c.sm_count;
     else return set_error(QCB_EINVAL, "unknown stat '%s'", k.c_str());
     return QCB_OK;
@@ -362,6 +363,7 @@ static int new_state(int nqubits, int dtype, void *wrap, bool sharded, qcb_state
             return set_error(e == cudaErrorMemoryAllocation ? QCB_ENOMEM : QCB_ECUDA, "cudaMalloc(%zu bytes): %s", (size_t)(amp_bytes(dtype) << (nqubits - gbits)), cudaGetErrorString(e));
         }
         s->owned = true;
+        if (sharded) dist_alloc_alt(s); // optional second buffer; failure just selects chunked in-place swaps
     }
     *out = s;
     return QCB_OK;
@@ -381,6 +383,7 @@ int qcb_state_destroy(qcb_state *s)
     if (s->owned && s->d) {
         if (ctx().inited) cudaStreamSynchronize(ctx().stream);
         cudaFree(s->d);
+        if (s->alt) cudaFree(s->alt);
     }
     delete s;
     return QCB_OK;

@@ -10,7 +10,6 @@
 
 namespace qcb {
 
-int dist_make_progress(qcb_state *s, const std::vector<GateOp> &gates, const std::vector<char> &done); // dist.cu
 
 template <typename R, int TB> static int launch_pass(qcb_state *s, const PassParams<R> &P)
 {
@@ -68,6 +67,33 @@ template <typename R> static int run_simple(qcb_state *s, const std::vector<Gate
     return QCB_OK;
 }
 
+SchedOptions current_sched_options(const qcb_state *s)
+{
+    Ctx &c = ctx();
+    SchedOptions opt;
+    opt.tile_bits = (int)std::max<long>(kMinTB, std::min<long>(kMaxTB, c.tile_bits));
+    opt.low_bits = (int)std::max<long>(0, std::min<long>(c.low_bits, opt.tile_bits - kRegBits));
+    opt.max_gates_per_pass = (int)std::max<long>(1, std::min<long>(c.max_gates_per_pass, 1 << 30));
+    (void)s;
+    return opt;
+}
+
+int launch_plan(qcb_state *s, const PassPlan &pl, const std::vector<GateOp> &gates, const double *mats, bool adjoint)
+{
+    try {
+        if (s->dtype == QCB_C128) {
+            static thread_local PassParams<double> P;
+            fill_params<double>(pl, s->nloc, gates, mats, adjoint, P);
+            return launch_pass_tb<double>(s, pl.TB, P);
+        }
+        static thread_local PassParams<float> P;
+        fill_params<float>(pl, s->nloc, gates, mats, adjoint, P);
+        return launch_pass_tb<float>(s, pl.TB, P);
+    } catch (const std::exception &e) {
+        return set_error(QCB_EINVAL, "pass parameters: %s", e.what());
+    }
+}
+
 static std::string plan_key(const qcb_state *s, const std::vector<GateOp> &gates, const SchedOptions &o)
 {
     // FNV-1a over everything the plan depends on
@@ -85,53 +111,32 @@ static std::string plan_key(const qcb_state *s, const std::vector<GateOp> &gates
 template <typename R> static int run_fused(qcb_state *s, const std::vector<GateOp> &gates, const double *mats, bool adjoint)
 {
     Ctx &c = ctx();
-    SchedOptions opt;
-    opt.tile_bits = (int)std::max<long>(kMinTB, std::min<long>(kMaxTB, c.tile_bits));
-    if (sizeof(R) == 8 && opt.tile_bits > 13) opt.tile_bits = 13;
-    opt.low_bits = (int)std::max<long>(0, std::min<long>(c.low_bits, opt.tile_bits - kRegBits));
-    opt.max_gates_per_pass = (int)std::max<long>(1, std::min<long>(c.max_gates_per_pass, 1 << 30));
-    std::vector<GateOp> pending = gates;
-    for (int guard = 0; !pending.empty(); guard++) {
-        if (guard > 4096) return set_error(QCB_EINVAL, "scheduler made no progress");
+    const SchedOptions opt = current_sched_options(s);
+    const std::string key = plan_key(s, gates, opt);
+    auto it = c.plan_cache.find(key);
+    if (it == c.plan_cache.end()) {
+        std::vector<PassPlan> plans;
         std::vector<char> done;
-        const std::string key = plan_key(s, pending, opt);
-        auto it = c.plan_cache.find(key);
-        if (it == c.plan_cache.end()) {
-            std::vector<PassPlan> plans;
-            try {
-                plans = plan_passes(s->nloc, s->phys, pending, opt, &done);
-            } catch (const std::exception &e) {
-                return set_error(QCB_EINVAL, "scheduler: %s", e.what());
-            }
-            if (c.plan_cache.size() > 64) c.plan_cache.clear();
-            it = c.plan_cache.emplace(key, std::move(plans)).first;
-        } else {
-            // recompute `done` from the cached plan
-            done.assign(pending.size(), 0);
-            for (const PassPlan &pl : it->second)
-                for (const StagePlan &sp : pl.stages)
-                    for (int slot = 0; slot < kSlots; slot++)
-                        if (sp.gate[slot] >= 0) done[sp.gate[slot]] = 1;
+        try {
+            plans = plan_passes(s->nloc, s->phys, gates, opt, &done);
+        } catch (const std::exception &e) {
+            return set_error(QCB_EINVAL, "scheduler: %s", e.what());
         }
-        static thread_local PassParams<R> P; // ~13 KB, reused
-        for (const PassPlan &pl : it->second) {
-            try {
-                fill_params<R>(pl, s->nloc, pending, mats, adjoint, P);
-            } catch (const std::exception &e) {
-                return set_error(QCB_EINVAL, "pass parameters: %s", e.what());
-            }
-            QCB_TRY(launch_pass_tb<R>(s, pl.TB, P));
-            c.st_passes += 1;
-            c.st_stages += (double)pl.stages.size();
+        for (char d : done)
+            if (!d) return set_error(QCB_EINVAL, "gate list could not be scheduled");
+        if (c.plan_cache.size() > 64) c.plan_cache.clear();
+        it = c.plan_cache.emplace(key, std::move(plans)).first;
+    }
+    static thread_local PassParams<R> P; // ~13 KB, reused
+    for (const PassPlan &pl : it->second) {
+        try {
+            fill_params<R>(pl, s->nloc, gates, mats, adjoint, P);
+        } catch (const std::exception &e) {
+            return set_error(QCB_EINVAL, "pass parameters: %s", e.what());
         }
-        std::vector<GateOp> rest;
-        for (size_t i = 0; i < pending.size(); i++)
-            if (!done[i]) rest.push_back(pending[i]);
-        if (rest.empty()) break;
-        if (!s->sharded) return set_error(QCB_EINVAL, "gate list could not be scheduled");
-        // blocked by qubits that live in the rank bits: exchange them for local ones
-        QCB_TRY(dist_make_progress(s, rest, std::vector<char>()));
-        pending.swap(rest);
+        QCB_TRY(launch_pass_tb<R>(s, pl.TB, P));
+        c.st_passes += 1;
+        c.st_stages += (double)pl.stages.size();
     }
     return QCB_OK;
 }
@@ -139,12 +144,13 @@ template <typename R> static int run_fused(qcb_state *s, const std::vector<GateO
 int run_gate_list(qcb_state *s, const std::vector<GateOp> &gates, const double *mats, bool adjoint)
 {
     Ctx &c = ctx();
-    c.st_passes = c.st_stages = c.st_launches = 0;
+    c.st_passes = c.st_stages = c.st_launches = c.st_swaps = 0;
     c.st_gates = (double)gates.size();
     if (gates.empty()) return QCB_OK;
     for (const GateOp &g : gates)
         if (g.q < 0 || g.q + 1 >= s->n)
             return set_error(QCB_EINVAL, "The gate cannot be applied as it sits outside the qubit space.");
+    if (s->sharded) return dist_run_gate_list(s, gates, mats, adjoint);
     const bool simple = c.force_simple || s->nloc < kMinTB;
     if (s->dtype == QCB_C128)
         return simple ? run_simple<double>(s, gates, mats, adjoint) : run_fused<double>(s, gates, mats, adjoint);

@@ -21,6 +21,7 @@ struct qcb_state {
     bool sharded = false;
     size_t bytes = 0;
     std::vector<int> phys; // logical qubit -> physical index bit (>= nloc: rank bit nloc + k)
+    void *alt = nullptr;   // sharded states: second buffer for out-of-place qubit swaps (nullptr: chunked in-place swaps)
 };
 
 namespace qcb {
@@ -34,7 +35,7 @@ struct Ctx {
     // options
     long tile_bits = 11, low_bits = 3, max_gates_per_pass = 1 << 30, force_simple = 0;
     // stats
-    double st_passes = 0, st_stages = 0, st_launches = 0, st_gates = 0, st_launches_total = 0;
+    double st_passes = 0, st_stages = 0, st_launches = 0, st_gates = 0, st_launches_total = 0, st_swaps = 0;
     // scratch
     double *d_partial = nullptr; // reduction partials
     size_t partial_cap = 0;      // in doubles
@@ -84,8 +85,12 @@ inline void count_launch(int k = 1)
 
 // gate-list execution (passes.cu)
 int run_gate_list(qcb_state *s, const std::vector<GateOp> &gates, const double *mats, bool adjoint);
+int launch_plan(qcb_state *s, const PassPlan &plan, const std::vector<GateOp> &gates, const double *mats, bool adjoint);
+SchedOptions current_sched_options(const qcb_state *s);
 
 // distributed (dist.cu)
 int dist_state_canonicalize(qcb_state *s);
+int dist_run_gate_list(qcb_state *s, const std::vector<GateOp> &gates, const double *mats, bool adjoint);
+int dist_alloc_alt(qcb_state *s);
 
 } // namespace qcb

@@ -1,0 +1,102 @@
+"""Sharded statevectors: one process per GPU, amplitudes split by the top log2(P) qubits.
+
+No reference counterpart (the reference keeps one array in one memory).  torch.distributed is
+only the bootstrap channel (it ships the 128-byte NCCL id and sums scalars); the qubit swaps are NCCL
+all-to-alls issued by libqcb200.so itself (csrc/dist.cu).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _lib
+from .state import _NP2QCB
+
+_dist_ready = False
+
+
+def init_from_torch():
+    """Every rank of an initialised torch.distributed job calls this once."""
+    global _dist_ready
+    import torch
+    import torch.distributed as dist
+
+    if _dist_ready:
+        return
+    _lib.init(int(os.environ.get("LOCAL_RANK", "0")))
+    rank, world = dist.get_rank(), dist.get_world_size()
+    uid = np.zeros(128, dtype=np.uint8)
+    if rank == 0:
+        _lib.check(_lib.lib().qcb_dist_unique_id(uid.ctypes.data_as(C.c_void_p)))
+    box = [uid.tobytes()]
+    dist.broadcast_object_list(box, src=0)
+    uid = np.frombuffer(box[0], dtype=np.uint8).copy()
+    _lib.check(_lib.lib().qcb_dist_init(C.c_int(rank), C.c_int(world), uid.ctypes.data_as(C.c_void_p)))
+    torch.cuda.synchronize()
+    _dist_ready = True
+
+
+def finalize():
+    global _dist_ready
+    if _dist_ready:
+        _lib.check(_lib.lib().qcb_dist_finalize())
+        _dist_ready = False
+
+
+class ShardedState:
+    """2^n amplitudes over all ranks; this rank holds the canonical slice [rank * 2^nloc, (rank+1) * 2^nloc)
+    when `canonical` (after upload / download); between swaps the library tracks the permuted layout."""
+
+    def __init__(self, nqubits, dtype=np.complex128):
+        self.nqubits, self.dtype = int(nqubits), np.dtype(dtype)
+        self._handle = C.c_void_p()
+        _lib.check(_lib.lib().qcb_state_create_sharded(C.c_int(self.nqubits), C.c_int(_NP2QCB[self.dtype]), C.byref(self._handle)))
+        nloc = C.c_int(0)
+        _lib.check(_lib.lib().qcb_state_local_qubits(self._handle, C.byref(nloc)))
+        self.local_qubits = nloc.value
+        self.set_zero_state()
+
+    def set_zero_state(self):
+        _lib.check(_lib.lib().qcb_state_set_zero_state(self._handle))
+
+    def upload_shard(self, host):
+        host = np.ascontiguousarray(host, dtype=self.dtype)
+        assert host.size == 1 << self.local_qubits
+        _lib.check(_lib.lib().qcb_state_upload_shard(self._handle, host.ctypes.data_as(C.c_void_p)))
+
+    def download_shard(self):
+        out = np.empty(1 << self.local_qubits, dtype=self.dtype)
+        _lib.check(_lib.lib().qcb_state_download_shard(self._handle, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def apply_circuit(self, circuit, first=0, last=None, adjoint=False):
+        last = circuit.ngates if last is None else last
+        a = circuit.angles_abi()
+        _lib.check(_lib.lib().qcb_apply_brickwork_range(self._handle, C.c_int(circuit.nbits), C.c_int(circuit.nlayers),
+                                                        a.ctypes.data_as(C.c_void_p), C.c_int(first), C.c_int(last),
+                                                        C.c_int(1 if adjoint else 0)))
+
+    def apply_gates(self, gates):
+        from .apply import _apply_list_inplace
+
+        _apply_list_inplace(self, list(gates))
+
+    def norm2(self):
+        import torch
+        import torch.distributed as dist
+
+        out = C.c_double(0)
+        _lib.check(_lib.lib().qcb_state_norm2(self._handle, C.byref(out)))
+        t = torch.tensor([out.value], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t)
+        return float(t.item())
+
+    def __del__(self):
+        try:
+            if self._handle:
+                _lib.lib().qcb_state_destroy(self._handle)
+                self._handle = C.c_void_p()
+        except Exception:
+            pass

@@ -1,0 +1,222 @@
+# B200Backend.jl -- thin `ccall` shim that puts libqcb200.so behind the QuantumCircuits.jl API.
+#
+# Usage (from a session that has QuantumCircuits loaded):
+#
+#     ENV["QCB200_LIB"] = "/path/to/quantumcircuits.jl_b200/libqcb200.so"
+#     include("B200Backend.jl"); using .B200Backend
+#     psi = B200State(zero_state_tensor(30))            # where the reference's examples write CuArray(psi0)
+#     E, grads = gradients(TFIMHamiltonian(1.0, 0.1, 0.5), psi, circuit; calculate_energy=true)
+#
+# No CUDA.jl, no KernelAbstractions dispatch, no CPU fallback: every method below is one ccall.
+# NOTE: Julia is not installed in the build image, so this file has not been executed there; the same C ABI
+# is exercised end to end by the Python mirror (quantumcircuits.jl_b200/*.py) and the tests.
+module B200Backend
+
+using LinearAlgebra
+import QuantumCircuits
+import QuantumCircuits: apply, apply!, measure, measure!, gradients, gradients!, optimise!,
+    construct_apply_cache, construct_grads_cache, propagate_forwards!, mat,
+    GenericBrickworkCircuit, Localised1SpinGate, Localised2SpinAdjGate, AbstractGate,
+    TFIMHamiltonian, EastModelHamiltonian, AbstractKernelHamiltonian, imaginary_energy_limit
+
+export B200State, B200ApplyCache
+
+const LIB = get(ENV, "QCB200_LIB", joinpath(@__DIR__, "..", "libqcb200.so"))
+
+const QCB_C64 = Cint(0)
+const QCB_C128 = Cint(1)
+
+last_error() = unsafe_string(ccall((:qcb_last_error, LIB), Cstring, ()))
+
+function check(rc::Cint)
+    rc == 0 && return nothing
+    msg = last_error()
+    # the reference raises AssertionError for K outside the qubit space (src/apply.jl:27,45,112) and
+    # ErrorException for a size mismatch (src/apply.jl:21,40,108)
+    occursin("outside the qubit space", msg) && throw(AssertionError(msg))
+    error(msg)
+end
+
+function __init__()
+    dev = parse(Int, get(ENV, "QCB200_DEVICE", "0"))
+    check(ccall((:qcb_init, LIB), Cint, (Cint,), dev))
+end
+
+dtype_code(::Type{Float32}) = QCB_C64
+dtype_code(::Type{Float64}) = QCB_C128
+
+# ------------------------------------------------------------------------------------------------
+# device state: stands where the CuArray stands in the reference's GPU usage (examples/test_gpu.jl:21-24)
+# ------------------------------------------------------------------------------------------------
+mutable struct B200State{T<:AbstractFloat,N} <: AbstractArray{Complex{T},N}
+    handle::Ptr{Cvoid}
+    function B200State{T,N}() where {T,N}
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:qcb_state_create, LIB), Cint, (Cint, Cint, Ptr{Ptr{Cvoid}}), N, dtype_code(T), h))
+        s = new{T,N}(h[])
+        finalizer(x -> ccall((:qcb_state_destroy, LIB), Cint, (Ptr{Cvoid},), x.handle), s)
+        return s
+    end
+end
+
+function B200State(psi::Array{Complex{T},N}) where {T,N}
+    all(==(2), size(psi)) || error("states are 2x2x...x2 tensors (src/utils.jl:61-66)")
+    s = B200State{T,N}()
+    check(ccall((:qcb_state_upload, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), s.handle, psi))
+    return s
+end
+
+Base.size(::B200State{T,N}) where {T,N} = ntuple(_ -> 2, N)
+Base.similar(::B200State{T,N}) where {T,N} = B200State{T,N}()
+function Base.copy(s::B200State{T,N}) where {T,N}
+    d = B200State{T,N}()
+    check(ccall((:qcb_state_copy, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), d.handle, s.handle))
+    return d
+end
+function Base.copyto!(dst::B200State{T,N}, src::B200State{T,N}) where {T,N}
+    check(ccall((:qcb_state_copy, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), dst.handle, src.handle))
+    return dst
+end
+function Base.copyto!(dst::B200State{T,N}, src::Array{Complex{T},N}) where {T,N}
+    check(ccall((:qcb_state_upload, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), dst.handle, src))
+    return dst
+end
+function Base.Array(s::B200State{T,N}) where {T,N}
+    out = Array{Complex{T},N}(undef, size(s))
+    check(ccall((:qcb_state_download, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), s.handle, out))
+    return out
+end
+# scalar indexing exists only so that printing works; it downloads the whole state
+Base.getindex(s::B200State, i::Int...) = Array(s)[i...]
+# `psi .= psi0`, `psi'' .= psi` (src/gradients.jl:90,118,129,138)
+Base.materialize!(dst::B200State, bc::Base.Broadcast.Broadcasted{<:Any,<:Any,typeof(identity),<:Tuple{Union{B200State,Array}}}) =
+    copyto!(dst, bc.args[1])
+LinearAlgebra.norm(s::B200State) = begin
+    out = Ref{Cdouble}(0)
+    check(ccall((:qcb_state_norm2, LIB), Cint, (Ptr{Cvoid}, Ptr{Cdouble}), s.handle, out))
+    sqrt(out[])
+end
+
+# ------------------------------------------------------------------------------------------------
+# apply.jl seam: construct_apply_cache (src/apply.jl:95-104) and apply! (src/apply.jl:20,39,117,121)
+# ------------------------------------------------------------------------------------------------
+struct B200ApplyCache end
+construct_apply_cache(::B200State) = B200ApplyCache()
+
+gate_block(u::AbstractArray) = (m = zeros(ComplexF64, 16); m[1:length(u)] .= vec(ComplexF64.(u)); m)
+
+function _check_pair(a::B200State, b::B200State)
+    size(a) == size(b) && eltype(a) == eltype(b) || error("ψ′ must be the same size as ψ.")
+    nothing
+end
+
+# kernels run in place; psi' receives a copy of psi first so the (psi', psi) ping-pong of the callers keeps working
+function apply!(psi_out::B200State, psi::B200State, gate::Localised2SpinAdjGate)
+    _check_pair(psi_out, psi)
+    psi_out === psi || copyto!(psi_out, psi)
+    check(ccall((:qcb_apply_2q, LIB), Cint, (Ptr{Cvoid}, Ptr{ComplexF64}, Cint), psi_out.handle, gate_block(mat(gate)), gate.target_gate_dim))
+    return psi_out
+end
+function apply!(psi_out::B200State, psi::B200State, gate::Localised1SpinGate)
+    _check_pair(psi_out, psi)
+    psi_out === psi || copyto!(psi_out, psi)
+    check(ccall((:qcb_apply_1q, LIB), Cint, (Ptr{Cvoid}, Ptr{ComplexF64}, Cint), psi_out.handle, gate_block(mat(gate)), gate.target_gate_dim))
+    return psi_out
+end
+apply!(::B200ApplyCache, psi_out::B200State, psi::B200State, gate::Localised2SpinAdjGate) = apply!(psi_out, psi, gate)
+
+# apply(psi, gates) (src/apply.jl:5-18): one fused call for the whole list
+function apply(psi::B200State, gates::AbstractArray{<:AbstractGate})
+    out = copy(psi)
+    G = length(gates)
+    K = Cint[g.target_gate_dim for g in gates]
+    ar = Cint[g isa QuantumCircuits.Abstract2SpinGate ? 2 : 1 for g in gates]
+    mats = zeros(ComplexF64, 16, G)
+    for (i, g) in enumerate(gates)
+        mats[:, i] .= gate_block(mat(g))
+    end
+    check(ccall((:qcb_apply_gates, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Cint}, Ptr{Cint}, Ptr{ComplexF64}), out.handle, G, K, ar, mats))
+    return out
+end
+apply(psi::B200State, gate::AbstractGate) = apply(psi, AbstractGate[gate])
+
+# circuits.jl:19-42 (quirk Q3: the reference has no GPU method for this; the backend supplies one)
+function _apply_circuit!(s::B200State, c::GenericBrickworkCircuit, first::Integer, last::Integer, adj::Bool)
+    angles = Matrix{Float64}(c.gate_angles)
+    check(ccall((:qcb_apply_brickwork_range, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Cdouble}, Cint, Cint, Cint),
+                s.handle, c.nbits, c.nlayers, angles, first, last, adj ? 1 : 0))
+    return s
+end
+function apply!(::B200ApplyCache, psi_out::B200State, psi::B200State, circuit::GenericBrickworkCircuit)
+    _check_pair(psi_out, psi)
+    psi_out === psi || copyto!(psi_out, psi)
+    return _apply_circuit!(psi_out, circuit, 0, circuit.ngates, false)
+end
+apply(psi::B200State, circuit::GenericBrickworkCircuit) = _apply_circuit!(copy(psi), circuit, 0, circuit.ngates, false)
+
+# ------------------------------------------------------------------------------------------------
+# hamiltonians.jl seam: measure! (src/hamiltonians/hamiltonians.jl:31-50)
+# ------------------------------------------------------------------------------------------------
+function _measure(H::TFIMHamiltonian, s::B200State)
+    E = zeros(Cdouble, 2)
+    check(ccall((:qcb_measure_tfim, LIB), Cint, (Ptr{Cvoid}, Cdouble, Cdouble, Cdouble, Ptr{Cdouble}), s.handle, H.J, H.h, H.g, E))
+    return E
+end
+function _measure(H::EastModelHamiltonian, s::B200State)
+    E = zeros(Cdouble, 2)
+    check(ccall((:qcb_measure_east, LIB), Cint, (Ptr{Cvoid}, Cdouble, Cdouble, Cdouble, Ptr{Cdouble}), s.handle, H.c, H.A, H.B, E))
+    return E
+end
+function measure!(::Union{B200State,Nothing}, H::AbstractKernelHamiltonian, psi::B200State)
+    E = _measure(H, psi)
+    if E[2] > imaginary_energy_limit(H)
+        @warn "Imaginary energy of $(E[2]) -> above threshold!"
+    end
+    return E[1]
+end
+measure(H::AbstractKernelHamiltonian, psi::B200State) = measure!(nothing, H, psi)
+measure(H::AbstractKernelHamiltonian, psi::B200State, circuit::GenericBrickworkCircuit) = measure!(nothing, H, apply(psi, circuit))
+
+# ------------------------------------------------------------------------------------------------
+# gradients.jl seam (src/gradients.jl:1-17,54-152)
+# ------------------------------------------------------------------------------------------------
+ham_kind(::TFIMHamiltonian) = Cint(0)
+ham_kind(::EastModelHamiltonian) = Cint(1)
+ham_params(H::TFIMHamiltonian) = Cdouble[H.J, H.h, H.g]
+ham_params(H::EastModelHamiltonian) = Cdouble[H.c, H.A, H.B]
+
+# same 4-tuple shape as the reference (examples/hpc/utils.jl:57); the work states live inside the library
+construct_grads_cache(psi::B200State) = (B200ApplyCache(), nothing, nothing, nothing)
+
+function gradients!(::B200ApplyCache, _psi_p, _psi_pp, _psi, H::AbstractKernelHamiltonian, psi0::B200State,
+                    circuit::GenericBrickworkCircuit; calculate_energy::Bool=false)
+    grads = similar(circuit.gate_angles, Float64)
+    angles = Matrix{Float64}(circuit.gate_angles)
+    E = Ref{Cdouble}(0)
+    check(ccall((:qcb_gradients_brickwork, LIB), Cint,
+                (Ptr{Cvoid}, Cint, Cint, Ptr{Cdouble}, Cint, Ptr{Cdouble}, Cint, Ptr{Cdouble}, Ptr{Cdouble}),
+                psi0.handle, circuit.nbits, circuit.nlayers, angles, ham_kind(H), ham_params(H), calculate_energy ? 1 : 0, E, grads))
+    return calculate_energy ? (E[], grads) : grads
+end
+gradients(H::AbstractKernelHamiltonian, psi::B200State, circuit::GenericBrickworkCircuit; kwargs...) =
+    gradients!(construct_grads_cache(psi)..., H, psi, circuit; kwargs...)
+
+function propagate_forwards!(::B200ApplyCache, psi_p::B200State, psi::B200State, circuit::GenericBrickworkCircuit,
+                             start_layer::Int, layer_gate_idx::Int, gate_idx::Int)
+    copyto!(psi_p, psi)
+    _apply_circuit!(psi_p, circuit, gate_idx - 1, circuit.ngates, false)
+    return psi_p, psi
+end
+
+# optimise! with quirk Q1 resolved to the intended semantics (SURVEY.md 8a): energy + full gradient per epoch
+function optimise!(circuit::GenericBrickworkCircuit, H::AbstractKernelHamiltonian, psi0::B200State, epochs, lr; use_progress=true)
+    energies = zeros(Float64, epochs + 1)
+    angles = Matrix{Float64}(circuit.gate_angles)
+    check(ccall((:qcb_optimise_brickwork, LIB), Cint,
+                (Ptr{Cvoid}, Cint, Cint, Ptr{Cdouble}, Cint, Ptr{Cdouble}, Cint, Cdouble, Ptr{Cdouble}),
+                psi0.handle, circuit.nbits, circuit.nlayers, angles, ham_kind(H), ham_params(H), epochs, lr, energies))
+    circuit.gate_angles .= angles
+    return energies
+end
+
+end # module

@@ -1,0 +1,77 @@
+"""Worker for the multi-GPU parity tests (launched with torch.distributed.run, one rank per GPU).
+Compares the sharded path against the oracle on the same seeded inputs; rank 0 prints PASS/FAIL lines."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+
+    import oracle
+    import qcb200 as qc
+    from qcb200 import dist as qdist
+    from oracle import oracle_np as onp
+
+    local_rank = int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    rank, world = dist.get_rank(), dist.get_world_size()
+    qdist.init_from_torch()
+    ok = True
+    cases = [(20, 12, np.complex128), (21, 30, np.complex128), (22, 9, np.complex64), (24, 40, np.complex128)]
+    for n, layers, dt in cases:
+        rng = np.random.default_rng(n * 100 + layers)
+        c = qc.GenericBrickworkCircuit(n, layers)
+        c.gate_angles[...] = rng.uniform(0, 2 * np.pi, c.gate_angles.shape)
+        v = rng.standard_normal(2 ** n) + 1j * rng.standard_normal(2 ** n)
+        psi0 = (v / np.linalg.norm(v)).astype(dt)
+        st = qdist.ShardedState(n, dt)
+        per = 1 << st.local_qubits
+        st.upload_shard(psi0[rank * per:(rank + 1) * per])
+        st.apply_circuit(c)
+        swaps = qc.get_stat("swaps")
+        n2 = st.norm2()
+        shard = st.download_shard()
+        if rank == 0:
+            ref = oracle.apply_brickwork(psi0.astype(np.complex128), n, layers, c.gate_angles)
+        else:
+            ref = None
+        box = [ref]
+        dist.broadcast_object_list(box, src=0)
+        ref = box[0][rank * per:(rank + 1) * per]
+        err2 = torch.tensor([np.linalg.norm(shard - ref) ** 2, np.linalg.norm(ref) ** 2], dtype=torch.float64, device="cuda")
+        dist.all_reduce(err2)
+        relerr = float(torch.sqrt(err2[0] / err2[1]).item())
+        tol = 1e-12 if dt == np.complex128 else 1e-5
+        good = relerr < tol and abs(n2 - 1) < (1e-12 if dt == np.complex128 else 1e-5) and swaps >= 1
+        ok = ok and good
+        if rank == 0:
+            print(f"{'PASS' if good else 'FAIL'} sharded n={n} layers={layers} {np.dtype(dt).name} P={world} rel={relerr:.2e} "
+                  f"norm2-1={n2 - 1:.1e} swaps={int(swaps)}", flush=True)
+        # round trip: circuit then inverse circuit on the sharded state
+        st.apply_circuit(c, adjoint=True)
+        back = st.download_shard()
+        e2 = torch.tensor([np.linalg.norm(back - psi0[rank * per:(rank + 1) * per]) ** 2], dtype=torch.float64, device="cuda")
+        dist.all_reduce(e2)
+        rt = float(torch.sqrt(e2[0]).item())
+        good = rt < (1e-12 if dt == np.complex128 else 2e-5)
+        ok = ok and good
+        if rank == 0:
+            print(f"{'PASS' if good else 'FAIL'} round-trip n={n} err={rt:.2e}", flush=True)
+        del st
+    flag = torch.tensor([0 if ok else 1], device="cuda")
+    dist.all_reduce(flag)
+    dist.barrier()
+    qdist.finalize()
+    dist.destroy_process_group()
+    sys.exit(0 if flag.item() == 0 else 1)
+
+
+if __name__ == "__main__":
+    main()

@@ -4,7 +4,7 @@
 // the oracle in the CPU-only test suite.  Not part of the product library.
 #include <cstdio>
 #include <vector>
-#include "../../quantumcircuits.jl_b200/csrc/schedule.hpp"
+#include "../../quantumcircuits.jl_b200/csrc/dist_plan.hpp"
 
 using namespace qcb;
 
@@ -86,4 +86,155 @@ extern "C" int emu_plan_brickwork(int nbits, int nlayers, int tile_bits, int low
     for (auto &p : passes) { nst += (int)p.stages.size(); ng += p.ngates; }
     stats[0] = (int)passes.size(); stats[1] = nst; stats[2] = ng;
     return 0;
+}
+
+// ---- simulated ranks: P shards in one process, swap_top as a block transposition ----------------
+template <typename R> struct EmuShards : ShardExecutor {
+    using V = typename Vec2<R>::type;
+    int nloc, g;
+    std::vector<std::vector<V>> shard; // [rank][2^nloc]
+    int npass = 0, nswap = 0;
+    int run_pass(const PassPlan &pl, const std::vector<GateOp> &gates, const double *mats, bool adjoint) override
+    {
+        PassParams<R> *P = new PassParams<R>;
+        fill_params<R>(pl, nloc, gates, mats, adjoint, *P);
+        for (auto &sh : shard) {
+            switch (pl.TB) {
+#define CASE(T) case T: run_pass_impl<T>(sh.data(), *P); break;
+            CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(11) CASE(12) CASE(13)
+#undef CASE
+            default: delete P; return 3;
+            }
+        }
+        delete P;
+        npass++;
+        return 0;
+    }
+    template <int TB> void run_pass_impl(V *psi, const PassParams<R> &P) { ::run_pass<R, TB>(psi, nloc, P); }
+    int swap_top() override
+    {
+        const int P = (int)shard.size();
+        const size_t blk = (size_t)1 << (nloc - g);
+        std::vector<std::vector<V>> out = shard;
+        for (int r = 0; r < P; r++)
+            for (int j = 0; j < P; j++) // block j of rank r <-> block r of rank j
+                std::copy(shard[r].begin() + j * blk, shard[r].begin() + (j + 1) * blk, out[j].begin() + r * blk);
+        shard.swap(out);
+        nswap++;
+        return 0;
+    }
+};
+
+// psi: full canonical state of n qubits (complex128), split over P = 2^g simulated ranks.
+extern "C" int emu_sharded_apply_gates(int n, int g, void *psi_, int ngates, const int *q, const double *mats, int tile_bits,
+                                       int low_bits, int adjoint, int canonical_out, int *phys_out, int *stats)
+{
+    using V = double2;
+    try {
+        EmuShards<double> ex;
+        ex.nloc = n - g; ex.g = g;
+        const int P = 1 << g;
+        const size_t per = (size_t)1 << ex.nloc;
+        V *psi = (V *)psi_;
+        ex.shard.resize(P);
+        for (int r = 0; r < P; r++) ex.shard[r].assign(psi + r * per, psi + (r + 1) * per);
+        ShardLayout L;
+        L.n = n; L.nloc = ex.nloc; L.g = g;
+        L.phys.resize(n);
+        for (int i = 0; i < n; i++) L.phys[i] = i;
+        std::vector<GateOp> gates(ngates);
+        for (int i = 0; i < ngates; i++) gates[i] = GateOp{q[i], i};
+        SchedOptions opt;
+        opt.tile_bits = tile_bits; opt.low_bits = low_bits;
+        double st[3] = {0, 0, 0};
+        int rc = run_gates_sharded(ex, L, gates, mats, adjoint != 0, opt, st);
+        if (rc) return 10 + (rc < 0 ? -rc : rc);
+        if (canonical_out) {
+            rc = canonicalize(ex, L, opt);
+            if (rc) return 20 + rc;
+        }
+        for (int r = 0; r < P; r++) std::copy(ex.shard[r].begin(), ex.shard[r].end(), psi + r * per);
+        for (int i = 0; i < n; i++) phys_out[i] = L.phys[i];
+        if (stats) { stats[0] = (int)st[0]; stats[1] = (int)st[1]; stats[2] = ex.nswap; stats[3] = ex.npass; }
+        return 0;
+    } catch (const std::exception &e) {
+        std::fprintf(stderr, "emu sharded: %s\n", e.what());
+        return 1;
+    }
+}
+
+// planning statistics for a sharded brickwork circuit (no state)
+struct NullExec : ShardExecutor {
+    int npass = 0, nswap = 0, nperm = 0;
+    int run_pass(const PassPlan &pl, const std::vector<GateOp> &, const double *, bool) override { npass++; if (pl.stages.empty()) nperm++; return 0; }
+    int swap_top() override { nswap++; return 0; }
+};
+extern "C" int emu_plan_sharded_brickwork(int nbits, int nlayers, int g, int tile_bits, int low_bits, int *stats)
+{
+    std::vector<int> pos = brickwork_positions(nbits, nlayers);
+    std::vector<GateOp> gates(pos.size());
+    for (size_t i = 0; i < pos.size(); i++) gates[i] = GateOp{pos[i], (int)i};
+    ShardLayout L;
+    L.n = nbits; L.nloc = nbits - g; L.g = g;
+    L.phys.resize(nbits);
+    for (int i = 0; i < nbits; i++) L.phys[i] = i;
+    SchedOptions opt;
+    opt.tile_bits = tile_bits; opt.low_bits = low_bits;
+    NullExec ex;
+    double st[3] = {0, 0, 0};
+    struct NoFill : NullExec {};
+    int rc = run_gates_sharded(ex, L, gates, nullptr, false, opt, st);
+    if (rc) return rc;
+    const int before = ex.npass;
+    rc = canonicalize(ex, L, opt);
+    stats[0] = before; stats[1] = (int)st[1]; stats[2] = ex.nswap; stats[3] = ex.npass - before; stats[4] = ex.nperm;
+    return rc;
+}
+
+// ---- one real process per rank (tests: torch.distributed gloo, world_size 2): this process holds ONE shard,
+// the exchange itself is delegated to the host framework through a callback ----------------------------
+typedef int (*emu_swap_cb)(void *shard, int nloc, int g);
+struct EmuOneRank : ShardExecutor {
+    int nloc, g;
+    double2 *shard;
+    emu_swap_cb cb;
+    int run_pass(const PassPlan &pl, const std::vector<GateOp> &gates, const double *mats, bool adjoint) override
+    {
+        PassParams<double> *P = new PassParams<double>;
+        fill_params<double>(pl, nloc, gates, mats, adjoint, *P);
+        switch (pl.TB) {
+#define CASE(T) case T: ::run_pass<double, T>(shard, nloc, *P); break;
+        CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(11) CASE(12) CASE(13)
+#undef CASE
+        default: delete P; return 3;
+        }
+        delete P;
+        return 0;
+    }
+    int swap_top() override { return cb(shard, nloc, g); }
+};
+
+extern "C" int emu_rank_apply_gates(int n, int g, void *shard, int ngates, const int *q, const double *mats, int tile_bits,
+                                    int low_bits, int canonical_out, emu_swap_cb cb, int *phys_out)
+{
+    try {
+        EmuOneRank ex;
+        ex.nloc = n - g; ex.g = g; ex.shard = (double2 *)shard; ex.cb = cb;
+        ShardLayout L;
+        L.n = n; L.nloc = n - g; L.g = g;
+        L.phys.resize(n);
+        for (int i = 0; i < n; i++) L.phys[i] = i;
+        std::vector<GateOp> gates(ngates);
+        for (int i = 0; i < ngates; i++) gates[i] = GateOp{q[i], i};
+        SchedOptions opt;
+        opt.tile_bits = tile_bits; opt.low_bits = low_bits;
+        int rc = run_gates_sharded(ex, L, gates, mats, false, opt, nullptr);
+        if (rc) return 10 + (rc < 0 ? -rc : rc);
+        if (canonical_out) { rc = canonicalize(ex, L, opt); if (rc) return 20 + rc; }
+        for (int i = 0; i < n; i++) phys_out[i] = L.phys[i];
+        return 0;
+    } catch (const std::exception &e) {
+        std::fprintf(stderr, "emu rank: %s\n", e.what());
+        return 1;
+    }
 }

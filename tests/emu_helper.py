@@ -12,7 +12,7 @@ _lib = None
 
 
 def build(force=False):
-    srcs = [os.path.join(_HERE, "emu_tile.cu"), os.path.join(_CSRC, "tile.cuh"), os.path.join(_CSRC, "schedule.hpp")]
+    srcs = [os.path.join(_HERE, "emu_tile.cu"), os.path.join(_CSRC, "tile.cuh"), os.path.join(_CSRC, "schedule.hpp"), os.path.join(_CSRC, "dist_plan.hpp")]
     if force or not os.path.exists(_SO) or any(os.path.getmtime(_SO) < os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["nvcc", "-O2", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler",
                                "-fPIC", "-shared", "-o", _SO, srcs[0]], cwd=_HERE)
@@ -51,3 +51,29 @@ def plan_brickwork(nbits, nlayers, tile_bits, low_bits, max_gates=0):
     lib().emu_plan_brickwork(C.c_int(nbits), C.c_int(nlayers), C.c_int(tile_bits), C.c_int(low_bits), C.c_int(max_gates),
                              stats.ctypes.data_as(C.c_void_p))
     return dict(passes=int(stats[0]), stages=int(stats[1]), gates=int(stats[2]))
+
+
+def sharded_apply_gates(psi, g, q0, mats, tile_bits, low_bits, adjoint=False, canonical_out=True):
+    """Simulated 2^g ranks.  psi: full canonical complex128 state.  Returns (state, phys, stats)."""
+    psi = np.ascontiguousarray(psi, dtype=np.complex128).copy()
+    n = int(psi.size).bit_length() - 1
+    q0 = np.ascontiguousarray(q0, dtype=np.int32)
+    m = np.ascontiguousarray(np.stack([np.asarray(M, dtype=np.complex128).reshape(-1, order="F") for M in mats]))
+    stats = np.zeros(8, dtype=np.int32)
+    phys = np.zeros(n, dtype=np.int32)
+    rc = lib().emu_sharded_apply_gates(C.c_int(n), C.c_int(g), psi.ctypes.data_as(C.c_void_p), C.c_int(len(q0)),
+                                       q0.ctypes.data_as(C.c_void_p), m.ctypes.data_as(C.c_void_p), C.c_int(tile_bits),
+                                       C.c_int(low_bits), C.c_int(1 if adjoint else 0), C.c_int(1 if canonical_out else 0),
+                                       phys.ctypes.data_as(C.c_void_p), stats.ctypes.data_as(C.c_void_p))
+    if rc:
+        raise RuntimeError(f"emu_sharded_apply_gates rc={rc}")
+    return psi, phys, dict(gate_passes=int(stats[0]), stages=int(stats[1]), swaps=int(stats[2]), passes=int(stats[3]))
+
+
+def plan_sharded_brickwork(nbits, nlayers, g, tile_bits, low_bits):
+    stats = np.zeros(8, dtype=np.int32)
+    rc = lib().emu_plan_sharded_brickwork(C.c_int(nbits), C.c_int(nlayers), C.c_int(g), C.c_int(tile_bits), C.c_int(low_bits),
+                                          stats.ctypes.data_as(C.c_void_p))
+    if rc:
+        raise RuntimeError(f"emu_plan_sharded_brickwork rc={rc}")
+    return dict(passes=int(stats[0]), stages=int(stats[1]), swaps=int(stats[2]), canon_passes=int(stats[3]), permute_passes=int(stats[4]))

@@ -117,3 +117,48 @@ def test_schedule_statistics(emu):
     assert st["passes"] <= 100 and st["stages"] <= 520
     st4 = emu.plan_brickwork(30, 100, 11, 3, max_gates=4)
     assert st4["gates"] == 1450 and st4["passes"] >= 1450 // 4
+
+
+# ---- sharded path with simulated ranks: scheduler, bit-permuting passes, swap bookkeeping ----------------
+@pytest.mark.parametrize("n,g,layers,tb,c", [(13, 1, 12, 9, 3), (14, 2, 20, 9, 3), (15, 3, 30, 9, 3), (14, 2, 9, 10, 4), (16, 3, 25, 11, 3)])
+def test_emu_sharded_brickwork(emu, oracle, n, g, layers, tb, c):
+    rng = np.random.default_rng(n * 1000 + g * 100 + layers)
+    G = onp.brickwork_num_gates(n, layers)
+    angles = rng.uniform(0, 2 * np.pi, (15, G))
+    q0 = np.array(onp.brickwork_gate_positions(n, layers)) - 1
+    mats = [oracle.build_general_unitary_gate(angles[:, i]) for i in range(G)]
+    psi0 = rand_state(rng, n)
+    ref = oracle.apply_brickwork(psi0, n, layers, angles)
+    out, phys, st = emu.sharded_apply_gates(psi0, g, q0, mats, tb, c)
+    assert list(phys) == list(range(n))
+    assert rel(out, ref) < 1e-13
+    assert st["swaps"] >= 1  # the top qubits had to be exchanged at least once
+    # without canonicalisation the result is the same state in a permuted physical layout
+    out2, phys2, _ = emu.sharded_apply_gates(psi0, g, q0, mats, tb, c, canonical_out=False)
+    idx = np.arange(2 ** n)
+    pidx = np.zeros_like(idx)
+    for q in range(n):
+        pidx |= ((idx >> q) & 1) << int(phys2[q])
+    assert rel(out2[pidx], ref) < 1e-13
+
+
+def test_emu_sharded_random_gate_list(emu, oracle):
+    rng = np.random.default_rng(99)
+    n, g, G = 14, 2, 80
+    q0 = rng.integers(0, n - 1, size=G)
+    mats = []
+    for _ in range(G):
+        u = rng.standard_normal((4, 4)) + 1j * rng.standard_normal((4, 4))
+        mats.append(u / np.linalg.det(u) ** 0.25)
+    psi0 = rand_state(rng, n)
+    ref = psi0
+    for q, M in zip(q0, mats):
+        ref = oracle.apply_2q(ref, M, int(q) + 1)
+    out, phys, st = emu.sharded_apply_gates(psi0, g, q0, mats, 9, 3)
+    assert rel(out, ref) < 1e-12
+
+
+def test_sharded_schedule_34q(emu):
+    # BASELINE config C4: 34 qubits x 100 half-layers on 8 ranks: a handful of all-to-all swaps
+    st = emu.plan_sharded_brickwork(34, 100, 3, 11, 3)
+    assert st["swaps"] <= 6 and st["passes"] <= 110

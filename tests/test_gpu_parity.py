@@ -20,8 +20,9 @@ def rand_state(rng, n, dtype=np.complex128):
 
 
 def rel(a, b):
-    a = np.asarray(a, dtype=np.complex128).reshape(-1)
-    b = np.asarray(b, dtype=np.complex128).reshape(-1)
+    # tensors are column-major 2x2x...x2 (Julia layout): flatten in Fortran order
+    a = np.asarray(a, dtype=np.complex128).reshape(-1, order="F")
+    b = np.asarray(b, dtype=np.complex128).reshape(-1, order="F")
     return np.linalg.norm(a - b) / np.linalg.norm(b)
 
 
