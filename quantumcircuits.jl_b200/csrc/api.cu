@@ -174,12 +174,12 @@ static int gradients_impl(const qcb_state *psi0, int nbits, int nlayers, const d
         if (psi0->dtype == QCB_C128) {
             GateMat<double> Ud;
             for (int r = 0; r < 4; r++)
-                for (int cc = 0; cc < 4; cc++) { Ud.v[2 * (r + 4 * cc)] = m[2 * (cc + 4 * r)]; Ud.v[2 * (r + 4 * cc) + 1] = -m[2 * (cc + 4 * r) + 1]; }
+                for (int cc = 0; cc < 4; cc++) gate_set(Ud, r, cc, m[2 * (cc + 4 * r)], -m[2 * (cc + 4 * r) + 1]);
             k_adjoint_step<double><<<blocks, kRedThreads, 0, c.stream>>>((double2 *)A.d, (double2 *)B.d, nquads, pos[g], Ud, c.d_partial);
         } else {
             GateMat<float> Ud;
             for (int r = 0; r < 4; r++)
-                for (int cc = 0; cc < 4; cc++) { Ud.v[2 * (r + 4 * cc)] = (float)m[2 * (cc + 4 * r)]; Ud.v[2 * (r + 4 * cc) + 1] = (float)-m[2 * (cc + 4 * r) + 1]; }
+                for (int cc = 0; cc < 4; cc++) gate_set(Ud, r, cc, m[2 * (cc + 4 * r)], -m[2 * (cc + 4 * r) + 1]);
             k_adjoint_step<float><<<blocks, kRedThreads, 0, c.stream>>>((float2 *)A.d, (float2 *)B.d, nquads, pos[g], Ud, c.d_partial);
         }
         QCB_CUDA(cudaGetLastError());
@@ -241,6 +241,9 @@ int qcb_init(int device)
     c.stream = nullptr; // the CUDA default stream, shared with the host framework unless qcb_set_stream is called
     QCB_CUDA(cudaEventCreate(&c.ev0));
     QCB_CUDA(cudaEventCreate(&c.ev1));
+    QCB_CUDA(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++)
+        for (int k = 0; k < 16; k++) QCB_CUDA(cudaEventCreateWithFlags(&c.chunk_ev[i][k], cudaEventDisableTiming));
     c.device = device;
     c.inited = true;
     return QCB_OK;
@@ -258,6 +261,9 @@ int qcb_finalize(void)
     c.d_partial = c.d_out = c.h_out = nullptr;
     c.partial_cap = c.out_cap = 0;
     cudaEventDestroy(c.ev0); cudaEventDestroy(c.ev1);
+    for (int i = 0; i < 2; i++)
+        for (int k = 0; k < 16; k++) if (c.chunk_ev[i][k]) { cudaEventDestroy(c.chunk_ev[i][k]); c.chunk_ev[i][k] = nullptr; }
+    if (c.copy_stream) { cudaStreamDestroy(c.copy_stream); c.copy_stream = nullptr; }
     c.stream = nullptr;
     c.plan_cache.clear();
     c.inited = false;
@@ -573,6 +579,11 @@ int qcb_apply_brickwork(qcb_state *s, int nbits, int nlayers, const double *angl
     return qcb_apply_brickwork_range(s, nbits, nlayers, angles, 0, qcb_brickwork_num_gates(nbits, nlayers), 0);
 }
 
+// Host-buffer form.  The transfers are pipelined with the part of the circuit that is local to a contiguous
+// chunk of the state: the state is cut into 2^b chunks (the top b index bits); the gates that do not depend on
+// the top b qubits ("head", a light-cone triangle at the start of the circuit) run on chunk k while chunk k+1 is
+// still on the PCIe bus, and symmetrically the gates nothing else depends on ("tail") run chunk by chunk while
+// finished chunks already travel back.  Only the middle part needs the whole state resident.
 int qcb_apply_brickwork_host(int dtype, int nbits, int nlayers, const double *angles, const void *psi_in_host, void *psi_out_host)
 {
     QCB_REQUIRE_INIT();
@@ -586,11 +597,77 @@ int qcb_apply_brickwork_host(int dtype, int nbits, int nlayers, const double *an
     s.n = s.nloc = nbits; s.dtype = dtype; s.d = c.scratch[2]; s.bytes = bytes;
     s.phys.resize(nbits);
     for (int q = 0; q < nbits; q++) s.phys[q] = q;
-    if (psi_in_host) QCB_CUDA(cudaMemcpyAsync(s.d, psi_in_host, bytes, cudaMemcpyHostToDevice, c.stream));
-    else QCB_TRY(qcb_state_set_zero_state(&s));
-    QCB_TRY(qcb_apply_brickwork(&s, nbits, nlayers, angles));
-    QCB_CUDA(cudaMemcpyAsync(psi_out_host, s.d, bytes, cudaMemcpyDeviceToHost, c.stream));
-    QCB_CUDA(cudaStreamSynchronize(c.stream));
+    const int G = qcb_brickwork_num_gates(nbits, nlayers);
+    std::vector<GateOp> gates;
+    std::vector<double> mats;
+    if (G > 0) QCB_TRY(brickwork_gates(nbits, nlayers, angles, 0, G, false, gates, mats));
+    const int b = nbits >= 27 ? 3 : (nbits >= 25 ? 2 : 0); // chunk = 2^(n-b) amplitudes
+    double tot_passes = 0, tot_stages = 0, tot_launches = 0;
+    auto run = [&](qcb_state *st, const std::vector<GateOp> &g) -> int {
+        if (g.empty()) return QCB_OK;
+        const int rc = run_gate_list(st, g, mats.data(), false);
+        tot_passes += c.st_passes; tot_stages += c.st_stages; tot_launches += c.st_launches;
+        return rc;
+    };
+    if (b == 0 || c.force_simple) {
+        if (psi_in_host) QCB_CUDA(cudaMemcpyAsync(s.d, psi_in_host, bytes, cudaMemcpyHostToDevice, c.stream));
+        else QCB_TRY(qcb_state_set_zero_state(&s));
+        QCB_TRY(run(&s, gates));
+        QCB_CUDA(cudaMemcpyAsync(psi_out_host, s.d, bytes, cudaMemcpyDeviceToHost, c.stream));
+        QCB_CUDA(cudaStreamSynchronize(c.stream));
+    } else {
+        // split: head (dependency-closed prefix below the top b qubits), tail (closed suffix), middle
+        const int nc = nbits - b;
+        std::vector<char> tag(G, 0); // 1 head, 2 tail
+        {
+            std::vector<char> dead(nbits, 0);
+            for (int q = nc; q < nbits; q++) dead[q] = 1;
+            if (psi_in_host)
+                for (int g = 0; g < G; g++) {
+                    const int q = gates[g].q;
+                    if (dead[q] || dead[q + 1]) dead[q] = dead[q + 1] = 1;
+                    else tag[g] = 1;
+                }
+            std::fill(dead.begin(), dead.end(), 0);
+            for (int q = nc; q < nbits; q++) dead[q] = 1;
+            for (int g = G - 1; g >= 0; g--) {
+                const int q = gates[g].q;
+                if (tag[g] == 1 || dead[q] || dead[q + 1]) dead[q] = dead[q + 1] = 1;
+                else tag[g] = 2;
+            }
+        }
+        std::vector<GateOp> head, mid, tail;
+        for (int g = 0; g < G; g++) (tag[g] == 1 ? head : tag[g] == 2 ? tail : mid).push_back(gates[g]);
+        const int nchunks = 1 << b;
+        const size_t cbytes = bytes >> b;
+        qcb_state view = s;
+        view.n = view.nloc = nc; view.bytes = cbytes;
+        view.phys.resize(nc);
+        if (psi_in_host) {
+            for (int k = 0; k < nchunks; k++) {
+                char *dk = (char *)s.d + (size_t)k * cbytes;
+                QCB_CUDA(cudaMemcpyAsync(dk, (const char *)psi_in_host + (size_t)k * cbytes, cbytes, cudaMemcpyHostToDevice, c.copy_stream));
+                QCB_CUDA(cudaEventRecord(c.chunk_ev[0][k], c.copy_stream));
+                QCB_CUDA(cudaStreamWaitEvent(c.stream, c.chunk_ev[0][k], 0));
+                view.d = dk;
+                QCB_TRY(run(&view, head));
+            }
+        } else {
+            QCB_TRY(qcb_state_set_zero_state(&s));
+        }
+        QCB_TRY(run(&s, mid));
+        for (int k = 0; k < nchunks; k++) {
+            char *dk = (char *)s.d + (size_t)k * cbytes;
+            view.d = dk;
+            QCB_TRY(run(&view, tail));
+            QCB_CUDA(cudaEventRecord(c.chunk_ev[1][k], c.stream));
+            QCB_CUDA(cudaStreamWaitEvent(c.copy_stream, c.chunk_ev[1][k], 0));
+            QCB_CUDA(cudaMemcpyAsync((char *)psi_out_host + (size_t)k * cbytes, dk, cbytes, cudaMemcpyDeviceToHost, c.copy_stream));
+        }
+        QCB_CUDA(cudaStreamSynchronize(c.copy_stream));
+        QCB_CUDA(cudaStreamSynchronize(c.stream));
+    }
+    c.st_passes = tot_passes; c.st_stages = tot_stages; c.st_launches = tot_launches; c.st_gates = G;
     return QCB_OK;
 }
 

@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(256) k_apply_2q_simple(typename Vec2<R>::type 
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < nquads; i += stride) {
         const unsigned long long base = ((i >> kb) << (kb + 2)) | (i & low);
         V x0 = psi[base], x1 = psi[base | (1ull << kb)], x2 = psi[base | (2ull << kb)], x3 = psi[base | (3ull << kb)];
-        apply_quad<R, V>(x0, x1, x2, x3, U);
+        apply_quad(x0, x1, x2, x3, U);
         psi[base] = x0; psi[base | (1ull << kb)] = x1; psi[base | (2ull << kb)] = x2; psi[base | (3ull << kb)] = x3;
     }
 }
@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(kRedThreads) k_adjoint_step(typename Vec2<R>::
         V x[4], l[4];
 #pragma unroll
         for (int j = 0; j < 4; j++) { x[j] = psi[base | ((unsigned long long)j << kb)]; l[j] = lam[base | ((unsigned long long)j << kb)]; }
-        apply_quad<R, V>(x[0], x[1], x[2], x[3], Ud);
+        apply_quad(x[0], x[1], x[2], x[3], Ud);
 #pragma unroll
         for (int c = 0; c < 4; c++)
 #pragma unroll
@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(kRedThreads) k_adjoint_step(typename Vec2<R>::
                 acc[2 * (r + 4 * c)] += lr * xr + li * xi;     // Re conj(l) x
                 acc[2 * (r + 4 * c) + 1] += lr * xi - li * xr; // Im conj(l) x
             }
-        apply_quad<R, V>(l[0], l[1], l[2], l[3], Ud);
+        apply_quad(l[0], l[1], l[2], l[3], Ud);
 #pragma unroll
         for (int j = 0; j < 4; j++) { psi[base | ((unsigned long long)j << kb)] = x[j]; lam[base | ((unsigned long long)j << kb)] = l[j]; }
     }

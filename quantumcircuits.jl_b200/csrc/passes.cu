@@ -56,8 +56,7 @@ template <typename R> static int run_simple(qcb_state *s, const std::vector<Gate
         for (int r = 0; r < 4; r++)
             for (int c = 0; c < 4; c++) {
                 const int src = adjoint ? (c + 4 * r) : (r + 4 * c);
-                U.v[2 * (r + 4 * c)] = (R)m[2 * src];
-                U.v[2 * (r + 4 * c) + 1] = (R)(adjoint ? -m[2 * src + 1] : m[2 * src + 1]);
+                gate_set(U, r, c, m[2 * src], adjoint ? -m[2 * src + 1] : m[2 * src + 1]);
             }
         k_apply_2q_simple<R><<<blocks, 256, 0, ctx().stream>>>((V *)s->d, nquads, pb0, U);
         QCB_CUDA(cudaGetLastError());

@@ -31,6 +31,8 @@ struct Ctx {
     int device = -1;
     int sm_count = 148;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr; // non-blocking, for H2D/D2H chunks overlapped with compute
+    cudaEvent_t chunk_ev[2][16] = {};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // options
     long tile_bits = 11, low_bits = 3, max_gates_per_pass = 1 << 30, force_simple = 0;

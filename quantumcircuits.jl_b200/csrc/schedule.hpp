@@ -297,13 +297,8 @@ inline void fill_params(const PassPlan &plan, int nloc, const std::vector<GateOp
             GateMat<R> &U = P.U[s * kSlots + slot];
             for (int r = 0; r < 4; r++)
                 for (int cc = 0; cc < 4; cc++) {
-                    if (!adjoint) {
-                        U.v[2 * (r + 4 * cc)] = (R)m[2 * (r + 4 * cc)];
-                        U.v[2 * (r + 4 * cc) + 1] = (R)m[2 * (r + 4 * cc) + 1];
-                    } else { // conjugate transpose, src/gradients.jl:27-32
-                        U.v[2 * (r + 4 * cc)] = (R)m[2 * (cc + 4 * r)];
-                        U.v[2 * (r + 4 * cc) + 1] = (R)(-m[2 * (cc + 4 * r) + 1]);
-                    }
+                    if (!adjoint) gate_set(U, r, cc, m[2 * (r + 4 * cc)], m[2 * (r + 4 * cc) + 1]);
+                    else gate_set(U, r, cc, m[2 * (cc + 4 * r)], -m[2 * (cc + 4 * r) + 1]); // conjugate transpose, src/gradients.jl:27-32
                 }
         }
     }

@@ -62,7 +62,22 @@ template <int SWB> QCB_HD uint32_t swz(uint32_t e)
     return e ^ (((e >> 4) ^ (e >> 8) ^ (e >> 12)) & 15u);
 }
 
-template <typename R> struct GateMat { R v[32]; }; // v[2*(r+4c)] = Re, v[2*(r+4c)+1] = Im ; r = out, c = in
+// Gate matrix as the kernels consume it (r = output index, c = input index of the 4x4 form).
+//   double: v[2k] = Re u, v[2k+1] = Im u, k = r + 4c.
+//   float : packed for FFMA2 (sm_100 fma.rn.f32x2): v[4k..4k+3] = (Re u, Re u, -Im u, Im u), so that
+//           (re, im) += (Re u, Re u) * (x.re, x.im) + (-Im u, Im u) * (x.im, x.re) is two packed FMAs.
+template <typename R> struct GateMat { R v[32]; };
+template <> struct GateMat<float> { float v[64]; };
+QCB_HD void gate_set(GateMat<double> &U, int r, int c, double re, double im)
+{
+    U.v[2 * (r + 4 * c)] = re;
+    U.v[2 * (r + 4 * c) + 1] = im;
+}
+QCB_HD void gate_set(GateMat<float> &U, int r, int c, double re, double im)
+{
+    float *p = U.v + 4 * (r + 4 * c);
+    p[0] = (float)re; p[1] = (float)re; p[2] = (float)-im; p[3] = (float)im;
+}
 
 struct StageDesc {
     uint8_t p0;                        // first local bit of the register window
@@ -89,19 +104,19 @@ template <typename R> struct PassParams {
 // ---------------------------------------------------------------------------------
 // one gate on one amplitude quad held in registers
 // ---------------------------------------------------------------------------------
-template <typename R, typename V> QCB_HD void apply_quad(V &x0, V &x1, V &x2, V &x3, const GateMat<R> &U)
+QCB_HD void apply_quad(double2 &x0, double2 &x1, double2 &x2, double2 &x3, const GateMat<double> &U)
 {
-    const V in[4] = {x0, x1, x2, x3};
-    V out[4];
+    const double2 in[4] = {x0, x1, x2, x3};
+    double2 out[4];
 #pragma unroll
     for (int r = 0; r < 4; r++) {
-        R re = U.v[2 * r] * in[0].x;
-        R im = U.v[2 * r] * in[0].y;
+        double re = U.v[2 * r] * in[0].x;
+        double im = U.v[2 * r] * in[0].y;
         re = fma(-U.v[2 * r + 1], in[0].y, re);
         im = fma(U.v[2 * r + 1], in[0].x, im);
 #pragma unroll
         for (int c = 1; c < 4; c++) {
-            const R ur = U.v[2 * (r + 4 * c)], ui = U.v[2 * (r + 4 * c) + 1];
+            const double ur = U.v[2 * (r + 4 * c)], ui = U.v[2 * (r + 4 * c) + 1];
             re = fma(ur, in[c].x, re);
             im = fma(ur, in[c].y, im);
             re = fma(-ui, in[c].y, re);
@@ -110,6 +125,50 @@ template <typename R, typename V> QCB_HD void apply_quad(V &x0, V &x1, V &x2, V 
         out[r].x = re;
         out[r].y = im;
     }
+    x0 = out[0]; x1 = out[1]; x2 = out[2]; x3 = out[3];
+}
+
+QCB_HD void apply_quad(float2 &x0, float2 &x1, float2 &x2, float2 &x3, const GateMat<float> &U)
+{
+    const float2 in[4] = {x0, x1, x2, x3};
+    float2 out[4];
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 1000
+    // packed FP32: one FFMA2 issue slot per two FMAs, operands straight from uniform registers
+    float2 sw[4];
+#pragma unroll
+    for (int c = 0; c < 4; c++) sw[c] = make_float2(in[c].y, in[c].x);
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const float2 *u = reinterpret_cast<const float2 *>(U.v) + 2 * r;
+        float2 acc = __fmul2_rn(u[0], in[0]);
+        acc = __ffma2_rn(u[1], sw[0], acc);
+#pragma unroll
+        for (int c = 1; c < 4; c++) {
+            acc = __ffma2_rn(u[8 * c], in[c], acc);
+            acc = __ffma2_rn(u[8 * c + 1], sw[c], acc);
+        }
+        out[r] = acc;
+    }
+#else
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const float *u = U.v + 4 * r;
+        float re = u[0] * in[0].x;
+        float im = u[1] * in[0].y;
+        re = fmaf(u[2], in[0].y, re);
+        im = fmaf(u[3], in[0].x, im);
+#pragma unroll
+        for (int c = 1; c < 4; c++) {
+            const float *w = U.v + 4 * (r + 4 * c);
+            re = fmaf(w[0], in[c].x, re);
+            im = fmaf(w[1], in[c].y, im);
+            re = fmaf(w[2], in[c].y, re);
+            im = fmaf(w[3], in[c].x, im);
+        }
+        out[r].x = re;
+        out[r].y = im;
+    }
+#endif
     x0 = out[0]; x1 = out[1]; x2 = out[2]; x3 = out[3];
 }
 
@@ -123,7 +182,7 @@ template <int LO, typename R, typename V> QCB_HD void apply_window_gate(V (&a)[k
 #pragma unroll
         for (int b = 0; b < 4; b++)
             if (b != LO && b != LO + 1) { other |= (qq & 1) << b; qq >>= 1; }
-        apply_quad<R, V>(a[other], a[other | (1 << LO)], a[other | (2 << LO)], a[other | (3 << LO)], U);
+        apply_quad(a[other], a[other | (1 << LO)], a[other | (2 << LO)], a[other | (3 << LO)], U);
     }
 }
 

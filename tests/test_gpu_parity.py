@@ -367,3 +367,18 @@ def test_full_size_30q_properties(oracle):
     assert abs(qc.measure_(None, H, st) + ((n - 1) + 0.1 * n)) < 1e-10
     head = st.tensor[:4].cpu().numpy()
     assert abs(head[0] - 1) < 1e-12 and np.all(np.abs(head[1:]) < 1e-12)
+
+
+def test_host_buffer_pipeline_equals_device_path():
+    """apply(psi::Array, circuit) pipelines H2D / D2H chunks with the chunk-local head and tail of the circuit
+    (n >= 25); the result must equal the resident-state path bit for bit up to FMA-order rounding."""
+    rng = np.random.default_rng(2525)
+    for n, layers, dtype in [(25, 9, np.complex128), (26, 30, np.complex64)]:
+        c = circuit(n, layers, rng)
+        psi0 = rand_state(rng, n, dtype)
+        out_host = qc.apply(psi0, c)
+        st = qc.B200State(psi0)
+        qc.apply_(st, st, c)
+        ref = st.to_numpy()
+        assert rel(out_host, ref) < (1e-13 if dtype == np.complex128 else 2e-6)
+        assert abs(np.vdot(out_host, out_host).real - 1) < (1e-12 if dtype == np.complex128 else 1e-5)

@@ -10,13 +10,13 @@ echo "== pytest gpu"; timeout 1800 python -m pytest tests -m gpu -x -q > gpurun_
 echo "== bench"; timeout 1200 python bench.py --steps 3 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"; cat gpurun_out/bench.json; tail -5 gpurun_out/bench.err
 if [ "$1" != "quick" ]; then
 echo "== sweep"
-for tb in 11 12 13; do for lb in 3 4; do
+for tb in 11 12; do for lb in 3; do
   timeout 600 python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline --tile-bits $tb --low-bits $lb >> gpurun_out/sweep.jsonl 2>> gpurun_out/sweep.err
 done; done
-for mg in 2 4 6 8; do
+for mg in 3 5; do
   timeout 600 python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --max-gates-per-pass $mg >> gpurun_out/sweep_maxg.jsonl 2>> gpurun_out/sweep.err
 done
-timeout 600 python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline --dtype c64 >> gpurun_out/sweep_c64.jsonl 2>> gpurun_out/sweep.err
+for tb in 11 12; do timeout 600 python bench.py --steps 2 --warmup 1 --no-cpu-baseline --dtype c64 --tile-bits $tb >> gpurun_out/sweep_c64.jsonl 2>> gpurun_out/sweep.err; done
 python - <<'PY'
 import json
 for f in ("sweep.jsonl","sweep_maxg.jsonl","sweep_c64.jsonl"):
@@ -27,10 +27,14 @@ for f in ("sweep.jsonl","sweep_maxg.jsonl","sweep_c64.jsonl"):
     except Exception as e: print(f, "ERR", e)
 PY
 fi
+echo "== gradients"; timeout 900 python tools/bench_gradients.py > gpurun_out/gradients.jsonl 2> gpurun_out/gradients.err; cat gpurun_out/gradients.jsonl; tail -3 gpurun_out/gradients.err
 echo "== ncu"
-CMD="python bench.py --nqubits 28 --steps 1 --warmup 1 --no-e2e --no-cpu-baseline"
+CMD="python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline"
 $CMD > gpurun_out/plain.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
 echo "ncu launches rc=$?"
 $CMD > gpurun_out/plain2.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:tile_pass -s 30 -c 3 -f -o gpurun_out/prof_tile $CMD > gpurun_out/ncu_full.log 2>&1
 echo "ncu full rc=$?"; tail -3 gpurun_out/ncu_full.log
 ls -la gpurun_out
+CMD2="python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --dtype c64"
+$CMD2 > gpurun_out/plain3.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:tile_pass -s 30 -c 3 -f -o gpurun_out/prof_tile_c64 $CMD2 > gpurun_out/ncu_full_c64.log 2>&1
+echo "ncu full c64 rc=$?"; tail -3 gpurun_out/ncu_full_c64.log
