@@ -26,6 +26,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md, used only if MEASURED_PEAKS.json is absent
+UNIT_MULTI = "gate-apps/s in 2^30-amplitude units (n-qubit gate-app counts 2^(n-30))"
 NOMINAL_FP64_TFLOPS = 37.0  # 148 SMs x 64 DFMA/clk x 1.965 GHz x 2 (datasheet-level figure; measured one preferred)
 
 
@@ -173,14 +174,18 @@ def run_reference(args):
         rates.append(r)
     wall = time.perf_counter() - t0
     value = float(np.mean(rates)) if rates else 0.0
+    unit = "gate-apps/s"
+    if args.gpus > 1:  # same normalisation as our arm: 2^30-amplitude gate applications per second
+        value *= 2.0 ** (n - 30)
+        unit = UNIT_MULTI
     line = {
-        "impl": "reference", "metric": "gate_apps_per_sec", "value": value, "unit": "gate-apps/s", "n_gpus": args.gpus,
+        "impl": "reference", "metric": "gate_apps_per_sec", "value": value, "unit": unit, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(1, args.steps), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64" if args.dtype == "c128" else "f32", "data": "synthetic",
         "config": {"workload": f"{n}-qubit brickwork circuit, {layers} half-layers ({G} gates), Complex{'F64' if args.dtype == 'c128' else 'F32'}",
                    "step": "bounded sample: leading gates of the circuit, gate-apps/s = gates / time"},
-        "cpu_baseline": {"value": value, "unit": "gate-apps/s", "cores": cores, "kind": "port", "sample": desc},
-        "e2e": {"value": value, "unit": "gate-apps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
@@ -289,9 +294,9 @@ def run_ours(args):
 
     # ---- roofline of the dominant kernel (tile_pass_kernel): HBM bytes per launch / average launch duration
     bytes_pass = 2.0 * amp_bytes * (2.0 ** nloc)
-    launch_ms = ms_step / max(passes, 1.0) if world == 1 else None
+    launch_ms = ms_step / max(passes, 1.0)  # N > 1: the step also contains the NCCL swaps, so this is an upper bound
     peak, peak_src = measured_peaks()
-    traffic = profile_note("r01_tile_pass_traffic.json")
+    traffic = profile_note("r01_tile_pass_traffic.json" if args.dtype == "c128" else "r01_tile_pass_traffic_c64.json")
     fp64 = profile_note("r01_fp64_peak.json")
     roofline = None
     if launch_ms:
@@ -340,6 +345,62 @@ def run_ours(args):
                "check_norm2_first_2^20": nrm}
         del h_in, h_out
 
+    if not args.no_e2e and world > 1:
+        # sharded end-to-end: every rank moves its canonical shard host -> device, runs the circuit, and reads the
+        # canonical result shard back (download includes the qubit swaps that restore the reference's index order).
+        # If the host cannot pin the shards (34 q = 256 GiB in total), the step is |0...0> built in HBM + circuit +
+        # an all-reduced norm read back to the host, and the line says so.
+        per_rank = amp_bytes << nloc
+        try:
+            import psutil
+
+            avail = psutil.virtual_memory().available / max(1, world)
+        except Exception:
+            avail = 0
+        use_host = avail > 1.6 * per_rank
+        flag = torch.tensor([1 if use_host else 0], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        use_host = bool(flag.item())
+        k = max(1, min(args.steps, 2))
+        if use_host:
+            tdt = torch.complex128 if args.dtype == "c128" else torch.complex64
+            h = torch.zeros(1 << nloc, dtype=tdt, pin_memory=True)
+            if rank == 0:
+                h[0] = 1
+            hn = h.numpy()
+
+            def e2e_step():
+                state.upload_shard(hn)
+                state.apply_circuit(circuit)
+                hn[...] = state.download_shard()
+        else:
+            def e2e_step():
+                state.set_zero_state()
+                state.apply_circuit(circuit)
+                return state.norm2()
+        e2e_step()
+        barrier()
+        l0 = qc.get_stat("launches_total")
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(k):
+            e2e_step()
+        e1.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        ms = max(e0.elapsed_time(e1), wall * 1e3) / k
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        launches += (qc.get_stat("launches_total") - l0) * world
+        e2e = {"value": G / (ms * 1e-3) * (2.0 ** (n - 30)), "unit": UNIT_MULTI,
+               "h2d_bytes_per_step": int(world * per_rank + angles.nbytes) if use_host else int(angles.nbytes * world),
+               "d2h_bytes_per_step": int(world * per_rank) if use_host else 8 * world, "ms_per_step": ms, "steps": k,
+               "api": ("ShardedState.upload_shard + apply_circuit + download_shard (pinned host shards on every rank)" if use_host else
+                       "ShardedState.set_zero_state + apply_circuit + norm2 read-back (host RAM cannot hold the 2^n-amplitude state; "
+                       "inputs = gate angles, result = all-reduced norm)")}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, cores, desc = cpu_sample(n, layers, angles, args.dtype, args.cpu_seconds)
@@ -349,7 +410,7 @@ def run_ours(args):
         cname = "ComplexF64" if args.dtype == "c128" else "ComplexF32"
         line = {
             "metric": "gate_apps_per_sec", "value": value,
-            "unit": "gate-apps/s" if world == 1 else "gate-apps/s in 2^30-amplitude units (n-qubit gate-app counts 2^(n-30))",
+            "unit": "gate-apps/s" if world == 1 else UNIT_MULTI,
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64" if args.dtype == "c128" else "f32", "data": "synthetic",
             "config": {"workload": f"{n}-qubit brickwork circuit, {layers} half-layers ({G} gates), {cname}, psi0=|0...0>, angles U[0,2pi)",

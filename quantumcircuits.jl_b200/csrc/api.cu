@@ -165,27 +165,38 @@ static int gradients_impl(const qcb_state *psi0, int nbits, int nlayers, const d
         count_launch();
     }
     // backward sweep: un-apply gate g on psi and lambda, reduce the 4x4 environment
-    const unsigned long long nquads = namps >> 2;
-    const unsigned blocks = grid_for(nquads, kRedThreads, 4);
-    QCB_TRY(ensure_partial((size_t)blocks * 32));
     QCB_TRY(ensure_out((size_t)32 * G));
-    for (int g = G - 1; g >= 0; g--) {
-        const double *m = mats.data() + 32 * (size_t)g;
-        if (psi0->dtype == QCB_C128) {
-            GateMat<double> Ud;
-            for (int r = 0; r < 4; r++)
-                for (int cc = 0; cc < 4; cc++) gate_set(Ud, r, cc, m[2 * (cc + 4 * r)], -m[2 * (cc + 4 * r) + 1]);
-            k_adjoint_step<double><<<blocks, kRedThreads, 0, c.stream>>>((double2 *)A.d, (double2 *)B.d, nquads, pos[g], Ud, c.d_partial);
-        } else {
-            GateMat<float> Ud;
-            for (int r = 0; r < 4; r++)
-                for (int cc = 0; cc < 4; cc++) gate_set(Ud, r, cc, m[2 * (cc + 4 * r)], -m[2 * (cc + 4 * r) + 1]);
-            k_adjoint_step<float><<<blocks, kRedThreads, 0, c.stream>>>((float2 *)A.d, (float2 *)B.d, nquads, pos[g], Ud, c.d_partial);
+    double bw_passes = 0, bw_stages = 0;
+    if (!c.force_simple && nbits >= kMinTB) {
+        // fused: the reversed circuit goes through the pass planner, one launch per trapezoid of gates
+        std::vector<GateOp> rev(G);
+        for (int i = 0; i < G; i++) rev[i] = GateOp{pos[G - 1 - i], G - 1 - i};
+        const double p0 = c.st_passes, s0 = c.st_stages;
+        QCB_TRY(run_adjoint_fused(&A, &B, rev, mats.data(), c.d_out));
+        bw_passes = c.st_passes - p0; bw_stages = c.st_stages - s0;
+    } else {
+        const unsigned long long nquads = namps >> 2;
+        const unsigned blocks = grid_for(nquads, kRedThreads, 4);
+        QCB_TRY(ensure_partial((size_t)blocks * 32));
+        for (int g = G - 1; g >= 0; g--) {
+            const double *m = mats.data() + 32 * (size_t)g;
+            if (psi0->dtype == QCB_C128) {
+                GateMat<double> Ud;
+                for (int r = 0; r < 4; r++)
+                    for (int cc = 0; cc < 4; cc++) gate_set(Ud, r, cc, m[2 * (cc + 4 * r)], -m[2 * (cc + 4 * r) + 1]);
+                k_adjoint_step<double><<<blocks, kRedThreads, 0, c.stream>>>((double2 *)A.d, (double2 *)B.d, nquads, pos[g], Ud, c.d_partial);
+            } else {
+                GateMat<float> Ud;
+                for (int r = 0; r < 4; r++)
+                    for (int cc = 0; cc < 4; cc++) gate_set(Ud, r, cc, m[2 * (cc + 4 * r)], -m[2 * (cc + 4 * r) + 1]);
+                k_adjoint_step<float><<<blocks, kRedThreads, 0, c.stream>>>((float2 *)A.d, (float2 *)B.d, nquads, pos[g], Ud, c.d_partial);
+            }
+            QCB_CUDA(cudaGetLastError());
+            k_final_sum<<<32, 128, 0, c.stream>>>(c.d_partial, (int)blocks, 32, c.d_out + 32 * (size_t)g);
+            QCB_CUDA(cudaGetLastError());
+            count_launch(2);
         }
-        QCB_CUDA(cudaGetLastError());
-        k_final_sum<<<32, 128, 0, c.stream>>>(c.d_partial, (int)blocks, 32, c.d_out + 32 * (size_t)g);
-        QCB_CUDA(cudaGetLastError());
-        count_launch(2);
+        bw_passes = G;
     }
     QCB_CUDA(cudaMemcpyAsync(c.h_out, c.d_out, sizeof(double) * 32 * (size_t)G, cudaMemcpyDeviceToHost, c.stream));
     QCB_CUDA(cudaStreamSynchronize(c.stream));
@@ -199,7 +210,7 @@ static int gradients_impl(const qcb_state *psi0, int nbits, int nlayers, const d
             out_grads[k + 15 * (size_t)g] = 2 * s;
         }
     }
-    c.st_passes += fw_passes + G; c.st_stages += fw_stages; c.st_launches += fw_launches; c.st_gates = 4.0 * G;
+    c.st_passes = fw_passes + bw_passes; c.st_stages = fw_stages + bw_stages; c.st_launches += fw_launches; c.st_gates = 4.0 * G;
     return QCB_OK;
 }
 

@@ -5,6 +5,7 @@
 // one synchronize per gate (src/apply.jl:134-142).
 #include <sstream>
 
+#include "adjoint.cuh"
 #include "kernels.cuh"
 #include "qcb_internal.hpp"
 
@@ -138,6 +139,109 @@ template <typename R> static int run_fused(qcb_state *s, const std::vector<GateO
         c.st_stages += (double)pl.stages.size();
     }
     return QCB_OK;
+}
+
+// ---- fused backward pass of the adjoint gradient sweep (adjoint.cuh) -------------------------------------
+struct EnvIds { int id[kAdjMaxGates]; int n; };
+
+static __global__ void k_env_final(const double *__restrict__ partial, int nblocks, EnvIds ids, double *env_out)
+{
+    // block = (gate ordinal, element); fixed-order sum over the persistent CTAs' partials
+    const int ord = blockIdx.x >> 5, el = blockIdx.x & 31;
+    double s = 0;
+    for (int b = threadIdx.x; b < nblocks; b += blockDim.x) s += partial[(size_t)b * (kAdjMaxGates * 32) + ord * 32 + el];
+    __shared__ double red[32];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += red[w];
+        env_out[(size_t)ids.id[ord] * 32 + el] = t;
+    }
+}
+
+template <typename R, int TB> static int launch_adjoint(qcb_state *psi, qcb_state *lam, const AdjParams<R> &A, const EnvIds &ids, double *d_env)
+{
+    using V = typename Vec2<R>::type;
+    constexpr int NT = 1 << (TB - kRegBits);
+    constexpr int NW = (NT + 31) / 32;
+    constexpr int MINB = TB >= 12 ? 1 : 2;
+    auto kern = adjoint_pass_kernel<R, TB, MINB>;
+    const size_t smem = 2 * (sizeof(V) << TB) + sizeof(double) * NW * kAdjMaxGates * 32;
+    static bool attr_set = false;
+    static int ctas_per_sm = 1;
+    if (!attr_set) {
+        QCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        QCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, NT, smem));
+        if (ctas_per_sm < 1) ctas_per_sm = 1;
+        attr_set = true;
+    }
+    const unsigned long long ntiles = 1ull << (psi->nloc - TB);
+    const unsigned grid = (unsigned)std::min<unsigned long long>(ntiles, (unsigned long long)ctx().sm_count * ctas_per_sm);
+    QCB_TRY(ensure_partial((size_t)grid * kAdjMaxGates * 32));
+    kern<<<grid, NT, smem, ctx().stream>>>((V *)psi->d, (V *)lam->d, A, ntiles, ctx().d_partial);
+    QCB_CUDA(cudaGetLastError());
+    k_env_final<<<ids.n * 32, 128, 0, ctx().stream>>>(ctx().d_partial, (int)grid, ids, d_env);
+    QCB_CUDA(cudaGetLastError());
+    count_launch(2);
+    return QCB_OK;
+}
+
+template <typename R> static int run_adjoint_fused_t(qcb_state *psi, qcb_state *lam, const std::vector<GateOp> &rev, const double *mats, double *d_env)
+{
+    Ctx &c = ctx();
+    SchedOptions opt = current_sched_options(psi);
+    opt.max_gates_per_pass = std::min(opt.max_gates_per_pass, kAdjMaxGates);
+    if (sizeof(R) == 8 && opt.tile_bits > 12) opt.tile_bits = 12; // two tiles + accumulators must fit shared memory
+    std::vector<PassPlan> plans;
+    std::vector<char> done;
+    try {
+        plans = plan_passes(psi->nloc, psi->phys, rev, opt, &done);
+    } catch (const std::exception &e) {
+        return set_error(QCB_EINVAL, "scheduler: %s", e.what());
+    }
+    for (char d : done)
+        if (!d) return set_error(QCB_EINVAL, "gate list could not be scheduled");
+    static thread_local AdjParams<R> A;
+    for (const PassPlan &pl : plans) {
+        try {
+            fill_params<R>(pl, psi->nloc, rev, mats, true, A.P);
+        } catch (const std::exception &e) {
+            return set_error(QCB_EINVAL, "pass parameters: %s", e.what());
+        }
+        EnvIds ids;
+        ids.n = 0;
+        std::memset(A.slot_gate, 0, sizeof A.slot_gate);
+        for (size_t st = 0; st < pl.stages.size(); st++)
+            for (int slot = 0; slot < kSlots; slot++) {
+                const int g = pl.stages[st].gate[slot];
+                if (g < 0) continue;
+                if (ids.n >= kAdjMaxGates) return set_error(QCB_EINVAL, "too many gates in a backward pass");
+                A.slot_gate[st * kSlots + slot] = (uint8_t)ids.n;
+                ids.id[ids.n++] = rev[g].mat;
+            }
+        A.ngates = ids.n;
+        int rc;
+        switch (pl.TB) {
+        case 9: rc = launch_adjoint<R, 9>(psi, lam, A, ids, d_env); break;
+        case 10: rc = launch_adjoint<R, 10>(psi, lam, A, ids, d_env); break;
+        case 11: rc = launch_adjoint<R, 11>(psi, lam, A, ids, d_env); break;
+        case 12: rc = launch_adjoint<R, 12>(psi, lam, A, ids, d_env); break;
+        default: rc = set_error(QCB_EINVAL, "unsupported tile size %d for the backward pass", pl.TB);
+        }
+        QCB_TRY(rc);
+        c.st_passes += 1;
+        c.st_stages += (double)pl.stages.size();
+    }
+    return QCB_OK;
+}
+
+// rev: the circuit's gates in reverse order, GateOp.mat = original gate index (also the row of d_env, 32 doubles each)
+int run_adjoint_fused(qcb_state *psi, qcb_state *lam, const std::vector<GateOp> &rev, const double *mats, double *d_env)
+{
+    if (psi->dtype == QCB_C128) return run_adjoint_fused_t<double>(psi, lam, rev, mats, d_env);
+    return run_adjoint_fused_t<float>(psi, lam, rev, mats, d_env);
 }
 
 int run_gate_list(qcb_state *s, const std::vector<GateOp> &gates, const double *mats, bool adjoint)

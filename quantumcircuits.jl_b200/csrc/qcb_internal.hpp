@@ -87,6 +87,7 @@ inline void count_launch(int k = 1)
 
 // gate-list execution (passes.cu)
 int run_gate_list(qcb_state *s, const std::vector<GateOp> &gates, const double *mats, bool adjoint);
+int run_adjoint_fused(qcb_state *psi, qcb_state *lam, const std::vector<GateOp> &rev, const double *mats, double *d_env);
 int launch_plan(qcb_state *s, const PassPlan &plan, const std::vector<GateOp> &gates, const double *mats, bool adjoint);
 SchedOptions current_sched_options(const qcb_state *s);
 

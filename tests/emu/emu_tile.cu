@@ -238,3 +238,73 @@ extern "C" int emu_rank_apply_gates(int n, int g, void *shard, int ngates, const
         return 1;
     }
 }
+
+// ---- fused backward pass of the adjoint sweep (adjoint.cuh) replayed on the CPU ---------------------------
+#include "../../quantumcircuits.jl_b200/csrc/adjoint.cuh"
+
+template <typename R, int TB>
+static void run_adjoint_pass(typename Vec2<R>::type *psi, typename Vec2<R>::type *lam, int nloc, const AdjParams<R> &A, double *acc)
+{
+    using V = typename Vec2<R>::type;
+    const uint32_t NT = 1u << (TB - kRegBits);
+    const unsigned long long ntiles = 1ull << (nloc - TB);
+    std::vector<V> smP(1u << TB), smL(1u << TB);
+    for (unsigned long long b = 0; b < ntiles; b++) {
+        for (uint32_t t = 0; t < NT; t++) { tile_load<R, TB>(psi, A.P, smP.data(), t, b); tile_load<R, TB>(lam, A.P, smL.data(), t, b); }
+        for (int s = 0; s < A.P.nstages; s++)
+            for (uint32_t t = 0; t < NT; t++) adjoint_stage<R, TB>(A, s, smP.data(), smL.data(), acc, t);
+        for (uint32_t t = 0; t < NT; t++) { tile_store<R, TB>(psi, A.P, smP.data(), t, b); tile_store<R, TB>(lam, A.P, smL.data(), t, b); }
+    }
+}
+
+// psi, lam: states (modified: both get every gate un-applied, in reverse order); env_out: [ngates][32] indexed like the gate list
+template <typename R>
+static int adjoint_all(void *psi, void *lam, int n, int ngates, const int *q, const double *mats, int tile_bits, int low_bits, double *env_out)
+{
+    using V = typename Vec2<R>::type;
+    std::vector<GateOp> rev(ngates);
+    for (int i = 0; i < ngates; i++) rev[i] = GateOp{q[ngates - 1 - i], ngates - 1 - i};
+    std::vector<int> phys(n);
+    for (int i = 0; i < n; i++) phys[i] = i;
+    SchedOptions opt;
+    opt.tile_bits = tile_bits; opt.low_bits = low_bits; opt.max_gates_per_pass = kAdjMaxGates;
+    std::vector<char> done;
+    std::vector<PassPlan> plans = plan_passes(n, phys, rev, opt, &done);
+    for (char d : done) if (!d) return 2;
+    AdjParams<R> *A = new AdjParams<R>;
+    for (const PassPlan &pl : plans) {
+        fill_params<R>(pl, n, rev, mats, true, A->P);
+        int ids[kAdjMaxGates], nid = 0;
+        std::memset(A->slot_gate, 0, sizeof A->slot_gate);
+        for (size_t st = 0; st < pl.stages.size(); st++)
+            for (int slot = 0; slot < kSlots; slot++) {
+                const int g = pl.stages[st].gate[slot];
+                if (g < 0) continue;
+                A->slot_gate[st * kSlots + slot] = (uint8_t)nid;
+                ids[nid++] = rev[g].mat;
+            }
+        std::vector<double> acc(kAdjMaxGates * 32, 0.0);
+        switch (pl.TB) {
+#define CASE(T) case T: run_adjoint_pass<R, T>((V *)psi, (V *)lam, n, *A, acc.data()); break;
+        CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(11) CASE(12)
+#undef CASE
+        default: delete A; return 3;
+        }
+        for (int k = 0; k < nid; k++)
+            for (int i = 0; i < 32; i++) env_out[(size_t)ids[k] * 32 + i] = acc[k * 32 + i];
+    }
+    delete A;
+    return 0;
+}
+
+extern "C" int emu_adjoint_sweep(int dtype, int n, void *psi, void *lam, int ngates, const int *q, const double *mats, int tile_bits,
+                                 int low_bits, double *env_out)
+{
+    try {
+        if (dtype) return adjoint_all<double>(psi, lam, n, ngates, q, mats, tile_bits, low_bits, env_out);
+        return adjoint_all<float>(psi, lam, n, ngates, q, mats, tile_bits, low_bits, env_out);
+    } catch (const std::exception &e) {
+        std::fprintf(stderr, "emu adjoint: %s\n", e.what());
+        return 1;
+    }
+}

@@ -12,7 +12,7 @@ _lib = None
 
 
 def build(force=False):
-    srcs = [os.path.join(_HERE, "emu_tile.cu"), os.path.join(_CSRC, "tile.cuh"), os.path.join(_CSRC, "schedule.hpp"), os.path.join(_CSRC, "dist_plan.hpp")]
+    srcs = [os.path.join(_HERE, "emu_tile.cu"), os.path.join(_CSRC, "tile.cuh"), os.path.join(_CSRC, "schedule.hpp"), os.path.join(_CSRC, "dist_plan.hpp"), os.path.join(_CSRC, "adjoint.cuh")]
     if force or not os.path.exists(_SO) or any(os.path.getmtime(_SO) < os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["nvcc", "-O2", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler",
                                "-fPIC", "-shared", "-o", _SO, srcs[0]], cwd=_HERE)
@@ -77,3 +77,20 @@ def plan_sharded_brickwork(nbits, nlayers, g, tile_bits, low_bits):
     if rc:
         raise RuntimeError(f"emu_plan_sharded_brickwork rc={rc}")
     return dict(passes=int(stats[0]), stages=int(stats[1]), swaps=int(stats[2]), canon_passes=int(stats[3]), permute_passes=int(stats[4]))
+
+
+def adjoint_sweep(psi, lam, q0, mats, tile_bits, low_bits):
+    """Backward sweep replay: returns (psi_0, lam_0, env[G, 4, 4]) with env[g][r, c] = sum conj(lam_g[r]) psi_{g-1}[c]."""
+    psi = np.ascontiguousarray(psi).copy()
+    lam = np.ascontiguousarray(lam).astype(psi.dtype).copy()
+    n = int(psi.size).bit_length() - 1
+    q0 = np.ascontiguousarray(q0, dtype=np.int32)
+    m = np.ascontiguousarray(np.stack([np.asarray(M, dtype=np.complex128).reshape(-1, order="F") for M in mats]))
+    env = np.zeros((len(q0), 32), dtype=np.float64)
+    rc = lib().emu_adjoint_sweep(C.c_int(1 if psi.dtype == np.complex128 else 0), C.c_int(n), psi.ctypes.data_as(C.c_void_p),
+                                 lam.ctypes.data_as(C.c_void_p), C.c_int(len(q0)), q0.ctypes.data_as(C.c_void_p),
+                                 m.ctypes.data_as(C.c_void_p), C.c_int(tile_bits), C.c_int(low_bits), env.ctypes.data_as(C.c_void_p))
+    if rc:
+        raise RuntimeError(f"emu_adjoint_sweep rc={rc}")
+    envc = (env[:, 0::2] + 1j * env[:, 1::2]).reshape(len(q0), 4, 4).transpose(0, 2, 1)  # stored column-major r + 4c
+    return psi, lam, envc

@@ -162,3 +162,42 @@ def test_sharded_schedule_34q(emu):
     # BASELINE config C4: 34 qubits x 100 half-layers on 8 ranks: a handful of all-to-all swaps
     st = emu.plan_sharded_brickwork(34, 100, 3, 11, 3)
     assert st["swaps"] <= 6 and st["passes"] <= 110
+
+
+# ---- fused backward pass of the adjoint gradient sweep ----------------------------------------------------
+@pytest.mark.parametrize("n,layers,tb,dtype", [(9, 4, 9, np.complex128), (12, 6, 10, np.complex128), (13, 5, 11, np.complex128), (12, 4, 11, np.complex64)])
+def test_emu_adjoint_sweep_gradients(emu, oracle, n, layers, tb, dtype):
+    """env from the fused backward pass, contracted with the analytic dU/dtheta, equals the reference's
+    parameter-shift gradients (oracle restatement of src/gradients.jl:88-152)."""
+    import ctypes as C
+
+    from qcb200 import _lib
+
+    rng = np.random.default_rng(n * 7 + layers)
+    G = onp.brickwork_num_gates(n, layers)
+    angles = rng.uniform(0, 2 * np.pi, (15, G))
+    q0 = np.array(onp.brickwork_gate_positions(n, layers)) - 1
+    mats = [oracle.build_general_unitary_gate(angles[:, g]) for g in range(G)]
+    psi0 = onp.zero_state(n)
+    hp = (1.0, 0.1, 0.5)
+    psiG = oracle.apply_brickwork(psi0, n, layers, angles)
+    H = onp.dense_tfim(n, *hp) if n <= 10 else None
+    if H is not None:
+        lamG = H @ psiG
+    else:  # matrix-free H psi for the TFIM
+        C_ = np.arange(2 ** n)
+        zz = sum(np.where(((C_ >> i) & 3 == 0) | ((C_ >> i) & 3 == 3), 1.0, -1.0) for i in range(n - 1))
+        z = n - 2 * sum((C_ >> i) & 1 for i in range(n))
+        lamG = -hp[0] * ((zz + hp[1] * z) * psiG + hp[2] * sum(psiG[C_ ^ (1 << i)] for i in range(n)))
+    back_psi, back_lam, env = emu.adjoint_sweep(psiG.astype(dtype), lamG.astype(dtype), q0, mats, tb, 3)
+    tol = 1e-12 if dtype == np.complex128 else 2e-5
+    assert rel(back_psi.astype(np.complex128), psi0) < tol  # every gate was un-applied
+    grads = np.zeros((15, G))
+    for g in range(G):
+        a = np.ascontiguousarray(angles[:, g])
+        for k in range(15):
+            d = np.empty(16, dtype=np.complex128)
+            _lib.check(_lib.lib().qcb_general_unitary_gate_derivative(a.ctypes.data_as(C.c_void_p), C.c_int(k), d.ctypes.data_as(C.c_void_p)))
+            grads[k, g] = 2 * np.real(np.sum(env[g] * d.reshape(4, 4, order="F")))
+    _, g_ref = oracle.gradients_brickwork(psi0, n, layers, angles, 0, hp)
+    assert np.max(np.abs(grads - g_ref)) < tol * max(1.0, np.max(np.abs(g_ref)))

@@ -381,4 +381,4 @@ def test_host_buffer_pipeline_equals_device_path():
         qc.apply_(st, st, c)
         ref = st.to_numpy()
         assert rel(out_host, ref) < (1e-13 if dtype == np.complex128 else 2e-6)
-        assert abs(np.vdot(out_host, out_host).real - 1) < (1e-12 if dtype == np.complex128 else 1e-5)
+        assert abs(np.linalg.norm(out_host.astype(np.complex128)) ** 2 - 1) < (1e-12 if dtype == np.complex128 else 1e-5)

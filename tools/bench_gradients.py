@@ -22,7 +22,10 @@ def main():
     qc.init(0)
     cfgs = [("C2", 20, 4, (1.0, 0.1, 0.5), np.complex128), ("C5", 28, 4, (1.0, 0.9045, 1.4), np.complex128),
             ("C5", 28, 4, (1.0, 0.9045, 1.4), np.complex64), ("C1", 12, 20, (1.0, 0.1, 0.5), np.complex128)]
+    only = sys.argv[1] if len(sys.argv) > 1 else None
     for tag, n, layers, hp, dt in cfgs:
+        if only and (tag != only or dt != np.complex128):
+            continue
         rng = np.random.default_rng(n)
         c = qc.GenericBrickworkCircuit(n, layers)
         c.gate_angles[...] = rng.standard_normal(c.gate_angles.shape) * 0.01
@@ -30,7 +33,7 @@ def main():
         psi0 = qc.B200State(n, dt)
         qc.gradients(H, psi0, c, calculate_energy=True)  # warm-up
         torch.cuda.synchronize()
-        reps = 3
+        reps = 1 if only else 3
         t0 = time.perf_counter()
         for _ in range(reps):
             E, g = qc.gradients(H, psi0, c, calculate_energy=True)
