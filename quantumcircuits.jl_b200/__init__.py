@@ -13,4 +13,5 @@ from .state import B200State, zero_state_vec, zero_state_tensor  # noqa: F401
 from .apply import B200ApplyCache, construct_apply_cache, apply, apply_, apply_circuit_host  # noqa: F401
 from .hamiltonians import (AbstractKernelHamiltonian, TFIMHamiltonian, EastModelHamiltonian, measure, measure_,  # noqa: F401
                            imaginary_energy_limit)
+from . import dist  # noqa: F401
 from .gradients import construct_grads_cache, gradients, gradients_, optimise_, propagate_forwards_  # noqa: F401

@@ -18,7 +18,7 @@
 
 namespace qcb {
 
-constexpr int kAdjMaxGates = 16; // gates per backward pass (bounds the shared-memory accumulators)
+constexpr int kAdjMaxGates = 10; // gates per backward pass (bounds the shared-memory accumulators)
 
 template <typename R> struct AdjParams {
     PassParams<R> P;                          // geometry, stages, U^dagger matrices

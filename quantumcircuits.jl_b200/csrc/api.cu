@@ -146,23 +146,35 @@ static int gradients_impl(const qcb_state *psi0, int nbits, int nlayers, const d
     QCB_TRY(brickwork_gates(nbits, nlayers, angles, 0, G, false, gates, mats));
     QCB_TRY(run_gate_list(&A, gates, mats.data(), false)); // forward pass  gradients.jl:92-101
     const double fw_passes = c.st_passes, fw_stages = c.st_stages, fw_launches = c.st_launches;
-    if (want_energy) {
-        double E2[2];
-        QCB_TRY(measure_impl(&A, ham_kind, hp[0], hp[1], hp[2], E2)); // gradients.jl:104
-        *out_E = E2[0];
+    if (G == 0) {
+        if (want_energy) {
+            double E2[2];
+            QCB_TRY(measure_impl(&A, ham_kind, hp[0], hp[1], hp[2], E2)); // gradients.jl:104
+            *out_E = E2[0];
+        }
+        return QCB_OK;
     }
-    if (G == 0) return QCB_OK;
-    // lambda = H psi_G
+    // lambda = H psi_G, and E = <psi_G|lambda> from the same sweep (gradients.jl:104)
     const unsigned long long namps = 1ull << nbits;
     HamEval H{ham_kind, nbits, hp[0], hp[1], hp[2]};
     {
-        const unsigned blocks = grid_for(namps, 256, 16);
+        const unsigned blocks = grid_for(namps, kRedThreads, 8);
+        QCB_TRY(ensure_partial((size_t)blocks * 2));
+        QCB_TRY(ensure_out(64));
         if (psi0->dtype == QCB_C128)
-            k_apply_ham<double><<<blocks, 256, 0, c.stream>>>((double2 *)B.d, (const double2 *)A.d, namps, H);
+            k_apply_ham<double><<<blocks, kRedThreads, 0, c.stream>>>((double2 *)B.d, (const double2 *)A.d, namps, H, (double2 *)c.d_partial);
         else
-            k_apply_ham<float><<<blocks, 256, 0, c.stream>>>((float2 *)B.d, (const float2 *)A.d, namps, H);
+            k_apply_ham<float><<<blocks, kRedThreads, 0, c.stream>>>((float2 *)B.d, (const float2 *)A.d, namps, H, (double2 *)c.d_partial);
         QCB_CUDA(cudaGetLastError());
         count_launch();
+        if (want_energy) {
+            k_final_sum<<<2, 256, 0, c.stream>>>(c.d_partial, (int)blocks, 2, c.d_out);
+            QCB_CUDA(cudaGetLastError());
+            count_launch();
+            QCB_CUDA(cudaMemcpyAsync(c.h_out, c.d_out, 2 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+            QCB_CUDA(cudaStreamSynchronize(c.stream));
+            *out_E = c.h_out[0];
+        }
     }
     // backward sweep: un-apply gate g on psi and lambda, reduce the 4x4 environment
     QCB_TRY(ensure_out((size_t)32 * G));

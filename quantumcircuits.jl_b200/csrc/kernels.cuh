@@ -154,15 +154,17 @@ __global__ void __launch_bounds__(kRedThreads) k_measure(const typename Vec2<R>:
     if (threadIdx.x == 0) partial[blockIdx.x] = make_double2(out[0], out[1]);
 }
 
-// lambda = H psi (out of place)
+// lambda = H psi (out of place); optionally also E = <psi|H|psi> = sum_C conj(psi[C]) lambda[C] in the same sweep
+// (partial != nullptr: one double2 per CTA, like k_measure).
 template <typename R>
-__global__ void __launch_bounds__(256) k_apply_ham(typename Vec2<R>::type *__restrict__ lam,
-                                                   const typename Vec2<R>::type *__restrict__ psi, unsigned long long namps,
-                                                   HamEval H)
+__global__ void __launch_bounds__(kRedThreads) k_apply_ham(typename Vec2<R>::type *__restrict__ lam,
+                                                           const typename Vec2<R>::type *__restrict__ psi, unsigned long long namps,
+                                                           HamEval H, double2 *partial)
 {
     using V = typename Vec2<R>::type;
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
     const double oc = H.offdiag_coef();
+    double acc[2] = {0.0, 0.0};
     for (unsigned long long C = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; C < namps; C += stride) {
         const V p = psi[C];
         double xr = 0, xi = 0;
@@ -173,10 +175,18 @@ __global__ void __launch_bounds__(256) k_apply_ham(typename Vec2<R>::type *__res
             xi += (double)o.y;
         }
         const double d = H.diag(C);
+        const double lr = d * (double)p.x + oc * xr, li = d * (double)p.y + oc * xi;
         V r;
-        r.x = (R)(d * (double)p.x + oc * xr);
-        r.y = (R)(d * (double)p.y + oc * xi);
+        r.x = (R)lr;
+        r.y = (R)li;
         lam[C] = r;
+        acc[0] += (double)p.x * lr + (double)p.y * li;
+        acc[1] += (double)p.x * li - (double)p.y * lr;
+    }
+    if (partial) {
+        __shared__ double out[2];
+        block_sum<2>(acc, out);
+        if (threadIdx.x == 0) partial[blockIdx.x] = make_double2(out[0], out[1]);
     }
 }
 

@@ -166,7 +166,8 @@ template <typename R, int TB> static int launch_adjoint(qcb_state *psi, qcb_stat
     using V = typename Vec2<R>::type;
     constexpr int NT = 1 << (TB - kRegBits);
     constexpr int NW = (NT + 31) / 32;
-    constexpr int MINB = TB >= 12 ? 1 : 2;
+    // registers (<= 168 per thread) and shared memory (two tiles + accumulators) both allow this many CTAs per SM
+    constexpr int MINB = TB >= 12 ? 1 : (TB == 11 ? 3 : (TB == 10 ? 6 : 8));
     auto kern = adjoint_pass_kernel<R, TB, MINB>;
     const size_t smem = 2 * (sizeof(V) << TB) + sizeof(double) * NW * kAdjMaxGates * 32;
     static bool attr_set = false;
@@ -193,7 +194,9 @@ template <typename R> static int run_adjoint_fused_t(qcb_state *psi, qcb_state *
     Ctx &c = ctx();
     SchedOptions opt = current_sched_options(psi);
     opt.max_gates_per_pass = std::min(opt.max_gates_per_pass, kAdjMaxGates);
-    if (sizeof(R) == 8 && opt.tile_bits > 12) opt.tile_bits = 12; // two tiles + accumulators must fit shared memory
+    // two tiles + accumulators per CTA: smaller tiles than the forward pass keep 6 (double) / 3-6 (float) CTAs per SM
+    // resident, which is what hides the tile loads of this persistent kernel
+    opt.tile_bits = std::min(opt.tile_bits, sizeof(R) == 8 ? 10 : 11);
     std::vector<PassPlan> plans;
     std::vector<char> done;
     try {

@@ -382,3 +382,30 @@ def test_host_buffer_pipeline_equals_device_path():
         ref = st.to_numpy()
         assert rel(out_host, ref) < (1e-13 if dtype == np.complex128 else 2e-6)
         assert abs(np.linalg.norm(out_host.astype(np.complex128)) ** 2 - 1) < (1e-12 if dtype == np.complex128 else 1e-5)
+
+
+def test_hamiltonian_layer_autograd(oracle):
+    """examples/nns/circuit_layer.jl shape: Dense(1 => nangles) -> x*pi -> reshape(15, G) -> HamiltonianLayer -> E;
+    the reverse rule calls gradients!(...; calculate_energy=true).  float32 network parameters, like Flux."""
+    import torch
+
+    from qcb200.nn import HamiltonianLayer
+
+    torch.manual_seed(0)
+    n, layers = 10, 4
+    G = qc.brickwork_num_gates(n, layers)
+    H = qc.TFIMHamiltonian(1.0, 0.9045, 1.4)
+    layer = HamiltonianLayer(n, layers, qc.zero_state_tensor(n), H)
+    dense = torch.nn.Linear(1, 15 * G, bias=False)
+    x = torch.ones(1)
+    angles = (dense(x) * np.pi).reshape(G, 15).T  # column g = gate g
+    E = layer(angles)
+    E.backward()
+    a64 = angles.detach().double().numpy()
+    E_ref, g_ref = oracle.gradients_brickwork(onp.zero_state(n), n, layers, a64, 0, H.params())
+    assert abs(float(E) - E_ref) < 1e-5 * abs(E_ref)
+    expect = (g_ref.T.reshape(-1) * np.pi)  # dE/dW = dE/dangle * pi * x
+    got = dense.weight.grad.reshape(-1).double().numpy()
+    assert np.max(np.abs(got - expect)) < 1e-5 * max(1.0, np.max(np.abs(expect)))
+    with torch.no_grad():  # inference path: plain measure
+        assert abs(float(layer(angles.detach())) - E_ref) < 1e-5 * abs(E_ref)
