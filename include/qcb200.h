@@ -68,7 +68,8 @@ int qcb_set_stream(void *cuda_stream);
 /* CUDA-event stopwatch on the library stream for hosts without their own event API. */
 int qcb_timer_start(void);
 int qcb_timer_stop(float *out_ms);
-/* Tunables: "tile_bits", "low_bits", "max_gates_per_pass", "force_simple" (1 = one unfused launch per gate). */
+/* Tunables: "tile_bits", "low_bits", "max_gates_per_pass", "adjoint_tile_bits" (0 = auto), "force_simple" (1 = one
+ * unfused launch per gate). */
 int qcb_set_option(const char *key, long value);
 /* Counters of the most recent apply / gradient call: "passes", "stages", "launches", "gates",
  * and "launches_total" (all kernels launched by this library since qcb_init). */

@@ -56,54 +56,16 @@ __device__ __forceinline__ void warp_transpose_reduce(double (&v)[32])
 }
 #endif
 
-// one gate slot of one stage for one thread: un-apply on psi and lambda, environment into acc_gate[32]
-// (acc_gate = this warp's accumulator row for the gate; on the host replay every thread adds all 32 values).
-template <int LO, typename R>
-QCB_HD void adjoint_slot(typename Vec2<R>::type *smP, typename Vec2<R>::type *smL, uint32_t e, const uint16_t (&roff)[kRegAmps],
-                         const GateMat<R> &Ud, double *acc_gate)
-{
-    using V = typename Vec2<R>::type;
-    R env[32];
-#pragma unroll
-    for (int i = 0; i < 32; i++) env[i] = (R)0;
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-        int other = 0, qq = q;
-#pragma unroll
-        for (int b = 0; b < 4; b++)
-            if (b != LO && b != LO + 1) { other |= (qq & 1) << b; qq >>= 1; }
-        V x[4], l[4];
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const uint32_t off = e ^ roff[other | (j << LO)];
-            x[j] = smP[off];
-            l[j] = smL[off];
-        }
-        apply_quad(x[0], x[1], x[2], x[3], Ud);
-        env_accumulate<V, R>(env, l, x);
-        apply_quad(l[0], l[1], l[2], l[3], Ud);
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const uint32_t off = e ^ roff[other | (j << LO)];
-            smP[off] = x[j];
-            smL[off] = l[j];
-        }
-    }
-#if defined(__CUDA_ARCH__)
-    double v[32];
-#pragma unroll
-    for (int i = 0; i < 32; i++) v[i] = (double)env[i];
-    warp_transpose_reduce(v);
-    acc_gate[threadIdx.x & 31u] += v[0]; // the row is private to this warp: plain read-modify-write
-#else
-    for (int i = 0; i < 32; i++) acc_gate[i] += (double)env[i];
-#endif
-}
-
+// One stage for one thread.  Unlike the forward pass nothing is kept in registers between gates, so the slot and the
+// amplitude quad are *runtime* loop indices: one copy of the 192-FMA quad body (un-apply psi, environment, un-apply
+// lambda) instead of sixteen -- the fully unrolled form overflowed the instruction cache (ncu: `no_instructions` was the
+// top stall reason).  acc_warp = this warp's accumulator rows [kAdjMaxGates][32]; on the host replay every thread adds
+// all 32 values of a row.
 template <typename R, int TB>
 QCB_HD void adjoint_stage(const AdjParams<R> &A, int s, typename Vec2<R>::type *smP, typename Vec2<R>::type *smL,
-                          double *acc_warp /* [kAdjMaxGates][32] of this warp */, uint32_t tid)
+                          double *acc_warp, uint32_t tid)
 {
+    using V = typename Vec2<R>::type;
     constexpr int SWB = Vec2<R>::SWB;
     constexpr int TBITS = TB - kRegBits;
     const StageDesc &S = A.P.stage[s];
@@ -112,10 +74,46 @@ QCB_HD void adjoint_stage(const AdjParams<R> &A, int s, typename Vec2<R>::type *
     for (int k = 0; k < TBITS; k++) e |= ((tid >> k) & 1u) << S.tpos[k];
     e = swz<SWB>(e);
     const uint32_t mask = S.mask;
-    if (mask & 1u) adjoint_slot<1, R>(smP, smL, e, S.roff, A.P.U[s * kSlots + 0], acc_warp + 32 * A.slot_gate[s * kSlots + 0]);
-    if (mask & 2u) adjoint_slot<0, R>(smP, smL, e, S.roff, A.P.U[s * kSlots + 1], acc_warp + 32 * A.slot_gate[s * kSlots + 1]);
-    if (mask & 4u) adjoint_slot<2, R>(smP, smL, e, S.roff, A.P.U[s * kSlots + 2], acc_warp + 32 * A.slot_gate[s * kSlots + 2]);
-    if (mask & 8u) adjoint_slot<1, R>(smP, smL, e, S.roff, A.P.U[s * kSlots + 3], acc_warp + 32 * A.slot_gate[s * kSlots + 3]);
+#pragma unroll 1
+    for (int slot = 0; slot < kSlots; slot++) {
+        if (!((mask >> slot) & 1u)) continue;
+        const int LO = slot_lo(slot);
+        const GateMat<R> &Ud = A.P.U[s * kSlots + slot];
+        double *acc_gate = acc_warp + 32 * A.slot_gate[s * kSlots + slot];
+        R env[32];
+#pragma unroll
+        for (int i = 0; i < 32; i++) env[i] = (R)0;
+#pragma unroll 1
+        for (int q = 0; q < 4; q++) {
+            // spread the two bits of q over the window bits other than LO, LO+1
+            const int other = LO == 0 ? (q << 2) : (LO == 1 ? ((q & 1) | ((q & 2) << 2)) : q);
+            V x[4], l[4];
+            uint32_t off[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                off[j] = e ^ S.roff[other | (j << LO)];
+                x[j] = smP[off[j]];
+                l[j] = smL[off[j]];
+            }
+            apply_quad(x[0], x[1], x[2], x[3], Ud);
+            env_accumulate<V, R>(env, l, x);
+            apply_quad(l[0], l[1], l[2], l[3], Ud);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                smP[off[j]] = x[j];
+                smL[off[j]] = l[j];
+            }
+        }
+#if defined(__CUDA_ARCH__)
+        double v[32];
+#pragma unroll
+        for (int i = 0; i < 32; i++) v[i] = (double)env[i];
+        warp_transpose_reduce(v);
+        acc_gate[threadIdx.x & 31u] += v[0]; // the row is private to this warp: plain read-modify-write
+#else
+        for (int i = 0; i < 32; i++) acc_gate[i] += (double)env[i];
+#endif
+    }
 }
 
 #if defined(__CUDACC__)

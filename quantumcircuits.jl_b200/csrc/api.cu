@@ -337,6 +337,9 @@ int qcb_set_option(const char *key, long value)
     } else if (k == "max_gates_per_pass") {
         if (value < 1) return set_error(QCB_EINVAL, "max_gates_per_pass must be >= 1");
         c.max_gates_per_pass = value;
+    } else if (k == "adjoint_tile_bits") {
+        if (value != 0 && (value < kMinTB || value > 12)) return set_error(QCB_EINVAL, "adjoint_tile_bits must be 0 (auto) or in [%d, 12]", kMinTB);
+        c.adjoint_tile_bits = value;
     } else if (k == "force_simple") {
         c.force_simple = value ? 1 : 0;
     } else

@@ -196,7 +196,7 @@ template <typename R> static int run_adjoint_fused_t(qcb_state *psi, qcb_state *
     opt.max_gates_per_pass = std::min(opt.max_gates_per_pass, kAdjMaxGates);
     // two tiles + accumulators per CTA: smaller tiles than the forward pass keep 6 (double) / 3-6 (float) CTAs per SM
     // resident, which is what hides the tile loads of this persistent kernel
-    opt.tile_bits = std::min(opt.tile_bits, sizeof(R) == 8 ? 10 : 11);
+    opt.tile_bits = c.adjoint_tile_bits ? (int)c.adjoint_tile_bits : std::min(opt.tile_bits, sizeof(R) == 8 ? 10 : 11);
     std::vector<PassPlan> plans;
     std::vector<char> done;
     try {

@@ -24,7 +24,7 @@ def main():
     rank, world = dist.get_rank(), dist.get_world_size()
     qdist.init_from_torch()
     ok = True
-    cases = [(20, 12, np.complex128), (21, 30, np.complex128), (22, 9, np.complex64), (24, 40, np.complex128)]
+    cases = [(20, 12, np.complex128), (21, 30, np.complex128), (22, 9, np.complex64), (23, 16, np.complex128)]
     for n, layers, dt in cases:
         rng = np.random.default_rng(n * 100 + layers)
         c = qc.GenericBrickworkCircuit(n, layers)

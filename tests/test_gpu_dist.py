@@ -15,6 +15,9 @@ def test_sharded_vs_oracle(nproc):
 
     if torch.cuda.device_count() < nproc:
         pytest.skip(f"needs {nproc} GPUs")
+    only = os.environ.get("QCB_DIST_NPROC")
+    if only and int(only) != nproc:
+        pytest.skip(f"QCB_DIST_NPROC={only}")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr", "127.0.0.1",
            "--master-port", str(29500 + nproc), os.path.join(ROOT, "tests", "dist_worker.py")]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=900)

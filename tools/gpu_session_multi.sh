@@ -4,7 +4,6 @@ N=${1:-2}
 mkdir -p gpurun_out
 nvidia-smi -L > gpurun_out/nvsmi_multi_$N.txt 2>&1
 nvidia-smi topo -m >> gpurun_out/nvsmi_multi_$N.txt 2>&1
-echo "== dist tests"; timeout 1500 python -m pytest tests/test_gpu_dist.py -x -q -m gpu > gpurun_out/pytest_dist_$N.log 2>&1; echo "rc=$?"; tail -30 gpurun_out/pytest_dist_$N.log
+echo "== dist tests"; QCB_DIST_NPROC=$N timeout 1500 python -m pytest tests/test_gpu_dist.py -x -q -m gpu > gpurun_out/pytest_dist_$N.log 2>&1; echo "rc=$?"; tail -30 gpurun_out/pytest_dist_$N.log
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29655"
-echo "== bench small"; timeout 900 $TR bench.py --gpus $N --nqubits $((30 + ${2:-1})) --steps 2 --warmup 1 > gpurun_out/bench_multi_${N}_small.json 2> gpurun_out/bench_multi_${N}_small.err; echo "rc=$?"; cat gpurun_out/bench_multi_${N}_small.json; grep -v "^W\|^\*\|OMP_NUM" gpurun_out/bench_multi_${N}_small.err | tail -15
 echo "== bench 34q"; timeout 1500 $TR bench.py --gpus $N --steps 2 --warmup 1 > gpurun_out/bench_multi_${N}_34q.json 2> gpurun_out/bench_multi_${N}_34q.err; echo "rc=$?"; cat gpurun_out/bench_multi_${N}_34q.json; grep -v "^W\|^\*\|OMP_NUM" gpurun_out/bench_multi_${N}_34q.err | tail -15
