@@ -130,6 +130,13 @@ int qcb_gradients_brickwork(const qcb_state *psi0, int nbits, int nlayers, const
 int qcb_optimise_brickwork(const qcb_state *psi0, int nbits, int nlayers, double *angles_inout, int ham_kind,
                            const double *ham_params3, int epochs, double lr, double *energies_out);
 
+/* ---- building blocks of the statevector polar optimiser (ext/MPSExt/polar_optimise.jl:83-102) ----------------
+ * qcb_state_inner: out = (re, im) of <a|b> = sum conj(a) b  (the overlap at polar_optimise.jl:140).
+ * qcb_environment_2q: out_env32 = 4x4 complex, column-major E[r + 4c] = sum_rest conj(lam[r, rest]) psi[c, rest] for the
+ * qubit pair (K, K+1) -- the contraction of upper and lower state over all other qubits (polar_optimise.jl:88-90). */
+int qcb_state_inner(const qcb_state *a, const qcb_state *b, double *out2);
+int qcb_environment_2q(const qcb_state *lam, const qcb_state *psi, int K, double *out_env32);
+
 /* ---- multi-GPU: one process per GPU, amplitudes sharded by the top log2(nranks) qubits ---------
  * No reference counterpart (the reference holds one array in one memory).  Bootstrap: rank 0 calls
  * qcb_dist_unique_id and ships the 128 bytes to the other ranks by any host channel

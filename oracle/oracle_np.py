@@ -212,3 +212,41 @@ def zero_state(n, dtype=np.complex128):
     psi = np.zeros(2 ** n, dtype=dtype)
     psi[0] = 1
     return psi
+
+
+# ------------------------------------------------ statevector polar optimiser
+def polar_optimise(circuit, psi_GS, energy_fn, N, iterations=100):
+    """ext/MPSExt/polar_optimise.jl:105-147 restated on flat state vectors.
+
+    circuit: list of brick layers, each a list of N-1 gates given as 4x4 matrices M[i+2j, a+2b] (the reshape(.,4,4) of
+    the reference's 2x2x2x2 arrays); gates 1..N/2 of a layer sit on sites 1,3,5,.. and gates N/2+1..N-1 on sites 2,4,..
+    (:124-137).  `MatrixProductStates.contract(gate, psi, [3,4], [site,site+1])` + `permutedims(perm_idxs)` (:31-33) is
+    the ordinary application of the gate on (site, site+1); with [1,2] (:63-65) it is the application of the transpose.
+    NOTE: MatrixProductStates.jl is not vendored in the reference tree, so this reading of `contract` (contract the listed
+    dimensions, free dimensions of the first argument first) is inferred from the call sites: parity for this row is
+    unpinned.  Returns (circuit, overlaps, energies)."""
+    assert N % 2 == 0
+    circuit = [[np.array(g, dtype=np.complex128) for g in layer] for layer in circuit]
+    sites = [2 * idx - 1 for idx in range(1, N // 2 + 1)] + [2 * idx - N for idx in range(N // 2 + 1, N)]
+    overlaps, energies = [], []
+    for _ in range(iterations):
+        lower = zero_state(N)
+        upper = np.conj(np.asarray(psi_GS, dtype=np.complex128).reshape(-1))  # create_upper_state :52-78
+        for layer in reversed(circuit):
+            for idx in range(N - 1, 0, -1):
+                upper = apply_2q(upper, layer[idx - 1].T, sites[idx - 1])
+        for layer in circuit:
+            for idx in range(1, N):
+                site = sites[idx - 1]
+                upper = apply_2q(upper, np.conj(layer[idx - 1]), site)  # :85-86
+                lo = 2 ** (site - 1)
+                u3 = upper.reshape(-1, 4, lo)
+                l3 = lower.reshape(-1, 4, lo)
+                E = np.einsum("prq,pcq->rc", u3, l3)  # :88-92  E[(i,j),(a,b)] = sum_rest upper * lower
+                U_, _, Vt = np.linalg.svd(E)
+                new = np.conj(U_ @ Vt)  # :94
+                layer[idx - 1] = new
+                lower = apply_2q(lower, new, site)  # :97-98
+        overlaps.append(abs(np.vdot(np.asarray(psi_GS).reshape(-1), lower)))  # :140
+        energies.append(energy_fn(lower))  # :141
+    return circuit, np.array(overlaps), np.array(energies)

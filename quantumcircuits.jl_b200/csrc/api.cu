@@ -709,6 +709,57 @@ int qcb_measure_east(const qcb_state *s, double c, double A, double B, double *o
     return measure_impl(s, QCB_HAM_EAST, c, A, B, out_E2);
 }
 
+// ---- polar-optimiser building blocks -----------------------------------------------------------------------------
+int qcb_state_inner(const qcb_state *a, const qcb_state *b, double *out2)
+{
+    QCB_REQUIRE_INIT();
+    QCB_TRY(check_state(a));
+    QCB_TRY(check_state(b));
+    if (!out2) return set_error(QCB_EINVAL, "null output");
+    if (a->n != b->n || a->dtype != b->dtype || a->sharded || b->sharded) return set_error(QCB_EINVAL, "states must have the same size and type");
+    Ctx &c = ctx();
+    const unsigned long long namps = 1ull << a->nloc;
+    const unsigned blocks = grid_for(namps, kRedThreads, 8);
+    QCB_TRY(ensure_partial((size_t)blocks * 2));
+    QCB_TRY(ensure_out(64));
+    if (a->dtype == QCB_C128) k_inner<double><<<blocks, kRedThreads, 0, c.stream>>>((const double2 *)a->d, (const double2 *)b->d, namps, (double2 *)c.d_partial);
+    else k_inner<float><<<blocks, kRedThreads, 0, c.stream>>>((const float2 *)a->d, (const float2 *)b->d, namps, (double2 *)c.d_partial);
+    QCB_CUDA(cudaGetLastError());
+    k_final_sum<<<2, 256, 0, c.stream>>>(c.d_partial, (int)blocks, 2, c.d_out);
+    QCB_CUDA(cudaGetLastError());
+    count_launch(2);
+    QCB_CUDA(cudaMemcpyAsync(c.h_out, c.d_out, 2 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    QCB_CUDA(cudaStreamSynchronize(c.stream));
+    out2[0] = c.h_out[0];
+    out2[1] = c.h_out[1];
+    return QCB_OK;
+}
+
+int qcb_environment_2q(const qcb_state *lam, const qcb_state *psi, int K, double *out_env32)
+{
+    QCB_REQUIRE_INIT();
+    QCB_TRY(check_state(lam));
+    QCB_TRY(check_state(psi));
+    if (!out_env32) return set_error(QCB_EINVAL, "null output");
+    if (lam->n != psi->n || lam->dtype != psi->dtype || lam->sharded || psi->sharded) return set_error(QCB_EINVAL, "states must have the same size and type");
+    if (!(K > 0 && K < psi->n)) return set_error(QCB_EINVAL, "The gate cannot be applied as it sits outside the qubit space.");
+    Ctx &c = ctx();
+    const unsigned long long nquads = 1ull << (psi->nloc - 2);
+    const unsigned blocks = grid_for(nquads, kRedThreads, 4);
+    QCB_TRY(ensure_partial((size_t)blocks * 32));
+    QCB_TRY(ensure_out(64));
+    if (psi->dtype == QCB_C128) k_env_2q<double><<<blocks, kRedThreads, 0, c.stream>>>((const double2 *)psi->d, (const double2 *)lam->d, nquads, K - 1, c.d_partial);
+    else k_env_2q<float><<<blocks, kRedThreads, 0, c.stream>>>((const float2 *)psi->d, (const float2 *)lam->d, nquads, K - 1, c.d_partial);
+    QCB_CUDA(cudaGetLastError());
+    k_final_sum<<<32, 128, 0, c.stream>>>(c.d_partial, (int)blocks, 32, c.d_out);
+    QCB_CUDA(cudaGetLastError());
+    count_launch(2);
+    QCB_CUDA(cudaMemcpyAsync(c.h_out, c.d_out, 32 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    QCB_CUDA(cudaStreamSynchronize(c.stream));
+    std::memcpy(out_env32, c.h_out, 32 * sizeof(double));
+    return QCB_OK;
+}
+
 // ---- gradients / optimisation -----------------------------------------------------------------
 int qcb_gradients_brickwork(const qcb_state *psi0, int nbits, int nlayers, const double *angles, int ham_kind,
                             const double *ham_params3, int want_energy, double *out_E, double *out_grads)

@@ -223,6 +223,54 @@ __global__ void __launch_bounds__(kRedThreads) k_norm2(const typename Vec2<R>::t
     if (threadIdx.x == 0) partial[blockIdx.x] = out[0];
 }
 
+// <a|b> = sum conj(a) b
+template <typename R>
+__global__ void __launch_bounds__(kRedThreads) k_inner(const typename Vec2<R>::type *__restrict__ a, const typename Vec2<R>::type *__restrict__ b,
+                                                       unsigned long long namps, double2 *partial)
+{
+    double acc[2] = {0.0, 0.0};
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long C = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; C < namps; C += stride) {
+        const auto x = a[C];
+        const auto y = b[C];
+        acc[0] += (double)x.x * (double)y.x + (double)x.y * (double)y.y;
+        acc[1] += (double)x.x * (double)y.y - (double)x.y * (double)y.x;
+    }
+    __shared__ double out[2];
+    block_sum<2>(acc, out);
+    if (threadIdx.x == 0) partial[blockIdx.x] = make_double2(out[0], out[1]);
+}
+
+// 4x4 environment of the qubit pair (kb, kb+1): env[r + 4c] = sum_rest conj(lam[r, rest]) psi[c, rest]  (no state is modified)
+template <typename R>
+__global__ void __launch_bounds__(kRedThreads) k_env_2q(const typename Vec2<R>::type *__restrict__ psi, const typename Vec2<R>::type *__restrict__ lam,
+                                                        unsigned long long nquads, int kb, double *partial)
+{
+    using V = typename Vec2<R>::type;
+    double acc[32];
+#pragma unroll
+    for (int i = 0; i < 32; i++) acc[i] = 0.0;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    const unsigned long long low = (1ull << kb) - 1ull;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < nquads; i += stride) {
+        const unsigned long long base = ((i >> kb) << (kb + 2)) | (i & low);
+        V x[4], l[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) { x[j] = psi[base | ((unsigned long long)j << kb)]; l[j] = lam[base | ((unsigned long long)j << kb)]; }
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                const double lr = (double)l[r].x, li = (double)l[r].y, xr = (double)x[c].x, xi = (double)x[c].y;
+                acc[2 * (r + 4 * c)] += lr * xr + li * xi;
+                acc[2 * (r + 4 * c) + 1] += lr * xi - li * xr;
+            }
+    }
+    __shared__ double out[32];
+    block_sum<32>(acc, out);
+    if (threadIdx.x < 32) partial[(size_t)blockIdx.x * 32 + threadIdx.x] = out[threadIdx.x];
+}
+
 // ---- adjoint sweep, unfused step for one gate on bits (kb, kb+1) ---------------------
 //   psi <- U^dagger psi ;  env[r + 4c] += conj(lam[r]) psi[c] ;  lam <- U^dagger lam
 // Ud holds U^dagger.  partial: [gridDim.x][32] doubles.

@@ -409,3 +409,26 @@ def test_hamiltonian_layer_autograd(oracle):
     assert np.max(np.abs(got - expect)) < 1e-5 * max(1.0, np.max(np.abs(expect)))
     with torch.no_grad():  # inference path: plain measure
         assert abs(float(layer(angles.detach())) - E_ref) < 1e-5 * abs(E_ref)
+
+
+@pytest.mark.parametrize("N,nl", [(6, 1), (8, 2), (10, 2)])
+def test_polar_optimise_statevector(N, nl):
+    """SURVEY 8f rank 1 (examples/test_optimise.jl shape: identity start, TFIM ground state target): the GPU path
+    (environment kernel + host SVD) follows the NumPy restatement of ext/MPSExt/polar_optimise.jl."""
+    from qcb200.polar import polar_optimise
+
+    hp = (1.0, 0.9045, 1.4)
+    Hd = onp.dense_tfim(N, *hp)
+    w, v = np.linalg.eigh(Hd)
+    gs = v[:, 0].astype(np.complex128)
+    ident = [[np.eye(4, dtype=np.complex128) for _ in range(N - 1)] for _ in range(nl)]
+    its = 6
+    c_ref, ov_ref, en_ref = onp.polar_optimise(ident, gs, lambda s: onp.measure_tfim(s, *hp).real, N, its)
+    c_gpu, ov, en = polar_optimise(ident, gs, qc.TFIMHamiltonian(*hp), N, its)
+    np.testing.assert_allclose(ov, ov_ref, atol=1e-9)
+    np.testing.assert_allclose(en, en_ref, atol=1e-8)
+    assert ov[-1] > ov[0] - 1e-12 and en[-1] < en[0] + 1e-9  # the sweep improves overlap and energy
+    for lg, lr in zip(c_gpu, c_ref):
+        for a, b in zip(lg, lr):
+            m = a.reshape(4, 4, order="F")
+            np.testing.assert_allclose(m @ m.conj().T, np.eye(4), atol=1e-12)

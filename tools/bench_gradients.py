@@ -23,6 +23,8 @@ def main():
     cfgs = [("C2", 20, 4, (1.0, 0.1, 0.5), np.complex128), ("C5", 28, 4, (1.0, 0.9045, 1.4), np.complex128),
             ("C5", 28, 4, (1.0, 0.9045, 1.4), np.complex64), ("C1", 12, 20, (1.0, 0.1, 0.5), np.complex128)]
     only = sys.argv[1] if len(sys.argv) > 1 else None
+    if len(sys.argv) > 2:
+        qc.set_option("adjoint_tile_bits", int(sys.argv[2]))
     for tag, n, layers, hp, dt in cfgs:
         if only and (tag != only or dt != np.complex128):
             continue

@@ -4,6 +4,7 @@ mkdir -p gpurun_out
 echo "== smoke"; timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -2 gpurun_out/smoke.log
 echo "== pytest gpu"; timeout 1800 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -8 gpurun_out/pytest_gpu.log
 echo "== gradients"; timeout 900 python tools/bench_gradients.py > gpurun_out/gradients.jsonl 2> gpurun_out/gradients.err; cat gpurun_out/gradients.jsonl | cut -c1-420; tail -3 gpurun_out/gradients.err
+for tb in 9 10 11 12; do echo "adjoint tb=$tb"; timeout 300 python tools/bench_gradients.py C5 $tb 2>&1 | cut -c1-200; done
 echo "== bench c64"; timeout 600 python bench.py --steps 2 --warmup 2 --dtype c64 --no-cpu-baseline > gpurun_out/bench_c64.json 2> gpurun_out/bench_c64.err; cut -c1-400 gpurun_out/bench_c64.json
 echo "== ncu adjoint"
 CMD="python tools/bench_gradients.py C5"
