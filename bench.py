@@ -228,6 +228,8 @@ def run_ours(args):
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}; launch with torch.distributed.run --nproc-per-node {args.gpus}")
     torch.cuda.set_device(local_rank)
     qc.init(local_rank)
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     if args.tile_bits is not None:
@@ -301,7 +303,7 @@ def run_ours(args):
     roofline = None
     if launch_ms:
         achieved = bytes_pass / (launch_ms * 1e-3) / 1e9
-        flops = 32.0 * (2.0 ** n) * G / (ms_step * 1e-3) / 1e12  # 16 FMA per amplitude per gate
+        flops = 32.0 * (2.0 ** n) * G / (ms_step * 1e-3) / 1e12 / world  # 16 FMA per amplitude per gate; per GPU
         peak_fl = (fp64 or {}).get("dfma_tflops" if args.dtype == "c128" else "ffma_tflops")
         roofline = {
             "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -362,17 +364,25 @@ def run_ours(args):
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         use_host = bool(flag.item())
         k = max(1, min(args.steps, 2))
+        hn = None
         if use_host:
-            tdt = torch.complex128 if args.dtype == "c128" else torch.complex64
-            h = torch.zeros(1 << nloc, dtype=tdt, pin_memory=True)
-            if rank == 0:
-                h[0] = 1
-            hn = h.numpy()
+            try:
+                tdt = torch.complex128 if args.dtype == "c128" else torch.complex64
+                h = torch.zeros(1 << nloc, dtype=tdt, pin_memory=True)
+                if rank == 0:
+                    h[0] = 1
+                hn = h.numpy()
+            except Exception:  # pinning refused (memlock / cgroup limit): fall back to the device-built input
+                hn = None
+            ok = torch.tensor([1 if hn is not None else 0], device="cuda")
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            use_host = bool(ok.item())
+        if use_host:
 
             def e2e_step():
                 state.upload_shard(hn)
                 state.apply_circuit(circuit)
-                hn[...] = state.download_shard()
+                state.download_shard(out=hn)
         else:
             def e2e_step():
                 state.set_zero_state()

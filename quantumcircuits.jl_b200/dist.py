@@ -66,8 +66,11 @@ class ShardedState:
         assert host.size == 1 << self.local_qubits
         _lib.check(_lib.lib().qcb_state_upload_shard(self._handle, host.ctypes.data_as(C.c_void_p)))
 
-    def download_shard(self):
-        out = np.empty(1 << self.local_qubits, dtype=self.dtype)
+    def download_shard(self, out=None):
+        """Canonical slice of this rank; `out` may be a (pinned) host array to receive it without an extra copy."""
+        if out is None:
+            out = np.empty(1 << self.local_qubits, dtype=self.dtype)
+        assert out.dtype == self.dtype and out.size == 1 << self.local_qubits and out.flags.c_contiguous
         _lib.check(_lib.lib().qcb_state_download_shard(self._handle, out.ctypes.data_as(C.c_void_p)))
         return out
 

@@ -219,4 +219,19 @@ function optimise!(circuit::GenericBrickworkCircuit, H::AbstractKernelHamiltonia
     return energies
 end
 
+# ------------------------------------------------------------------------------------------------
+# building blocks of the statevector polar optimiser (ext/MPSExt/polar_optimise.jl:83-102)
+# ------------------------------------------------------------------------------------------------
+"E[r, c] = sum_rest conj(lam[r, rest]) psi[c, rest] for the qubit pair (K, K+1), as a 4x4 ComplexF64 matrix."
+function environment_2q(lam::B200State, psi::B200State, K::Integer)
+    E = zeros(ComplexF64, 4, 4)
+    check(ccall((:qcb_environment_2q, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Ptr{ComplexF64}), lam.handle, psi.handle, K, E))
+    return E
+end
+function LinearAlgebra.dot(a::B200State, b::B200State)
+    out = zeros(Cdouble, 2)
+    check(ccall((:qcb_state_inner, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cdouble}), a.handle, b.handle, out))
+    return complex(out[1], out[2])
+end
+
 end # module
