@@ -9,9 +9,8 @@
 // One launch of adjoint_pass_kernel does this for a whole trapezoid of gates (the reversed circuit is scheduled
 // by the same pass planner as the forward circuit): a persistent CTA stages a psi tile and a lambda tile in
 // shared memory, walks the register stages, and for every gate un-applies it on both tiles and accumulates the
-// 4x4 environment: thread-local partial sums -> warp transpose-reduction with shuffles (31 exchanges for 32
-// values) -> per-warp shared-memory accumulators that live across all tiles of the CTA -> one partial per CTA
-// -> fixed-order final sum (deterministic).  HBM traffic per pass: read + write of both states, independent of
+// 4x4 environment with FP64 tensor-core MMAs (2 accumulators per lane) -> per-warp shared-memory accumulators that
+// live across all tiles of the CTA -> one partial per CTA -> fixed-order final sum (deterministic).  HBM traffic per pass: read + write of both states, independent of
 // the number of gates fused.
 #pragma once
 #include "tile.cuh"
@@ -38,29 +37,20 @@ template <typename V, typename A> QCB_HD void env_accumulate(A (&env)[32], const
         }
 }
 
-#if defined(__CUDA_ARCH__)
-// after the call lane L holds in v[0] the warp-wide sum of element L
-__device__ __forceinline__ void warp_transpose_reduce(double (&v)[32])
-{
-    const unsigned lane = threadIdx.x & 31u;
-#pragma unroll
-    for (int s = 16; s >= 1; s >>= 1) {
-        const bool up = (lane & s) != 0;
-#pragma unroll
-        for (int i = 0; i < s; i++) {
-            const double send = up ? v[i] : v[i + s];
-            const double keep = up ? v[i + s] : v[i];
-            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
-        }
-    }
-}
-#endif
 
-// One stage for one thread.  Unlike the forward pass nothing is kept in registers between gates, so the slot and the
-// amplitude quad are *runtime* loop indices: one copy of the 192-FMA quad body (un-apply psi, environment, un-apply
-// lambda) instead of sixteen -- the fully unrolled form overflowed the instruction cache (ncu: `no_instructions` was the
-// top stall reason).  acc_warp = this warp's accumulator rows [kAdjMaxGates][32]; on the host replay every thread adds
-// all 32 values of a row.
+// One stage for one thread.  Nothing is kept in registers between gates, so the slot and the amplitude quad are
+// *runtime* loop indices: one copy of each quad body instead of sixteen (the fully unrolled form overflowed the
+// instruction cache; ncu: `no_instructions` was the top stall reason).
+//
+// Device path, per gate:  (1) every thread un-applies the gate on its 4 psi quads (shared memory -> registers ->
+// shared memory);  (2) the warp contracts lambda with the updated psi over its 128 quads with FP64 tensor-core MMAs
+// (mma.sync m8n8k4): A[m][k] = component m of lambda (Re/Im of the 4 amplitudes) of quad k, B[k][n] = component n of
+// psi of quad k, so D[m][n] = sum_quads lambda_m psi_n lands distributed over the warp, 2 accumulators per lane
+// instead of 32 per thread -- this is what lifts the register cap on occupancy, and no shuffle reduction is needed;
+// (3) every thread un-applies the gate on its 4 lambda quads.  env[r,c] = sum conj(lambda_r) psi_c is assembled from D
+// with one lane exchange: Re = D[2r][2c] + D[2r+1][2c+1], Im = D[2r][2c+1] - D[2r+1][2c].
+// Host replay: the same three phases with a scalar environment accumulation.
+// acc_warp = this warp's accumulator rows [kAdjMaxGates][32] (on the host every thread adds all 32 values of a row).
 template <typename R, int TB>
 QCB_HD void adjoint_stage(const AdjParams<R> &A, int s, typename Vec2<R>::type *smP, typename Vec2<R>::type *smL,
                           double *acc_warp, uint32_t tid)
@@ -74,22 +64,80 @@ QCB_HD void adjoint_stage(const AdjParams<R> &A, int s, typename Vec2<R>::type *
     for (int k = 0; k < TBITS; k++) e |= ((tid >> k) & 1u) << S.tpos[k];
     e = swz<SWB>(e);
     const uint32_t mask = S.mask;
+#if defined(__CUDA_ARCH__)
+    const uint32_t lane = tid & 31u, g = lane >> 2, t = lane & 3u;
+    uint32_t eo[8]; // swizzled bases of the 8 owner lanes whose quads this lane reads in phase 2
+#pragma unroll
+    for (int i = 0; i < 8; i++) eo[i] = __shfl_sync(0xffffffffu, e, 4 * i + (int)t);
+#endif
 #pragma unroll 1
     for (int slot = 0; slot < kSlots; slot++) {
         if (!((mask >> slot) & 1u)) continue;
         const int LO = slot_lo(slot);
         const GateMat<R> &Ud = A.P.U[s * kSlots + slot];
         double *acc_gate = acc_warp + 32 * A.slot_gate[s * kSlots + slot];
-        R env[32];
-#pragma unroll
-        for (int i = 0; i < 32; i++) env[i] = (R)0;
+#if defined(__CUDA_ARCH__)
+        // (1) psi <- U^dagger psi
 #pragma unroll 1
         for (int q = 0; q < 4; q++) {
-            // spread the two bits of q over the window bits other than LO, LO+1
+            const int other = LO == 0 ? (q << 2) : (LO == 1 ? ((q & 1) | ((q & 2) << 2)) : q);
+            V x[4];
+            uint32_t off[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) { off[j] = e ^ S.roff[other | (j << LO)]; x[j] = smP[off[j]]; }
+            apply_quad(x[0], x[1], x[2], x[3], Ud);
+#pragma unroll
+            for (int j = 0; j < 4; j++) smP[off[j]] = x[j];
+        }
+        __syncwarp();
+        // (2) D += Lambda^T Psi over the warp's 128 quads, 4 quads per MMA
+        {
+            const int j = (int)(g >> 1), part = (int)(g & 1u);
+            uint32_t myoff[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int other = LO == 0 ? (q << 2) : (LO == 1 ? ((q & 1) | ((q & 2) << 2)) : q);
+                myoff[q] = S.roff[other | (j << LO)];
+            }
+            const R *pL = reinterpret_cast<const R *>(smL) + part;
+            const R *pP = reinterpret_cast<const R *>(smP) + part;
+            double d0[4] = {0.0, 0.0, 0.0, 0.0}, d1[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+            for (int d = 0; d < 32; d++) {
+                const uint32_t idx = eo[d & 7] ^ myoff[d >> 3];
+                const double a = (double)pL[2 * idx], b = (double)pP[2 * idx];
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                             : "+d"(d0[d & 3]), "+d"(d1[d & 3]) : "d"(a), "d"(b));
+            }
+            const double s0 = (d0[0] + d0[1]) + (d0[2] + d0[3]), s1 = (d1[0] + d1[1]) + (d1[2] + d1[3]);
+            const double o0 = __shfl_xor_sync(0xffffffffu, s0, 4), o1 = __shfl_xor_sync(0xffffffffu, s1, 4);
+            if (!part) { // lane holds Re(lambda_j) rows: env[j, t]
+                const int k = j + 4 * (int)t;
+                acc_gate[2 * k] += s0 + o1;
+                acc_gate[2 * k + 1] += s1 - o0;
+            }
+        }
+        __syncwarp();
+        // (3) lambda <- U^dagger lambda
+#pragma unroll 1
+        for (int q = 0; q < 4; q++) {
+            const int other = LO == 0 ? (q << 2) : (LO == 1 ? ((q & 1) | ((q & 2) << 2)) : q);
+            V l[4];
+            uint32_t off[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) { off[j] = e ^ S.roff[other | (j << LO)]; l[j] = smL[off[j]]; }
+            apply_quad(l[0], l[1], l[2], l[3], Ud);
+#pragma unroll
+            for (int j = 0; j < 4; j++) smL[off[j]] = l[j];
+        }
+        __syncwarp();
+#else
+        for (int q = 0; q < 4; q++) {
             const int other = LO == 0 ? (q << 2) : (LO == 1 ? ((q & 1) | ((q & 2) << 2)) : q);
             V x[4], l[4];
             uint32_t off[4];
-#pragma unroll
+            R env[32];
+            for (int i = 0; i < 32; i++) env[i] = (R)0;
             for (int j = 0; j < 4; j++) {
                 off[j] = e ^ S.roff[other | (j << LO)];
                 x[j] = smP[off[j]];
@@ -98,20 +146,12 @@ QCB_HD void adjoint_stage(const AdjParams<R> &A, int s, typename Vec2<R>::type *
             apply_quad(x[0], x[1], x[2], x[3], Ud);
             env_accumulate<V, R>(env, l, x);
             apply_quad(l[0], l[1], l[2], l[3], Ud);
-#pragma unroll
             for (int j = 0; j < 4; j++) {
                 smP[off[j]] = x[j];
                 smL[off[j]] = l[j];
             }
+            for (int i = 0; i < 32; i++) acc_gate[i] += (double)env[i];
         }
-#if defined(__CUDA_ARCH__)
-        double v[32];
-#pragma unroll
-        for (int i = 0; i < 32; i++) v[i] = (double)env[i];
-        warp_transpose_reduce(v);
-        acc_gate[threadIdx.x & 31u] += v[0]; // the row is private to this warp: plain read-modify-write
-#else
-        for (int i = 0; i < 32; i++) acc_gate[i] += (double)env[i];
 #endif
     }
 }

@@ -14,11 +14,6 @@ namespace qcb {
 
 constexpr int kRedThreads = 256;
 
-template <typename R> struct HamParams {
-    int kind;       // 0 TFIM (p0 = J, p1 = h, p2 = g); 1 East (p0 = c, p1 = A, p2 = B)
-    double p0, p1, p2;
-};
-
 __device__ __forceinline__ double warp_sum(double v)
 {
 #pragma unroll
@@ -97,7 +92,7 @@ __global__ void __launch_bounds__(256) k_set_zero_state(typename Vec2<R>::type *
 // C is the full logical configuration.  diag(C): coefficient of |psi[C]|^2 ; the off-diagonal
 // part is coef * sum_i w_i(C) psi[C ^ 2^i].
 struct HamEval {
-    int kind, n;
+    int kind, n;          // 0 TFIM (p0 = J, p1 = h, p2 = g); 1 East (p0 = c, p1 = A, p2 = B)
     double p0, p1, p2;
     __device__ __forceinline__ double diag(unsigned long long C) const
     {
@@ -126,7 +121,6 @@ struct HamEval {
 };
 
 // E = sum_C conj(psi[C]) (H psi)[C], accumulated in double; one pass, no scratch state.
-// `base` / `perm` support sharded states: logical C = base | deposit(local index).
 template <typename R>
 __global__ void __launch_bounds__(kRedThreads) k_measure(const typename Vec2<R>::type *__restrict__ psi,
                                                          unsigned long long namps, HamEval H, double2 *partial)

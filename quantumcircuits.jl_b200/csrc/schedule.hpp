@@ -100,8 +100,8 @@ inline std::vector<StagePlan> pack_stages(const std::vector<int> &lpos_of_gate, 
 // nloc      : number of local physical index bits (n on one GPU, n - log2(P) when sharded)
 // phys[q]   : physical bit of logical qubit q (>= nloc means "global", not addressable here)
 // gates     : program order
-// returns the passes; `ndone` receives how many gates were scheduled (== gates.size() unless a
-// gate touches a global qubit, in which case planning stops at the blocked frontier).
+// returns the passes; `done_out` flags the gates that were scheduled (all of them unless a gate
+// touches a global qubit, in which case planning stops at the blocked frontier).
 inline std::vector<PassPlan> plan_passes(int nloc, const std::vector<int> &phys, const std::vector<GateOp> &gates,
                                          const SchedOptions &opt, std::vector<char> *done_out = nullptr)
 {
@@ -125,17 +125,10 @@ inline std::vector<PassPlan> plan_passes(int nloc, const std::vector<int> &phys,
     size_t ndone = 0;
     std::vector<PassPlan> passes;
 
-    struct Cand {
-        std::vector<int> lpos_of_logical; // -1 if not in tile
-        std::vector<int> tile_phys;       // ascending
-        std::vector<int> tile_lpos;       // local position per tile_phys entry
-    };
-
     while (ndone < gates.size()) {
         int best_cnt = 0;
         PassPlan best_plan;
         std::vector<int> best_sched;
-        std::vector<char> seen_tiles; // (not deduplicated; n candidates only)
         for (int a = 0; a < n; a++) {
             if (phys[a] >= nloc) continue;
             // window of consecutive local logical qubits starting at a
@@ -228,8 +221,6 @@ inline std::vector<PassPlan> plan_passes(int nloc, const std::vector<int> &phys,
 // ---------------------------------------------------------------------------------
 // PassPlan -> kernel parameter block
 // ---------------------------------------------------------------------------------
-template <int SWB> inline uint32_t swz_host(uint32_t e) { return swz<SWB>(e); }
-
 template <typename R>
 inline void fill_params(const PassPlan &plan, int nloc, const std::vector<GateOp> &gates, const double *mats /*32 doubles per matrix*/,
                         bool adjoint, PassParams<R> &P)
