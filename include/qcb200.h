@@ -74,6 +74,8 @@ int qcb_set_option(const char *key, long value);
 /* Counters of the most recent apply / gradient call: "passes", "stages", "launches", "gates",
  * and "launches_total" (all kernels launched by this library since qcb_init). */
 int qcb_get_stat(const char *key, double *out);
+/* Frees the library's cached work buffers (gradient work states, host-call staging state, reduction partials). */
+int qcb_trim(void);
 
 /* ---- states  (zero_state_tensor src/utils.jl:61-66; similar/copy/.= used at gradients.jl:74-76,90,118) */
 int qcb_state_create(int nqubits, int dtype, qcb_state **out);

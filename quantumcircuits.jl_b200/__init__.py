@@ -3,7 +3,7 @@
 The export list follows src/QuantumCircuits.jl:9-18 of the reference; Julia's `f!` is `f_` here.
 The Julia-side ccall shim over the same C ABI is julia/B200Backend.jl.
 """
-from ._lib import QCBError, GateOutsideQubitSpace, get_stat, init, set_option, sync  # noqa: F401
+from ._lib import QCBError, GateOutsideQubitSpace, get_stat, init, set_option, sync, trim  # noqa: F401
 from .gates import (AbstractGate, Abstract1SpinGate, Abstract2SpinGate, XGate, ZGate, NGate, HadamardGate,  # noqa: F401
                     IdentityGate, CNOTGate, ReverseCNOTGate, RZGate, RYGate, RXGate, RotationGate, Generic1SpinGate,
                     Generic2SpinGate, Localised1SpinGate, Localised2SpinAdjGate, mat, adjoint,

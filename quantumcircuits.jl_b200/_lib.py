@@ -65,6 +65,8 @@ def check(rc):
         msg = lib().qcb_last_error().decode("utf-8", "replace")
         if "outside the qubit space" in msg:
             raise GateOutsideQubitSpace(msg)
+        if "must be the same size" in msg:  # the reference's error("ψ′ must be the same size as ψ.")  src/apply.jl:108
+            raise ValueError(msg)
         raise QCBError(rc, msg)
 
 
@@ -102,3 +104,8 @@ def get_stat(key):
 
 def sync():
     check(lib().qcb_sync())
+
+
+def trim():
+    """Free the library's cached work buffers (gradient work states, host-call staging, partials)."""
+    check(lib().qcb_trim())

@@ -66,9 +66,6 @@ QCB_HD void adjoint_stage(const AdjParams<R> &A, int s, typename Vec2<R>::type *
     const uint32_t mask = S.mask;
 #if defined(__CUDA_ARCH__)
     const uint32_t lane = tid & 31u, g = lane >> 2, t = lane & 3u;
-    uint32_t eo[8]; // swizzled bases of the 8 owner lanes whose quads this lane reads in phase 2
-#pragma unroll
-    for (int i = 0; i < 8; i++) eo[i] = __shfl_sync(0xffffffffu, e, 4 * i + (int)t);
 #endif
 #pragma unroll 1
     for (int slot = 0; slot < kSlots; slot++) {
@@ -90,21 +87,19 @@ QCB_HD void adjoint_stage(const AdjParams<R> &A, int s, typename Vec2<R>::type *
             for (int j = 0; j < 4; j++) smP[off[j]] = x[j];
         }
         __syncwarp();
-        // (2) D += Lambda^T Psi over the warp's 128 quads, 4 quads per MMA
+        // (2) D += Lambda^T Psi over the warp's 128 quads.  MMA number d contracts the 4 quads owned by lane d: lane
+        // (g, t) supplies component g (amplitude g/2, Re or Im) of that lane's quad t.  The 16 amplitudes touched by one
+        // MMA are the owner's 4-bit register window, which the XOR swizzle spreads evenly over the banks.
         {
             const int j = (int)(g >> 1), part = (int)(g & 1u);
-            uint32_t myoff[4];
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-                const int other = LO == 0 ? (q << 2) : (LO == 1 ? ((q & 1) | ((q & 2) << 2)) : q);
-                myoff[q] = S.roff[other | (j << LO)];
-            }
+            const int other = LO == 0 ? ((int)t << 2) : (LO == 1 ? (((int)t & 1) | (((int)t & 2) << 2)) : (int)t);
+            const uint32_t myoff = S.roff[other | (j << LO)];
             const R *pL = reinterpret_cast<const R *>(smL) + part;
             const R *pP = reinterpret_cast<const R *>(smP) + part;
             double d0[4] = {0.0, 0.0, 0.0, 0.0}, d1[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
             for (int d = 0; d < 32; d++) {
-                const uint32_t idx = eo[d & 7] ^ myoff[d >> 3];
+                const uint32_t idx = __shfl_sync(0xffffffffu, e, d) ^ myoff;
                 const double a = (double)pL[2 * idx], b = (double)pP[2 * idx];
                 asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                              : "+d"(d0[d & 3]), "+d"(d1[d & 3]) : "d"(a), "d"(b));

@@ -293,6 +293,23 @@ int qcb_finalize(void)
     return QCB_OK;
 }
 
+int qcb_trim(void)
+{
+    Ctx &c = ctx();
+    if (!c.inited) return QCB_OK;
+    QCB_CUDA(cudaStreamSynchronize(c.stream));
+    QCB_CUDA(cudaStreamSynchronize(c.copy_stream));
+    for (int i = 0; i < 3; i++) {
+        if (c.scratch[i]) cudaFree(c.scratch[i]);
+        c.scratch[i] = nullptr;
+        c.scratch_bytes[i] = 0;
+    }
+    if (c.d_partial) cudaFree(c.d_partial);
+    c.d_partial = nullptr;
+    c.partial_cap = 0;
+    return QCB_OK;
+}
+
 int qcb_sync(void)
 {
     QCB_REQUIRE_INIT();
@@ -405,6 +422,7 @@ int qcb_state_create(int nqubits, int dtype, qcb_state **out) { return new_state
 int qcb_state_wrap(int nqubits, int dtype, void *device_ptr, qcb_state **out)
 {
     if (!device_ptr) return set_error(QCB_EINVAL, "null device pointer");
+    if ((uintptr_t)device_ptr % 16 != 0) return set_error(QCB_EINVAL, "device pointer must be 16-byte aligned");
     return new_state(nqubits, dtype, device_ptr, false, out);
 }
 int qcb_state_create_sharded(int nqubits, int dtype, qcb_state **out) { return new_state(nqubits, dtype, nullptr, true, out); }
