@@ -361,7 +361,7 @@ def run_ours(args):
             avail = psutil.virtual_memory().available / max(1, world)
         except Exception:
             avail = 0
-        use_host = avail > 1.6 * per_rank
+        use_host = avail > 1.6 * per_rank and per_rank <= (72 << 30)  # pinning > 72 GiB per rank takes minutes
         flag = torch.tensor([1 if use_host else 0], device="cuda")
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         use_host = bool(flag.item())
