@@ -5,6 +5,7 @@
 
 #include "gates_host.hpp"
 #include "kernels.cuh"
+#include "measure_plan.hpp"
 #include "qcb_internal.hpp"
 
 namespace qcb {
@@ -72,17 +73,58 @@ static int check_state(const qcb_state *s)
 }
 
 // ---- measure ------------------------------------------------------------------------
+template <typename R, int TB, int MINB> static int launch_measure_pass(const qcb_state *s, const MeasParams<R> &P, double2 *partial)
+{
+    using V = typename Vec2<R>::type;
+    auto kern = measure_tile_kernel<R, TB, MINB>;
+    const size_t smem = sizeof(V) << TB;
+    static bool attr_set = false;
+    if (!attr_set) {
+        QCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    kern<<<(unsigned)(1ull << (s->nloc - TB)), 1 << (TB - kRegBits), smem, ctx().stream>>>((const V *)s->d, P, partial);
+    QCB_CUDA(cudaGetLastError());
+    count_launch();
+    return QCB_OK;
+}
+
+// tiled path: ceil((n - TB) / (TB - low_bits)) + 1 reads of the state, flips done in shared memory
+template <typename R> static int measure_tiled(const qcb_state *s, const HamEval &H, double *out2)
+{
+    Ctx &c = ctx();
+    constexpr int TB = sizeof(R) == 8 ? 12 : 13; // 64 KiB tiles
+    const std::vector<MeasParams<R>> passes = plan_measure<R>(s->n, TB, (int)c.low_bits, H);
+    const size_t ntiles = (size_t)1 << (s->nloc - TB);
+    QCB_TRY(ensure_partial(2 * ntiles * passes.size()));
+    QCB_TRY(ensure_out(64));
+    for (size_t p = 0; p < passes.size(); p++)
+        QCB_TRY((launch_measure_pass<R, TB, (sizeof(R) == 8 ? 2 : 1)>(s, passes[p], (double2 *)c.d_partial + p * ntiles)));
+    k_final_sum<<<2, 256, 0, c.stream>>>(c.d_partial, (int)(ntiles * passes.size()), 2, c.d_out);
+    QCB_CUDA(cudaGetLastError());
+    count_launch();
+    QCB_CUDA(cudaMemcpyAsync(c.h_out, c.d_out, 2 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    QCB_CUDA(cudaStreamSynchronize(c.stream));
+    const double oc = H.kind == 0 ? -H.p0 * H.p2 : H.p1;
+    out2[0] = c.h_out[0] + oc * c.h_out[1];
+    out2[1] = 0.0; // the two orientations of every flip pair have exactly opposite imaginary parts
+    c.st_passes = (double)passes.size();
+    return QCB_OK;
+}
+
 static int measure_impl(const qcb_state *s, int kind, double p0, double p1, double p2, double *out2)
 {
     QCB_REQUIRE_INIT();
     QCB_TRY(check_state(s));
     if (s->sharded) return set_error(QCB_EUNSUPPORTED, "measure on a sharded state: use qcb_state_download_shard or gather first");
     Ctx &c = ctx();
+    HamEval H{kind, s->n, p0, p1, p2};
+    if (!c.force_simple && s->nloc >= 13)
+        return s->dtype == QCB_C128 ? measure_tiled<double>(s, H, out2) : measure_tiled<float>(s, H, out2);
     const unsigned long long namps = 1ull << s->nloc;
     const unsigned blocks = grid_for(namps, kRedThreads, 8);
     QCB_TRY(ensure_partial((size_t)blocks * 2));
     QCB_TRY(ensure_out(64));
-    HamEval H{kind, s->n, p0, p1, p2};
     if (s->dtype == QCB_C128)
         k_measure<double><<<blocks, kRedThreads, 0, c.stream>>>((const double2 *)s->d, namps, H, (double2 *)c.d_partial);
     else

@@ -21,10 +21,10 @@ __device__ __forceinline__ double warp_sum(double v)
     return v;
 }
 
-// sums NV doubles per thread over the CTA; result valid in thread 0 (written to out[0..NV)).
-template <int NV> __device__ __forceinline__ void block_sum(double (&v)[NV], double *out)
+// sums NV doubles per thread over a CTA of NWARPS warps; result in out[0..NV) (valid after the call for all threads)
+template <int NV, int NWARPS> __device__ __forceinline__ void block_sum_n(double (&v)[NV], double *out)
 {
-    __shared__ double red[kRedThreads / 32][NV];
+    __shared__ double red[NWARPS][NV];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int i = 0; i < NV; i++) {
@@ -34,11 +34,13 @@ template <int NV> __device__ __forceinline__ void block_sum(double (&v)[NV], dou
     __syncthreads();
     if (threadIdx.x < NV) {
         double s = 0;
-        for (int w = 0; w < (int)(blockDim.x >> 5); w++) s += red[w][threadIdx.x];
+#pragma unroll
+        for (int w = 0; w < NWARPS; w++) s += red[w][threadIdx.x];
         out[threadIdx.x] = s;
     }
     __syncthreads();
 }
+template <int NV> __device__ __forceinline__ void block_sum(double (&v)[NV], double *out) { block_sum_n<NV, kRedThreads / 32>(v, out); }
 
 // ---- in-place single gates --------------------------------------------------------
 template <typename R>

@@ -1,0 +1,167 @@
+// measure_tile.cuh -- tiled sweep-and-reduce expectation value of the kernel Hamiltonians.
+//
+// Replaces _tfim_measure! / _eastmodel_measure! (src/hamiltonians/tfim.jl:17-54, east_model.jl:30-52) plus the
+// separate sum(psi') pass (src/hamiltonians/hamiltonians.jl:41).  The reference gathers N+1 amplitudes per
+// amplitude; k_measure (kernels.cuh) does the same from L2/HBM.  Here the flips are done inside shared-memory
+// tiles: a pass stages 2^TB amplitudes, every thread pulls 16-amplitude register windows (4 consecutive tile bits)
+// and accumulates  2 w_i(C) Re(conj(psi[C | 2^i]) psi[C])  for the window bits i (each pair once; the imaginary
+// parts of the two orientations cancel exactly) and, in the first stage of the first pass, diag(C) |psi[C]|^2.
+// HBM traffic: one read of the state per pass, ceil((n - TB) / (TB - low_bits)) + 1 passes; nothing is written.
+#pragma once
+#include "kernels.cuh"
+
+namespace qcb {
+
+constexpr int kMeasMaxStages = 4;
+
+struct MeasStage {
+    StageDesc sd;
+    uint8_t active;        // which of the 4 window bits contribute flips in this stage
+    uint8_t diag;          // 1: this stage also accumulates the diagonal part
+    uint8_t wphys[kRegBits]; // physical (== logical, states are canonical here) index bit of each window bit
+    uint8_t pad[2];
+};
+
+template <typename R> struct MeasParams {
+    int32_t nstages, nseg;
+    uint8_t seg_start[kMaxSeg], seg_len[kMaxSeg];
+    uint8_t ld_phys[kMaxTB], ld_lpos[kMaxTB];
+    unsigned long long ld_goff[kRegAmps];
+    uint16_t ld_eoff[kRegAmps];
+    MeasStage stage[kMeasMaxStages];
+    HamEval H;
+};
+
+struct HamEvalHD { // host/device twin of HamEval's arithmetic (kernels.cuh keeps the device-only popcount form)
+    template <typename H> static QCB_HD bool flip_on(const H &h, unsigned long long C, int i)
+    {
+        if (h.kind == 0 || i == 0) return true;
+        return ((C >> (i - 1)) & 1ull) == 0ull;
+    }
+};
+
+QCB_HD int popc64(unsigned long long x)
+{
+#if defined(__CUDA_ARCH__)
+    return __popcll(x);
+#else
+    return __builtin_popcountll(x);
+#endif
+}
+
+QCB_HD double ham_diag(const HamEval &h, unsigned long long C)
+{
+    const int n = h.n;
+    const unsigned long long pairmask = (n >= 2) ? ((1ull << (n - 1)) - 1ull) : 0ull;
+    if (h.kind == 0) {
+        const int eq = popc64(~(C ^ (C >> 1)) & pairmask);
+        return -h.p0 * ((double)(2 * eq - (n - 1)) + h.p1 * (double)(n - 2 * popc64(C)));
+    }
+    const unsigned long long all = (n >= 64) ? ~0ull : ((1ull << n) - 1ull);
+    const unsigned long long zero = ~C & all;
+    const unsigned long long prev = zero & pairmask;
+    return h.p2 * ((double)(zero & 1ull) + (double)popc64(prev & (zero >> 1)) + h.p0 * (double)popc64(prev)) + h.p0;
+}
+
+// one stage of one thread: returns the contribution to (diagonal sum, flip sum)
+template <typename R, int TB>
+QCB_HD void measure_stage(const MeasParams<R> &P, int s, const typename Vec2<R>::type *sm, uint32_t tid, unsigned long long tile_base,
+                          double &acc_diag, double &acc_flip)
+{
+    using V = typename Vec2<R>::type;
+    constexpr int SWB = Vec2<R>::SWB;
+    constexpr int TBITS = TB - kRegBits;
+    const MeasStage &S = P.stage[s];
+    uint32_t e = 0;
+    unsigned long long C0 = tile_base;
+#pragma unroll
+    for (int k = 0; k < TBITS; k++) {
+        const uint32_t bit = (tid >> k) & 1u;
+        const int lp = S.sd.tpos[k];
+        e |= bit << lp;
+        // local position -> physical bit: ld_phys is indexed by memory order, ld_lpos gives its local position
+    }
+    // physical index of this thread's element r = 0: deposit the local bits through the tile's position table
+#pragma unroll
+    for (int k = 0; k < TB; k++) C0 |= (unsigned long long)((e >> P.ld_lpos[k]) & 1u) << P.ld_phys[k];
+    const uint32_t es = swz<SWB>(e);
+    V a[kRegAmps];
+#pragma unroll
+    for (int r = 0; r < kRegAmps; r++) a[r] = sm[es ^ S.sd.roff[r]];
+    if (S.diag) {
+#pragma unroll
+        for (int r = 0; r < kRegAmps; r++) {
+            unsigned long long C = C0;
+#pragma unroll
+            for (int b = 0; b < kRegBits; b++) C |= (unsigned long long)((r >> b) & 1) << S.wphys[b];
+            acc_diag += ham_diag(P.H, C) * ((double)a[r].x * (double)a[r].x + (double)a[r].y * (double)a[r].y);
+        }
+    }
+#pragma unroll
+    for (int b = 0; b < kRegBits; b++) {
+        if (!((S.active >> b) & 1)) continue;
+        const int i = S.wphys[b];
+#pragma unroll
+        for (int r = 0; r < kRegAmps; r++) {
+            if ((r >> b) & 1) continue;
+            unsigned long long C = C0;
+#pragma unroll
+            for (int bb = 0; bb < kRegBits; bb++) C |= (unsigned long long)((r >> bb) & 1) << S.wphys[bb];
+            if (!HamEvalHD::flip_on(P.H, C, i)) continue;
+            const V x0 = a[r], x1 = a[r | (1 << b)];
+            acc_flip += 2.0 * ((double)x0.x * (double)x1.x + (double)x0.y * (double)x1.y);
+        }
+    }
+}
+
+template <typename R, int TB>
+QCB_HD void measure_tile_load(const typename Vec2<R>::type *__restrict__ src, const MeasParams<R> &P, typename Vec2<R>::type *sm,
+                              uint32_t tid, unsigned long long bid, unsigned long long &tile_base)
+{
+    using V = typename Vec2<R>::type;
+    constexpr int SWB = Vec2<R>::SWB;
+    constexpr int TBITS = TB - kRegBits;
+    unsigned long long g = 0, b = bid;
+    for (int s = 0; s < P.nseg; s++) {
+        const int len = P.seg_len[s];
+        g |= (b & ((1ull << len) - 1ull)) << P.seg_start[s];
+        b >>= len;
+    }
+    tile_base = g;
+    uint32_t e = 0;
+#pragma unroll
+    for (int k = 0; k < TBITS; k++) {
+        const uint32_t bit = (tid >> k) & 1u;
+        g |= (unsigned long long)bit << P.ld_phys[k];
+        e |= bit << P.ld_lpos[k];
+    }
+    e = swz<SWB>(e);
+    V tmp[kRegAmps];
+#pragma unroll
+    for (int i = 0; i < kRegAmps; i++) tmp[i] = src[g | P.ld_goff[i]];
+#pragma unroll
+    for (int i = 0; i < kRegAmps; i++) sm[e ^ P.ld_eoff[i]] = tmp[i];
+}
+
+#if defined(__CUDACC__)
+template <typename R, int TB, int MINB>
+__global__ void __launch_bounds__(1 << (TB - kRegBits), MINB)
+measure_tile_kernel(const typename Vec2<R>::type *psi, const __grid_constant__ MeasParams<R> P, double2 *partial)
+{
+    using V = typename Vec2<R>::type;
+    extern __shared__ __align__(16) unsigned char qcb_smem_raw[];
+    V *sm = reinterpret_cast<V *>(qcb_smem_raw);
+    const uint32_t tid = threadIdx.x;
+    unsigned long long tile_base;
+    measure_tile_load<R, TB>(psi, P, sm, tid, blockIdx.x, tile_base);
+    __syncthreads();
+    double acc[2] = {0.0, 0.0};
+#pragma unroll 1
+    for (int s = 0; s < P.nstages; s++) measure_stage<R, TB>(P, s, sm, tid, tile_base, acc[0], acc[1]);
+    __shared__ double out[2];
+    block_sum_n<2, (1 << (TB - kRegBits)) / 32>(acc, out);
+    if (tid == 0) partial[blockIdx.x] = make_double2(out[0], out[1]);
+}
+#endif
+
+} // namespace qcb

@@ -221,6 +221,27 @@ inline std::vector<PassPlan> plan_passes(int nloc, const std::vector<int> &phys,
 // ---------------------------------------------------------------------------------
 // PassPlan -> kernel parameter block
 // ---------------------------------------------------------------------------------
+// register window [p0, p0+4): thread bit k -> local position (outside the window), swizzled register offsets.
+// The first SWB thread bits get positions with distinct residues mod SWB, which makes the lanes of a quarter
+// (half) warp hit distinct bank groups under the XOR swizzle.
+template <int SWB> inline void fill_stage_desc(StageDesc &S, int p0, int TB)
+{
+    const int TBITS = TB - kRegBits;
+    S.p0 = (uint8_t)p0;
+    S.mask = 0;
+    std::vector<int> freepos;
+    for (int p = 0; p < TB; p++)
+        if (p < p0 || p >= p0 + kRegBits) freepos.push_back(p);
+    std::vector<int> order;
+    std::vector<char> used(TB, 0), res(SWB, 0);
+    for (int p : freepos)
+        if ((int)order.size() < SWB && !res[p % SWB]) { order.push_back(p); used[p] = 1; res[p % SWB] = 1; }
+    for (int p : freepos)
+        if (!used[p]) order.push_back(p);
+    for (int k = 0; k < TBITS; k++) S.tpos[k] = (uint8_t)order[k];
+    for (int r = 0; r < kRegAmps; r++) S.roff[r] = (uint16_t)swz<SWB>((uint32_t)r << p0);
+}
+
 template <typename R>
 inline void fill_params(const PassPlan &plan, int nloc, const std::vector<GateOp> &gates, const double *mats /*32 doubles per matrix*/,
                         bool adjoint, PassParams<R> &P)
@@ -266,20 +287,7 @@ inline void fill_params(const PassPlan &plan, int nloc, const std::vector<GateOp
     for (int s = 0; s < P.nstages; s++) {
         const StagePlan &sp = plan.stages[s];
         StageDesc &S = P.stage[s];
-        S.p0 = (uint8_t)sp.p0;
-        S.mask = 0;
-        // thread bits: first SWB positions with distinct residues mod SWB (bank-conflict free), then the rest
-        std::vector<int> freepos;
-        for (int p = 0; p < TB; p++)
-            if (p < sp.p0 || p >= sp.p0 + kRegBits) freepos.push_back(p);
-        std::vector<int> order;
-        std::vector<char> used(TB, 0), res(SWB, 0);
-        for (int p : freepos)
-            if ((int)order.size() < SWB && !res[p % SWB]) { order.push_back(p); used[p] = 1; res[p % SWB] = 1; }
-        for (int p : freepos)
-            if (!used[p]) order.push_back(p);
-        for (int k = 0; k < TBITS; k++) S.tpos[k] = (uint8_t)order[k];
-        for (int r = 0; r < kRegAmps; r++) S.roff[r] = (uint16_t)swz<SWB>((uint32_t)r << sp.p0);
+        fill_stage_desc<SWB>(S, sp.p0, TB);
         for (int slot = 0; slot < kSlots; slot++) {
             const int g = sp.gate[slot];
             if (g < 0) continue;

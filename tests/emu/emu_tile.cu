@@ -308,3 +308,53 @@ extern "C" int emu_adjoint_sweep(int dtype, int n, void *psi, void *lam, int nga
         return 1;
     }
 }
+
+// ---- tiled expectation value (measure_tile.cuh + measure_plan.hpp) replayed on the CPU ---------------------
+#include "../../quantumcircuits.jl_b200/csrc/measure_plan.hpp"
+
+template <typename R, int TB> static void emu_measure_pass(const typename Vec2<R>::type *psi, int n, const MeasParams<R> &P, double *acc)
+{
+    using V = typename Vec2<R>::type;
+    const uint32_t NT = 1u << (TB - kRegBits);
+    std::vector<V> sm(1u << TB);
+    for (unsigned long long b = 0; b < (1ull << (n - TB)); b++) {
+        unsigned long long base = 0;
+        for (uint32_t t = 0; t < NT; t++) measure_tile_load<R, TB>(psi, P, sm.data(), t, b, base);
+        for (int s = 0; s < P.nstages; s++)
+            for (uint32_t t = 0; t < NT; t++) measure_stage<R, TB>(P, s, sm.data(), t, base, acc[0], acc[1]);
+    }
+}
+
+extern "C" int emu_measure(int dtype, int n, const void *psi, int kind, double p0, double p1, double p2, int tile_bits, int low_bits,
+                           double *out_E, int *npasses)
+{
+    HamEval H{kind, n, p0, p1, p2};
+    double acc[2] = {0.0, 0.0};
+    try {
+        if (dtype) {
+            auto passes = plan_measure<double>(n, tile_bits, low_bits, H);
+            *npasses = (int)passes.size();
+            for (auto &P : passes) switch (tile_bits) {
+#define CASE(T) case T: emu_measure_pass<double, T>((const double2 *)psi, n, P, acc); break;
+                CASE(8) CASE(9) CASE(10) CASE(11) CASE(12) CASE(13)
+#undef CASE
+                default: return 3;
+            }
+        } else {
+            auto passes = plan_measure<float>(n, tile_bits, low_bits, H);
+            *npasses = (int)passes.size();
+            for (auto &P : passes) switch (tile_bits) {
+#define CASE(T) case T: emu_measure_pass<float, T>((const float2 *)psi, n, P, acc); break;
+                CASE(8) CASE(9) CASE(10) CASE(11) CASE(12) CASE(13)
+#undef CASE
+                default: return 3;
+            }
+        }
+    } catch (const std::exception &e) {
+        std::fprintf(stderr, "emu measure: %s\n", e.what());
+        return 1;
+    }
+    const double oc = kind == 0 ? -p0 * p2 : p1;
+    *out_E = acc[0] + oc * acc[1];
+    return 0;
+}

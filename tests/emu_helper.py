@@ -12,7 +12,7 @@ _lib = None
 
 
 def build(force=False):
-    srcs = [os.path.join(_HERE, "emu_tile.cu"), os.path.join(_CSRC, "tile.cuh"), os.path.join(_CSRC, "schedule.hpp"), os.path.join(_CSRC, "dist_plan.hpp"), os.path.join(_CSRC, "adjoint.cuh")]
+    srcs = [os.path.join(_HERE, "emu_tile.cu"), os.path.join(_CSRC, "tile.cuh"), os.path.join(_CSRC, "schedule.hpp"), os.path.join(_CSRC, "dist_plan.hpp"), os.path.join(_CSRC, "adjoint.cuh"), os.path.join(_CSRC, "measure_tile.cuh"), os.path.join(_CSRC, "measure_plan.hpp"), os.path.join(_CSRC, "kernels.cuh")]
     if force or not os.path.exists(_SO) or any(os.path.getmtime(_SO) < os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["nvcc", "-O2", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler",
                                "-fPIC", "-shared", "-o", _SO, srcs[0]], cwd=_HERE)
@@ -94,3 +94,17 @@ def adjoint_sweep(psi, lam, q0, mats, tile_bits, low_bits):
         raise RuntimeError(f"emu_adjoint_sweep rc={rc}")
     envc = (env[:, 0::2] + 1j * env[:, 1::2]).reshape(len(q0), 4, 4).transpose(0, 2, 1)  # stored column-major r + 4c
     return psi, lam, envc
+
+
+def measure(psi, kind, params, tile_bits, low_bits):
+    """Tiled expectation value replay.  kind 0: TFIM (J, h, g); 1: East (c, A, B).  Returns (E, number of passes)."""
+    psi = np.ascontiguousarray(psi)
+    n = int(psi.size).bit_length() - 1
+    E = C.c_double(0)
+    npass = C.c_int(0)
+    rc = lib().emu_measure(C.c_int(1 if psi.dtype == np.complex128 else 0), C.c_int(n), psi.ctypes.data_as(C.c_void_p), C.c_int(kind),
+                           C.c_double(params[0]), C.c_double(params[1]), C.c_double(params[2]), C.c_int(tile_bits), C.c_int(low_bits),
+                           C.byref(E), C.byref(npass))
+    if rc:
+        raise RuntimeError(f"emu_measure rc={rc}")
+    return E.value, npass.value

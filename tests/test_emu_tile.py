@@ -201,3 +201,19 @@ def test_emu_adjoint_sweep_gradients(emu, oracle, n, layers, tb, dtype):
             grads[k, g] = 2 * np.real(np.sum(env[g] * d.reshape(4, 4, order="F")))
     _, g_ref = oracle.gradients_brickwork(psi0, n, layers, angles, 0, hp)
     assert np.max(np.abs(grads - g_ref)) < tol * max(1.0, np.max(np.abs(g_ref)))
+
+
+# ---- tiled expectation value -----------------------------------------------------------------------------
+@pytest.mark.parametrize("n,tb,c", [(10, 8, 3), (13, 9, 3), (14, 12, 3), (15, 13, 3), (16, 10, 4), (17, 12, 3)])
+def test_emu_tiled_measure(emu, oracle, n, tb, c):
+    rng = np.random.default_rng(n * 31 + tb)
+    psi = rand_state(rng, n)
+    A, B = onp.east_params(0.1, -0.1)
+    for kind, hp, ref in [(0, (1.0, 0.1, 0.5), oracle.measure_tfim(psi, 1.0, 0.1, 0.5).real),
+                          (0, (0.7, -0.3, 1.4), oracle.measure_tfim(psi, 0.7, -0.3, 1.4).real),
+                          (1, (0.1, A, B), oracle.measure_east(psi, 0.1, A, B).real)]:
+        E, npass = emu.measure(psi, kind, hp, tb, c)
+        assert abs(E - ref) < 1e-12 * max(1.0, abs(ref))
+        assert npass == 1 + max(0, -(-(n - tb) // (tb - c)))
+    E32, _ = emu.measure(psi.astype(np.complex64), 0, (1.0, 0.1, 0.5), tb, c)
+    assert abs(E32 - oracle.measure_tfim(psi, 1.0, 0.1, 0.5).real) < 1e-5 * n

@@ -48,6 +48,17 @@ def main():
             qc.apply_(psi0.similar(), psi0, c)
         torch.cuda.synchronize()
         dt_fwd = (time.perf_counter() - t0) / reps
+        # standalone expectation value (tiled sweep-and-reduce)
+        st = qc.B200State(n, dt)
+        qc.apply_(st, st, c)
+        qc.measure_(None, H, st)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            qc.measure_(None, H, st)
+        dt_meas = (time.perf_counter() - t0) / reps
+        meas_passes = qc.get_stat("passes")
+        del st
         # CPU: one apply + one measure of the oracle at this size, scaled by the reference's operation counts
         G = c.ngates
         npdt = dt
@@ -64,7 +75,7 @@ def main():
         napply, nmeas = 2 * G + 15 * G * (G + 1), 30 * G
         cpu_est = napply * t_apply + nmeas * t_meas
         print(json.dumps({"config": tag, "nqubits": n, "half_layers": layers, "gates": G, "dtype": np.dtype(dt).name,
-                          "gpu_s_per_gradient": dt_gpu, "gpu_s_forward": dt_fwd, "gpu_launches_per_gradient": launches, "energy": E,
+                          "gpu_s_per_gradient": dt_gpu, "gpu_s_forward": dt_fwd, "gpu_s_measure": dt_meas, "measure_passes": meas_passes, "gpu_launches_per_gradient": launches, "energy": E,
                           "cpu_reference_algorithm_s_estimate": cpu_est, "cpu_threads": oracle.max_threads(),
                           "cpu_note": f"oracle per-apply {t_apply:.4f} s, per-measure {t_meas:.4f} s (measured at {n_cpu} q, scaled 2^{n - n_cpu}) x "
                                       f"{napply} applies + {nmeas} measures of src/gradients.jl:88-152",
