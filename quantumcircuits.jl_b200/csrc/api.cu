@@ -73,10 +73,10 @@ static int check_state(const qcb_state *s)
 }
 
 // ---- measure ------------------------------------------------------------------------
-template <typename R, int TB, int MINB> static int launch_measure_pass(const qcb_state *s, const MeasParams<R> &P, double2 *partial)
+template <typename R, int TB, int MINB, int KIND> static int launch_measure_pass(const qcb_state *s, const MeasParams<R> &P, double2 *partial)
 {
     using V = typename Vec2<R>::type;
-    auto kern = measure_tile_kernel<R, TB, MINB>;
+    auto kern = measure_tile_kernel<R, TB, MINB, KIND>;
     const size_t smem = sizeof(V) << TB;
     static bool attr_set = false;
     if (!attr_set) {
@@ -93,13 +93,14 @@ template <typename R, int TB, int MINB> static int launch_measure_pass(const qcb
 template <typename R> static int measure_tiled(const qcb_state *s, const HamEval &H, double *out2)
 {
     Ctx &c = ctx();
-    constexpr int TB = sizeof(R) == 8 ? 12 : 13; // 64 KiB tiles
+    constexpr int TB = 12; // 64 KiB (ComplexF64) / 32 KiB (ComplexF32) tiles, 256 threads
     const std::vector<MeasParams<R>> passes = plan_measure<R>(s->n, TB, (int)c.low_bits, H);
     const size_t ntiles = (size_t)1 << (s->nloc - TB);
     QCB_TRY(ensure_partial(2 * ntiles * passes.size()));
     QCB_TRY(ensure_out(64));
     for (size_t p = 0; p < passes.size(); p++)
-        QCB_TRY((launch_measure_pass<R, TB, (sizeof(R) == 8 ? 2 : 1)>(s, passes[p], (double2 *)c.d_partial + p * ntiles)));
+        QCB_TRY((H.kind == 0 ? launch_measure_pass<R, TB, 2, 0>(s, passes[p], (double2 *)c.d_partial + p * ntiles)
+                             : launch_measure_pass<R, TB, 2, 1>(s, passes[p], (double2 *)c.d_partial + p * ntiles)));
     k_final_sum<<<2, 256, 0, c.stream>>>(c.d_partial, (int)(ntiles * passes.size()), 2, c.d_out);
     QCB_CUDA(cudaGetLastError());
     count_launch();

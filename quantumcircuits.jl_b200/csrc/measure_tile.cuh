@@ -32,14 +32,6 @@ template <typename R> struct MeasParams {
     HamEval H;
 };
 
-struct HamEvalHD { // host/device twin of HamEval's arithmetic (kernels.cuh keeps the device-only popcount form)
-    template <typename H> static QCB_HD bool flip_on(const H &h, unsigned long long C, int i)
-    {
-        if (h.kind == 0 || i == 0) return true;
-        return ((C >> (i - 1)) & 1ull) == 0ull;
-    }
-};
-
 QCB_HD int popc64(unsigned long long x)
 {
 #if defined(__CUDA_ARCH__)
@@ -63,8 +55,9 @@ QCB_HD double ham_diag(const HamEval &h, unsigned long long C)
     return h.p2 * ((double)(zero & 1ull) + (double)popc64(prev & (zero >> 1)) + h.p0 * (double)popc64(prev)) + h.p0;
 }
 
-// one stage of one thread: returns the contribution to (diagonal sum, flip sum)
-template <typename R, int TB>
+// one stage of one thread: adds its contribution to (diagonal sum, flip sum).  KIND is the Hamiltonian (compile time:
+// the TFIM flips need no index arithmetic at all, the East flips need one control bit per pair).
+template <typename R, int TB, int KIND>
 QCB_HD void measure_stage(const MeasParams<R> &P, int s, const typename Vec2<R>::type *sm, uint32_t tid, unsigned long long tile_base,
                           double &acc_diag, double &acc_flip)
 {
@@ -73,21 +66,18 @@ QCB_HD void measure_stage(const MeasParams<R> &P, int s, const typename Vec2<R>:
     constexpr int TBITS = TB - kRegBits;
     const MeasStage &S = P.stage[s];
     uint32_t e = 0;
-    unsigned long long C0 = tile_base;
 #pragma unroll
-    for (int k = 0; k < TBITS; k++) {
-        const uint32_t bit = (tid >> k) & 1u;
-        const int lp = S.sd.tpos[k];
-        e |= bit << lp;
-        // local position -> physical bit: ld_phys is indexed by memory order, ld_lpos gives its local position
-    }
-    // physical index of this thread's element r = 0: deposit the local bits through the tile's position table
-#pragma unroll
-    for (int k = 0; k < TB; k++) C0 |= (unsigned long long)((e >> P.ld_lpos[k]) & 1u) << P.ld_phys[k];
+    for (int k = 0; k < TBITS; k++) e |= ((tid >> k) & 1u) << S.sd.tpos[k];
     const uint32_t es = swz<SWB>(e);
     V a[kRegAmps];
 #pragma unroll
     for (int r = 0; r < kRegAmps; r++) a[r] = sm[es ^ S.sd.roff[r]];
+    // physical index of this thread's element r = 0 (needed for the diagonal and for the East control bits)
+    unsigned long long C0 = tile_base;
+    if (S.diag || KIND == 1) {
+#pragma unroll
+        for (int k = 0; k < TB; k++) C0 |= (unsigned long long)((e >> P.ld_lpos[k]) & 1u) << P.ld_phys[k];
+    }
     if (S.diag) {
 #pragma unroll
         for (int r = 0; r < kRegAmps; r++) {
@@ -100,14 +90,18 @@ QCB_HD void measure_stage(const MeasParams<R> &P, int s, const typename Vec2<R>:
 #pragma unroll
     for (int b = 0; b < kRegBits; b++) {
         if (!((S.active >> b) & 1)) continue;
-        const int i = S.wphys[b];
+        // East: the flip of qubit i is weighted by n_{i-1} = [bit i-1 is 0]; bit i-1 is either the previous window
+        // bit (then it depends on r) or fixed for this thread
+        uint32_t allowed = 0xffffu;
+        if (KIND == 1 && S.wphys[b] != 0) {
+            const int ctl = S.wphys[b] - 1;
+            if (b > 0 && S.wphys[b - 1] == ctl) allowed = b == 1 ? 0x5555u : (b == 2 ? 0x3333u : 0x0f0fu);
+            else allowed = ((C0 >> ctl) & 1ull) ? 0u : 0xffffu;
+        }
 #pragma unroll
         for (int r = 0; r < kRegAmps; r++) {
             if ((r >> b) & 1) continue;
-            unsigned long long C = C0;
-#pragma unroll
-            for (int bb = 0; bb < kRegBits; bb++) C |= (unsigned long long)((r >> bb) & 1) << S.wphys[bb];
-            if (!HamEvalHD::flip_on(P.H, C, i)) continue;
+            if (KIND == 1 && !((allowed >> r) & 1u)) continue;
             const V x0 = a[r], x1 = a[r | (1 << b)];
             acc_flip += 2.0 * ((double)x0.x * (double)x1.x + (double)x0.y * (double)x1.y);
         }
@@ -144,7 +138,7 @@ QCB_HD void measure_tile_load(const typename Vec2<R>::type *__restrict__ src, co
 }
 
 #if defined(__CUDACC__)
-template <typename R, int TB, int MINB>
+template <typename R, int TB, int MINB, int KIND>
 __global__ void __launch_bounds__(1 << (TB - kRegBits), MINB)
 measure_tile_kernel(const typename Vec2<R>::type *psi, const __grid_constant__ MeasParams<R> P, double2 *partial)
 {
@@ -157,7 +151,7 @@ measure_tile_kernel(const typename Vec2<R>::type *psi, const __grid_constant__ M
     __syncthreads();
     double acc[2] = {0.0, 0.0};
 #pragma unroll 1
-    for (int s = 0; s < P.nstages; s++) measure_stage<R, TB>(P, s, sm, tid, tile_base, acc[0], acc[1]);
+    for (int s = 0; s < P.nstages; s++) measure_stage<R, TB, KIND>(P, s, sm, tid, tile_base, acc[0], acc[1]);
     __shared__ double out[2];
     block_sum_n<2, (1 << (TB - kRegBits)) / 32>(acc, out);
     if (tid == 0) partial[blockIdx.x] = make_double2(out[0], out[1]);

@@ -222,20 +222,26 @@ inline std::vector<PassPlan> plan_passes(int nloc, const std::vector<int> &phys,
 // PassPlan -> kernel parameter block
 // ---------------------------------------------------------------------------------
 // register window [p0, p0+4): thread bit k -> local position (outside the window), swizzled register offsets.
-// The first SWB thread bits get positions with distinct residues mod SWB, which makes the lanes of a quarter
+// The first SWB thread bits get positions with linearly independent bank vectors, which makes the lanes of a quarter
 // (half) warp hit distinct bank groups under the XOR swizzle.
 template <int SWB> inline void fill_stage_desc(StageDesc &S, int p0, int TB)
 {
-    const int TBITS = TB - kRegBits;
+    const int TBITS = std::min(TB, kMaxTB) - kRegBits;
     S.p0 = (uint8_t)p0;
     S.mask = 0;
     std::vector<int> freepos;
     for (int p = 0; p < TB; p++)
         if (p < p0 || p >= p0 + kRegBits) freepos.push_back(p);
+    // greedy: the first SWB thread bits get positions whose bank vectors are linearly independent over GF(2)
     std::vector<int> order;
-    std::vector<char> used(TB, 0), res(SWB, 0);
-    for (int p : freepos)
-        if ((int)order.size() < SWB && !res[p % SWB]) { order.push_back(p); used[p] = 1; res[p % SWB] = 1; }
+    std::vector<char> used(TB, 0);
+    std::vector<uint32_t> basis; // reduced basis of the chosen vectors
+    for (int p : freepos) {
+        if ((int)order.size() >= SWB) break;
+        uint32_t v = bank_vector<SWB>(p);
+        for (uint32_t bvec : basis) v = std::min(v, v ^ bvec);
+        if (v) { basis.push_back(v); order.push_back(p); used[p] = 1; }
+    }
     for (int p : freepos)
         if (!used[p]) order.push_back(p);
     for (int k = 0; k < TBITS; k++) S.tpos[k] = (uint8_t)order[k];

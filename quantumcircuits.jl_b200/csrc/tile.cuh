@@ -55,10 +55,24 @@ template <> struct Vec2<float> { using type = float2; static constexpr int SWB =
 // local bit pair (lo, lo+1) of each slot inside the 4-bit register window
 QCB_HD constexpr int slot_lo(int slot) { return slot == 1 ? 0 : (slot == 2 ? 2 : 1); }
 
-// XOR swizzle of a tile-local element index (modifies only the low SWB bits).
+// XOR swizzle of a tile-local element index (modifies only the low SWB bits = the bank group of the 16 B / 8 B chunk).
+// Every index bit b >= SWB toggles the bank-group bits given by bank_vector<SWB>(b).
+//   SWB = 4 (8 B chunks, 16 groups): bit b toggles group bit b mod 4.
+//   SWB = 3 (16 B chunks, 8 groups): the columns repeat with period 4 as 001, 010, 100, 111, so that ANY three of
+//            four consecutive index bits are linearly independent: a quarter warp that varies three bits of a 4-bit
+//            register window (stage loads, and the MMA operand loads of the backward pass) is conflict free.
+template <int SWB> QCB_HD constexpr uint32_t bank_vector(int b)
+{
+    return SWB == 4 ? (1u << (b & 3)) : ((b & 3) == 3 ? 7u : (1u << (b & 3)));
+}
 template <int SWB> QCB_HD uint32_t swz(uint32_t e)
 {
-    if (SWB == 3) return e ^ (((e >> 3) ^ (e >> 6) ^ (e >> 9) ^ (e >> 12)) & 7u);
+    if (SWB == 3) {
+        // index bits 3.. : fold in groups of 4 (bit i of h is index bit i + 3, i.e. column (i + 3) mod 4)
+        const uint32_t h = e >> 3;
+        const uint32_t x = (h ^ (h >> 4) ^ (h >> 8)) & 15u; // x0 <-> column 3 (111), x1 <-> 001, x2 <-> 010, x3 <-> 100
+        return e ^ ((x >> 1) ^ ((x & 1u) * 7u));
+    }
     return e ^ (((e >> 4) ^ (e >> 8) ^ (e >> 12)) & 15u);
 }
 

@@ -314,6 +314,7 @@ extern "C" int emu_adjoint_sweep(int dtype, int n, void *psi, void *lam, int nga
 
 template <typename R, int TB> static void emu_measure_pass(const typename Vec2<R>::type *psi, int n, const MeasParams<R> &P, double *acc)
 {
+    const int kind = P.H.kind;
     using V = typename Vec2<R>::type;
     const uint32_t NT = 1u << (TB - kRegBits);
     std::vector<V> sm(1u << TB);
@@ -321,7 +322,10 @@ template <typename R, int TB> static void emu_measure_pass(const typename Vec2<R
         unsigned long long base = 0;
         for (uint32_t t = 0; t < NT; t++) measure_tile_load<R, TB>(psi, P, sm.data(), t, b, base);
         for (int s = 0; s < P.nstages; s++)
-            for (uint32_t t = 0; t < NT; t++) measure_stage<R, TB>(P, s, sm.data(), t, base, acc[0], acc[1]);
+            for (uint32_t t = 0; t < NT; t++) {
+                if (kind == 0) measure_stage<R, TB, 0>(P, s, sm.data(), t, base, acc[0], acc[1]);
+                else measure_stage<R, TB, 1>(P, s, sm.data(), t, base, acc[0], acc[1]);
+            }
     }
 }
 
