@@ -230,8 +230,8 @@ def run_ours(args):
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}; launch with torch.distributed.run --nproc-per-node {args.gpus}")
     torch.cuda.set_device(local_rank)
     qc.init(local_rank)
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
+    # NCCL writes its version banner / debug lines to stdout by default; rank 0's stdout carries exactly one JSON line
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     if args.tile_bits is not None:

@@ -16,7 +16,9 @@ template <typename R, int TB> static int launch_pass(qcb_state *s, const PassPar
 {
     using V = typename Vec2<R>::type;
     constexpr int NT = 1 << (TB - kRegBits);
-    constexpr int MINB = (512 / NT) > 0 ? (512 / NT) : 1;
+    // resident threads per SM the register budget is sized for: 512 (ComplexF64, 128 registers) / 1024 (ComplexF32, 64)
+    constexpr int RES = sizeof(R) == 8 ? 512 : 1024;
+    constexpr int MINB = (RES / NT) > 0 ? ((RES / NT) > 32 ? 32 : (RES / NT)) : 1;
     auto kern = tile_pass_kernel<R, TB, MINB>;
     const size_t smem = sizeof(V) << TB;
     static bool attr_set = false;

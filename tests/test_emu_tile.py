@@ -217,3 +217,39 @@ def test_emu_tiled_measure(emu, oracle, n, tb, c):
         assert npass == 1 + max(0, -(-(n - tb) // (tb - c)))
     E32, _ = emu.measure(psi.astype(np.complex64), 0, (1.0, 0.1, 0.5), tb, c)
     assert abs(E32 - oracle.measure_tfim(psi, 1.0, 0.1, 0.5).real) < 1e-5 * n
+
+
+# ---- scheduler / tile-shape corner cases ------------------------------------------------------------------
+@pytest.mark.parametrize("n,tb,c,maxg", [(9, 13, 3, 0), (10, 10, 0, 0), (11, 9, 5, 0), (12, 12, 3, 1), (12, 9, 3, 2), (13, 11, 4, 5), (10, 9, 3, 3)])
+def test_emu_tile_shape_corner_cases(emu, oracle, n, tb, c, maxg):
+    """tile larger than the state (clamped), no coalescing bits, more low bits than usual, and fusion caps of 1-5 gates."""
+    rng = np.random.default_rng(n * 17 + tb * 3 + c + maxg)
+    G = 45
+    q0 = rng.integers(0, n - 1, size=G)
+    mats = []
+    for _ in range(G):
+        u = rng.standard_normal((4, 4)) + 1j * rng.standard_normal((4, 4))
+        mats.append(u / np.linalg.det(u) ** 0.25)
+    psi0 = rand_state(rng, n)
+    ref = psi0
+    for q, M in zip(q0, mats):
+        ref = oracle.apply_2q(ref, M, int(q) + 1)
+    out, (npass, nst) = emu.apply_gates(psi0, q0, mats, tb, c, max_gates=maxg)
+    assert rel(out, ref) < 1e-12
+    if maxg:
+        assert npass >= -(-G // maxg)
+
+
+def test_emu_repeated_gate_on_same_pair(emu, oracle):
+    """many consecutive gates on one qubit pair (no brickwork structure at all) still schedule and stay exact."""
+    rng = np.random.default_rng(5)
+    n, G = 11, 30
+    q0 = np.full(G, 4)
+    mats = [oracle.build_general_unitary_gate(rng.uniform(0, 2 * np.pi, 15)) for _ in range(G)]
+    psi0 = rand_state(rng, n)
+    ref = psi0
+    for M in mats:
+        ref = oracle.apply_2q(ref, M, 5)
+    out, (npass, nst) = emu.apply_gates(psi0, q0, mats, 9, 3)
+    assert rel(out, ref) < 1e-12
+    assert npass <= 4  # up to 12 stages x 1-2 gates per pass
