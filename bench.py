@@ -230,8 +230,11 @@ def run_ours(args):
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}; launch with torch.distributed.run --nproc-per-node {args.gpus}")
     torch.cuda.set_device(local_rank)
     qc.init(local_rank)
-    # NCCL writes its version banner / debug lines to stdout by default; rank 0's stdout carries exactly one JSON line
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    # Libraries (NCCL's version banner, torch warnings) may write to stdout; rank 0's stdout must carry exactly one JSON
+    # line, so file descriptor 1 is pointed at stderr for the duration of the run and the line goes to the saved fd.
+    sys.stdout.flush()
+    _json_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     if args.tile_bits is not None:
@@ -255,6 +258,8 @@ def run_ours(args):
         from qcb200 import dist as qdist
 
         qdist.init_from_torch()
+        if os.environ.get("QCB_FUSE_SWAPS") == "0":
+            qc.set_option("fuse_swaps", 0)
         state = qdist.ShardedState(n, npdt)
         step = lambda: state.apply_circuit(circuit)  # noqa: E731
         nloc = state.local_qubits
@@ -447,7 +452,9 @@ def run_ours(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f64" if args.dtype == "c128" else "f32", "data": "synthetic",
             "config": {"workload": f"{n}-qubit brickwork circuit, {layers} half-layers ({G} gates), {cname}, psi0=|0...0>, angles U[0,2pi)",
                        "state_bytes_per_gpu": int(amp_bytes * 2 ** nloc), "l2_policy": "state (>= 16 GiB) is far larger than the 126 MB L2",
-                       "sharding": "none" if world == 1 else f"top {n - nloc} qubits over {world} ranks, qubit swaps via NCCL all-to-all",
+                       "sharding": "none" if world == 1 else (f"top {n - nloc} qubits over {world} ranks; qubit swaps " + (
+                           "fused into gate passes as NVLink peer loads (CUDA IPC)" if getattr(state, "peers_mapped", False) else "via NCCL all-to-all")),
+                       "swaps_per_circuit": None if world == 1 else qc.get_stat("swaps"),
                        "gate_apps_per_sec_raw": gate_apps, "tile_bits": int(qc_opt("tile_bits", 11)), "low_bits": int(qc_opt("low_bits", 3))},
             "gpu_launches": int(launches), "clocks": clocks,
         }
@@ -457,8 +464,10 @@ def run_ours(args):
             line["cpu_baseline"] = cpu
         if e2e:
             line["e2e"] = e2e
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(_json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
+        state.close()
         dist.barrier()
         dist.destroy_process_group()
 

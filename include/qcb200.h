@@ -149,6 +149,13 @@ int qcb_dist_finalize(void);
 /* A sharded state holds 2^(nqubits - log2 nranks) amplitudes per rank. */
 int qcb_state_create_sharded(int nqubits, int dtype, qcb_state **out);
 int qcb_state_local_qubits(const qcb_state *s, int *out);
+/* Optional: let the ranks read each other's shards directly (CUDA IPC over NVLink).  Every rank exports 128 bytes, the
+ * host gathers them in rank order and every rank imports the whole table.  With peers mapped, a qubit swap is no longer
+ * a separate all-to-all: it is fused into the next gate pass, whose tile loads come straight from the peers' memory.
+ * Option "fuse_swaps" (default 1) switches the fusion off without unmapping. */
+int qcb_state_ipc_export(const qcb_state *s, void *out_128_bytes);
+int qcb_state_ipc_import(qcb_state *s, const void *all_handles);
+int qcb_state_ipc_close(qcb_state *s); /* unmap the peers' buffers; then synchronise the ranks before qcb_state_destroy */
 /* Upload / download of this rank's canonical shard (amplitudes [rank * 2^nloc, (rank+1) * 2^nloc)). */
 int qcb_state_upload_shard(qcb_state *s, const void *host_shard);
 int qcb_state_download_shard(qcb_state *s, void *host_shard);

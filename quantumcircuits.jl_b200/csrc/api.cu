@@ -400,6 +400,8 @@ int qcb_set_option(const char *key, long value)
     } else if (k == "adjoint_tile_bits") {
         if (value != 0 && (value < kMinTB || value > 12)) return set_error(QCB_EINVAL, "adjoint_tile_bits must be 0 (auto) or in [%d, 12]", kMinTB);
         c.adjoint_tile_bits = value;
+    } else if (k == "fuse_swaps") {
+        c.fuse_swaps = value ? 1 : 0;
     } else if (k == "force_simple") {
         c.force_simple = value ? 1 : 0;
     } else
@@ -418,6 +420,7 @@ int qcb_get_stat(const char *key, double *out)
     else if (k == "gates") *out = c.st_gates;
     else if (k == "launches_total") *out = c.st_launches_total;
     else if (k == "swaps") *out = c.st_swaps;
+    else if (k == "fused_swaps") *out = c.st_fused_swaps;
     else if (k == "sm_count") *out = c.sm_count;
     else return set_error(QCB_EINVAL, "unknown stat '%s'", k.c_str());
     return QCB_OK;
@@ -473,6 +476,7 @@ int qcb_state_create_sharded(int nqubits, int dtype, qcb_state **out) { return n
 int qcb_state_destroy(qcb_state *s)
 {
     if (!s) return QCB_OK;
+    if (!s->peer_d.empty()) qcb_state_ipc_close(s);
     if (s->owned && s->d) {
         if (ctx().inited) cudaStreamSynchronize(ctx().stream);
         cudaFree(s->d);

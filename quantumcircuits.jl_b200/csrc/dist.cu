@@ -75,16 +75,72 @@ static int swap_top_device(qcb_state *s)
     return QCB_OK;
 }
 
+// stream-ordered barrier across the ranks: a 1-int all-reduce on the work stream
+static int stream_barrier()
+{
+    Ctx &c = ctx();
+    if (!c.d_barrier) {
+        QCB_CUDA(cudaMalloc(&c.d_barrier, sizeof(int)));
+        QCB_CUDA(cudaMemsetAsync(c.d_barrier, 0, sizeof(int), c.stream));
+    }
+    QCB_NCCL(ncclAllReduce(c.d_barrier, c.d_barrier, 1, ncclInt, ncclSum, (ncclComm_t)c.nccl_comm, c.stream));
+    return QCB_OK;
+}
+
 struct GpuShardExec : ShardExecutor {
     qcb_state *s;
+    bool pending = false; // a swap_top whose data movement rides on the loads of the next pass
     explicit GpuShardExec(qcb_state *st) : s(st) {}
+    bool can_fuse() const { return ctx().fuse_swaps && s->alt && (int)s->peer_d.size() == ctx().nranks && (int)s->peer_alt.size() == ctx().nranks; }
     int run_pass(const PassPlan &pl, const std::vector<GateOp> &gates, const double *mats, bool adjoint) override
     {
-        const int rc = launch_plan(s, pl, gates, mats, adjoint);
-        if (rc == QCB_OK) { ctx().st_passes += 1; ctx().st_stages += (double)pl.stages.size(); }
+        Ctx &c = ctx();
+        int rc;
+        if (pending) {
+            // fused qubit swap: load this pass's tiles straight from the peers' shards (NVLink P2P), write the local
+            // second buffer.  Barrier before: every rank has finished writing its shard; barrier after: nobody still reads
+            // the buffer that becomes the next destination.
+            PeerSrc src;
+            int g = 0;
+            while ((1 << g) < c.nranks) g++;
+            src.shift = s->nloc - g;
+            const size_t ab = amp_bytes(s->dtype);
+            for (int r = 0; r < 8; r++)
+                src.base[r] = r < c.nranks ? (const void *)((const char *)s->peer_d[r] + (((size_t)c.rank << src.shift) * ab)) : nullptr;
+            QCB_TRY(stream_barrier());
+            rc = launch_plan_peer(s, src, s->alt, pl, gates, mats, adjoint);
+            if (rc != QCB_OK) return rc;
+            QCB_TRY(stream_barrier());
+            std::swap(s->d, s->alt);
+            s->peer_d.swap(s->peer_alt);
+            pending = false;
+            c.st_fused_swaps += 1;
+            count_launch(2);
+        } else {
+            rc = launch_plan(s, pl, gates, mats, adjoint);
+            if (rc != QCB_OK) return rc;
+        }
+        c.st_passes += 1;
+        c.st_stages += (double)pl.stages.size();
+        return QCB_OK;
+    }
+    int swap_top() override
+    {
+        if (can_fuse()) { pending = true; ctx().st_swaps += 1; return QCB_OK; }
+        const int rc = swap_top_device(s);
+        if (rc == QCB_OK && s->alt && !s->peer_d.empty()) s->peer_d.swap(s->peer_alt);
         return rc;
     }
-    int swap_top() override { return swap_top_device(s); }
+    int flush() override
+    {
+        if (!pending) return QCB_OK;
+        pending = false;
+        ctx().st_swaps -= 1; // swap_top_device counts it again
+        const int rc = swap_top_device(s);
+        // the NCCL path exchanges d <-> alt as well when alt exists: keep the peer views in step
+        if (rc == QCB_OK && s->alt && !s->peer_d.empty()) s->peer_d.swap(s->peer_alt);
+        return rc;
+    }
 };
 
 static ShardLayout layout_of(const qcb_state *s)
@@ -157,6 +213,71 @@ int qcb_dist_init(int rank, int nranks, const void *unique_id_128_bytes)
     c.nccl_comm = comm;
     c.rank = rank;
     c.nranks = nranks;
+    return QCB_OK;
+}
+
+/* CUDA IPC handles of this rank's two state buffers (2 x 64 bytes; the second is all zero when the state has no second
+ * buffer).  The host gathers the handles of all ranks (any channel) and passes them to qcb_state_ipc_import, after which
+ * qubit swaps are fused into the following gate pass as peer-memory loads over NVLink. */
+int qcb_state_ipc_export(const qcb_state *s, void *out_128_bytes)
+{
+    QCB_REQUIRE_INIT();
+    if (!s || !s->d || !out_128_bytes) return set_error(QCB_EINVAL, "null pointer");
+    if (!s->sharded || !s->owned) return set_error(QCB_EINVAL, "only library-owned sharded states can be exported");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    memset(out_128_bytes, 0, 128);
+    cudaIpcMemHandle_t h;
+    QCB_CUDA(cudaIpcGetMemHandle(&h, s->d));
+    memcpy(out_128_bytes, &h, 64);
+    if (s->alt) {
+        QCB_CUDA(cudaIpcGetMemHandle(&h, s->alt));
+        memcpy((char *)out_128_bytes + 64, &h, 64);
+    }
+    return QCB_OK;
+}
+
+int qcb_state_ipc_import(qcb_state *s, const void *all_handles /* nranks x 128 bytes, rank-major */)
+{
+    QCB_REQUIRE_INIT();
+    Ctx &c = ctx();
+    if (!s || !s->d || !all_handles) return set_error(QCB_EINVAL, "null pointer");
+    if (!s->sharded || c.nranks > 8) return set_error(QCB_EINVAL, "peer mapping needs a sharded state and at most 8 ranks");
+    s->peer_d.assign(c.nranks, nullptr);
+    s->peer_alt.assign(c.nranks, nullptr);
+    const char zero[64] = {0};
+    for (int r = 0; r < c.nranks; r++) {
+        const char *h = (const char *)all_handles + 128 * (size_t)r;
+        if (r == c.rank) { s->peer_d[r] = s->d; s->peer_alt[r] = s->alt; continue; }
+        if (!memcmp(h + 64, zero, 64) || !s->alt) { s->peer_d.clear(); s->peer_alt.clear(); return QCB_OK; } // some rank has no second buffer: stay on NCCL
+        cudaIpcMemHandle_t hd, ha;
+        memcpy(&hd, h, 64);
+        memcpy(&ha, h + 64, 64);
+        cudaError_t e1 = cudaIpcOpenMemHandle(&s->peer_d[r], hd, cudaIpcMemLazyEnablePeerAccess);
+        cudaError_t e2 = e1 == cudaSuccess ? cudaIpcOpenMemHandle(&s->peer_alt[r], ha, cudaIpcMemLazyEnablePeerAccess) : e1;
+        if (e1 != cudaSuccess || e2 != cudaSuccess) {
+            cudaGetLastError();
+            s->peer_d.clear();
+            s->peer_alt.clear();
+            return set_error(QCB_ECUDA, "cudaIpcOpenMemHandle(rank %d): %s", r, cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+        }
+    }
+    return QCB_OK;
+}
+
+/* Unmaps the peers' buffers again (call on every rank, then synchronise the ranks, before destroying the state). */
+int qcb_state_ipc_close(qcb_state *s)
+{
+    if (!s) return QCB_OK;
+    Ctx &c = ctx();
+    if (c.inited) cudaStreamSynchronize(c.stream);
+    for (size_t r = 0; r < s->peer_d.size(); r++) {
+        if ((int)r == c.rank) continue;
+        if (s->peer_d[r]) cudaIpcCloseMemHandle(s->peer_d[r]);
+        if (r < s->peer_alt.size() && s->peer_alt[r]) cudaIpcCloseMemHandle(s->peer_alt[r]);
+    }
+    s->peer_d.clear();
+    s->peer_alt.clear();
+    cudaGetLastError();
     return QCB_OK;
 }
 

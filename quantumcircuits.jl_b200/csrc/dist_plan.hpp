@@ -35,7 +35,10 @@ struct ShardLayout {
 struct ShardExecutor {
     virtual ~ShardExecutor() {}
     virtual int run_pass(const PassPlan &plan, const std::vector<GateOp> &gates, const double *mats, bool adjoint) = 0;
-    virtual int swap_top() = 0; // exchange rank bit k with local bit nloc-g+k, k = 0..g-1
+    // exchange rank bit k with local bit nloc-g+k, k = 0..g-1.  An executor may defer the data movement and fuse it
+    // into the loads of the next run_pass (peer-memory reads); flush() forces a deferred exchange to happen.
+    virtual int swap_top() = 0;
+    virtual int flush() { return 0; }
 };
 
 // gates executable (dependency-closed, program order) while the qubits flagged in `blocked` are unavailable
@@ -197,7 +200,7 @@ inline int run_gates_sharded(ShardExecutor &ex, ShardLayout &L, const std::vecto
         if (stats) stats[2] += 1;
         pending.swap(rest);
     }
-    return 0;
+    return ex.flush();
 }
 
 // Bring the state back to the canonical layout (phys[q] = q): the reference's index convention.
@@ -230,7 +233,7 @@ inline int canonicalize(ShardExecutor &ex, ShardLayout &L, const SchedOptions &o
         if (rc) return rc;
     }
     L.phys = ident;
-    return 0;
+    return ex.flush();
 }
 
 } // namespace qcb

@@ -33,6 +33,37 @@ template <typename R, int TB> static int launch_pass(qcb_state *s, const PassPar
     return QCB_OK;
 }
 
+template <typename R, int TB> static int launch_pass_peer(qcb_state *s, const PeerSrc &src, void *dst, const PassParams<R> &P)
+{
+    using V = typename Vec2<R>::type;
+    constexpr int NT = 1 << (TB - kRegBits);
+    constexpr int RES = sizeof(R) == 8 ? 512 : 1024;
+    constexpr int MINB = (RES / NT) > 0 ? ((RES / NT) > 32 ? 32 : (RES / NT)) : 1;
+    auto kern = tile_pass_peer_kernel<R, TB, MINB>;
+    const size_t smem = sizeof(V) << TB;
+    static bool attr_set = false;
+    if (!attr_set) {
+        QCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    kern<<<(unsigned)(1ull << (s->nloc - TB)), NT, smem, ctx().stream>>>(src, (V *)dst, P);
+    QCB_CUDA(cudaGetLastError());
+    count_launch();
+    return QCB_OK;
+}
+
+template <typename R> static int launch_pass_peer_tb(qcb_state *s, int TB, const PeerSrc &src, void *dst, const PassParams<R> &P)
+{
+    switch (TB) {
+    case 9: return launch_pass_peer<R, 9>(s, src, dst, P);
+    case 10: return launch_pass_peer<R, 10>(s, src, dst, P);
+    case 11: return launch_pass_peer<R, 11>(s, src, dst, P);
+    case 12: return launch_pass_peer<R, 12>(s, src, dst, P);
+    case 13: return launch_pass_peer<R, 13>(s, src, dst, P);
+    default: return set_error(QCB_EINVAL, "unsupported tile size %d", TB);
+    }
+}
+
 template <typename R> static int launch_pass_tb(qcb_state *s, int TB, const PassParams<R> &P)
 {
     switch (TB) {
@@ -91,6 +122,22 @@ int launch_plan(qcb_state *s, const PassPlan &pl, const std::vector<GateOp> &gat
         static thread_local PassParams<float> P;
         fill_params<float>(pl, s->nloc, gates, mats, adjoint, P);
         return launch_pass_tb<float>(s, pl.TB, P);
+    } catch (const std::exception &e) {
+        return set_error(QCB_EINVAL, "pass parameters: %s", e.what());
+    }
+}
+
+int launch_plan_peer(qcb_state *s, const PeerSrc &src, void *dst, const PassPlan &pl, const std::vector<GateOp> &gates, const double *mats, bool adjoint)
+{
+    try {
+        if (s->dtype == QCB_C128) {
+            static thread_local PassParams<double> P;
+            fill_params<double>(pl, s->nloc, gates, mats, adjoint, P);
+            return launch_pass_peer_tb<double>(s, pl.TB, src, dst, P);
+        }
+        static thread_local PassParams<float> P;
+        fill_params<float>(pl, s->nloc, gates, mats, adjoint, P);
+        return launch_pass_peer_tb<float>(s, pl.TB, src, dst, P);
     } catch (const std::exception &e) {
         return set_error(QCB_EINVAL, "pass parameters: %s", e.what());
     }
@@ -252,7 +299,7 @@ int run_adjoint_fused(qcb_state *psi, qcb_state *lam, const std::vector<GateOp> 
 int run_gate_list(qcb_state *s, const std::vector<GateOp> &gates, const double *mats, bool adjoint)
 {
     Ctx &c = ctx();
-    c.st_passes = c.st_stages = c.st_launches = c.st_swaps = 0;
+    c.st_passes = c.st_stages = c.st_launches = c.st_swaps = c.st_fused_swaps = 0;
     c.st_gates = (double)gates.size();
     if (gates.empty()) return QCB_OK;
     for (const GateOp &g : gates)

@@ -22,6 +22,8 @@ struct qcb_state {
     size_t bytes = 0;
     std::vector<int> phys; // logical qubit -> physical index bit (>= nloc: rank bit nloc + k)
     void *alt = nullptr;   // sharded states: second buffer for out-of-place qubit swaps (nullptr: chunked in-place swaps)
+    // peer-mapped views (CUDA IPC) of every rank's `d` and `alt`, indexed by rank; empty = swaps go through NCCL only
+    std::vector<void *> peer_d, peer_alt;
 };
 
 namespace qcb {
@@ -37,7 +39,9 @@ struct Ctx {
     // options
     long tile_bits = 11, low_bits = 3, max_gates_per_pass = 1 << 30, force_simple = 0, adjoint_tile_bits = 0;
     // stats
-    double st_passes = 0, st_stages = 0, st_launches = 0, st_gates = 0, st_launches_total = 0, st_swaps = 0;
+    double st_passes = 0, st_stages = 0, st_launches = 0, st_gates = 0, st_launches_total = 0, st_swaps = 0, st_fused_swaps = 0;
+    long fuse_swaps = 1;
+    int *d_barrier = nullptr; // 1 int for stream-ordered inter-rank barriers (NCCL all-reduce)
     // scratch
     double *d_partial = nullptr; // reduction partials
     size_t partial_cap = 0;      // in doubles
@@ -89,6 +93,7 @@ inline void count_launch(int k = 1)
 int run_gate_list(qcb_state *s, const std::vector<GateOp> &gates, const double *mats, bool adjoint);
 int run_adjoint_fused(qcb_state *psi, qcb_state *lam, const std::vector<GateOp> &rev, const double *mats, double *d_env);
 int launch_plan(qcb_state *s, const PassPlan &plan, const std::vector<GateOp> &gates, const double *mats, bool adjoint);
+int launch_plan_peer(qcb_state *s, const PeerSrc &src, void *dst, const PassPlan &plan, const std::vector<GateOp> &gates, const double *mats, bool adjoint);
 SchedOptions current_sched_options(const qcb_state *s);
 
 // distributed (dist.cu)

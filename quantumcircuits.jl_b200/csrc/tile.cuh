@@ -237,6 +237,41 @@ QCB_HD void tile_load(const typename Vec2<R>::type *__restrict__ src, const Pass
     for (int i = 0; i < kRegAmps; i++) sm[e ^ P.ld_eoff[i]] = tmp[i];
 }
 
+// Source of a pass that is fused with a global<->local qubit swap (sharded states, dist.cu): after swap_top the element
+// with new local index x = (r << shift) | off is the element (me << shift) | off of rank r's *old* shard, so the pass
+// loads straight from the peers' memory (NVLink P2P, IPC-mapped pointers) instead of waiting for an all-to-all to land:
+// base[r] = rank r's old buffer + (me << shift).
+struct PeerSrc {
+    const void *base[8];
+    int shift; // nloc - log2(number of ranks)
+};
+
+template <typename R, int TB>
+QCB_HD void tile_load_peer(const PeerSrc &S, const PassParams<R> &P, typename Vec2<R>::type *sm, uint32_t tid, unsigned long long bid)
+{
+    using V = typename Vec2<R>::type;
+    constexpr int SWB = Vec2<R>::SWB;
+    constexpr int TBITS = TB - kRegBits;
+    unsigned long long g = cta_base(P, bid);
+    uint32_t e = 0;
+#pragma unroll
+    for (int k = 0; k < TBITS; k++) {
+        const uint32_t bit = (tid >> k) & 1u;
+        g |= (unsigned long long)bit << P.ld_phys[k];
+        e |= bit << P.ld_lpos[k];
+    }
+    e = swz<SWB>(e);
+    const unsigned long long low = (1ull << S.shift) - 1ull;
+    V tmp[kRegAmps];
+#pragma unroll
+    for (int i = 0; i < kRegAmps; i++) {
+        const unsigned long long x = g | P.ld_goff[i];
+        tmp[i] = static_cast<const V *>(S.base[x >> S.shift])[x & low];
+    }
+#pragma unroll
+    for (int i = 0; i < kRegAmps; i++) sm[e ^ P.ld_eoff[i]] = tmp[i];
+}
+
 template <typename R, int TB>
 QCB_HD void tile_store(typename Vec2<R>::type *__restrict__ dst, const PassParams<R> &P,
                        const typename Vec2<R>::type *sm, uint32_t tid, unsigned long long bid)
@@ -291,6 +326,26 @@ tile_pass_kernel(const typename Vec2<R>::type *src, typename Vec2<R>::type *dst,
     const uint32_t tid = threadIdx.x;
     const unsigned long long bid = blockIdx.x;
     tile_load<R, TB>(src, P, sm, tid, bid);
+    __syncthreads();
+#pragma unroll 1
+    for (int s = 0; s < P.nstages; s++) {
+        tile_stage<R, TB>(P, s, sm, tid);
+        __syncthreads();
+    }
+    tile_store<R, TB>(dst, P, sm, tid, bid);
+}
+
+// the same pass with its loads taken from the peers' shards (fused qubit swap), always out of place
+template <typename R, int TB, int MINB>
+__global__ void __launch_bounds__(1 << (TB - kRegBits), MINB)
+tile_pass_peer_kernel(const __grid_constant__ PeerSrc S, typename Vec2<R>::type *dst, const __grid_constant__ PassParams<R> P)
+{
+    using V = typename Vec2<R>::type;
+    extern __shared__ __align__(16) unsigned char qcb_smem_raw[];
+    V *sm = reinterpret_cast<V *>(qcb_smem_raw);
+    const uint32_t tid = threadIdx.x;
+    const unsigned long long bid = blockIdx.x;
+    tile_load_peer<R, TB>(S, P, sm, tid, bid);
     __syncthreads();
 #pragma unroll 1
     for (int s = 0; s < P.nstages; s++) {

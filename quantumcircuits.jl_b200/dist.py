@@ -56,7 +56,39 @@ class ShardedState:
         nloc = C.c_int(0)
         _lib.check(_lib.lib().qcb_state_local_qubits(self._handle, C.byref(nloc)))
         self.local_qubits = nloc.value
+        self.peers_mapped = self._map_peers()
         self.set_zero_state()
+
+    def _map_peers(self):
+        """Exchange CUDA IPC handles so that qubit swaps can be fused into gate passes as NVLink peer loads."""
+        import torch.distributed as dist
+
+        mine = np.zeros(128, dtype=np.uint8)
+        rc = _lib.lib().qcb_state_ipc_export(self._handle, mine.ctypes.data_as(C.c_void_p))
+        table = [None] * dist.get_world_size()
+        dist.all_gather_object(table, mine.tobytes() if rc == 0 else bytes(128))
+        if rc != 0 or any(t[64:] == bytes(64) for t in table):
+            return False  # some rank has no second buffer (or export failed): swaps stay on NCCL
+        blob = np.frombuffer(b"".join(table), dtype=np.uint8).copy()
+        ok = _lib.lib().qcb_state_ipc_import(self._handle, blob.ctypes.data_as(C.c_void_p)) == 0
+        flags = [None] * dist.get_world_size()
+        dist.all_gather_object(flags, ok)
+        if not all(flags):
+            _lib.lib().qcb_state_ipc_close(self._handle)
+            return False
+        return True
+
+    def close(self):
+        """Collective: unmap peers on every rank, synchronise, free."""
+        import torch
+        import torch.distributed as dist
+
+        if self._handle:
+            torch.cuda.synchronize()
+            _lib.lib().qcb_state_ipc_close(self._handle)
+            dist.barrier()
+            _lib.lib().qcb_state_destroy(self._handle)
+            self._handle = C.c_void_p()
 
     def set_zero_state(self):
         _lib.check(_lib.lib().qcb_state_set_zero_state(self._handle))

@@ -35,7 +35,7 @@ def main():
         per = 1 << st.local_qubits
         st.upload_shard(psi0[rank * per:(rank + 1) * per])
         st.apply_circuit(c)
-        swaps = qc.get_stat("swaps")
+        swaps, fused = qc.get_stat("swaps"), qc.get_stat("fused_swaps")
         n2 = st.norm2()
         shard = st.download_shard()
         if rank == 0:
@@ -50,10 +50,23 @@ def main():
         relerr = float(torch.sqrt(err2[0] / err2[1]).item())
         tol = 1e-12 if dt == np.complex128 else 1e-5
         good = relerr < tol and abs(n2 - 1) < (1e-12 if dt == np.complex128 else 1e-5) and swaps >= 1
+        good = good and (not st.peers_mapped or fused >= 1)  # with peers mapped the exchanges ride on gate passes
         ok = ok and good
         if rank == 0:
             print(f"{'PASS' if good else 'FAIL'} sharded n={n} layers={layers} {np.dtype(dt).name} P={world} rel={relerr:.2e} "
-                  f"norm2-1={n2 - 1:.1e} swaps={int(swaps)}", flush=True)
+                  f"norm2-1={n2 - 1:.1e} swaps={int(swaps)} fused={int(fused)} peers={st.peers_mapped}", flush=True)
+        # the NCCL-only path must give the same state
+        qc.set_option("fuse_swaps", 0)
+        st.upload_shard(psi0[rank * per:(rank + 1) * per])
+        st.apply_circuit(c)
+        shard2 = st.download_shard()
+        qc.set_option("fuse_swaps", 1)
+        d2 = torch.tensor([np.linalg.norm(shard2 - shard) ** 2], dtype=torch.float64, device="cuda")
+        dist.all_reduce(d2)
+        good = float(torch.sqrt(d2[0]).item()) < (1e-13 if dt == np.complex128 else 1e-5)
+        ok = ok and good
+        if rank == 0:
+            print(f"{'PASS' if good else 'FAIL'} fused == nccl-only n={n} diff={float(torch.sqrt(d2[0]).item()):.2e}", flush=True)
         # round trip: circuit then inverse circuit on the sharded state
         st.apply_circuit(c, adjoint=True)
         back = st.download_shard()
@@ -64,7 +77,7 @@ def main():
         ok = ok and good
         if rank == 0:
             print(f"{'PASS' if good else 'FAIL'} round-trip n={n} err={rt:.2e}", flush=True)
-        del st
+        st.close()
     flag = torch.tensor([0 if ok else 1], device="cuda")
     dist.all_reduce(flag)
     dist.barrier()

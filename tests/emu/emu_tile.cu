@@ -93,25 +93,59 @@ template <typename R> struct EmuShards : ShardExecutor {
     using V = typename Vec2<R>::type;
     int nloc, g;
     std::vector<std::vector<V>> shard; // [rank][2^nloc]
-    int npass = 0, nswap = 0;
+    int npass = 0, nswap = 0, nfused = 0;
+    bool fuse = false;    // defer swap_top and fuse it into the next pass (peer reads), like the GPU executor with IPC peers
+    bool pending = false;
+    template <int TB> void run_pass_impl(V *psi, const PassParams<R> &P) { ::run_pass<R, TB>(psi, nloc, P); }
+    template <int TB> void run_pass_peer_impl(const PeerSrc &S, V *dst, const PassParams<R> &P)
+    {
+        const uint32_t NT = 1u << (TB - kRegBits);
+        std::vector<V> sm(1u << TB);
+        for (unsigned long long b = 0; b < (1ull << (nloc - TB)); b++) {
+            for (uint32_t t = 0; t < NT; t++) tile_load_peer<R, TB>(S, P, sm.data(), t, b);
+            for (int s = 0; s < P.nstages; s++)
+                for (uint32_t t = 0; t < NT; t++) tile_stage<R, TB>(P, s, sm.data(), t);
+            for (uint32_t t = 0; t < NT; t++) tile_store<R, TB>(dst, P, sm.data(), t, b);
+        }
+    }
     int run_pass(const PassPlan &pl, const std::vector<GateOp> &gates, const double *mats, bool adjoint) override
     {
         PassParams<R> *P = new PassParams<R>;
         fill_params<R>(pl, nloc, gates, mats, adjoint, *P);
-        for (auto &sh : shard) {
-            switch (pl.TB) {
-#define CASE(T) case T: run_pass_impl<T>(sh.data(), *P); break;
-            CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(11) CASE(12) CASE(13)
+        int rc = 0;
+        if (pending) {
+            // every rank reads its new-layout tiles from the peers' old shards and writes a fresh local buffer
+            const int NR = (int)shard.size();
+            std::vector<std::vector<V>> out(NR, std::vector<V>((size_t)1 << nloc));
+            for (int me = 0; me < NR && !rc; me++) {
+                PeerSrc S;
+                S.shift = nloc - g;
+                for (int r = 0; r < 8; r++) S.base[r] = r < NR ? (const void *)(shard[r].data() + ((size_t)me << S.shift)) : nullptr;
+                switch (pl.TB) {
+#define CASE(T) case T: run_pass_peer_impl<T>(S, out[me].data(), *P); break;
+                CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(11) CASE(12) CASE(13)
 #undef CASE
-            default: delete P; return 3;
+                default: rc = 3;
+                }
+            }
+            shard.swap(out);
+            pending = false;
+            nfused++;
+        } else {
+            for (auto &sh : shard) {
+                switch (pl.TB) {
+#define CASE(T) case T: run_pass_impl<T>(sh.data(), *P); break;
+                CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(11) CASE(12) CASE(13)
+#undef CASE
+                default: rc = 3;
+                }
             }
         }
         delete P;
         npass++;
-        return 0;
+        return rc;
     }
-    template <int TB> void run_pass_impl(V *psi, const PassParams<R> &P) { ::run_pass<R, TB>(psi, nloc, P); }
-    int swap_top() override
+    int exchange()
     {
         const int P = (int)shard.size();
         const size_t blk = (size_t)1 << (nloc - g);
@@ -120,8 +154,19 @@ template <typename R> struct EmuShards : ShardExecutor {
             for (int j = 0; j < P; j++) // block j of rank r <-> block r of rank j
                 std::copy(shard[r].begin() + j * blk, shard[r].begin() + (j + 1) * blk, out[j].begin() + r * blk);
         shard.swap(out);
-        nswap++;
         return 0;
+    }
+    int swap_top() override
+    {
+        nswap++;
+        if (fuse) { pending = true; return 0; }
+        return exchange();
+    }
+    int flush() override
+    {
+        if (!pending) return 0;
+        pending = false;
+        return exchange();
     }
 };
 
@@ -133,6 +178,8 @@ extern "C" int emu_sharded_apply_gates(int n, int g, void *psi_, int ngates, con
     try {
         EmuShards<double> ex;
         ex.nloc = n - g; ex.g = g;
+        ex.fuse = (canonical_out & 2) != 0; // bit 1 of the flag: fuse the swaps into the following pass
+        canonical_out &= 1;
         const int P = 1 << g;
         const size_t per = (size_t)1 << ex.nloc;
         V *psi = (V *)psi_;
@@ -155,7 +202,7 @@ extern "C" int emu_sharded_apply_gates(int n, int g, void *psi_, int ngates, con
         }
         for (int r = 0; r < P; r++) std::copy(ex.shard[r].begin(), ex.shard[r].end(), psi + r * per);
         for (int i = 0; i < n; i++) phys_out[i] = L.phys[i];
-        if (stats) { stats[0] = (int)st[0]; stats[1] = (int)st[1]; stats[2] = ex.nswap; stats[3] = ex.npass; }
+        if (stats) { stats[0] = (int)st[0]; stats[1] = (int)st[1]; stats[2] = ex.nswap; stats[3] = ex.npass; stats[4] = ex.nfused; }
         return 0;
     } catch (const std::exception &e) {
         std::fprintf(stderr, "emu sharded: %s\n", e.what());

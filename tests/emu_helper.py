@@ -53,7 +53,7 @@ def plan_brickwork(nbits, nlayers, tile_bits, low_bits, max_gates=0):
     return dict(passes=int(stats[0]), stages=int(stats[1]), gates=int(stats[2]))
 
 
-def sharded_apply_gates(psi, g, q0, mats, tile_bits, low_bits, adjoint=False, canonical_out=True):
+def sharded_apply_gates(psi, g, q0, mats, tile_bits, low_bits, adjoint=False, canonical_out=True, fuse_swaps=False):
     """Simulated 2^g ranks.  psi: full canonical complex128 state.  Returns (state, phys, stats)."""
     psi = np.ascontiguousarray(psi, dtype=np.complex128).copy()
     n = int(psi.size).bit_length() - 1
@@ -63,11 +63,11 @@ def sharded_apply_gates(psi, g, q0, mats, tile_bits, low_bits, adjoint=False, ca
     phys = np.zeros(n, dtype=np.int32)
     rc = lib().emu_sharded_apply_gates(C.c_int(n), C.c_int(g), psi.ctypes.data_as(C.c_void_p), C.c_int(len(q0)),
                                        q0.ctypes.data_as(C.c_void_p), m.ctypes.data_as(C.c_void_p), C.c_int(tile_bits),
-                                       C.c_int(low_bits), C.c_int(1 if adjoint else 0), C.c_int(1 if canonical_out else 0),
+                                       C.c_int(low_bits), C.c_int(1 if adjoint else 0), C.c_int((1 if canonical_out else 0) | (2 if fuse_swaps else 0)),
                                        phys.ctypes.data_as(C.c_void_p), stats.ctypes.data_as(C.c_void_p))
     if rc:
         raise RuntimeError(f"emu_sharded_apply_gates rc={rc}")
-    return psi, phys, dict(gate_passes=int(stats[0]), stages=int(stats[1]), swaps=int(stats[2]), passes=int(stats[3]))
+    return psi, phys, dict(gate_passes=int(stats[0]), stages=int(stats[1]), swaps=int(stats[2]), passes=int(stats[3]), fused=int(stats[4]))
 
 
 def plan_sharded_brickwork(nbits, nlayers, g, tile_bits, low_bits):

@@ -253,3 +253,20 @@ def test_emu_repeated_gate_on_same_pair(emu, oracle):
     out, (npass, nst) = emu.apply_gates(psi0, q0, mats, 9, 3)
     assert rel(out, ref) < 1e-12
     assert npass <= 4  # up to 12 stages x 1-2 gates per pass
+
+
+@pytest.mark.parametrize("n,g,layers,tb,c", [(13, 1, 14, 9, 3), (14, 2, 20, 9, 3), (15, 3, 30, 9, 3), (16, 3, 25, 11, 3)])
+def test_emu_sharded_fused_swaps(emu, oracle, n, g, layers, tb, c):
+    """qubit swaps fused into the following pass: every rank loads its tiles from the peers' old shards (the address
+    algebra of tile_load_peer / PeerSrc) instead of performing the all-to-all first."""
+    rng = np.random.default_rng(n * 1000 + g * 100 + layers + 7)
+    G = onp.brickwork_num_gates(n, layers)
+    angles = rng.uniform(0, 2 * np.pi, (15, G))
+    q0 = np.array(onp.brickwork_gate_positions(n, layers)) - 1
+    mats = [oracle.build_general_unitary_gate(angles[:, i]) for i in range(G)]
+    psi0 = rand_state(rng, n)
+    ref = oracle.apply_brickwork(psi0, n, layers, angles)
+    out, phys, st = emu.sharded_apply_gates(psi0, g, q0, mats, tb, c, fuse_swaps=True)
+    assert list(phys) == list(range(n))
+    assert rel(out, ref) < 1e-13
+    assert st["fused"] >= 1 and st["fused"] == st["swaps"]  # every exchange rode on a pass
