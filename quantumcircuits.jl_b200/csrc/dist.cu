@@ -1,7 +1,9 @@
 // dist.cu -- multi-GPU sharding: one process per GPU, amplitudes sharded by the top log2(P) index bits,
-// gates on those qubits handled by global<->local qubit swaps = an all-to-all of contiguous blocks over
-// NCCL (NVLink 5 / NVSwitch).  No reference counterpart; the schedule and the layout
-// bookkeeping are in dist_plan.hpp and are replayed on the CPU by tests/emu with simulated ranks.
+// gates on those qubits handled by global<->local qubit swaps.  A swap is an all-to-all of contiguous blocks; it
+// runs either as grouped NCCL send/recv over NVLink 5 / NVSwitch (swap_top_device) or -- when the ranks have mapped
+// each other's shards through CUDA IPC -- fused into the next gate pass, whose tile loads then come straight from
+// peer memory (GpuShardExec::run_pass, tile_pass_peer_kernel).  No reference counterpart; the
+// schedule and the layout bookkeeping are in dist_plan.hpp and are replayed on the CPU by tests/emu with simulated ranks.
 #include <nccl.h>
 
 #include "dist_plan.hpp"
@@ -289,6 +291,7 @@ int qcb_dist_finalize(void)
         ncclCommDestroy((ncclComm_t)c.nccl_comm);
         c.nccl_comm = nullptr;
     }
+    if (c.d_barrier) { cudaFree(c.d_barrier); c.d_barrier = nullptr; }
     c.rank = 0;
     c.nranks = 1;
     return QCB_OK;

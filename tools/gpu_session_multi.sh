@@ -1,9 +1,12 @@
 #!/bin/bash
-# multi-GPU session: usage tools/gpu_session_multi.sh N
-N=${1:-2}
+# usage: tools/gpu_session_multi2.sh N NQ   -- dist tests for N ranks + bench at NQ qubits (fused swaps need the second buffer)
+N=${1:-2}; NQ=${2:-31}
 mkdir -p gpurun_out
-nvidia-smi -L > gpurun_out/nvsmi_multi_$N.txt 2>&1; free -g >> gpurun_out/nvsmi_multi_$N.txt; nproc >> gpurun_out/nvsmi_multi_$N.txt
-nvidia-smi topo -m >> gpurun_out/nvsmi_multi_$N.txt 2>&1
-echo "== dist tests"; QCB_DIST_NPROC=$N timeout 1500 python -m pytest tests/test_gpu_dist.py -x -q -m gpu > gpurun_out/pytest_dist_$N.log 2>&1; echo "rc=$?"; tail -30 gpurun_out/pytest_dist_$N.log
+echo "== dist tests"; QCB_DIST_NPROC=$N timeout 1500 python -m pytest tests/test_gpu_dist.py -x -q -m gpu > gpurun_out/pytest_dist_$N.log 2>&1; echo "rc=$?"; tail -30 gpurun_out/pytest_dist_$N.log | cut -c1-250
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29655"
-echo "== bench 34q"; timeout 1500 $TR bench.py --gpus $N --steps 2 --warmup 1 > gpurun_out/bench_multi_${N}_34q.json 2> gpurun_out/bench_multi_${N}_34q.err; echo "rc=$?"; cat gpurun_out/bench_multi_${N}_34q.json; grep -v "^W\|^\*\|OMP_NUM" gpurun_out/bench_multi_${N}_34q.err | tail -15
+for fuse in 1 0; do
+echo "== bench ${NQ}q fuse=$fuse"; QCB_FUSE_SWAPS=$fuse timeout 1500 $TR bench.py --gpus $N --nqubits $NQ --steps 2 --warmup 1 > gpurun_out/bench_multi_${N}_${NQ}q_fuse$fuse.json 2> gpurun_out/bench_multi_${N}_${NQ}q_fuse$fuse.err; echo "rc=$?"; python -c "
+import json
+L=open('gpurun_out/bench_multi_${N}_${NQ}q_fuse$fuse.json').read().strip().splitlines(); print(len(L),'stdout lines')
+d=json.loads(L[-1]); print(d['value'], d['ms_per_step'], d['config']['sharding'], d['config'].get('swaps_per_circuit'), d.get('e2e'))"; grep -v "^W\|^\*\|OMP_NUM" gpurun_out/bench_multi_${N}_${NQ}q_fuse$fuse.err | tail -5
+done
