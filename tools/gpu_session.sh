@@ -23,3 +23,6 @@ CMD2="python tools/bench_gradients.py C5"
 $CMD2 > gpurun_out/plain3.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:"measure_tile|adjoint_pass" -s 0 -c 5 -f -o gpurun_out/prof_grad $CMD2 > gpurun_out/ncu_grad.log 2>&1
 echo "ncu grad rc=$?"
 fi
+if [ "$2" == "big" ]; then
+echo "== 34q ComplexF32 on one GPU (128 GiB state)"; timeout 900 python bench.py --nqubits 34 --dtype c64 --steps 1 --warmup 1 --no-e2e --no-cpu-baseline > gpurun_out/bench_34q_c64_1gpu.json 2> gpurun_out/bench_34q_c64_1gpu.err; cut -c1-300 gpurun_out/bench_34q_c64_1gpu.json; tail -2 gpurun_out/bench_34q_c64_1gpu.err
+fi
