@@ -432,3 +432,21 @@ def test_polar_optimise_statevector(N, nl):
         for a, b in zip(lg, lr):
             m = a.reshape(4, 4, order="F")
             np.testing.assert_allclose(m @ m.conj().T, np.eye(4), atol=1e-12)
+
+
+def test_trim_releases_and_reallocates_work_buffers(oracle):
+    import torch
+
+    rng = np.random.default_rng(3)
+    n, layers = 22, 3
+    c = circuit(n, layers, rng, 0.1)
+    H = qc.TFIMHamiltonian(1.0, 0.1, 0.5)
+    psi0 = qc.B200State(qc.zero_state_tensor(n))
+    g1 = qc.gradients(H, psi0, c)
+    torch.cuda.synchronize()
+    free_before, _ = torch.cuda.mem_get_info()
+    qc.trim()
+    free_after, _ = torch.cuda.mem_get_info()
+    assert free_after >= free_before + 2 * (16 << n) - (1 << 20)  # the two gradient work states are gone
+    g2 = qc.gradients(H, psi0, c)  # and come back on demand
+    np.testing.assert_array_equal(g1, g2)
