@@ -118,7 +118,8 @@ int qcb_apply_brickwork_host(int dtype, int nbits, int nlayers, const double *an
                              void *psi_out_host);
 
 /* ---- expectation values: measure!(psi', H, psi)  src/hamiltonians/hamiltonians.jl:31-50 ---- */
-/* out_E = (re, im) of sum(psi') so the shim can reproduce the imaginary-energy warning (:43-45). */
+/* out_E = (re, im) of sum(psi') so the shim can reproduce the imaginary-energy warning (:43-45).
+ * Sharded states: collective call (every rank), every rank receives the full expectation value. */
 int qcb_measure_tfim(const qcb_state *s, double J, double h, double g, double *out_E2); /* tfim.jl:17-54 */
 int qcb_measure_east(const qcb_state *s, double c, double A, double B, double *out_E2); /* east_model.jl:30-52 */
 

@@ -89,27 +89,44 @@ template <typename R, int TB, int MINB, int KIND> static int launch_measure_pass
     return QCB_OK;
 }
 
-// tiled path: ceil((n - TB) / (TB - low_bits)) + 1 reads of the state, flips done in shared memory
-template <typename R> static int measure_tiled(const qcb_state *s, const HamEval &H, double *out2)
+// tiled path: ceil((n - TB) / (TB - low_bits)) + 1 reads of the state, flips done in shared memory.
+// Sharded states: canonical layout first; the local passes see the rank bits through c_hi; the flips of the qubits that
+// live in the rank bits need amplitudes of other ranks, so one qubit swap brings them to the top local bits for one more
+// pass; the partial sums are all-reduced over the ranks (2 doubles).
+template <typename R> static int measure_tiled(qcb_state *s, const HamEval &H, double *out2)
 {
     Ctx &c = ctx();
     constexpr int TB = 12; // 64 KiB (ComplexF64) / 32 KiB (ComplexF32) tiles, 256 threads
-    const std::vector<MeasParams<R>> passes = plan_measure<R>(s->n, TB, (int)c.low_bits, H);
+    const int g = s->n - s->nloc;
+    unsigned long long c_hi = 0;
+    if (s->sharded) {
+        QCB_TRY(dist_state_canonicalize(s));
+        c_hi = (unsigned long long)c.rank << s->nloc;
+    }
+    const std::vector<MeasParams<R>> passes = plan_measure<R>(s->nloc, TB, (int)c.low_bits, H, c_hi);
     const size_t ntiles = (size_t)1 << (s->nloc - TB);
-    QCB_TRY(ensure_partial(2 * ntiles * passes.size()));
+    const size_t npass = passes.size() + (g > 0 ? 1 : 0);
+    QCB_TRY(ensure_partial(2 * ntiles * npass));
     QCB_TRY(ensure_out(64));
-    for (size_t p = 0; p < passes.size(); p++)
-        QCB_TRY((H.kind == 0 ? launch_measure_pass<R, TB, 2, 0>(s, passes[p], (double2 *)c.d_partial + p * ntiles)
-                             : launch_measure_pass<R, TB, 2, 1>(s, passes[p], (double2 *)c.d_partial + p * ntiles)));
-    k_final_sum<<<2, 256, 0, c.stream>>>(c.d_partial, (int)(ntiles * passes.size()), 2, c.d_out);
+    auto launch = [&](const MeasParams<R> &P, size_t slot) -> int {
+        return H.kind == 0 ? launch_measure_pass<R, TB, 2, 0>(s, P, (double2 *)c.d_partial + slot * ntiles)
+                           : launch_measure_pass<R, TB, 2, 1>(s, P, (double2 *)c.d_partial + slot * ntiles);
+    };
+    for (size_t p = 0; p < passes.size(); p++) QCB_TRY(launch(passes[p], p));
+    if (g > 0) {
+        QCB_TRY(dist_swap_top_now(s));
+        QCB_TRY(launch(plan_measure_top<R>(s->nloc, g, TB, (int)c.low_bits, H, c_hi), passes.size()));
+    }
+    k_final_sum<<<2, 256, 0, c.stream>>>(c.d_partial, (int)(ntiles * npass), 2, c.d_out);
     QCB_CUDA(cudaGetLastError());
     count_launch();
+    if (g > 0) QCB_TRY(dist_allreduce_sum(c.d_out, 2));
     QCB_CUDA(cudaMemcpyAsync(c.h_out, c.d_out, 2 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
     QCB_CUDA(cudaStreamSynchronize(c.stream));
     const double oc = H.kind == 0 ? -H.p0 * H.p2 : H.p1;
     out2[0] = c.h_out[0] + oc * c.h_out[1];
     out2[1] = 0.0; // the two orientations of every flip pair have exactly opposite imaginary parts
-    c.st_passes = (double)passes.size();
+    c.st_passes = (double)npass;
     return QCB_OK;
 }
 
@@ -117,11 +134,13 @@ static int measure_impl(const qcb_state *s, int kind, double p0, double p1, doub
 {
     QCB_REQUIRE_INIT();
     QCB_TRY(check_state(s));
-    if (s->sharded) return set_error(QCB_EUNSUPPORTED, "measure on a sharded state: use qcb_state_download_shard or gather first");
     Ctx &c = ctx();
     HamEval H{kind, s->n, p0, p1, p2};
-    if (!c.force_simple && s->nloc >= 13)
-        return s->dtype == QCB_C128 ? measure_tiled<double>(s, H, out2) : measure_tiled<float>(s, H, out2);
+    if (s->sharded || (!c.force_simple && s->nloc >= 13)) {
+        // (a sharded state may be re-laid-out: the handle is logically const, the amplitudes it represents do not change)
+        qcb_state *ms = const_cast<qcb_state *>(s);
+        return s->dtype == QCB_C128 ? measure_tiled<double>(ms, H, out2) : measure_tiled<float>(ms, H, out2);
+    }
     const unsigned long long namps = 1ull << s->nloc;
     const unsigned blocks = grid_for(namps, kRedThreads, 8);
     QCB_TRY(ensure_partial((size_t)blocks * 2));

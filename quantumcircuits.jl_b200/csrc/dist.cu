@@ -169,6 +169,25 @@ int dist_run_gate_list(qcb_state *s, const std::vector<GateOp> &gates, const dou
     return rc;
 }
 
+int dist_swap_top_now(qcb_state *s)
+{
+    if (!ctx().nccl_comm) return set_error(QCB_ENCCL, "qcb_dist_init has not been called");
+    QCB_TRY(swap_top_device(s));
+    if (s->alt && !s->peer_d.empty()) s->peer_d.swap(s->peer_alt);
+    ShardLayout L = layout_of(s);
+    swap_top_layout(L);
+    s->phys = L.phys;
+    return QCB_OK;
+}
+
+int dist_allreduce_sum(double *device_buf, int count)
+{
+    Ctx &c = ctx();
+    if (!c.nccl_comm) return set_error(QCB_ENCCL, "qcb_dist_init has not been called");
+    QCB_NCCL(ncclAllReduce(device_buf, device_buf, (size_t)count, ncclDouble, ncclSum, (ncclComm_t)c.nccl_comm, c.stream));
+    return QCB_OK;
+}
+
 int dist_state_canonicalize(qcb_state *s)
 {
     if (!ctx().nccl_comm) return set_error(QCB_ENCCL, "qcb_dist_init has not been called");

@@ -18,7 +18,9 @@ struct MeasStage {
     StageDesc sd;
     uint8_t active;        // which of the 4 window bits contribute flips in this stage
     uint8_t diag;          // 1: this stage also accumulates the diagonal part
-    uint8_t wphys[kRegBits]; // physical (== logical, states are canonical here) index bit of each window bit
+    uint8_t wphys[kRegBits]; // physical index bit of each window bit
+    int8_t ctl[kRegBits];    // East: physical index bit that holds the control qubit i-1 of window bit b (-1: none, qubit 0);
+                             // positions >= nloc address the rank bits of a sharded state (c_hi)
     uint8_t pad[2];
 };
 
@@ -30,6 +32,7 @@ template <typename R> struct MeasParams {
     uint16_t ld_eoff[kRegAmps];
     MeasStage stage[kMeasMaxStages];
     HamEval H;
+    unsigned long long c_hi; // index bits above the local shard (rank << nloc), 0 for unsharded states
 };
 
 QCB_HD int popc64(unsigned long long x)
@@ -73,7 +76,7 @@ QCB_HD void measure_stage(const MeasParams<R> &P, int s, const typename Vec2<R>:
 #pragma unroll
     for (int r = 0; r < kRegAmps; r++) a[r] = sm[es ^ S.sd.roff[r]];
     // physical index of this thread's element r = 0 (needed for the diagonal and for the East control bits)
-    unsigned long long C0 = tile_base;
+    unsigned long long C0 = tile_base | P.c_hi;
     if (S.diag || KIND == 1) {
 #pragma unroll
         for (int k = 0; k < TB; k++) C0 |= (unsigned long long)((e >> P.ld_lpos[k]) & 1u) << P.ld_phys[k];
@@ -93,8 +96,8 @@ QCB_HD void measure_stage(const MeasParams<R> &P, int s, const typename Vec2<R>:
         // East: the flip of qubit i is weighted by n_{i-1} = [bit i-1 is 0]; bit i-1 is either the previous window
         // bit (then it depends on r) or fixed for this thread
         uint32_t allowed = 0xffffu;
-        if (KIND == 1 && S.wphys[b] != 0) {
-            const int ctl = S.wphys[b] - 1;
+        if (KIND == 1 && S.ctl[b] >= 0) {
+            const int ctl = S.ctl[b];
             if (b > 0 && S.wphys[b - 1] == ctl) allowed = b == 1 ? 0x5555u : (b == 2 ? 0x3333u : 0x0f0fu);
             else allowed = ((C0 >> ctl) & 1ull) ? 0u : 0xffffu;
         }

@@ -100,5 +100,7 @@ SchedOptions current_sched_options(const qcb_state *s);
 int dist_state_canonicalize(qcb_state *s);
 int dist_run_gate_list(qcb_state *s, const std::vector<GateOp> &gates, const double *mats, bool adjoint);
 int dist_alloc_alt(qcb_state *s);
+int dist_swap_top_now(qcb_state *s);                 // NCCL exchange of the rank bits with the top local bits + layout update
+int dist_allreduce_sum(double *device_buf, int count); // in place, over all ranks, on the work stream
 
 } // namespace qcb

@@ -118,6 +118,12 @@ class ShardedState:
 
         _apply_list_inplace(self, list(gates))
 
+    def measure(self, H):
+        """measure(H, psi) on the sharded state (collective; every rank gets the value)."""
+        from .hamiltonians import _measure_state
+
+        return _measure_state(H, self)
+
     def norm2(self):
         import torch
         import torch.distributed as dist

@@ -67,6 +67,21 @@ def main():
         ok = ok and good
         if rank == 0:
             print(f"{'PASS' if good else 'FAIL'} fused == nccl-only n={n} diff={float(torch.sqrt(d2[0]).item()):.2e}", flush=True)
+        # expectation values on the sharded state (TFIM and East) against the oracle on the full state
+        if dt == np.complex128:
+            Ht, He = qc.TFIMHamiltonian(1.0, 0.1, 0.5), qc.EastModelHamiltonian(0.1, -0.1)
+            Et, Ee = st.measure(Ht), st.measure(He)
+            if rank == 0:
+                full = oracle.apply_brickwork(psi0.astype(np.complex128), n, layers, c.gate_angles)
+                refs = [oracle.measure_tfim(full, 1.0, 0.1, 0.5).real, oracle.measure_east(full, He.c, He.A, He.B).real]
+            else:
+                refs = None
+            box = [refs]
+            dist.broadcast_object_list(box, src=0)
+            good = abs(Et - box[0][0]) < 1e-11 * max(1, abs(box[0][0])) and abs(Ee - box[0][1]) < 1e-11 * max(1, abs(box[0][1]))
+            ok = ok and good
+            if rank == 0:
+                print(f"{'PASS' if good else 'FAIL'} sharded measure n={n}: TFIM {Et:.12f} vs {box[0][0]:.12f}, East {Ee:.12f} vs {box[0][1]:.12f}", flush=True)
         # round trip: circuit then inverse circuit on the sharded state
         st.apply_circuit(c, adjoint=True)
         back = st.download_shard()

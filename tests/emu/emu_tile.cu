@@ -409,3 +409,44 @@ extern "C" int emu_measure(int dtype, int n, const void *psi, int kind, double p
     *out_E = acc[0] + oc * acc[1];
     return 0;
 }
+
+// ---- sharded expectation value with simulated ranks: local passes (rank bits via c_hi), one swap_top, top pass ----------
+template <int TBX> static void emu_meas_dispatch(const double2 *psi, int nloc, const MeasParams<double> &P, double *acc)
+{
+    emu_measure_pass<double, TBX>(psi, nloc, P, acc);
+}
+extern "C" int emu_sharded_measure(int n, int g, const void *psi_, int kind, double p0, double p1, double p2, int tile_bits, int low_bits,
+                                   double *out_E)
+{
+    try {
+        EmuShards<double> ex;
+        ex.nloc = n - g; ex.g = g;
+        const int P = 1 << g, nloc = n - g;
+        const size_t per = (size_t)1 << nloc;
+        const double2 *psi = (const double2 *)psi_;
+        ex.shard.resize(P);
+        for (int r = 0; r < P; r++) ex.shard[r].assign(psi + r * per, psi + (r + 1) * per);
+        HamEval H{kind, n, p0, p1, p2};
+        double acc[2] = {0.0, 0.0};
+        auto run = [&](const MeasParams<double> &MP, const double2 *sh) -> int {
+            switch (tile_bits) {
+#define CASE(T) case T: emu_meas_dispatch<T>(sh, nloc, MP, acc); return 0;
+            CASE(8) CASE(9) CASE(10) CASE(11) CASE(12)
+#undef CASE
+            default: return 3;
+            }
+        };
+        for (int r = 0; r < P; r++)
+            for (auto &MP : plan_measure<double>(nloc, tile_bits, low_bits, H, (unsigned long long)r << nloc))
+                if (run(MP, ex.shard[r].data())) return 3;
+        ex.exchange();
+        for (int r = 0; r < P; r++)
+            if (run(plan_measure_top<double>(nloc, g, tile_bits, low_bits, H, (unsigned long long)r << nloc), ex.shard[r].data())) return 3;
+        const double oc = kind == 0 ? -p0 * p2 : p1;
+        *out_E = acc[0] + oc * acc[1];
+        return 0;
+    } catch (const std::exception &e) {
+        std::fprintf(stderr, "emu sharded measure: %s\n", e.what());
+        return 1;
+    }
+}

@@ -108,3 +108,15 @@ def measure(psi, kind, params, tile_bits, low_bits):
     if rc:
         raise RuntimeError(f"emu_measure rc={rc}")
     return E.value, npass.value
+
+
+def sharded_measure(psi, g, kind, params, tile_bits, low_bits):
+    """Expectation value of a state split over 2^g simulated ranks (canonical layout)."""
+    psi = np.ascontiguousarray(psi, dtype=np.complex128)
+    n = int(psi.size).bit_length() - 1
+    E = C.c_double(0)
+    rc = lib().emu_sharded_measure(C.c_int(n), C.c_int(g), psi.ctypes.data_as(C.c_void_p), C.c_int(kind), C.c_double(params[0]),
+                                   C.c_double(params[1]), C.c_double(params[2]), C.c_int(tile_bits), C.c_int(low_bits), C.byref(E))
+    if rc:
+        raise RuntimeError(f"emu_sharded_measure rc={rc}")
+    return E.value

@@ -270,3 +270,16 @@ def test_emu_sharded_fused_swaps(emu, oracle, n, g, layers, tb, c):
     assert list(phys) == list(range(n))
     assert rel(out, ref) < 1e-13
     assert st["fused"] >= 1 and st["fused"] == st["swaps"]  # every exchange rode on a pass
+
+
+@pytest.mark.parametrize("n,g,tb,c", [(13, 1, 9, 3), (14, 2, 9, 3), (15, 3, 10, 3), (16, 3, 12, 3)])
+def test_emu_sharded_measure(emu, oracle, n, g, tb, c):
+    """sharded expectation value: rank bits enter the diagonal / East controls through c_hi, the flips of the qubits in the
+    rank bits are taken after one qubit swap."""
+    rng = np.random.default_rng(n * 5 + g)
+    psi = rand_state(rng, n)
+    A, B = onp.east_params(0.1, -0.1)
+    for kind, hp, ref in [(0, (1.0, 0.1, 0.5), oracle.measure_tfim(psi, 1.0, 0.1, 0.5).real),
+                          (1, (0.1, A, B), oracle.measure_east(psi, 0.1, A, B).real)]:
+        E = emu.sharded_measure(psi, g, kind, hp, tb, c)
+        assert abs(E - ref) < 1e-12 * max(1.0, abs(ref))
