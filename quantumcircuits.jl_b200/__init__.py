@@ -10,6 +10,7 @@ from .gates import (AbstractGate, Abstract1SpinGate, Abstract2SpinGate, XGate, Z
                     build_general_unitary_gate)
 from .circuits import GenericBrickworkCircuit, circuit_layer_starts, brickwork_num_gates, reconstruct  # noqa: F401
 from .state import B200State, zero_state_vec, zero_state_tensor  # noqa: F401
+from .utils import convert_gates_to_matrix, operation_tensor  # noqa: F401
 from .apply import B200ApplyCache, construct_apply_cache, apply, apply_, apply_circuit_host  # noqa: F401
 from .hamiltonians import (AbstractKernelHamiltonian, TFIMHamiltonian, EastModelHamiltonian, measure, measure_,  # noqa: F401
                            imaginary_energy_limit)

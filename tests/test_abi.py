@@ -84,3 +84,23 @@ def test_zero_state_constructors():
     assert t.shape == (2, 2, 2) and t[0, 0, 0] == 1 and abs(t).sum() == 1
     v = qcb200.zero_state_vec(np.complex64, 3)
     assert v.dtype == np.complex64 and v[0] == 1
+
+
+def test_convert_gates_to_matrix_matches_checker():
+    # src/utils.jl:10-40 ; test/correctness_tests.jl:30-51 uses it to build the GHZ state with matrices
+    rng = np.random.default_rng(2)
+    nbits = 5
+    u1 = rng.standard_normal((2, 2)) + 1j * rng.standard_normal((2, 2))
+    u2 = rng.standard_normal((4, 4)) + 1j * rng.standard_normal((4, 4))
+    gates = [qcb200.Localised1SpinGate(qcb200.Generic1SpinGate(u1), 1),
+             qcb200.Localised2SpinAdjGate(qcb200.Generic2SpinGate(u2.reshape(2, 2, 2, 2, order="F")), 3)]
+    M = qcb200.convert_gates_to_matrix(nbits, gates)
+    np.testing.assert_allclose(M, onp.convert_gates_to_matrix(nbits, [(1, u1), (3, u2)]), atol=1e-15)
+    for n in (4, 5, 7):
+        psi = qcb200.zero_state_vec(n)
+        psi = qcb200.convert_gates_to_matrix(n, [qcb200.Localised1SpinGate(qcb200.HadamardGate(), 1)]) @ psi
+        for i in range(1, n):
+            psi = qcb200.convert_gates_to_matrix(n, [qcb200.Localised2SpinAdjGate(qcb200.CNOTGate(), i)]) @ psi
+        expected = np.zeros(2 ** n)
+        expected[0] = expected[-1] = 1 / np.sqrt(2)
+        np.testing.assert_allclose(psi, expected, atol=1e-15)
