@@ -72,6 +72,24 @@ template <int ILP> __global__ void __launch_bounds__(256) k_mixed(double *out, i
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// packed FP32 (FFMA2): operands from registers vs from the kernel-parameter bank (uniform registers)
+template <int ILP, bool UNIFORM> __global__ void __launch_bounds__(256) k_ffma2(float2 *out, int iters, float2 a, float2 b)
+{
+    float2 acc[ILP];
+#pragma unroll
+    for (int i = 0; i < ILP; i++) acc[i] = make_float2((float)(threadIdx.x + i), (float)i);
+    float2 ra = a, rb = b;
+    if (!UNIFORM) { ra.x += (float)threadIdx.x * 1e-30f; rb.y += (float)threadIdx.x * 1e-30f; } // force per-thread registers
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < ILP; i++) acc[i] = __ffma2_rn(acc[i], ra, rb);
+    }
+    float2 s = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < ILP; i++) { s.x += acc[i].x; s.y += acc[i].y; }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 template <typename F> static float time_ms(F f)
 {
     cudaEvent_t e0, e1;
@@ -100,14 +118,18 @@ int main(int argc, char **argv)
     float ms_f = time_ms([&] { k_fma<float, ILP><<<blocks, threads>>>((float *)out, iters, 1.0000001f, 1e-9f); });
     float ms_m = time_ms([&] { k_dmma<ILP><<<blocks, threads>>>(out, iters, 1.0000001, 1e-9); });
     float ms_x = time_ms([&] { k_mixed<ILP><<<blocks, threads>>>(out, iters, 1.0000001, 1e-9); });
+    float ms_p2r = time_ms([&] { k_ffma2<ILP, false><<<blocks, threads>>>((float2 *)out, iters, make_float2(1.0000001f, 0.9999999f), make_float2(1e-9f, 1e-9f)); });
+    float ms_p2u = time_ms([&] { k_ffma2<ILP, true><<<blocks, threads>>>((float2 *)out, iters, make_float2(1.0000001f, 0.9999999f), make_float2(1e-9f, 1e-9f)); });
     CK(cudaGetLastError());
+    const double fma_p2r = 2.0 * nthreads * iters * ILP / (ms_p2r * 1e-3), fma_p2u = 2.0 * nthreads * iters * ILP / (ms_p2u * 1e-3);
     const double fma_d = nthreads * iters * ILP / (ms_d * 1e-3);
     const double fma_f = nthreads * iters * ILP / (ms_f * 1e-3);
     const double fma_m = (nthreads / 32) * iters * ILP * 256.0 / (ms_m * 1e-3);
     const double fma_x = ((nthreads / 2) * iters * ILP + (nthreads / 64) * iters * ILP * 256.0) / (ms_x * 1e-3);
     printf("{\"gpu\": \"%s\", \"sms\": %d, \"dfma_tflops\": %.2f, \"ffma_tflops\": %.2f, \"dmma_tflops\": %.2f, "
-           "\"mixed_dfma_dmma_tflops\": %.2f, \"dfma_per_clk_per_sm_at_max_clock\": %.1f, \"ms\": [%.3f, %.3f, %.3f, %.3f]}\n",
-           p.name, sms, 2 * fma_d / 1e12, 2 * fma_f / 1e12, 2 * fma_m / 1e12, 2 * fma_x / 1e12,
+           "\"mixed_dfma_dmma_tflops\": %.2f, \"ffma2_reg_operand_tflops\": %.2f, \"ffma2_uniform_operand_tflops\": %.2f, "
+           "\"dfma_per_clk_per_sm_at_max_clock\": %.1f, \"ms\": [%.3f, %.3f, %.3f, %.3f]}\n",
+           p.name, sms, 2 * fma_d / 1e12, 2 * fma_f / 1e12, 2 * fma_m / 1e12, 2 * fma_x / 1e12, 2 * fma_p2r / 1e12, 2 * fma_p2u / 1e12,
            fma_d / sms / (p.clockRate * 1e3), ms_d, ms_f, ms_m, ms_x);
     return 0;
 }
