@@ -311,7 +311,8 @@ def run_ours(args):
     if launch_ms:
         achieved = bytes_pass / (launch_ms * 1e-3) / 1e9
         flops = 32.0 * (2.0 ** n) * G / (ms_step * 1e-3) / 1e12 / world  # 16 FMA per amplitude per gate; per GPU
-        peak_fl = (fp64 or {}).get("dfma_tflops" if args.dtype == "c128" else "ffma_tflops")
+        # ComplexF32 runs on packed FFMA2, whose measured issue roof is below the scalar-FFMA one
+        peak_fl = (fp64 or {}).get("dfma_tflops" if args.dtype == "c128" else "ffma2_reg_operand_tflops") or (fp64 or {}).get("ffma_tflops")
         roofline = {
             "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "binding_roof": "fp_fma_issue (see fma_roof); HBM-bound regime of the same kernel in hbm_bound_regime",
