@@ -1,0 +1,400 @@
+// adjoint_mma.cuh -- backward pass of the adjoint gradient sweep, ComplexF64, entirely on the FP64 tensor cores.
+//
+// Same contract as adjoint_pass_kernel (adjoint.cuh): one launch un-applies a trapezoid of gates of the reversed
+// circuit on a psi tile and a lambda tile and reduces one 4x4 cross-density matrix per gate (src/gradients.jl:107-139 is
+// what it replaces).  What changes is where the arithmetic and the data movement happen.  adjoint.cuh keeps one amplitude
+// quad per thread, so every gate costs three shared-memory round trips (psi, lambda, and the operand fetch of the
+// reduction MMAs): ncu showed it bound by shared-memory wavefronts (LSU 72 %, FP64 36 %).  Here a warp works on 8 quads at
+// a time in the MMA fragment layout (mma.sync.m8n8k4.f64; lane = 4 g + t):
+//
+//   un-apply  D[m][n] = sum_k A[m][k] B[k][n]   A = the real 8x8 form of U^dagger (rows m = (amplitude, Re/Im) of the
+//             output, 4 columns per MMA: the Re parts, then the Im parts of the 4 input amplitudes), B[k][n] = amplitude k
+//             of quad n: lane (g, t) feeds both MMAs from ONE 16-byte shared-memory load (amplitude t of quad g), and
+//             receives component g of quads 2t, 2t+1.
+//   reduce    E[m][n] += sum_k L'[m][k] P'[k][n]   with k = quad: lane (g, t) must supply component g of quad k for both
+//             operands -- exactly what the un-apply MMAs just left in its registers (quads 2t and 2t+1 -> two MMAs).
+//             No operand fetch at all; E = sum_quads lambda'_m psi'_n stays distributed over the warp (2 doubles/lane).
+//   store     two 8-byte stores per state per lane (component g of quads 2t, 2t+1).
+//
+// Shared-memory traffic per gate is one read + one write of both tiles (the minimum), no amplitude is held in a
+// register across gates (tens of registers per thread -> 20+ resident warps per SM instead of 12), and all FP64 work
+// runs at the DMMA rate.  The reduction uses the states AFTER the gate has been un-applied on both:
+//   M[r', c] = sum_rest conj(lambda_{g-1}[r', rest]) psi_{g-1}[c, rest],
+// and the environment the gradient needs, env[r, c] = sum conj(lambda_g[r]) psi_{g-1}[c], follows on the host as
+// env = conj(U) M because lambda_g = U lambda_{g-1} (U unitary -- the adjoint method already relies on it to recover
+// psi_{g-1} = U^dagger psi_g).
+//
+// Windows, stages and the XOR swizzle are those of tile.cuh: a warp owns WPW = 2^(TB-4)/NW of the tile's 16-amplitude
+// windows for the duration of a stage (gates of a stage stay inside a window, so warps only meet at stage boundaries); a
+// group of 8 quads = 2 whole windows that differ in warp-window bit `sel` (chosen on the host so that the 8-byte stores
+// of a half warp hit 16 distinct bank pairs; the 16-byte loads of a quarter warp vary 3 of the 4 window bits and are
+// conflict free by construction of the swizzle).
+#pragma once
+#include <cmath>
+#include <cstring>
+
+#include "adjoint.cuh"
+
+namespace qcb {
+
+struct AdjMmaParams {
+    AdjParams<double> A;
+    uint8_t sel[kMaxStages * kSlots]; // warp-window bit that pairs the two windows of a group, per (stage, slot)
+};
+
+// the two bits of q spread over the window bits other than LO, LO+1
+QCB_HD int adjm_other(int LO, int q) { return LO == 0 ? (q << 2) : (LO == 1 ? ((q & 1) | ((q & 2) << 2)) : q); }
+
+// swizzled tile-local offset of window `geom` (the thread index of tile_stage); XOR-linear in geom
+template <int TB> QCB_HD uint32_t adjm_win_base(const StageDesc &S, uint32_t geom)
+{
+    uint32_t e = 0;
+#pragma unroll
+    for (int k = 0; k < TB - kRegBits; k++) e |= ((geom >> k) & 1u) << S.tpos[k];
+    return swz<3>(e);
+}
+
+// Offsets are XOR-linear in the window id, so a stage needs only the warp's base window and one constant per warp-window
+// bit; a gate picks `sel` out of them and walks its groups in Gray-code order (one XOR per group).
+template <int N> struct Log2 { static constexpr int value = 1 + Log2<N / 2>::value; };
+template <> struct Log2<1> { static constexpr int value = 0; };
+
+template <int TB, int WB> struct AdjmStage {
+    uint32_t wbase;  // offset of the warp's first window
+    uint32_t cw[WB]; // offset toggled by warp-window bit k
+};
+template <int TB, int WB> QCB_HD AdjmStage<TB, WB> adjm_stage_consts(const StageDesc &S, uint32_t warp)
+{
+    AdjmStage<TB, WB> C;
+    C.wbase = adjm_win_base<TB>(S, warp << WB);
+#pragma unroll
+    for (int k = 0; k < WB; k++) C.cw[k] = adjm_win_base<TB>(S, 1u << k);
+    return C;
+}
+// per-gate lane constants: XOR them with the group offset to get the element index
+struct AdjmLane {
+    uint32_t ld;    // amplitude t of quad g (load)
+    uint32_t st[2]; // amplitude g>>1 of quads 2t, 2t+1 (store; the lane writes component g&1 of it)
+};
+template <int TB, int WB> struct AdjmGate {
+    AdjmLane L;
+    uint32_t cg[WB > 1 ? WB - 1 : 1]; // offsets toggled by the group-index bits (the warp-window bits other than sel)
+};
+template <int TB, int WB> QCB_HD AdjmGate<TB, WB> adjm_gate_consts(const AdjmStage<TB, WB> &C, const StageDesc &S, int LO, int sel, uint32_t lane)
+{
+    const uint32_t g = lane >> 2, t = lane & 3u;
+    AdjmGate<TB, WB> G;
+    uint32_t csel = 0;
+#pragma unroll
+    for (int k = 0; k < WB; k++) csel = k == sel ? C.cw[k] : csel;
+    G.cg[0] = 0;
+#pragma unroll
+    for (int j = 0; j + 1 < WB; j++) G.cg[j] = j >= sel ? C.cw[j + 1] : C.cw[j];
+    G.L.ld = C.wbase ^ ((g >> 2) ? csel : 0u) ^ swz<3>((uint32_t)(adjm_other(LO, (int)(g & 3u)) | (int)(t << LO)) << S.p0);
+    const uint32_t wst = C.wbase ^ ((t >> 1) ? csel : 0u);
+#pragma unroll
+    for (int j = 0; j < 2; j++)
+        G.L.st[j] = wst ^ swz<3>((uint32_t)(adjm_other(LO, (int)(2u * (t & 1u)) + j) | (int)((g >> 1) << LO)) << S.p0);
+    return G;
+}
+// group i -> group i+1 in Gray-code order: toggle group-index bit ctz(i+1)
+QCB_HD constexpr int adjm_gray_bit(int i)
+{
+    int b = 0;
+    while (!(((i + 1) >> b) & 1)) b++;
+    return b;
+}
+// A operands of the two un-apply MMAs for lane (g, t): row (amplitude a = g>>1, part = g&1) of the real form of U^dagger,
+// columns Re(in_t) and Im(in_t)
+QCB_HD void adjm_gate_operand(const GateMat<double> &Ud, uint32_t lane, double &a_re, double &a_im)
+{
+    const uint32_t g = lane >> 2, t = lane & 3u, a = g >> 1;
+    const double ur = Ud.v[2 * (a + 4 * t)], ui = Ud.v[2 * (a + 4 * t) + 1];
+    a_re = (g & 1u) ? ui : ur;
+    a_im = (g & 1u) ? ur : -ui;
+}
+
+// host choice of `sel`: the half-warp stores vary window bits LO and "other bit 1" plus warp-window bit sel
+inline void fill_adj_mma_sel(AdjMmaParams &M, int TB, int NW)
+{
+    int wbits = 0;
+    while ((1 << (wbits + 1)) <= ((1 << (TB - kRegBits)) / NW)) wbits++;
+    std::memset(M.sel, 0, sizeof M.sel);
+    for (int s = 0; s < M.A.P.nstages; s++) {
+        const StageDesc &S = M.A.P.stage[s];
+        for (int slot = 0; slot < kSlots; slot++) {
+            if (!((S.mask >> slot) & 1)) continue;
+            const int LO = slot_lo(slot);
+            const int ob1 = LO == 2 ? 1 : 3;
+            const uint32_t v1 = bank_vector<3>(S.p0 + LO), v2 = bank_vector<3>(S.p0 + ob1);
+            for (int k = 0; k < wbits; k++) {
+                const uint32_t v = bank_vector<3>(S.tpos[k]);
+                if (v != 0 && v != v1 && v != v2 && v != (v1 ^ v2)) { M.sel[s * kSlots + slot] = (uint8_t)k; break; }
+            }
+        }
+    }
+}
+
+#if defined(__CUDACC__)
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dmma(double &d0, double &d1, double a, double b)
+{
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+template <int TB, int NW>
+__device__ __forceinline__ void adjoint_stage_mma(const AdjMmaParams &M, int s, double2 *smP, double2 *smL, double *acc_warp, uint32_t tid)
+{
+    constexpr int WPW = (1 << (TB - kRegBits)) / NW; // windows per warp
+    constexpr int WB = Log2<WPW>::value;
+    constexpr int NG = WPW / 2;                      // groups of 8 quads per gate
+    static_assert(WPW >= 2, "a warp needs at least two windows");
+    const StageDesc &S = M.A.P.stage[s];
+    const uint32_t mask = S.mask;
+    const uint32_t lane = tid & 31u, warp = tid >> 5, g = lane >> 2, t = lane & 3u, part = g & 1u;
+    double *dP = reinterpret_cast<double *>(smP) + part, *dL = reinterpret_cast<double *>(smL) + part;
+    const AdjmStage<TB, WB> C = adjm_stage_consts<TB, WB>(S, warp);
+#pragma unroll 1
+    for (int slot = 0; slot < kSlots; slot++) {
+        if (!((mask >> slot) & 1u)) continue;
+        const int LO = slot_lo(slot);
+        const int sel = M.sel[s * kSlots + slot];
+        double a_re, a_im;
+        adjm_gate_operand(M.A.P.U[s * kSlots + slot], lane, a_re, a_im);
+        const AdjmGate<TB, WB> G = adjm_gate_consts<TB, WB>(C, S, LO, sel, lane);
+        double e0[2] = {0.0, 0.0}, e1[2] = {0.0, 0.0};
+        uint32_t gb = 0;
+        double2 x = smP[G.L.ld], l = smL[G.L.ld];
+#pragma unroll
+        for (int i = 0; i < NG; i++) {
+            const double2 xc = x, lc = l;
+            const uint32_t gbc = gb;
+            if (i + 1 < NG) { // next group's operands are in flight while this group's MMAs run
+                gb ^= G.cg[adjm_gray_bit(i)];
+                x = smP[gb ^ G.L.ld];
+                l = smL[gb ^ G.L.ld];
+            }
+            double p0 = 0.0, p1 = 0.0, l0 = 0.0, l1 = 0.0;
+            dmma(p0, p1, a_re, xc.x);
+            dmma(l0, l1, a_re, lc.x);
+            dmma(p0, p1, a_im, xc.y);
+            dmma(l0, l1, a_im, lc.y);
+            const uint32_t s0 = 2u * (gbc ^ G.L.st[0]), s1 = 2u * (gbc ^ G.L.st[1]);
+            dP[s0] = p0; dP[s1] = p1;
+            dL[s0] = l0; dL[s1] = l1;
+            dmma(e0[0], e1[0], l0, p0);
+            dmma(e0[1], e1[1], l1, p1);
+        }
+        // M[r', c] from E (rows (r', Re/Im of lambda), columns (c, Re/Im of psi)): Re = E[2r'][2c] + E[2r'+1][2c+1],
+        // Im = E[2r'][2c+1] - E[2r'+1][2c]; the odd rows live on lane ^ 4
+        const double q0 = e0[0] + e0[1], q1 = e1[0] + e1[1];
+        const double o0 = __shfl_xor_sync(0xffffffffu, q0, 4), o1 = __shfl_xor_sync(0xffffffffu, q1, 4);
+        if (!part) {
+            double *acc_gate = acc_warp + 32 * M.A.slot_gate[s * kSlots + slot];
+            const int k = (int)(g >> 1) + 4 * (int)t;
+            acc_gate[2 * k] += q0 + o1;
+            acc_gate[2 * k + 1] += q1 - o0;
+        }
+        __syncwarp();
+    }
+}
+
+// tile <-> shared memory with NT >= 2^(TB-4) threads: thread = (window id, part), each part moves 16 / PARTS elements
+template <int TB, int NT, bool STORE>
+__device__ __forceinline__ void adjm_tile_io(double2 *__restrict__ glob, const PassParams<double> &P, double2 *sm, uint32_t tid, unsigned long long tile)
+{
+    constexpr int TBITS = TB - kRegBits;
+    constexpr int PARTS = NT >> TBITS;
+    static_assert(PARTS >= 1 && PARTS <= kRegAmps, "thread count must be 1..16 times the number of windows");
+    const uint32_t geom = tid & ((1u << TBITS) - 1u), prt = tid >> TBITS;
+    unsigned long long gaddr = cta_base(P, tile);
+    uint32_t e = 0;
+#pragma unroll
+    for (int k = 0; k < TBITS; k++) {
+        const uint32_t bit = (geom >> k) & 1u;
+        gaddr |= (unsigned long long)bit << P.ld_phys[k];
+        e |= bit << (STORE ? P.st_lpos[k] : P.ld_lpos[k]);
+    }
+    e = swz<3>(e);
+    if (!STORE) {
+        double2 tmp[kRegAmps / PARTS];
+#pragma unroll
+        for (int i = 0; i < kRegAmps / PARTS; i++) tmp[i] = glob[gaddr | P.ld_goff[i * PARTS + prt]];
+#pragma unroll
+        for (int i = 0; i < kRegAmps / PARTS; i++) sm[e ^ P.ld_eoff[i * PARTS + prt]] = tmp[i];
+    } else {
+#pragma unroll
+        for (int i = 0; i < kRegAmps / PARTS; i++) glob[gaddr | P.ld_goff[i * PARTS + prt]] = sm[e ^ P.st_eoff[i * PARTS + prt]];
+    }
+}
+
+template <int TB, int NW, int MINB>
+__global__ void __launch_bounds__(32 * NW, MINB)
+adjoint_pass_mma_kernel(double2 *psi, double2 *lam, const __grid_constant__ AdjMmaParams M, unsigned long long ntiles,
+                        double *partial /* [gridDim.x][kAdjMaxGates][32] */)
+{
+    constexpr int NT = 32 * NW;
+    extern __shared__ __align__(16) unsigned char qcb_smem_raw[];
+    double2 *smP = reinterpret_cast<double2 *>(qcb_smem_raw);
+    double2 *smL = smP + (1 << TB);
+    double *acc = reinterpret_cast<double *>(smL + (1 << TB)); // [NW][kAdjMaxGates][32]
+    const uint32_t tid = threadIdx.x;
+    for (int i = tid; i < NW * kAdjMaxGates * 32; i += NT) acc[i] = 0.0;
+    __syncthreads();
+    double *acc_warp = acc + (tid >> 5) * (kAdjMaxGates * 32);
+    for (unsigned long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        adjm_tile_io<TB, NT, false>(psi, M.A.P, smP, tid, tile);
+        adjm_tile_io<TB, NT, false>(lam, M.A.P, smL, tid, tile);
+        __syncthreads();
+#pragma unroll 1
+        for (int s = 0; s < M.A.P.nstages; s++) {
+            adjoint_stage_mma<TB, NW>(M, s, smP, smL, acc_warp, tid);
+            __syncthreads();
+        }
+        adjm_tile_io<TB, NT, true>(psi, M.A.P, smP, tid, tile);
+        adjm_tile_io<TB, NT, true>(lam, M.A.P, smL, tid, tile);
+        __syncthreads();
+    }
+    for (int i = tid; i < kAdjMaxGates * 32; i += NT) {
+        double sum = 0;
+#pragma unroll
+        for (int w = 0; w < NW; w++) sum += acc[w * (kAdjMaxGates * 32) + i];
+        partial[(size_t)blockIdx.x * (kAdjMaxGates * 32) + i] = sum;
+    }
+}
+#endif
+
+// ---------------------------------------------------------------------------------------------------------------------
+// CPU replay of one stage, all warps, lane by lane, with a software model of the m8n8k4 fragment layout
+// (A: lane 4g+t holds A[g][t]; B: lane 4g+t holds B[t][g]; C/D: lane 4g+t holds D[g][2t], D[g][2t+1]).
+// conflicts (optional): [0] += shared-memory wavefronts issued, [1] += wavefronts a conflict-free layout would need.
+// ---------------------------------------------------------------------------------------------------------------------
+inline void adjm_soft_mma(double (&d0)[32], double (&d1)[32], const double (&a)[32], const double (&b)[32])
+{
+    double D[8][8];
+    for (int m = 0; m < 8; m++)
+        for (int n = 0; n < 8; n++) {
+            double acc = (n & 1) ? d1[4 * m + (n >> 1)] : d0[4 * m + (n >> 1)];
+            for (int k = 0; k < 4; k++) acc = std::fma(a[4 * m + k], b[4 * n + k], acc);
+            D[m][n] = acc;
+        }
+    for (int ln = 0; ln < 32; ln++) {
+        d0[ln] = D[ln >> 2][2 * (ln & 3)];
+        d1[ln] = D[ln >> 2][2 * (ln & 3) + 1];
+    }
+}
+
+// wavefronts of one warp-wide access of `bytes` (8 or 16) per lane at double-index addresses addr8[]
+inline void adjm_count_wavefronts(const uint32_t (&addr8)[32], int bytes, long long *conflicts)
+{
+    if (!conflicts) return;
+    const int lanes_per_req = 128 / bytes; // half warp for 8-byte, quarter warp for 16-byte accesses
+    for (int first = 0; first < 32; first += lanes_per_req) {
+        int worst = 0;
+        for (int bank = 0; bank < 16; bank++) { // 16 bank pairs of 8 bytes
+            uint32_t seen[32];
+            int ns = 0;
+            for (int ln = first; ln < first + lanes_per_req; ln++)
+                for (int w = 0; w < bytes / 8; w++) {
+                    const uint32_t a = addr8[ln] + (uint32_t)w;
+                    if ((int)(a & 15u) != bank) continue;
+                    bool dup = false;
+                    for (int z = 0; z < ns; z++) dup = dup || seen[z] == a;
+                    if (!dup) seen[ns++] = a;
+                }
+            worst = ns > worst ? ns : worst;
+        }
+        conflicts[0] += worst;
+        conflicts[1] += 1;
+    }
+}
+
+template <int TB, int NW>
+inline void adjoint_stage_mma_host(const AdjMmaParams &M, int s, double2 *smP, double2 *smL, double *acc /*[NW][kAdjMaxGates][32]*/,
+                                   long long *conflicts = nullptr)
+{
+    constexpr int WPW = (1 << (TB - kRegBits)) / NW;
+    constexpr int NG = WPW / 2;
+    constexpr int WB = Log2<WPW>::value;
+    static_assert(WPW >= 2, "a warp needs at least two windows");
+    const StageDesc &S = M.A.P.stage[s];
+    double *fP = reinterpret_cast<double *>(smP), *fL = reinterpret_cast<double *>(smL);
+    for (uint32_t warp = 0; warp < (uint32_t)NW; warp++)
+        for (int slot = 0; slot < kSlots; slot++) {
+            if (!((S.mask >> slot) & 1u)) continue;
+            const int LO = slot_lo(slot);
+            const int sel = M.sel[s * kSlots + slot];
+            double a_re[32], a_im[32];
+            AdjmLane L[32];
+            const AdjmStage<TB, WB> C = adjm_stage_consts<TB, WB>(S, warp);
+            AdjmGate<TB, WB> G0{};
+            for (uint32_t ln = 0; ln < 32; ln++) {
+                adjm_gate_operand(M.A.P.U[s * kSlots + slot], ln, a_re[ln], a_im[ln]);
+                G0 = adjm_gate_consts<TB, WB>(C, S, LO, sel, ln);
+                L[ln] = G0.L;
+            }
+            double e0[32] = {0}, e1[32] = {0};
+            uint32_t gb = 0;
+            for (int i = 0; i < NG; i++) {
+                if (i > 0) gb ^= G0.cg[adjm_gray_bit(i - 1)];
+                double xr[32], xi[32], lr[32], li[32];
+                uint32_t a8[32];
+                for (int ln = 0; ln < 32; ln++) {
+                    const uint32_t idx = gb ^ L[ln].ld;
+                    xr[ln] = smP[idx].x; xi[ln] = smP[idx].y;
+                    lr[ln] = smL[idx].x; li[ln] = smL[idx].y;
+                    a8[ln] = 2 * idx;
+                }
+                adjm_count_wavefronts(a8, 16, conflicts);
+                adjm_count_wavefronts(a8, 16, conflicts);
+                double p0[32] = {0}, p1[32] = {0}, l0[32] = {0}, l1[32] = {0};
+                adjm_soft_mma(p0, p1, a_re, xr);
+                adjm_soft_mma(l0, l1, a_re, lr);
+                adjm_soft_mma(p0, p1, a_im, xi);
+                adjm_soft_mma(l0, l1, a_im, li);
+                for (int j = 0; j < 2; j++) {
+                    for (int ln = 0; ln < 32; ln++) {
+                        const uint32_t part = ((uint32_t)ln >> 2) & 1u;
+                        const uint32_t at = 2u * (gb ^ L[ln].st[j]) + part;
+                        fP[at] = j ? p1[ln] : p0[ln];
+                        fL[at] = j ? l1[ln] : l0[ln];
+                        a8[ln] = at;
+                    }
+                    adjm_count_wavefronts(a8, 8, conflicts);
+                    adjm_count_wavefronts(a8, 8, conflicts);
+                }
+                adjm_soft_mma(e0, e1, l0, p0);
+                adjm_soft_mma(e0, e1, l1, p1);
+            }
+            double *acc_gate = acc + (size_t)warp * (kAdjMaxGates * 32) + 32 * M.A.slot_gate[s * kSlots + slot];
+            for (int ln = 0; ln < 32; ln++) {
+                const int g = ln >> 2, t = ln & 3;
+                if (g & 1) continue;
+                const int k = (g >> 1) + 4 * t;
+                acc_gate[2 * k] += e0[ln] + e1[ln ^ 4];
+                acc_gate[2 * k + 1] += e1[ln] - e0[ln ^ 4];
+            }
+        }
+}
+
+// env[r, c] = sum_r' conj(U[r, r']) M[r', c], in place on 32 doubles laid out [2 (r + 4 c)] (Re, Im); U32 = the forward gate
+// in the same layout
+inline void adjm_env_from_post(const double *U32, double *env32)
+{
+    double out[32];
+    for (int r = 0; r < 4; r++)
+        for (int c = 0; c < 4; c++) {
+            double re = 0, im = 0;
+            for (int k = 0; k < 4; k++) {
+                const double ur = U32[2 * (r + 4 * k)], ui = -U32[2 * (r + 4 * k) + 1];
+                const double mr = env32[2 * (k + 4 * c)], mi = env32[2 * (k + 4 * c) + 1];
+                re += ur * mr - ui * mi;
+                im += ur * mi + ui * mr;
+            }
+            out[2 * (r + 4 * c)] = re;
+            out[2 * (r + 4 * c) + 1] = im;
+        }
+    std::memcpy(env32, out, sizeof out);
+}
+
+} // namespace qcb

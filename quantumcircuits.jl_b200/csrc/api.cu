@@ -3,6 +3,7 @@
 #include <cmath>
 #include <cstring>
 
+#include "adjoint_mma.cuh"
 #include "gates_host.hpp"
 #include "kernels.cuh"
 #include "measure_plan.hpp"
@@ -241,12 +242,13 @@ static int gradients_impl(const qcb_state *psi0, int nbits, int nlayers, const d
     // backward sweep: un-apply gate g on psi and lambda, reduce the 4x4 environment
     QCB_TRY(ensure_out((size_t)32 * G));
     double bw_passes = 0, bw_stages = 0;
+    bool env_post = false;
     if (!c.force_simple && nbits >= kMinTB) {
         // fused: the reversed circuit goes through the pass planner, one launch per trapezoid of gates
         std::vector<GateOp> rev(G);
         for (int i = 0; i < G; i++) rev[i] = GateOp{pos[G - 1 - i], G - 1 - i};
         const double p0 = c.st_passes, s0 = c.st_stages;
-        QCB_TRY(run_adjoint_fused(&A, &B, rev, mats.data(), c.d_out));
+        QCB_TRY(run_adjoint_fused(&A, &B, rev, mats.data(), c.d_out, &env_post));
         bw_passes = c.st_passes - p0; bw_stages = c.st_stages - s0;
     } else {
         const unsigned long long nquads = namps >> 2;
@@ -276,7 +278,8 @@ static int gradients_impl(const qcb_state *psi0, int nbits, int nlayers, const d
     QCB_CUDA(cudaStreamSynchronize(c.stream));
     // grads[k, g] = 2 Re sum_{r,c} env_g[r,c] dU_g/dtheta_k [r,c]
     for (int g = 0; g < G; g++) {
-        const double *env = c.h_out + 32 * (size_t)g;
+        double *env = c.h_out + 32 * (size_t)g;
+        if (env_post) adjm_env_from_post(mats.data() + 32 * (size_t)g, env);
         for (int k = 0; k < 15; k++) {
             const M4 dU = general_unitary(angles + 15 * (size_t)g, k);
             double s = 0;
@@ -419,6 +422,11 @@ int qcb_set_option(const char *key, long value)
     } else if (k == "adjoint_tile_bits") {
         if (value != 0 && (value < kMinTB || value > 12)) return set_error(QCB_EINVAL, "adjoint_tile_bits must be 0 (auto) or in [%d, 12]", kMinTB);
         c.adjoint_tile_bits = value;
+    } else if (k == "adjoint_mma") {
+        c.adjoint_mma = value ? 1 : 0;
+    } else if (k == "adjoint_warps") {
+        if (value != 0 && value != 4 && value != 8) return set_error(QCB_EINVAL, "adjoint_warps must be 0 (auto), 4 or 8");
+        c.adjoint_warps = value;
     } else if (k == "fuse_swaps") {
         c.fuse_swaps = value ? 1 : 0;
     } else if (k == "force_simple") {

@@ -5,7 +5,7 @@
 // one synchronize per gate (src/apply.jl:134-142).
 #include <sstream>
 
-#include "adjoint.cuh"
+#include "adjoint_mma.cuh"
 #include "kernels.cuh"
 #include "qcb_internal.hpp"
 
@@ -238,7 +238,75 @@ template <typename R, int TB> static int launch_adjoint(qcb_state *psi, qcb_stat
     return QCB_OK;
 }
 
-template <typename R> static int run_adjoint_fused_t(qcb_state *psi, qcb_state *lam, const std::vector<GateOp> &rev, const double *mats, double *d_env)
+// ComplexF64: the tensor-core form (adjoint_mma.cuh); env rows hold the post-gate matrix M, see run_adjoint_fused
+template <int TB, int NW> static int launch_adjoint_mma(qcb_state *psi, qcb_state *lam, const AdjMmaParams &M, const EnvIds &ids, double *d_env)
+{
+    constexpr int NT = 32 * NW;
+    // two tiles + per-warp accumulators per CTA; registers are not the limit (< 100 per thread)
+    constexpr int MINB = TB >= 12 ? 1 : (TB == 11 ? (NW == 8 ? 2 : 3) : (TB == 10 ? (NW == 8 ? 3 : 5) : 8));
+    auto kern = adjoint_pass_mma_kernel<TB, NW, MINB>;
+    const size_t smem = 2 * (sizeof(double2) << TB) + sizeof(double) * NW * kAdjMaxGates * 32;
+    static bool attr_set = false;
+    static int ctas_per_sm = 1;
+    if (!attr_set) {
+        QCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        QCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, NT, smem));
+        if (ctas_per_sm < 1) ctas_per_sm = 1;
+        attr_set = true;
+    }
+    const unsigned long long ntiles = 1ull << (psi->nloc - TB);
+    const unsigned grid = (unsigned)std::min<unsigned long long>(ntiles, (unsigned long long)ctx().sm_count * ctas_per_sm);
+    QCB_TRY(ensure_partial((size_t)grid * kAdjMaxGates * 32));
+    kern<<<grid, NT, smem, ctx().stream>>>((double2 *)psi->d, (double2 *)lam->d, M, ntiles, ctx().d_partial);
+    QCB_CUDA(cudaGetLastError());
+    k_env_final<<<ids.n * 32, 128, 0, ctx().stream>>>(ctx().d_partial, (int)grid, ids, d_env);
+    QCB_CUDA(cudaGetLastError());
+    count_launch(2);
+    return QCB_OK;
+}
+
+template <typename R> static int launch_adjoint_any(qcb_state *psi, qcb_state *lam, int TB, bool mma, AdjParams<R> &A, const EnvIds &ids, double *d_env);
+
+template <> int launch_adjoint_any<float>(qcb_state *psi, qcb_state *lam, int TB, bool, AdjParams<float> &A, const EnvIds &ids, double *d_env)
+{
+    switch (TB) {
+    case 9: return launch_adjoint<float, 9>(psi, lam, A, ids, d_env);
+    case 10: return launch_adjoint<float, 10>(psi, lam, A, ids, d_env);
+    case 11: return launch_adjoint<float, 11>(psi, lam, A, ids, d_env);
+    case 12: return launch_adjoint<float, 12>(psi, lam, A, ids, d_env);
+    default: return set_error(QCB_EINVAL, "unsupported tile size %d for the backward pass", TB);
+    }
+}
+
+template <> int launch_adjoint_any<double>(qcb_state *psi, qcb_state *lam, int TB, bool mma, AdjParams<double> &A, const EnvIds &ids, double *d_env)
+{
+    if (mma) {
+        static thread_local AdjMmaParams M;
+        M.A = A;
+        // warps per CTA: 4 keeps 16 windows per warp at TB = 10 (8 MMA groups per gate, 5 CTAs per SM); "adjoint_warps" overrides
+        const long want = ctx().adjoint_warps;
+        const int NW = TB >= 12 ? 8 : (TB == 9 ? 4 : (want == 4 || want == 8 ? (int)want : (TB == 11 ? 8 : 4)));
+        fill_adj_mma_sel(M, TB, NW);
+        switch (TB * 100 + NW) {
+        case 904: return launch_adjoint_mma<9, 4>(psi, lam, M, ids, d_env);
+        case 1004: return launch_adjoint_mma<10, 4>(psi, lam, M, ids, d_env);
+        case 1008: return launch_adjoint_mma<10, 8>(psi, lam, M, ids, d_env);
+        case 1104: return launch_adjoint_mma<11, 4>(psi, lam, M, ids, d_env);
+        case 1108: return launch_adjoint_mma<11, 8>(psi, lam, M, ids, d_env);
+        case 1208: return launch_adjoint_mma<12, 8>(psi, lam, M, ids, d_env);
+        default: return set_error(QCB_EINVAL, "unsupported tile size %d for the backward pass", TB);
+        }
+    }
+    switch (TB) {
+    case 9: return launch_adjoint<double, 9>(psi, lam, A, ids, d_env);
+    case 10: return launch_adjoint<double, 10>(psi, lam, A, ids, d_env);
+    case 11: return launch_adjoint<double, 11>(psi, lam, A, ids, d_env);
+    case 12: return launch_adjoint<double, 12>(psi, lam, A, ids, d_env);
+    default: return set_error(QCB_EINVAL, "unsupported tile size %d for the backward pass", TB);
+    }
+}
+
+template <typename R> static int run_adjoint_fused_t(qcb_state *psi, qcb_state *lam, const std::vector<GateOp> &rev, const double *mats, double *d_env, bool mma)
 {
     Ctx &c = ctx();
     SchedOptions opt = current_sched_options(psi);
@@ -274,26 +342,22 @@ template <typename R> static int run_adjoint_fused_t(qcb_state *psi, qcb_state *
                 ids.id[ids.n++] = rev[g].mat;
             }
         A.ngates = ids.n;
-        int rc;
-        switch (pl.TB) {
-        case 9: rc = launch_adjoint<R, 9>(psi, lam, A, ids, d_env); break;
-        case 10: rc = launch_adjoint<R, 10>(psi, lam, A, ids, d_env); break;
-        case 11: rc = launch_adjoint<R, 11>(psi, lam, A, ids, d_env); break;
-        case 12: rc = launch_adjoint<R, 12>(psi, lam, A, ids, d_env); break;
-        default: rc = set_error(QCB_EINVAL, "unsupported tile size %d for the backward pass", pl.TB);
-        }
-        QCB_TRY(rc);
+        QCB_TRY(launch_adjoint_any<R>(psi, lam, pl.TB, mma, A, ids, d_env));
         c.st_passes += 1;
         c.st_stages += (double)pl.stages.size();
     }
     return QCB_OK;
 }
 
-// rev: the circuit's gates in reverse order, GateOp.mat = original gate index (also the row of d_env, 32 doubles each)
-int run_adjoint_fused(qcb_state *psi, qcb_state *lam, const std::vector<GateOp> &rev, const double *mats, double *d_env)
+// rev: the circuit's gates in reverse order, GateOp.mat = original gate index (also the row of d_env, 32 doubles each).
+// *env_post = false: row g holds env_g[r,c] = sum conj(lam_g[r]) psi_{g-1}[c];  true (ComplexF64 tensor-core pass): row g holds
+// M_g[r,c] = sum conj(lam_{g-1}[r]) psi_{g-1}[c], to be turned into env_g = conj(U_g) M_g by the caller (adjm_env_from_post).
+int run_adjoint_fused(qcb_state *psi, qcb_state *lam, const std::vector<GateOp> &rev, const double *mats, double *d_env, bool *env_post)
 {
-    if (psi->dtype == QCB_C128) return run_adjoint_fused_t<double>(psi, lam, rev, mats, d_env);
-    return run_adjoint_fused_t<float>(psi, lam, rev, mats, d_env);
+    const bool mma = psi->dtype == QCB_C128 && ctx().adjoint_mma != 0;
+    if (env_post) *env_post = mma;
+    if (psi->dtype == QCB_C128) return run_adjoint_fused_t<double>(psi, lam, rev, mats, d_env, mma);
+    return run_adjoint_fused_t<float>(psi, lam, rev, mats, d_env, false);
 }
 
 int run_gate_list(qcb_state *s, const std::vector<GateOp> &gates, const double *mats, bool adjoint)

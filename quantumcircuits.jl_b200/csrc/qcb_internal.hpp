@@ -37,7 +37,7 @@ struct Ctx {
     cudaEvent_t chunk_ev[2][16] = {};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // options
-    long tile_bits = 11, low_bits = 3, max_gates_per_pass = 1 << 30, force_simple = 0, adjoint_tile_bits = 0;
+    long tile_bits = 11, low_bits = 3, max_gates_per_pass = 1 << 30, force_simple = 0, adjoint_tile_bits = 0, adjoint_mma = 1, adjoint_warps = 0;
     // stats
     double st_passes = 0, st_stages = 0, st_launches = 0, st_gates = 0, st_launches_total = 0, st_swaps = 0, st_fused_swaps = 0;
     long fuse_swaps = 1;
@@ -91,7 +91,7 @@ inline void count_launch(int k = 1)
 
 // gate-list execution (passes.cu)
 int run_gate_list(qcb_state *s, const std::vector<GateOp> &gates, const double *mats, bool adjoint);
-int run_adjoint_fused(qcb_state *psi, qcb_state *lam, const std::vector<GateOp> &rev, const double *mats, double *d_env);
+int run_adjoint_fused(qcb_state *psi, qcb_state *lam, const std::vector<GateOp> &rev, const double *mats, double *d_env, bool *env_post);
 int launch_plan(qcb_state *s, const PassPlan &plan, const std::vector<GateOp> &gates, const double *mats, bool adjoint);
 int launch_plan_peer(qcb_state *s, const PeerSrc &src, void *dst, const PassPlan &plan, const std::vector<GateOp> &gates, const double *mats, bool adjoint);
 SchedOptions current_sched_options(const qcb_state *s);

@@ -287,7 +287,7 @@ extern "C" int emu_rank_apply_gates(int n, int g, void *shard, int ngates, const
 }
 
 // ---- fused backward pass of the adjoint sweep (adjoint.cuh) replayed on the CPU ---------------------------
-#include "../../quantumcircuits.jl_b200/csrc/adjoint.cuh"
+#include "../../quantumcircuits.jl_b200/csrc/adjoint_mma.cuh"
 
 template <typename R, int TB>
 static void run_adjoint_pass(typename Vec2<R>::type *psi, typename Vec2<R>::type *lam, int nloc, const AdjParams<R> &A, double *acc)
@@ -352,6 +352,76 @@ extern "C" int emu_adjoint_sweep(int dtype, int n, void *psi, void *lam, int nga
         return adjoint_all<float>(psi, lam, n, ngates, q, mats, tile_bits, low_bits, env_out);
     } catch (const std::exception &e) {
         std::fprintf(stderr, "emu adjoint: %s\n", e.what());
+        return 1;
+    }
+}
+
+// ---- the tensor-core form of the same pass (adjoint_mma.cuh): software model of the MMA fragment layout ---------------
+template <int TB, int NW>
+static void run_adjoint_pass_mma(double2 *psi, double2 *lam, int nloc, const AdjMmaParams &M, double *acc_out, long long *conflicts)
+{
+    const uint32_t NT = 1u << (TB - kRegBits);
+    const unsigned long long ntiles = 1ull << (nloc - TB);
+    std::vector<double2> smP(1u << TB), smL(1u << TB);
+    std::vector<double> acc((size_t)NW * kAdjMaxGates * 32, 0.0);
+    for (unsigned long long b = 0; b < ntiles; b++) {
+        for (uint32_t t = 0; t < NT; t++) { tile_load<double, TB>(psi, M.A.P, smP.data(), t, b); tile_load<double, TB>(lam, M.A.P, smL.data(), t, b); }
+        for (int s = 0; s < M.A.P.nstages; s++) adjoint_stage_mma_host<TB, NW>(M, s, smP.data(), smL.data(), acc.data(), conflicts);
+        for (uint32_t t = 0; t < NT; t++) { tile_store<double, TB>(psi, M.A.P, smP.data(), t, b); tile_store<double, TB>(lam, M.A.P, smL.data(), t, b); }
+    }
+    for (int w = 0; w < NW; w++)
+        for (int i = 0; i < kAdjMaxGates * 32; i++) acc_out[i] += acc[(size_t)w * kAdjMaxGates * 32 + i];
+}
+
+// ComplexF64 only.  env_out as in emu_adjoint_sweep (already converted from the post-gate cross-density matrix);
+// conflicts[0] = shared-memory wavefronts of the stage loads/stores, conflicts[1] = the conflict-free count.
+extern "C" int emu_adjoint_sweep_mma(int n, void *psi, void *lam, int ngates, const int *q, const double *mats, int tile_bits,
+                                     int low_bits, int nwarps, double *env_out, long long *conflicts)
+{
+    try {
+        std::vector<GateOp> rev(ngates);
+        for (int i = 0; i < ngates; i++) rev[i] = GateOp{q[ngates - 1 - i], ngates - 1 - i};
+        std::vector<int> phys(n);
+        for (int i = 0; i < n; i++) phys[i] = i;
+        SchedOptions opt;
+        opt.tile_bits = tile_bits; opt.low_bits = low_bits; opt.max_gates_per_pass = kAdjMaxGates;
+        std::vector<char> done;
+        std::vector<PassPlan> plans = plan_passes(n, phys, rev, opt, &done);
+        for (char d : done) if (!d) return 2;
+        AdjMmaParams *M = new AdjMmaParams;
+        int rc = 0;
+        for (const PassPlan &pl : plans) {
+            fill_params<double>(pl, n, rev, mats, true, M->A.P);
+            int ids[kAdjMaxGates], nid = 0;
+            std::memset(M->A.slot_gate, 0, sizeof M->A.slot_gate);
+            for (size_t st = 0; st < pl.stages.size(); st++)
+                for (int slot = 0; slot < kSlots; slot++) {
+                    const int g = pl.stages[st].gate[slot];
+                    if (g < 0) continue;
+                    M->A.slot_gate[st * kSlots + slot] = (uint8_t)nid;
+                    ids[nid++] = rev[g].mat;
+                }
+            M->A.ngates = nid;
+            fill_adj_mma_sel(*M, pl.TB, nwarps);
+            std::vector<double> acc(kAdjMaxGates * 32, 0.0);
+            const int key = pl.TB * 100 + nwarps;
+            switch (key) {
+#define CASE(T, W) case T * 100 + W: run_adjoint_pass_mma<T, W>((double2 *)psi, (double2 *)lam, n, *M, acc.data(), conflicts); break;
+            CASE(6, 1) CASE(6, 2) CASE(7, 2) CASE(8, 2) CASE(8, 4) CASE(9, 4) CASE(9, 2) CASE(10, 4) CASE(10, 8) CASE(10, 2) CASE(11, 8) CASE(11, 4) CASE(12, 8)
+#undef CASE
+            default: rc = 3;
+            }
+            if (rc) break;
+            for (int k = 0; k < nid; k++) {
+                double *e = env_out + (size_t)ids[k] * 32;
+                for (int i = 0; i < 32; i++) e[i] = acc[k * 32 + i];
+                adjm_env_from_post(mats + 32 * (size_t)ids[k], e);
+            }
+        }
+        delete M;
+        return rc;
+    } catch (const std::exception &e) {
+        std::fprintf(stderr, "emu adjoint mma: %s\n", e.what());
         return 1;
     }
 }

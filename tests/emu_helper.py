@@ -12,7 +12,7 @@ _lib = None
 
 
 def build(force=False):
-    srcs = [os.path.join(_HERE, "emu_tile.cu"), os.path.join(_CSRC, "tile.cuh"), os.path.join(_CSRC, "schedule.hpp"), os.path.join(_CSRC, "dist_plan.hpp"), os.path.join(_CSRC, "adjoint.cuh"), os.path.join(_CSRC, "measure_tile.cuh"), os.path.join(_CSRC, "measure_plan.hpp"), os.path.join(_CSRC, "kernels.cuh")]
+    srcs = [os.path.join(_HERE, "emu_tile.cu"), os.path.join(_CSRC, "tile.cuh"), os.path.join(_CSRC, "schedule.hpp"), os.path.join(_CSRC, "dist_plan.hpp"), os.path.join(_CSRC, "adjoint.cuh"), os.path.join(_CSRC, "adjoint_mma.cuh"), os.path.join(_CSRC, "measure_tile.cuh"), os.path.join(_CSRC, "measure_plan.hpp"), os.path.join(_CSRC, "kernels.cuh")]
     if force or not os.path.exists(_SO) or any(os.path.getmtime(_SO) < os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["nvcc", "-O2", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler",
                                "-fPIC", "-shared", "-o", _SO, srcs[0]], cwd=_HERE)
@@ -94,6 +94,25 @@ def adjoint_sweep(psi, lam, q0, mats, tile_bits, low_bits):
         raise RuntimeError(f"emu_adjoint_sweep rc={rc}")
     envc = (env[:, 0::2] + 1j * env[:, 1::2]).reshape(len(q0), 4, 4).transpose(0, 2, 1)  # stored column-major r + 4c
     return psi, lam, envc
+
+
+def adjoint_sweep_mma(psi, lam, q0, mats, tile_bits, low_bits, nwarps):
+    """Tensor-core form of the backward sweep (adjoint_mma.cuh), complex128 only.  Returns (psi_0, lam_0, env, (wavefronts,
+    conflict-free wavefronts) of the stage loads/stores)."""
+    psi = np.ascontiguousarray(psi, dtype=np.complex128).copy()
+    lam = np.ascontiguousarray(lam, dtype=np.complex128).copy()
+    n = int(psi.size).bit_length() - 1
+    q0 = np.ascontiguousarray(q0, dtype=np.int32)
+    m = np.ascontiguousarray(np.stack([np.asarray(M, dtype=np.complex128).reshape(-1, order="F") for M in mats]))
+    env = np.zeros((len(q0), 32), dtype=np.float64)
+    conf = np.zeros(2, dtype=np.int64)
+    rc = lib().emu_adjoint_sweep_mma(C.c_int(n), psi.ctypes.data_as(C.c_void_p), lam.ctypes.data_as(C.c_void_p), C.c_int(len(q0)),
+                                     q0.ctypes.data_as(C.c_void_p), m.ctypes.data_as(C.c_void_p), C.c_int(tile_bits), C.c_int(low_bits),
+                                     C.c_int(nwarps), env.ctypes.data_as(C.c_void_p), conf.ctypes.data_as(C.c_void_p))
+    if rc:
+        raise RuntimeError(f"emu_adjoint_sweep_mma rc={rc}")
+    envc = (env[:, 0::2] + 1j * env[:, 1::2]).reshape(len(q0), 4, 4).transpose(0, 2, 1)
+    return psi, lam, envc, (int(conf[0]), int(conf[1]))
 
 
 def measure(psi, kind, params, tile_bits, low_bits):

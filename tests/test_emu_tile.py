@@ -203,6 +203,34 @@ def test_emu_adjoint_sweep_gradients(emu, oracle, n, layers, tb, dtype):
     assert np.max(np.abs(grads - g_ref)) < tol * max(1.0, np.max(np.abs(g_ref)))
 
 
+@pytest.mark.parametrize("n,layers,tb,nw", [(9, 4, 9, 4), (12, 6, 10, 4), (12, 5, 10, 8), (13, 5, 11, 8), (12, 3, 12, 8), (10, 4, 9, 2)])
+def test_emu_adjoint_sweep_mma(emu, oracle, n, layers, tb, nw):
+    """The tensor-core backward pass (adjoint_mma.cuh, software model of the m8n8k4 fragments) gives the same un-applied
+    states and -- after env = conj(U) M on the host -- the same environments as the scalar pass, and its stage
+    loads/stores are shared-memory bank-conflict free."""
+    rng = np.random.default_rng(n * 11 + layers + nw)
+    G = onp.brickwork_num_gates(n, layers)
+    angles = rng.uniform(0, 2 * np.pi, (15, G))
+    q0 = np.array(onp.brickwork_gate_positions(n, layers)) - 1
+    mats = [oracle.build_general_unitary_gate(angles[:, g]) for g in range(G)]
+    psiG, lamG = rand_state(rng, n), rand_state(rng, n)
+    p_ref, l_ref, env_ref = emu.adjoint_sweep(psiG, lamG, q0, mats, tb, 3)
+    p, l, env, (wf, wf_min) = emu.adjoint_sweep_mma(psiG, lamG, q0, mats, tb, 3, nw)
+    assert rel(p, p_ref) < 1e-13 and rel(l, l_ref) < 1e-13
+    assert np.max(np.abs(env - env_ref)) < 1e-13
+    # independent definition of the environment: env[g][r, c] = sum conj(lam_g[r]) psi_{g-1}[c]
+    psi, lam = psiG.copy(), lamG.copy()
+    for g in range(G - 1, -1, -1):
+        Ud = np.conj(mats[g].reshape(4, 4)).T
+        psi = oracle.apply_2q(psi, Ud, int(q0[g]) + 1)
+        k = int(q0[g])
+        L4 = np.moveaxis(lam.reshape(2 ** (n - k - 2), 4, 2 ** k), 1, 0).reshape(4, -1)
+        P4 = np.moveaxis(psi.reshape(2 ** (n - k - 2), 4, 2 ** k), 1, 0).reshape(4, -1)
+        assert np.max(np.abs(env[g] - np.conj(L4) @ P4.T)) < 1e-13
+        lam = oracle.apply_2q(lam, Ud, int(q0[g]) + 1)
+    assert wf == wf_min, f"{wf - wf_min} bank-conflict wavefronts out of {wf_min}"
+
+
 # ---- tiled expectation value -----------------------------------------------------------------------------
 @pytest.mark.parametrize("n,tb,c", [(10, 8, 3), (13, 9, 3), (14, 12, 3), (15, 13, 3), (16, 10, 4), (17, 12, 3)])
 def test_emu_tiled_measure(emu, oracle, n, tb, c):

@@ -47,6 +47,8 @@ def _defaults():
     qc.set_option("tile_bits", 11)
     qc.set_option("low_bits", 3)
     qc.set_option("max_gates_per_pass", 1 << 30)
+    qc.set_option("adjoint_mma", 1)
+    qc.set_option("adjoint_tile_bits", 0)
     yield
 
 
@@ -271,6 +273,27 @@ def test_gradients_vs_reference_algorithm(oracle, n, layers, scale, ham):
     E32, g32 = qc.gradients(H, psi0.astype(np.complex64), c, calculate_energy=True)
     assert abs(E32 - E_ref) < 1e-5 * max(1.0, abs(E_ref))
     assert np.max(np.abs(g32 - g_ref)) < 1e-5 * max(scale_g, 1.0)
+
+
+@pytest.mark.parametrize("n,layers,atb", [(13, 5, 0), (16, 6, 9), (18, 4, 10), (18, 7, 11), (20, 3, 12), (22, 4, 0)])
+def test_gradients_tensor_core_pass_equals_scalar_pass(oracle, n, layers, atb):
+    """ComplexF64 backward pass on the FP64 tensor cores (adjoint_mma.cuh, default) vs the scalar-FMA pass (adjoint.cuh),
+    every tile size; at n <= 13 also against the oracle's restatement of the reference's shift sweep."""
+    rng = np.random.default_rng(1000 * n + layers)
+    c = circuit(n, layers, rng)
+    H = qc.TFIMHamiltonian(1.0, 0.1, 0.5) if n % 2 else qc.EastModelHamiltonian(0.1, -0.1)
+    psi0 = qc.B200State(rand_state(rng, n))
+    qc.set_option("adjoint_tile_bits", atb)
+    qc.set_option("adjoint_mma", 0)
+    E0, g0 = qc.gradients(H, psi0, c, calculate_energy=True)
+    qc.set_option("adjoint_mma", 1)
+    E1, g1 = qc.gradients(H, psi0, c, calculate_energy=True)
+    scale_g = max(np.max(np.abs(g0)), 1e-6)
+    assert abs(E1 - E0) < 1e-13 * max(1.0, abs(E0))
+    assert np.max(np.abs(g1 - g0)) < 1e-12 * max(scale_g, 1.0)
+    if n <= 13:
+        _, g_ref = oracle.gradients_brickwork(psi0.to_numpy(), n, layers, c.gate_angles, 0 if n % 2 else 1, H.params())
+        assert np.max(np.abs(g1 - g_ref)) < 1e-12 * max(scale_g, 1.0)
 
 
 def test_gradients_c2_shape_against_shift_subset(oracle):

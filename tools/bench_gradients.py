@@ -25,6 +25,10 @@ def main():
     only = sys.argv[1] if len(sys.argv) > 1 else None
     if len(sys.argv) > 2:
         qc.set_option("adjoint_tile_bits", int(sys.argv[2]))
+    # backward-pass variants: ADJ_MMA=0 selects the scalar-FMA pass (adjoint.cuh), ADJ_WARPS=4|8 the CTA size of the tensor-core pass
+    adj_mma = int(os.environ.get("ADJ_MMA", "1"))
+    qc.set_option("adjoint_mma", adj_mma)
+    qc.set_option("adjoint_warps", int(os.environ.get("ADJ_WARPS", "0")))
     for tag, n, layers, hp, dt in cfgs:
         if only and (tag != only or dt != np.complex128):
             continue
@@ -74,7 +78,7 @@ def main():
         t_meas = (time.perf_counter() - t0) * 2 ** (n - n_cpu)
         napply, nmeas = 2 * G + 15 * G * (G + 1), 30 * G
         cpu_est = napply * t_apply + nmeas * t_meas
-        print(json.dumps({"config": tag, "nqubits": n, "half_layers": layers, "gates": G, "dtype": np.dtype(dt).name,
+        print(json.dumps({"config": tag, "nqubits": n, "half_layers": layers, "gates": G, "dtype": np.dtype(dt).name, "adjoint_mma": adj_mma, "adjoint_warps": int(os.environ.get("ADJ_WARPS", "0")),
                           "gpu_s_per_gradient": dt_gpu, "gpu_s_forward": dt_fwd, "gpu_s_measure": dt_meas, "measure_passes": meas_passes, "gpu_launches_per_gradient": launches, "energy": E,
                           "cpu_reference_algorithm_s_estimate": cpu_est, "cpu_threads": oracle.max_threads(),
                           "cpu_note": f"oracle per-apply {t_apply:.4f} s, per-measure {t_meas:.4f} s (measured at {n_cpu} q, scaled 2^{n - n_cpu}) x "
