@@ -17,8 +17,8 @@
 //   store     two 8-byte stores per state per lane (component g of quads 2t, 2t+1).
 //
 // Shared-memory traffic per gate is one read + one write of both tiles (the minimum), no amplitude is held in a
-// register across gates (tens of registers per thread -> 20+ resident warps per SM instead of 12), and all FP64 work
-// runs at the DMMA rate.  The reduction uses the states AFTER the gate has been un-applied on both:
+// register across gates, and all FP64 work runs at the DMMA rate.  The reduction uses the states AFTER the gate has been
+// un-applied on both:
 //   M[r', c] = sum_rest conj(lambda_{g-1}[r', rest]) psi_{g-1}[c, rest],
 // and the environment the gradient needs, env[r, c] = sum conj(lambda_g[r]) psi_{g-1}[c], follows on the host as
 // env = conj(U) M because lambda_g = U lambda_{g-1} (U unitary -- the adjoint method already relies on it to recover
@@ -29,6 +29,12 @@
 // group of 8 quads = 2 whole windows that differ in warp-window bit `sel` (chosen on the host so that the 8-byte stores
 // of a half warp hit 16 distinct bank pairs; the 16-byte loads of a quarter warp vary 3 of the 4 window bits and are
 // conflict free by construction of the swizzle).
+//
+// Everything a thread needs for one gate -- its two MMA operands, its load / store offsets, the Gray-code steps from group
+// to group, the kind of barrier that follows -- is a 32-byte AdjmLaneProg record computed on the host with the functions
+// below (the same ones the CPU replay uses) and fetched from global memory one gate ahead: two coalesced 16-byte loads
+// instead of a chain of dependent constant-bank reads per gate (ncu on the first version of this kernel: 19 % of the
+// warps' stall samples sat on a 32-way divergent constant fetch of the operands, 17 % on the per-gate reduction).
 #pragma once
 #include <cmath>
 #include <cstring>
@@ -41,6 +47,17 @@ struct AdjMmaParams {
     AdjParams<double> A;
     uint8_t sel[kMaxStages * kSlots]; // warp-window bit that pairs the two windows of a group, per (stage, slot)
 };
+
+// one thread's program for one gate of the pass (index [gate ordinal][thread of the CTA])
+struct AdjmLaneProg {
+    double a_re, a_im; // A operands of the two un-apply MMAs: row (amplitude g>>1, part g&1) of the real form of U^dagger
+    uint16_t ld;       // element offset of amplitude t of quad g of the warp's first group (load)
+    uint16_t st[2];    // ... of amplitude g>>1 of quads 2t, 2t+1 (store; the lane writes component g&1)
+    uint16_t cg[3];    // offsets toggled by the group-index bits (Gray-code walk over the groups)
+    uint16_t flags;    // bit 0: last gate of its stage (CTA barrier after it instead of a warp barrier)
+    uint16_t pad;      // 0 (the kernel uses it as a zero the compiler cannot see through)
+};
+static_assert(sizeof(AdjmLaneProg) == 32, "two 16-byte loads per gate");
 
 // the two bits of q spread over the window bits other than LO, LO+1
 QCB_HD int adjm_other(int LO, int q) { return LO == 0 ? (q << 2) : (LO == 1 ? ((q & 1) | ((q & 2) << 2)) : q); }
@@ -114,8 +131,9 @@ QCB_HD void adjm_gate_operand(const GateMat<double> &Ud, uint32_t lane, double &
     a_im = (g & 1u) ? ur : -ui;
 }
 
-// host choice of `sel`: the half-warp stores vary window bits LO and "other bit 1" plus warp-window bit sel
-inline void fill_adj_mma_sel(AdjMmaParams &M, int TB, int NW)
+// host side: the choice of `sel` per gate (the half-warp stores vary window bits LO and "other bit 1" plus warp-window bit
+// sel: their bank vectors must be independent) ...
+inline void fill_adj_mma(AdjMmaParams &M, int TB, int NW)
 {
     int wbits = 0;
     while ((1 << (wbits + 1)) <= ((1 << (TB - kRegBits)) / NW)) wbits++;
@@ -134,6 +152,51 @@ inline void fill_adj_mma_sel(AdjMmaParams &M, int TB, int NW)
         }
     }
 }
+// ... and the threads' programs, prog[ordinal * 32 NW + thread], gates in processing order (stage by stage, slot by slot =
+// the ordinals of A.slot_gate)
+template <int TB, int NW> inline void build_adj_mma_prog(const AdjMmaParams &M, AdjmLaneProg *prog)
+{
+    constexpr int WPW = (1 << (TB - kRegBits)) / NW;
+    constexpr int WB = Log2<WPW>::value;
+    static_assert(WB >= 1 && WB <= 4, "2 to 16 windows per warp");
+    for (int s = 0; s < M.A.P.nstages; s++) {
+        const StageDesc &S = M.A.P.stage[s];
+        int last_slot = -1;
+        for (int slot = 0; slot < kSlots; slot++)
+            if ((S.mask >> slot) & 1) last_slot = slot;
+        for (int slot = 0; slot < kSlots; slot++) {
+            if (!((S.mask >> slot) & 1)) continue;
+            const int ord = M.A.slot_gate[s * kSlots + slot];
+            for (uint32_t warp = 0; warp < (uint32_t)NW; warp++) {
+                const AdjmStage<TB, WB> C = adjm_stage_consts<TB, WB>(S, warp);
+                for (uint32_t ln = 0; ln < 32; ln++) {
+                    const AdjmGate<TB, WB> G = adjm_gate_consts<TB, WB>(C, S, slot_lo(slot), M.sel[s * kSlots + slot], ln);
+                    AdjmLaneProg &p = prog[(size_t)ord * (32 * NW) + warp * 32 + ln];
+                    std::memset(&p, 0, sizeof p);
+                    adjm_gate_operand(M.A.P.U[s * kSlots + slot], ln, p.a_re, p.a_im);
+                    p.ld = (uint16_t)G.L.ld;
+                    p.st[0] = (uint16_t)G.L.st[0];
+                    p.st[1] = (uint16_t)G.L.st[1];
+                    for (int j = 0; j + 1 < WB; j++) p.cg[j] = (uint16_t)G.cg[j];
+                    p.flags = slot == last_slot ? 1 : 0;
+                }
+            }
+        }
+    }
+}
+
+// raw[j * 32 + lane] = E[g][2t + j] (lane = 4g + t; rows m = (r', Re/Im of lambda), columns n = (c, Re/Im of psi)) ->
+// M[r', c] in the layout of the environments, out32[2 (r' + 4c)] = Re, + 1 = Im:
+// Re = E[2r'][2c] + E[2r'+1][2c+1], Im = E[2r'][2c+1] - E[2r'+1][2c]
+QCB_HD void adjm_combine_raw(const double *raw, double *out32)
+{
+    for (int r = 0; r < 4; r++)
+        for (int c = 0; c < 4; c++) {
+            const int top = 4 * (2 * r) + c, bot = 4 * (2 * r + 1) + c; // lanes holding columns 2c, 2c+1 of rows 2r', 2r'+1
+            out32[2 * (r + 4 * c)] = raw[top] + raw[32 + bot];
+            out32[2 * (r + 4 * c) + 1] = raw[32 + top] - raw[bot];
+        }
+}
 
 #if defined(__CUDACC__)
 // ---------------------------------------------------------------------------------------------------------------------
@@ -142,125 +205,178 @@ __device__ __forceinline__ void dmma(double &d0, double &d1, double a, double b)
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
-template <int TB, int NW>
-__device__ __forceinline__ void adjoint_stage_mma(const AdjMmaParams &M, int s, double2 *smP, double2 *smL, double *acc_warp, uint32_t tid)
+// State a thread carries from gate to gate (across stages and tiles): the MMA accumulators of the gate it finished last and
+// the program of the gate it will work on next.  The accumulators are flushed in the middle of the NEXT gate, when the MMAs
+// that produce them have long retired (an in-order warp that consumed them right away would stall at every gate end), and
+// without touching the FP64 pipe, which the MMAs keep busy (ncu on an earlier version: a DADD waits tens of cycles for a
+// slot): each lane adds its two raw values E[g][2t], E[g][2t+1] to a row in global memory that belongs to its warp alone
+// with fire-and-forget reductions (red.global.add.f64, executed by the L2).  One writer per address and same-address
+// program order make the sums reproducible; the rows are summed in fixed order and turned into the complex 4x4 matrix by
+// k_env_reduce_raw / adjm_combine_raw afterwards.
+struct AdjmCarry {
+    double e0, e1; // pending accumulators E[g][2t], E[g][2t+1]
+    double *row;   // their row: [2][32] doubles (column parity, lane)
+    uint4 prog[2]; // AdjmLaneProg of the next gate
+};
+
+__device__ __forceinline__ void adjm_flush(const AdjmCarry &C, uint32_t lane)
 {
-    constexpr int WPW = (1 << (TB - kRegBits)) / NW; // windows per warp
-    constexpr int WB = Log2<WPW>::value;
-    constexpr int NG = WPW / 2;                      // groups of 8 quads per gate
-    static_assert(WPW >= 2, "a warp needs at least two windows");
-    const StageDesc &S = M.A.P.stage[s];
-    const uint32_t mask = S.mask;
-    const uint32_t lane = tid & 31u, warp = tid >> 5, g = lane >> 2, t = lane & 3u, part = g & 1u;
-    double *dP = reinterpret_cast<double *>(smP) + part, *dL = reinterpret_cast<double *>(smL) + part;
-    const AdjmStage<TB, WB> C = adjm_stage_consts<TB, WB>(S, warp);
-#pragma unroll 1
-    for (int slot = 0; slot < kSlots; slot++) {
-        if (!((mask >> slot) & 1u)) continue;
-        const int LO = slot_lo(slot);
-        const int sel = M.sel[s * kSlots + slot];
-        double a_re, a_im;
-        adjm_gate_operand(M.A.P.U[s * kSlots + slot], lane, a_re, a_im);
-        const AdjmGate<TB, WB> G = adjm_gate_consts<TB, WB>(C, S, LO, sel, lane);
-        double e0[2] = {0.0, 0.0}, e1[2] = {0.0, 0.0};
-        uint32_t gb = 0;
-        double2 x = smP[G.L.ld], l = smL[G.L.ld];
-#pragma unroll
-        for (int i = 0; i < NG; i++) {
-            const double2 xc = x, lc = l;
-            const uint32_t gbc = gb;
-            if (i + 1 < NG) { // next group's operands are in flight while this group's MMAs run
-                gb ^= G.cg[adjm_gray_bit(i)];
-                x = smP[gb ^ G.L.ld];
-                l = smL[gb ^ G.L.ld];
-            }
-            double p0 = 0.0, p1 = 0.0, l0 = 0.0, l1 = 0.0;
-            dmma(p0, p1, a_re, xc.x);
-            dmma(l0, l1, a_re, lc.x);
-            dmma(p0, p1, a_im, xc.y);
-            dmma(l0, l1, a_im, lc.y);
-            const uint32_t s0 = 2u * (gbc ^ G.L.st[0]), s1 = 2u * (gbc ^ G.L.st[1]);
-            dP[s0] = p0; dP[s1] = p1;
-            dL[s0] = l0; dL[s1] = l1;
-            dmma(e0[0], e1[0], l0, p0);
-            dmma(e0[1], e1[1], l1, p1);
-        }
-        // M[r', c] from E (rows (r', Re/Im of lambda), columns (c, Re/Im of psi)): Re = E[2r'][2c] + E[2r'+1][2c+1],
-        // Im = E[2r'][2c+1] - E[2r'+1][2c]; the odd rows live on lane ^ 4
-        const double q0 = e0[0] + e0[1], q1 = e1[0] + e1[1];
-        const double o0 = __shfl_xor_sync(0xffffffffu, q0, 4), o1 = __shfl_xor_sync(0xffffffffu, q1, 4);
-        if (!part) {
-            double *acc_gate = acc_warp + 32 * M.A.slot_gate[s * kSlots + slot];
-            const int k = (int)(g >> 1) + 4 * (int)t;
-            acc_gate[2 * k] += q0 + o1;
-            acc_gate[2 * k + 1] += q1 - o0;
-        }
-        __syncwarp();
-    }
+    asm volatile("red.global.add.f64 [%0], %1;" ::"l"(C.row + lane), "d"(C.e0) : "memory");
+    asm volatile("red.global.add.f64 [%0], %1;" ::"l"(C.row + 32 + lane), "d"(C.e1) : "memory");
 }
 
-// tile <-> shared memory with NT >= 2^(TB-4) threads: thread = (window id, part), each part moves 16 / PARTS elements
-template <int TB, int NT, bool STORE>
-__device__ __forceinline__ void adjm_tile_io(double2 *__restrict__ glob, const PassParams<double> &P, double2 *sm, uint32_t tid, unsigned long long tile)
+// one gate of the pass on the warp's windows; returns the program's flags
+template <int TB, int NW>
+__device__ __forceinline__ uint32_t adjoint_gate_mma(double2 *smP, double2 *smL, double *row, uint32_t lane, AdjmCarry &carry,
+                                                     const uint4 *__restrict__ next_prog)
 {
-    constexpr int TBITS = TB - kRegBits;
-    constexpr int PARTS = NT >> TBITS;
-    static_assert(PARTS >= 1 && PARTS <= kRegAmps, "thread count must be 1..16 times the number of windows");
-    const uint32_t geom = tid & ((1u << TBITS) - 1u), prt = tid >> TBITS;
-    unsigned long long gaddr = cta_base(P, tile);
-    uint32_t e = 0;
+    constexpr int WPW = (1 << (TB - kRegBits)) / NW; // windows per warp
+    constexpr int NG = WPW / 2;                      // groups of 8 quads per gate
+    static_assert(WPW >= 2 && WPW <= 16, "2 to 16 windows per warp");
+    const uint32_t part = (lane >> 2) & 1u;
+    double *dP = reinterpret_cast<double *>(smP) + part, *dL = reinterpret_cast<double *>(smL) + part;
+    // unpack this gate's program, start fetching the next one
+    const uint4 w0 = carry.prog[0], w1 = carry.prog[1];
+    carry.prog[0] = __ldg(next_prog);
+    carry.prog[1] = __ldg(next_prog + 1);
+    const double a_re = __hiloint2double((int)w0.y, (int)w0.x), a_im = __hiloint2double((int)w0.w, (int)w0.z);
+    const uint32_t ld = w1.x & 0xffffu, st0 = w1.x >> 16, st1 = w1.y & 0xffffu;
+    const uint32_t cg[3] = {w1.y >> 16, w1.z & 0xffffu, w1.z >> 16};
+    const uint32_t zero = w1.w >> 16; // AdjmLaneProg::pad: 0, but only the host knows
+    double e0 = 0.0, e1 = 0.0;
+    uint32_t gb = 0;
+    double2 x = smP[ld], l = smL[ld];
 #pragma unroll
-    for (int k = 0; k < TBITS; k++) {
-        const uint32_t bit = (geom >> k) & 1u;
-        gaddr |= (unsigned long long)bit << P.ld_phys[k];
-        e |= bit << (STORE ? P.st_lpos[k] : P.ld_lpos[k]);
+    for (int i = 0; i < NG; i++) {
+        const double2 xc = x, lc = l;
+        const uint32_t gbc = gb;
+        if (i + 1 < NG) { // next group's operands are in flight while this group's MMAs run
+            gb ^= cg[adjm_gray_bit(i)];
+            x = smP[gb ^ ld];
+            l = smL[gb ^ ld];
+        }
+        double p0 = 0.0, p1 = 0.0, l0 = 0.0, l1 = 0.0;
+        dmma(p0, p1, a_re, xc.x);
+        dmma(l0, l1, a_re, lc.x);
+        dmma(p0, p1, a_im, xc.y);
+        dmma(l0, l1, a_im, lc.y);
+        const uint32_t s0 = 2u * (gbc ^ st0), s1 = 2u * (gbc ^ st1);
+        dP[s0] = p0; dP[s1] = p1;
+        dL[s0] = l0; dL[s1] = l1;
+        dmma(e0, e1, l0, p0);
+        dmma(e0, e1, l1, p1);
+        if (i == (NG > 1 ? 1 : 0)) {
+            // the previous gate's accumulators.  The XOR with (bits of this group's result) & 0 ties the flush to a value of THIS
+            // group at the cost of two integer instructions: without a true dependency ptxas may hoist it to the top of the
+            // gate, where the in-order warp would wait for the previous gate's last MMAs after all
+            const int tie = __double2hiint(l1) & (int)zero;
+            carry.e0 = __hiloint2double(__double2hiint(carry.e0), __double2loint(carry.e0) ^ tie);
+            carry.e1 = __hiloint2double(__double2hiint(carry.e1), __double2loint(carry.e1) ^ tie);
+            adjm_flush(carry, lane);
+        }
     }
-    e = swz<3>(e);
-    if (!STORE) {
-        double2 tmp[kRegAmps / PARTS];
-#pragma unroll
-        for (int i = 0; i < kRegAmps / PARTS; i++) tmp[i] = glob[gaddr | P.ld_goff[i * PARTS + prt]];
-#pragma unroll
-        for (int i = 0; i < kRegAmps / PARTS; i++) sm[e ^ P.ld_eoff[i * PARTS + prt]] = tmp[i];
-    } else {
-#pragma unroll
-        for (int i = 0; i < kRegAmps / PARTS; i++) glob[gaddr | P.ld_goff[i * PARTS + prt]] = sm[e ^ P.st_eoff[i * PARTS + prt]];
-    }
+    carry.e0 = e0; carry.e1 = e1;
+    carry.row = row;
+    return w1.w & 0xffffu;
 }
+
+// tile <-> shared memory with NT >= 2^(TB-4) threads: thread = (window id, part), each part moves 16 / PARTS elements of
+// each state.  A thread stores to global memory exactly the shared-memory slots it fills on a load (the backward pass
+// never permutes bits: st_lpos == ld_lpos, checked on the host), so a tile's write-back and the next tile's fill need no
+// barrier between them, and the next tile's global loads are issued before the write-back starts (one state at a time:
+// 32 registers in flight).
+template <int TB, int NT> struct AdjmTileIo {
+    static constexpr int TBITS = TB - kRegBits;
+    static constexpr int PARTS = NT >> TBITS;
+    static constexpr int NE = kRegAmps / PARTS;
+    static_assert(PARTS >= 1 && PARTS <= kRegAmps, "thread count must be 1..16 times the number of windows");
+    uint32_t e, prt;
+    unsigned long long gthread; // the thread's share of the global index (without the tile's)
+    __device__ __forceinline__ AdjmTileIo(const PassParams<double> &P, uint32_t tid)
+    {
+        const uint32_t geom = tid & ((1u << TBITS) - 1u);
+        prt = tid >> TBITS;
+        gthread = 0;
+        e = 0;
+#pragma unroll
+        for (int k = 0; k < TBITS; k++) {
+            const uint32_t bit = (geom >> k) & 1u;
+            gthread |= (unsigned long long)bit << P.ld_phys[k];
+            e |= bit << P.ld_lpos[k];
+        }
+        e = swz<3>(e);
+    }
+    __device__ __forceinline__ void fetch(const double2 *__restrict__ st, const PassParams<double> &P, unsigned long long tile, double2 (&r)[NE]) const
+    {
+        const unsigned long long g = cta_base(P, tile) | gthread;
+#pragma unroll
+        for (int i = 0; i < NE; i++) r[i] = st[g | P.ld_goff[i * PARTS + prt]];
+    }
+    __device__ __forceinline__ void fill(const PassParams<double> &P, double2 *sm, const double2 (&r)[NE]) const
+    {
+#pragma unroll
+        for (int i = 0; i < NE; i++) sm[e ^ P.ld_eoff[i * PARTS + prt]] = r[i];
+    }
+    __device__ __forceinline__ void write_back(double2 *__restrict__ st, const PassParams<double> &P, unsigned long long tile, const double2 *sm) const
+    {
+        const unsigned long long g = cta_base(P, tile) | gthread;
+#pragma unroll
+        for (int i = 0; i < NE; i++) st[g | P.ld_goff[i * PARTS + prt]] = sm[e ^ P.ld_eoff[i * PARTS + prt]];
+    }
+};
+
+constexpr int kAdjmRow = 64; // raw accumulators per warp and gate
 
 template <int TB, int NW, int MINB>
 __global__ void __launch_bounds__(32 * NW, MINB)
-adjoint_pass_mma_kernel(double2 *psi, double2 *lam, const __grid_constant__ AdjMmaParams M, unsigned long long ntiles,
-                        double *partial /* [gridDim.x][kAdjMaxGates][32] */)
+adjoint_pass_mma_kernel(double2 *psi, double2 *lam, const __grid_constant__ PassParams<double> P, int ngates,
+                        const uint4 *__restrict__ prog /* AdjmLaneProg [ngates][32 NW] */, unsigned long long ntiles,
+                        double *rows /* [gridDim.x][NW][kAdjMaxGates][kAdjmRow], zeroed */)
 {
     constexpr int NT = 32 * NW;
     extern __shared__ __align__(16) unsigned char qcb_smem_raw[];
     double2 *smP = reinterpret_cast<double2 *>(qcb_smem_raw);
     double2 *smL = smP + (1 << TB);
-    double *acc = reinterpret_cast<double *>(smL + (1 << TB)); // [NW][kAdjMaxGates][32]
-    const uint32_t tid = threadIdx.x;
-    for (int i = tid; i < NW * kAdjMaxGates * 32; i += NT) acc[i] = 0.0;
-    __syncthreads();
-    double *acc_warp = acc + (tid >> 5) * (kAdjMaxGates * 32);
-    for (unsigned long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        adjm_tile_io<TB, NT, false>(psi, M.A.P, smP, tid, tile);
-        adjm_tile_io<TB, NT, false>(lam, M.A.P, smL, tid, tile);
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    double *rows_warp = rows + ((size_t)blockIdx.x * NW + warp) * (kAdjMaxGates * kAdjmRow);
+    const uint4 *my_prog = prog + 2 * tid;
+    AdjmCarry carry;
+    carry.e0 = carry.e1 = 0.0; // nothing pending: the first flush adds zeros to row 0
+    carry.row = rows_warp;
+    carry.prog[0] = __ldg(my_prog);
+    carry.prog[1] = __ldg(my_prog + 1);
+    const AdjmTileIo<TB, NT> io(P, tid);
+    double2 r[AdjmTileIo<TB, NT>::NE];
+    unsigned long long tile = blockIdx.x; // (the host launches at most ntiles CTAs)
+    io.fetch(psi, P, tile, r);
+    io.fill(P, smP, r);
+    io.fetch(lam, P, tile, r);
+    io.fill(P, smL, r);
+    while (true) {
         __syncthreads();
 #pragma unroll 1
-        for (int s = 0; s < M.A.P.nstages; s++) {
-            adjoint_stage_mma<TB, NW>(M, s, smP, smL, acc_warp, tid);
-            __syncthreads();
+        for (int gi = 0; gi < ngates; gi++) {
+            const int gn = gi + 1 < ngates ? gi + 1 : 0; // (the next tile runs the same program)
+            const uint32_t flags = adjoint_gate_mma<TB, NW>(smP, smL, rows_warp + kAdjmRow * gi, lane, carry, my_prog + (size_t)gn * (2 * NT));
+            if (flags & 1u) __syncthreads(); // gates of the next stage regroup the tile's windows over the warps
+            else __syncwarp();
         }
-        adjm_tile_io<TB, NT, true>(psi, M.A.P, smP, tid, tile);
-        adjm_tile_io<TB, NT, true>(lam, M.A.P, smL, tid, tile);
-        __syncthreads();
+        // (the last gate of the pass ends a stage: the CTA barrier above orders the gate phase before the write-back)
+        const unsigned long long next = tile + gridDim.x;
+        if (next >= ntiles) {
+            io.write_back(psi, P, tile, smP);
+            io.write_back(lam, P, tile, smL);
+            break;
+        }
+        io.fetch(psi, P, next, r); // in flight during the write-back
+        io.write_back(psi, P, tile, smP);
+        io.fill(P, smP, r);
+        io.fetch(lam, P, next, r);
+        io.write_back(lam, P, tile, smL);
+        io.fill(P, smL, r);
+        tile = next;
     }
-    for (int i = tid; i < kAdjMaxGates * 32; i += NT) {
-        double sum = 0;
-#pragma unroll
-        for (int w = 0; w < NW; w++) sum += acc[w * (kAdjMaxGates * 32) + i];
-        partial[(size_t)blockIdx.x * (kAdjMaxGates * 32) + i] = sum;
-    }
+    adjm_flush(carry, lane);
 }
 #endif
 
@@ -309,34 +425,24 @@ inline void adjm_count_wavefronts(const uint32_t (&addr8)[32], int bytes, long l
     }
 }
 
+// all gates of a pass on one tile, driven by the same lane programs the GPU fetches
 template <int TB, int NW>
-inline void adjoint_stage_mma_host(const AdjMmaParams &M, int s, double2 *smP, double2 *smL, double *acc /*[NW][kAdjMaxGates][32]*/,
-                                   long long *conflicts = nullptr)
+inline void adjoint_tile_mma_host(const AdjmLaneProg *prog, int ngates, double2 *smP, double2 *smL, double *rows /*[NW][kAdjMaxGates][64] raw*/,
+                                  long long *conflicts = nullptr)
 {
     constexpr int WPW = (1 << (TB - kRegBits)) / NW;
     constexpr int NG = WPW / 2;
-    constexpr int WB = Log2<WPW>::value;
-    static_assert(WPW >= 2, "a warp needs at least two windows");
-    const StageDesc &S = M.A.P.stage[s];
+    static_assert(WPW >= 2 && WPW <= 16, "2 to 16 windows per warp");
     double *fP = reinterpret_cast<double *>(smP), *fL = reinterpret_cast<double *>(smL);
-    for (uint32_t warp = 0; warp < (uint32_t)NW; warp++)
-        for (int slot = 0; slot < kSlots; slot++) {
-            if (!((S.mask >> slot) & 1u)) continue;
-            const int LO = slot_lo(slot);
-            const int sel = M.sel[s * kSlots + slot];
+    for (int gi = 0; gi < ngates; gi++)
+        for (uint32_t warp = 0; warp < (uint32_t)NW; warp++) {
+            const AdjmLaneProg *L = prog + (size_t)gi * (32 * NW) + warp * 32;
             double a_re[32], a_im[32];
-            AdjmLane L[32];
-            const AdjmStage<TB, WB> C = adjm_stage_consts<TB, WB>(S, warp);
-            AdjmGate<TB, WB> G0{};
-            for (uint32_t ln = 0; ln < 32; ln++) {
-                adjm_gate_operand(M.A.P.U[s * kSlots + slot], ln, a_re[ln], a_im[ln]);
-                G0 = adjm_gate_consts<TB, WB>(C, S, LO, sel, ln);
-                L[ln] = G0.L;
-            }
+            for (int ln = 0; ln < 32; ln++) { a_re[ln] = L[ln].a_re; a_im[ln] = L[ln].a_im; }
             double e0[32] = {0}, e1[32] = {0};
             uint32_t gb = 0;
             for (int i = 0; i < NG; i++) {
-                if (i > 0) gb ^= G0.cg[adjm_gray_bit(i - 1)];
+                if (i > 0) gb ^= L[0].cg[adjm_gray_bit(i - 1)];
                 double xr[32], xi[32], lr[32], li[32];
                 uint32_t a8[32];
                 for (int ln = 0; ln < 32; ln++) {
@@ -366,13 +472,10 @@ inline void adjoint_stage_mma_host(const AdjMmaParams &M, int s, double2 *smP, d
                 adjm_soft_mma(e0, e1, l0, p0);
                 adjm_soft_mma(e0, e1, l1, p1);
             }
-            double *acc_gate = acc + (size_t)warp * (kAdjMaxGates * 32) + 32 * M.A.slot_gate[s * kSlots + slot];
+            double *row = rows + ((size_t)warp * kAdjMaxGates + gi) * 64;
             for (int ln = 0; ln < 32; ln++) {
-                const int g = ln >> 2, t = ln & 3;
-                if (g & 1) continue;
-                const int k = (g >> 1) + 4 * t;
-                acc_gate[2 * k] += e0[ln] + e1[ln ^ 4];
-                acc_gate[2 * k + 1] += e1[ln] - e0[ln ^ 4];
+                row[ln] += e0[ln];
+                row[32 + ln] += e1[ln];
             }
         }
 }

@@ -238,14 +238,36 @@ template <typename R, int TB> static int launch_adjoint(qcb_state *psi, qcb_stat
     return QCB_OK;
 }
 
-// ComplexF64: the tensor-core form (adjoint_mma.cuh); env rows hold the post-gate matrix M, see run_adjoint_fused
+// ComplexF64: the tensor-core form (adjoint_mma.cuh); env rows hold the post-gate matrix M, see run_adjoint_fused.
+// Final reduction of its raw accumulator rows: block = (gate ordinal, raw element); fixed-order sum over all warps' rows.
+static __global__ void k_env_reduce_raw(const double *__restrict__ rows, int nrows /* CTAs x warps */, double *raw_out /* [ngates][64] */)
+{
+    const int ord = blockIdx.x >> 6, el = blockIdx.x & 63;
+    double s = 0;
+    for (int r = threadIdx.x; r < nrows; r += blockDim.x) s += rows[((size_t)r * kAdjMaxGates + ord) * kAdjmRow + el];
+    __shared__ double red[32];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += red[w];
+        raw_out[ord * kAdjmRow + el] = t;
+    }
+}
+static __global__ void k_env_combine_raw(const double *__restrict__ raw, EnvIds ids, double *env_out)
+{
+    const int ord = threadIdx.x;
+    if (ord < ids.n) adjm_combine_raw(raw + ord * kAdjmRow, env_out + (size_t)ids.id[ord] * 32);
+}
+
 template <int TB, int NW> static int launch_adjoint_mma(qcb_state *psi, qcb_state *lam, const AdjMmaParams &M, const EnvIds &ids, double *d_env)
 {
     constexpr int NT = 32 * NW;
-    // two tiles + per-warp accumulators per CTA; registers are not the limit (< 100 per thread)
-    constexpr int MINB = TB >= 12 ? 1 : (TB == 11 ? (NW == 8 ? 2 : 3) : (TB == 10 ? (NW == 8 ? 3 : 5) : 8));
+    // two tiles per CTA and at most 80 registers per thread: 6 CTAs = 24 warps per SM at TB = 10
+    constexpr int MINB = TB >= 12 ? 1 : (TB == 11 ? 2 : (TB == 10 ? (NW == 8 ? 3 : 6) : 6));
     auto kern = adjoint_pass_mma_kernel<TB, NW, MINB>;
-    const size_t smem = 2 * (sizeof(double2) << TB) + sizeof(double) * NW * kAdjMaxGates * 32;
+    const size_t smem = 2 * (sizeof(double2) << TB);
     static bool attr_set = false;
     static int ctas_per_sm = 1;
     if (!attr_set) {
@@ -256,12 +278,25 @@ template <int TB, int NW> static int launch_adjoint_mma(qcb_state *psi, qcb_stat
     }
     const unsigned long long ntiles = 1ull << (psi->nloc - TB);
     const unsigned grid = (unsigned)std::min<unsigned long long>(ntiles, (unsigned long long)ctx().sm_count * ctas_per_sm);
-    QCB_TRY(ensure_partial((size_t)grid * kAdjMaxGates * 32));
-    kern<<<grid, NT, smem, ctx().stream>>>((double2 *)psi->d, (double2 *)lam->d, M, ntiles, ctx().d_partial);
+    // device work area: [accumulator rows of every warp | their sums | the threads' per-gate programs]
+    static thread_local std::vector<AdjmLaneProg> prog;
+    prog.resize((size_t)kAdjMaxGates * NT);
+    build_adj_mma_prog<TB, NW>(M, prog.data());
+    const size_t nrows = (size_t)grid * NW;
+    const size_t rows_doubles = nrows * kAdjMaxGates * kAdjmRow, raw_doubles = (size_t)kAdjMaxGates * kAdjmRow;
+    const size_t prog_bytes = (size_t)M.A.ngates * NT * sizeof(AdjmLaneProg);
+    QCB_TRY(ensure_partial(rows_doubles + raw_doubles + (size_t)kAdjMaxGates * 16 * 32 * sizeof(AdjmLaneProg) / sizeof(double)));
+    double *d_rows = ctx().d_partial, *d_raw = d_rows + rows_doubles, *d_prog = d_raw + raw_doubles;
+    QCB_CUDA(cudaMemsetAsync(d_rows, 0, rows_doubles * sizeof(double), ctx().stream));
+    // (stream-ordered upload from pageable memory: the driver stages the source, so it may be reused at once)
+    QCB_CUDA(cudaMemcpyAsync(d_prog, prog.data(), prog_bytes, cudaMemcpyHostToDevice, ctx().stream));
+    kern<<<grid, NT, smem, ctx().stream>>>((double2 *)psi->d, (double2 *)lam->d, M.A.P, M.A.ngates, (const uint4 *)d_prog, ntiles, d_rows);
     QCB_CUDA(cudaGetLastError());
-    k_env_final<<<ids.n * 32, 128, 0, ctx().stream>>>(ctx().d_partial, (int)grid, ids, d_env);
+    k_env_reduce_raw<<<ids.n * kAdjmRow, 128, 0, ctx().stream>>>(d_rows, (int)nrows, d_raw);
     QCB_CUDA(cudaGetLastError());
-    count_launch(2);
+    k_env_combine_raw<<<1, 32, 0, ctx().stream>>>(d_raw, ids, d_env);
+    QCB_CUDA(cudaGetLastError());
+    count_launch(3);
     return QCB_OK;
 }
 
@@ -285,15 +320,16 @@ template <> int launch_adjoint_any<double>(qcb_state *psi, qcb_state *lam, int T
         M.A = A;
         // warps per CTA: 4 keeps 16 windows per warp at TB = 10 (8 MMA groups per gate, 5 CTAs per SM); "adjoint_warps" overrides
         const long want = ctx().adjoint_warps;
-        const int NW = TB >= 12 ? 8 : (TB == 9 ? 4 : (want == 4 || want == 8 ? (int)want : (TB == 11 ? 8 : 4)));
-        fill_adj_mma_sel(M, TB, NW);
+        const int NW = TB == 12 ? 16 : (TB == 11 ? 8 : (TB == 9 ? 4 : (want == 4 || want == 8 ? (int)want : 4)));
+        for (int k = 0; k < TB; k++)
+            if (A.P.ld_lpos[k] != A.P.st_lpos[k]) return set_error(QCB_EINVAL, "the backward pass does not permute bits");
+        fill_adj_mma(M, TB, NW);
         switch (TB * 100 + NW) {
         case 904: return launch_adjoint_mma<9, 4>(psi, lam, M, ids, d_env);
         case 1004: return launch_adjoint_mma<10, 4>(psi, lam, M, ids, d_env);
         case 1008: return launch_adjoint_mma<10, 8>(psi, lam, M, ids, d_env);
-        case 1104: return launch_adjoint_mma<11, 4>(psi, lam, M, ids, d_env);
         case 1108: return launch_adjoint_mma<11, 8>(psi, lam, M, ids, d_env);
-        case 1208: return launch_adjoint_mma<12, 8>(psi, lam, M, ids, d_env);
+        case 1216: return launch_adjoint_mma<12, 16>(psi, lam, M, ids, d_env);
         default: return set_error(QCB_EINVAL, "unsupported tile size %d for the backward pass", TB);
         }
     }

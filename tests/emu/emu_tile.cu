@@ -360,17 +360,24 @@ extern "C" int emu_adjoint_sweep(int dtype, int n, void *psi, void *lam, int nga
 template <int TB, int NW>
 static void run_adjoint_pass_mma(double2 *psi, double2 *lam, int nloc, const AdjMmaParams &M, double *acc_out, long long *conflicts)
 {
+    std::vector<AdjmLaneProg> prog((size_t)M.A.ngates * 32 * NW);
+    build_adj_mma_prog<TB, NW>(M, prog.data());
     const uint32_t NT = 1u << (TB - kRegBits);
     const unsigned long long ntiles = 1ull << (nloc - TB);
     std::vector<double2> smP(1u << TB), smL(1u << TB);
-    std::vector<double> acc((size_t)NW * kAdjMaxGates * 32, 0.0);
+    std::vector<double> rows((size_t)NW * kAdjMaxGates * 64, 0.0);
     for (unsigned long long b = 0; b < ntiles; b++) {
         for (uint32_t t = 0; t < NT; t++) { tile_load<double, TB>(psi, M.A.P, smP.data(), t, b); tile_load<double, TB>(lam, M.A.P, smL.data(), t, b); }
-        for (int s = 0; s < M.A.P.nstages; s++) adjoint_stage_mma_host<TB, NW>(M, s, smP.data(), smL.data(), acc.data(), conflicts);
+        adjoint_tile_mma_host<TB, NW>(prog.data(), M.A.ngates, smP.data(), smL.data(), rows.data(), conflicts);
         for (uint32_t t = 0; t < NT; t++) { tile_store<double, TB>(psi, M.A.P, smP.data(), t, b); tile_store<double, TB>(lam, M.A.P, smL.data(), t, b); }
     }
-    for (int w = 0; w < NW; w++)
-        for (int i = 0; i < kAdjMaxGates * 32; i++) acc_out[i] += acc[(size_t)w * kAdjMaxGates * 32 + i];
+    // fixed-order sum of the warps' rows, then the complex 4x4 matrix (what k_env_reduce_raw does on the GPU)
+    for (int gi = 0; gi < M.A.ngates; gi++) {
+        double raw[64] = {0};
+        for (int w = 0; w < NW; w++)
+            for (int i = 0; i < 64; i++) raw[i] += rows[((size_t)w * kAdjMaxGates + gi) * 64 + i];
+        adjm_combine_raw(raw, acc_out + 32 * gi);
+    }
 }
 
 // ComplexF64 only.  env_out as in emu_adjoint_sweep (already converted from the post-gate cross-density matrix);
@@ -402,12 +409,12 @@ extern "C" int emu_adjoint_sweep_mma(int n, void *psi, void *lam, int ngates, co
                     ids[nid++] = rev[g].mat;
                 }
             M->A.ngates = nid;
-            fill_adj_mma_sel(*M, pl.TB, nwarps);
+            fill_adj_mma(*M, pl.TB, nwarps);
             std::vector<double> acc(kAdjMaxGates * 32, 0.0);
             const int key = pl.TB * 100 + nwarps;
             switch (key) {
 #define CASE(T, W) case T * 100 + W: run_adjoint_pass_mma<T, W>((double2 *)psi, (double2 *)lam, n, *M, acc.data(), conflicts); break;
-            CASE(6, 1) CASE(6, 2) CASE(7, 2) CASE(8, 2) CASE(8, 4) CASE(9, 4) CASE(9, 2) CASE(10, 4) CASE(10, 8) CASE(10, 2) CASE(11, 8) CASE(11, 4) CASE(12, 8)
+            CASE(6, 1) CASE(6, 2) CASE(7, 2) CASE(8, 2) CASE(8, 4) CASE(9, 4) CASE(9, 2) CASE(10, 4) CASE(10, 8) CASE(11, 8) CASE(12, 16)
 #undef CASE
             default: rc = 3;
             }

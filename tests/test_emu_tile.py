@@ -203,7 +203,7 @@ def test_emu_adjoint_sweep_gradients(emu, oracle, n, layers, tb, dtype):
     assert np.max(np.abs(grads - g_ref)) < tol * max(1.0, np.max(np.abs(g_ref)))
 
 
-@pytest.mark.parametrize("n,layers,tb,nw", [(9, 4, 9, 4), (12, 6, 10, 4), (12, 5, 10, 8), (13, 5, 11, 8), (12, 3, 12, 8), (10, 4, 9, 2)])
+@pytest.mark.parametrize("n,layers,tb,nw", [(9, 4, 9, 4), (12, 6, 10, 4), (12, 5, 10, 8), (13, 5, 11, 8), (12, 3, 12, 16), (10, 4, 9, 2)])
 def test_emu_adjoint_sweep_mma(emu, oracle, n, layers, tb, nw):
     """The tensor-core backward pass (adjoint_mma.cuh, software model of the m8n8k4 fragments) gives the same un-applied
     states and -- after env = conj(U) M on the host -- the same environments as the scalar pass, and its stage

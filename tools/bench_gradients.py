@@ -39,7 +39,7 @@ def main():
         psi0 = qc.B200State(n, dt)
         qc.gradients(H, psi0, c, calculate_energy=True)  # warm-up
         torch.cuda.synchronize()
-        reps = 1 if only else 3
+        reps = int(os.environ.get("REPS", "1" if only else "3"))
         t0 = time.perf_counter()
         for _ in range(reps):
             E, g = qc.gradients(H, psi0, c, calculate_energy=True)
