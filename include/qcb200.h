@@ -124,6 +124,13 @@ int qcb_apply_brickwork_host(int dtype, int nbits, int nlayers, const double *an
 int qcb_measure_tfim(const qcb_state *s, double J, double h, double g, double *out_E2); /* tfim.jl:17-54 */
 int qcb_measure_east(const qcb_state *s, double c, double A, double B, double *out_E2); /* east_model.jl:30-52 */
 
+/* measure(H::AbstractMatrix, psi) = real(dot(psi, H, psi))  src/circuits.jl:49-55 (also measure!(psi', H, psi) :56-58 and, after
+ * qcb_apply_brickwork, measure(H, psi, circuit) :59-62).  H is 2^n x 2^n in CSR form on the host: rowptr[nrows+1], colidx[nnz]
+ * (0-based, 64-bit), vals = nnz (re, im) pairs; a dense matrix is passed as the CSR holding every entry.  out_E2 = (re, im);
+ * the reference asserts im < 1e-12.  Not for sharded states. */
+int qcb_measure_csr(const qcb_state *s, long long nrows, const long long *rowptr, const long long *colidx, const double *vals_reim,
+                    double *out_E2);
+
 /* ---- gradients!(cache, psi', psi'', psi, H, psi0, circuit; calculate_energy)  src/gradients.jl:88-152 ----
  * Same numbers as the reference's parameter-shift sweep, computed by the O(G) adjoint sweep
  * (SURVEY.md appendix A).  psi0 is not modified.  out_grads is 15 x G column-major. */

@@ -13,6 +13,6 @@ from .state import B200State, zero_state_vec, zero_state_tensor  # noqa: F401
 from .utils import convert_gates_to_matrix, operation_tensor  # noqa: F401
 from .apply import B200ApplyCache, construct_apply_cache, apply, apply_, apply_circuit_host  # noqa: F401
 from .hamiltonians import (AbstractKernelHamiltonian, TFIMHamiltonian, EastModelHamiltonian, measure, measure_,  # noqa: F401
-                           imaginary_energy_limit)
+                           imaginary_energy_limit, build_sparse_tfim_hamiltonian, find_tfim_ground_state, east_model_matrix)
 from . import dist  # noqa: F401
 from .gradients import construct_grads_cache, gradients, gradients_, optimise_, propagate_forwards_  # noqa: F401

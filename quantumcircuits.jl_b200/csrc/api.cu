@@ -223,7 +223,7 @@ static int gradients_impl(const qcb_state *psi0, int nbits, int nlayers, const d
     {
         const unsigned blocks = grid_for(namps, kRedThreads, 8);
         QCB_TRY(ensure_partial((size_t)blocks * 2));
-        QCB_TRY(ensure_out(64));
+        QCB_TRY(ensure_out((size_t)32 * G + 2)); // [environments | E]: one download, one synchronisation at the end
         if (psi0->dtype == QCB_C128)
             k_apply_ham<double><<<blocks, kRedThreads, 0, c.stream>>>((double2 *)B.d, (const double2 *)A.d, namps, H, (double2 *)c.d_partial);
         else
@@ -231,16 +231,12 @@ static int gradients_impl(const qcb_state *psi0, int nbits, int nlayers, const d
         QCB_CUDA(cudaGetLastError());
         count_launch();
         if (want_energy) {
-            k_final_sum<<<2, 256, 0, c.stream>>>(c.d_partial, (int)blocks, 2, c.d_out);
+            k_final_sum<<<2, 256, 0, c.stream>>>(c.d_partial, (int)blocks, 2, c.d_out + 32 * (size_t)G);
             QCB_CUDA(cudaGetLastError());
             count_launch();
-            QCB_CUDA(cudaMemcpyAsync(c.h_out, c.d_out, 2 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
-            QCB_CUDA(cudaStreamSynchronize(c.stream));
-            *out_E = c.h_out[0];
         }
     }
     // backward sweep: un-apply gate g on psi and lambda, reduce the 4x4 environment
-    QCB_TRY(ensure_out((size_t)32 * G));
     double bw_passes = 0, bw_stages = 0;
     bool env_post = false;
     if (!c.force_simple && nbits >= kMinTB) {
@@ -274,8 +270,9 @@ static int gradients_impl(const qcb_state *psi0, int nbits, int nlayers, const d
         }
         bw_passes = G;
     }
-    QCB_CUDA(cudaMemcpyAsync(c.h_out, c.d_out, sizeof(double) * 32 * (size_t)G, cudaMemcpyDeviceToHost, c.stream));
+    QCB_CUDA(cudaMemcpyAsync(c.h_out, c.d_out, sizeof(double) * (32 * (size_t)G + 2), cudaMemcpyDeviceToHost, c.stream));
     QCB_CUDA(cudaStreamSynchronize(c.stream));
+    if (want_energy) *out_E = c.h_out[32 * (size_t)G];
     // grads[k, g] = 2 Re sum_{r,c} env_g[r,c] dU_g/dtheta_k [r,c]
     for (int g = 0; g < G; g++) {
         double *env = c.h_out + 32 * (size_t)g;
@@ -799,6 +796,50 @@ int qcb_measure_east(const qcb_state *s, double c, double A, double B, double *o
 {
     if (!out_E2) return set_error(QCB_EINVAL, "null output");
     return measure_impl(s, QCB_HAM_EAST, c, A, B, out_E2);
+}
+
+// measure(H::AbstractMatrix, psi)  src/circuits.jl:49-55 -- explicit Hamiltonian, CSR on the host (a dense matrix is the CSR
+// with every entry).  The matrix is uploaded for the call (this is the reference's small-n cross-check path).
+int qcb_measure_csr(const qcb_state *s, long long nrows, const long long *rowptr, const long long *colidx, const double *vals_reim, double *out_E2)
+{
+    QCB_REQUIRE_INIT();
+    QCB_TRY(check_state(s));
+    if (!rowptr || !out_E2) return set_error(QCB_EINVAL, "null pointer");
+    if (s->sharded) return set_error(QCB_EUNSUPPORTED, "matrix Hamiltonians are not supported on sharded states");
+    if (nrows != (1ll << s->n)) return set_error(QCB_EINVAL, "H must be 2^n x 2^n with n = %d", s->n);
+    const long long nnz = rowptr[nrows];
+    if (rowptr[0] != 0 || nnz < 0 || (nnz > 0 && (!colidx || !vals_reim))) return set_error(QCB_EINVAL, "bad CSR arrays");
+    for (long long r = 0; r < nrows; r++)
+        if (rowptr[r + 1] < rowptr[r]) return set_error(QCB_EINVAL, "rowptr must be non-decreasing");
+    for (long long k = 0; k < nnz; k++)
+        if (colidx[k] < 0 || colidx[k] >= nrows) return set_error(QCB_EINVAL, "column index out of range");
+    Ctx &c = ctx();
+    const size_t b_ptr = sizeof(long long) * (size_t)(nrows + 1), b_col = sizeof(long long) * (size_t)nnz, b_val = 16 * (size_t)nnz;
+    char *d = nullptr;
+    QCB_CUDA(cudaMalloc(&d, b_ptr + b_col + b_val + 64));
+    long long *d_ptr = (long long *)d, *d_col = (long long *)(d + b_ptr);
+    double2 *d_val = (double2 *)(d + b_ptr + b_col + ((16 - (b_ptr + b_col) % 16) % 16));
+    int rc = QCB_OK;
+    auto upload = [&](void *dst, const void *src, size_t n) { return n == 0 || cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, c.stream) == cudaSuccess; };
+    if (!upload(d_ptr, rowptr, b_ptr) || !upload(d_col, colidx, b_col) || !upload(d_val, vals_reim, b_val))
+        rc = set_error(QCB_ECUDA, "upload of the CSR arrays failed");
+    const unsigned blocks = grid_for((unsigned long long)nrows, kRedThreads, 8);
+    if (rc == QCB_OK) rc = ensure_partial((size_t)blocks * 2);
+    if (rc == QCB_OK) rc = ensure_out(64);
+    if (rc == QCB_OK) {
+        if (s->dtype == QCB_C128) k_measure_csr<double><<<blocks, kRedThreads, 0, c.stream>>>((const double2 *)s->d, nrows, d_ptr, d_col, d_val, (double2 *)c.d_partial);
+        else k_measure_csr<float><<<blocks, kRedThreads, 0, c.stream>>>((const float2 *)s->d, nrows, d_ptr, d_col, d_val, (double2 *)c.d_partial);
+        k_final_sum<<<2, 256, 0, c.stream>>>(c.d_partial, (int)blocks, 2, c.d_out);
+        count_launch(2);
+        if (cudaGetLastError() != cudaSuccess || cudaMemcpyAsync(c.h_out, c.d_out, 2 * sizeof(double), cudaMemcpyDeviceToHost, c.stream) != cudaSuccess ||
+            cudaStreamSynchronize(c.stream) != cudaSuccess)
+            rc = set_error(QCB_ECUDA, "matrix expectation value failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    cudaFree(d);
+    if (rc != QCB_OK) return rc;
+    out_E2[0] = c.h_out[0];
+    out_E2[1] = c.h_out[1];
+    return QCB_OK;
 }
 
 // ---- polar-optimiser building blocks -----------------------------------------------------------------------------

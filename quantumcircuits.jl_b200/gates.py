@@ -156,7 +156,13 @@ class Localised2SpinAdjGate(Abstract2SpinGate):  # src/gates.jl:127-131 ; acts o
         return Localised2SpinAdjGate(adjoint(self.gate), self.target_gate_dim)
 
 
-def mat(gate):
+def mat(gate, nbits=None):
+    if nbits is not None:  # mat(H::EastModelHamiltonian, nbits)  src/hamiltonians/east_model.jl:57
+        from .hamiltonians import EastModelHamiltonian, east_model_matrix
+
+        if isinstance(gate, EastModelHamiltonian):
+            return east_model_matrix(gate, nbits)
+        raise TypeError(f"Unimplemented matrix representation for {type(gate)}")
     if not isinstance(gate, AbstractGate) or not hasattr(gate, "mat"):
         raise TypeError(f"Unimplemented matrix representation for {type(gate)}")  # src/gates.jl:6-8
     return gate.mat()

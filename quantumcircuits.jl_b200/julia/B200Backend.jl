@@ -14,6 +14,7 @@ module B200Backend
 
 using LinearAlgebra
 import QuantumCircuits
+import SparseArrays
 import QuantumCircuits: apply, apply!, measure, measure!, gradients, gradients!, optimise!,
     construct_apply_cache, construct_grads_cache, propagate_forwards!, mat,
     GenericBrickworkCircuit, Localised1SpinGate, Localised2SpinAdjGate, AbstractGate,
@@ -176,6 +177,35 @@ function measure!(::Union{B200State,Nothing}, H::AbstractKernelHamiltonian, psi:
 end
 measure(H::AbstractKernelHamiltonian, psi::B200State) = measure!(nothing, H, psi)
 measure(H::AbstractKernelHamiltonian, psi::B200State, circuit::GenericBrickworkCircuit) = measure!(nothing, H, apply(psi, circuit))
+
+# matrix Hamiltonians (src/circuits.jl:49-62): dense or sparse H as a 0-based CSR triple, real(dot(psi, H, psi)) on the device
+function _csr(H::AbstractMatrix)
+    n = size(H, 1)
+    rowptr = Vector{Int64}(undef, n + 1); rowptr[1] = 0
+    cols = Int64[]; vals = ComplexF64[]
+    Ht = H isa SparseArrays.AbstractSparseMatrix ? SparseArrays.sparse(transpose(H)) : nothing  # CSC of H^T = CSR of H
+    for r in 1:n
+        if Ht === nothing
+            append!(cols, 0:(size(H, 2) - 1)); append!(vals, ComplexF64.(H[r, :]))
+        else
+            rng = SparseArrays.nzrange(Ht, r)
+            append!(cols, SparseArrays.rowvals(Ht)[rng] .- 1); append!(vals, ComplexF64.(SparseArrays.nonzeros(Ht)[rng]))
+        end
+        rowptr[r + 1] = length(cols)
+    end
+    return rowptr, cols, vals
+end
+function measure(H::AbstractMatrix, psi::B200State)
+    @assert ndims(H) == 2                                     # src/circuits.jl:50
+    rowptr, cols, vals = _csr(H)
+    E = zeros(Cdouble, 2)
+    check(ccall((:qcb_measure_csr, LIB), Cint, (Ptr{Cvoid}, Clonglong, Ptr{Int64}, Ptr{Int64}, Ptr{ComplexF64}, Ptr{Cdouble}),
+                psi.handle, size(H, 1), rowptr, cols, vals, E))
+    @assert E[2] < 1e-12                                      # :53
+    return E[1]
+end
+measure!(::Union{B200State,Nothing}, H::AbstractMatrix, psi::B200State) = measure(H, psi)                       # :56-58
+measure(H::AbstractMatrix, psi::B200State, circuit::GenericBrickworkCircuit) = measure(H, apply(psi, circuit))  # :59-62
 
 # ------------------------------------------------------------------------------------------------
 # gradients.jl seam (src/gradients.jl:1-17,54-152)

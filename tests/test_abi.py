@@ -104,3 +104,31 @@ def test_convert_gates_to_matrix_matches_checker():
         expected = np.zeros(2 ** n)
         expected[0] = expected[-1] = 1 / np.sqrt(2)
         np.testing.assert_allclose(psi, expected, atol=1e-15)
+
+
+# ---- matrix Hamiltonians: host builders (src/hamiltonians/tfim.jl:58-92, east_model.jl:57-81) ----------------------------
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 8])
+def test_sparse_tfim_matrix_matches_dense_kronecker_definition(n):
+    J, h, g = 1.0, 0.1, 0.5  # examples/test_gradients.jl:12-16
+    H = qcb200.build_sparse_tfim_hamiltonian(n, J, h, g)
+    assert H.shape == (2 ** n, 2 ** n)
+    np.testing.assert_allclose(H.toarray(), onp.dense_tfim(n, J, h, g), atol=1e-13)
+    assert abs(H - H.T).max() == 0  # LinearAlgebra.Symmetric(H)   tfim.jl:84
+
+
+@pytest.mark.parametrize("n", [2, 3, 5])
+def test_east_model_matrix_matches_oracle(n):
+    H = qcb200.EastModelHamiltonian(0.1, -0.1)  # test/correctness_tests.jl:126-150
+    M = qcb200.mat(H, n)
+    np.testing.assert_allclose(M, onp.dense_east(n, 0.1, -0.1), atol=1e-13)
+    np.testing.assert_allclose(qcb200.east_model_matrix(H, n), M)
+    with pytest.raises(TypeError):
+        qcb200.mat(qcb200.TFIMHamiltonian(1.0, 0.1, 0.5), n)
+
+
+def test_find_tfim_ground_state():
+    n, J, h, g = 6, 1.0, 0.9045, 1.4  # examples/test_optimise.jl:9-16
+    E, v = qcb200.find_tfim_ground_state(n, J, h, g)
+    w, V = np.linalg.eigh(onp.dense_tfim(n, J, h, g))
+    assert abs(E - w[0]) < 1e-10
+    assert abs(abs(np.vdot(V[:, 0], v)) - 1) < 1e-8

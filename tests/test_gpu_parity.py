@@ -250,6 +250,44 @@ def test_measure_with_circuit(oracle):
     np.testing.assert_array_equal(st.to_numpy(), onp.zero_state(n))  # input not modified
 
 
+# ---- src/circuits.jl:49-62 : measure(H::AbstractMatrix, psi[, circuit]) on the device (CSR sweep)
+@pytest.mark.parametrize("n", [1, 3, 5, 8, 11])
+@pytest.mark.parametrize("dtype", [np.complex128, np.complex64])
+def test_measure_matrix_hamiltonian(oracle, n, dtype):
+    rng = np.random.default_rng(49 * n)
+    psi = rand_state(rng, n).astype(dtype)
+    tol = 1e-12 if dtype == np.complex128 else 1e-5
+    Hs = qc.build_sparse_tfim_hamiltonian(n, 1.0, 0.1, 0.5)
+    ref = onp.measure_matrix(Hs.toarray(), psi.astype(np.complex128))
+    for H in (Hs, Hs.toarray()) if n <= 8 else (Hs,):  # sparse and dense forms
+        assert abs(qc.measure(H, psi) - ref) < tol * max(1.0, abs(ref))
+        assert abs(qc.measure_(None, H, qc.B200State(psi)) - ref) < tol * max(1.0, abs(ref))
+    # examples/test_gradients.jl:10-28 : the kernel Hamiltonian and the sparse matrix give the same energy
+    assert abs(qc.measure(qc.TFIMHamiltonian(1.0, 0.1, 0.5), psi) - qc.measure(Hs, psi)) < tol * max(1.0, abs(ref))
+    if 2 <= n <= 8:  # test/correctness_tests.jl:126-150
+        He = qc.EastModelHamiltonian(0.1, -0.1)
+        assert abs(qc.measure(qc.mat(He, n), psi) - qc.measure(He, psi)) < tol * max(1.0, abs(ref))
+        # a complex Hermitian matrix (not in the reference's examples; exercises the imaginary parts)
+        A = rng.standard_normal((2 ** n, 2 ** n)) + 1j * rng.standard_normal((2 ** n, 2 ** n))
+        A = A + A.conj().T
+        refA = onp.measure_matrix(A, psi.astype(np.complex128))
+        assert abs(qc.measure(A, psi) - refA) < tol * max(1.0, abs(refA)) * 2 ** n
+
+
+def test_measure_matrix_with_circuit_and_errors(oracle):
+    rng = np.random.default_rng(62)
+    n, layers = 6, 4
+    c = circuit(n, layers, rng, 0.01)
+    Hs = qc.build_sparse_tfim_hamiltonian(n, 1.0, 0.1, 0.5)
+    psi0 = onp.zero_state(n)
+    ref = onp.measure_matrix(Hs.toarray(), oracle.apply_brickwork(psi0, n, layers, c.gate_angles))
+    assert abs(qc.measure(Hs, psi0, c) - ref) < 1e-12 * abs(ref)  # src/circuits.jl:59-62
+    with pytest.raises(qc.QCBError):  # wrong size
+        qc.measure(Hs, onp.zero_state(n + 1))
+    with pytest.raises(AssertionError):  # @assert imag(measurement) < 1e-12   src/circuits.jl:53
+        qc.measure(1j * np.eye(2 ** n), rand_state(rng, n))
+
+
 # ---- src/gradients.jl:88-152 : adjoint sweep == the reference's parameter-shift sweep
 @pytest.mark.parametrize("n,layers,scale", [(2, 3, None), (4, 3, 0.1), (5, 4, None), (8, 4, 0.01), (9, 3, None), (10, 4, None), (12, 3, None)])
 @pytest.mark.parametrize("ham", ["tfim", "east"])
