@@ -186,15 +186,107 @@ static int copy_state_raw(void *dst, const void *src, size_t bytes)
     return QCB_OK;
 }
 
+// grads[k, g] = 2 Re sum_{r,c} env_g[r,c] dU_g/dtheta_k [r,c]   (env: G rows of 32 doubles on the host, modified in place)
+static void contract_environments(int G, const double *angles, const double *mats, bool env_post, double *env_rows, double *out_grads)
+{
+    for (int g = 0; g < G; g++) {
+        double *env = env_rows + 32 * (size_t)g;
+        if (env_post) adjm_env_from_post(mats + 32 * (size_t)g, env);
+        for (int k = 0; k < 15; k++) {
+            const M4 dU = general_unitary(angles + 15 * (size_t)g, k);
+            double s = 0;
+            for (int i = 0; i < 16; i++) s += env[2 * i] * dU.m[i].real() - env[2 * i + 1] * dU.m[i].imag();
+            out_grads[k + 15 * (size_t)g] = 2 * s;
+        }
+    }
+}
+
+// Sharded states (collective call): forward circuit with qubit swaps, lambda = H psi in two sweeps around one swap (the
+// flips of the qubits that live in the rank bits pair amplitudes of different ranks), backward sweep on the pair
+// (dist.cu: PairShardExec), one all-reduce of the per-rank environments and energy parts.
+static int gradients_sharded_impl(const qcb_state *psi0, int nbits, int nlayers, const double *angles, int ham_kind, const double *hp,
+                                  int want_energy, double *out_E, double *out_grads)
+{
+    Ctx &c = ctx();
+    if (psi0->nloc < kMinTB) return set_error(QCB_EUNSUPPORTED, "sharded gradients need at least 2^%d amplitudes per rank", kMinTB);
+    if (nbits > 40) return set_error(QCB_EINVAL, "too many qubits");
+    const std::vector<int> pos = brickwork_positions(nbits, nlayers);
+    const int G = (int)pos.size();
+    const int g = psi0->n - psi0->nloc;
+    QCB_TRY(ensure_scratch(0, psi0->bytes));
+    QCB_TRY(ensure_scratch(1, psi0->bytes));
+    qcb_state A = *psi0, B = *psi0;
+    A.d = c.scratch[0]; A.owned = false; A.alt = nullptr; A.peer_d.clear(); A.peer_alt.clear();
+    B.d = c.scratch[1]; B.owned = false; B.alt = nullptr; B.peer_d.clear(); B.peer_alt.clear();
+    QCB_TRY(copy_state_raw(A.d, psi0->d, psi0->bytes));
+    std::vector<GateOp> gates;
+    std::vector<double> mats;
+    QCB_TRY(brickwork_gates(nbits, nlayers, angles, 0, G, false, gates, mats));
+    QCB_TRY(run_gate_list(&A, gates, mats.data(), false));
+    if (G == 0) {
+        if (want_energy) {
+            double E2[2];
+            QCB_TRY(measure_impl(&A, ham_kind, hp[0], hp[1], hp[2], E2));
+            *out_E = E2[0];
+        }
+        return QCB_OK;
+    }
+    QCB_TRY(dist_state_canonicalize(&A));
+    B.phys = A.phys;
+    const unsigned long long namps = 1ull << A.nloc;
+    HamEval H{ham_kind, nbits, hp[0], hp[1], hp[2]};
+    const unsigned blocks = grid_for(namps, kRedThreads, 8);
+    QCB_TRY(ensure_partial((size_t)blocks * 2));
+    QCB_TRY(ensure_out((size_t)32 * G + 4)); // [environments | E part 1 | E part 2]
+    QCB_CUDA(cudaMemsetAsync(c.d_out + 32 * (size_t)G, 0, 4 * sizeof(double), c.stream));
+    auto sweep = [&](unsigned long long mask, int first, int slot) -> int {
+        ShardMap M;
+        std::memset(&M, 0, sizeof M);
+        M.n = nbits; M.nloc = A.nloc; M.hi = (unsigned long long)c.rank << A.nloc;
+        for (int q = 0; q < nbits; q++) {
+            M.phys[q] = (unsigned char)A.phys[q];
+            if (((mask >> q) & 1ull) && A.phys[q] >= A.nloc) return set_error(QCB_EINVAL, "internal: flip of a qubit that is not local");
+        }
+        if (A.dtype == QCB_C128)
+            k_apply_ham_sharded<double><<<blocks, kRedThreads, 0, c.stream>>>((double2 *)B.d, (const double2 *)A.d, namps, M, H, mask, first, (double2 *)c.d_partial);
+        else
+            k_apply_ham_sharded<float><<<blocks, kRedThreads, 0, c.stream>>>((float2 *)B.d, (const float2 *)A.d, namps, M, H, mask, first, (double2 *)c.d_partial);
+        QCB_CUDA(cudaGetLastError());
+        k_final_sum<<<2, 256, 0, c.stream>>>(c.d_partial, (int)blocks, 2, c.d_out + 32 * (size_t)G + 2 * slot);
+        QCB_CUDA(cudaGetLastError());
+        count_launch(2);
+        return QCB_OK;
+    };
+    unsigned long long local_mask = 0;
+    for (int q = 0; q < nbits; q++)
+        if (A.phys[q] < A.nloc) local_mask |= 1ull << q;
+    QCB_TRY(sweep(local_mask, 1, 0));
+    if (g > 0) {
+        QCB_TRY(dist_swap_top_now(&A));
+        QCB_TRY(dist_swap_top_now(&B));
+        const unsigned long long all = nbits >= 64 ? ~0ull : ((1ull << nbits) - 1ull);
+        QCB_TRY(sweep(all & ~local_mask, 0, 1));
+    }
+    std::vector<GateOp> rev(G);
+    for (int i = 0; i < G; i++) rev[i] = GateOp{pos[G - 1 - i], G - 1 - i};
+    QCB_TRY(dist_run_adjoint_pair(&A, &B, rev, mats.data(), c.d_out));
+    QCB_TRY(dist_allreduce_sum(c.d_out, 32 * G + 4));
+    QCB_CUDA(cudaMemcpyAsync(c.h_out, c.d_out, sizeof(double) * (32 * (size_t)G + 4), cudaMemcpyDeviceToHost, c.stream));
+    QCB_CUDA(cudaStreamSynchronize(c.stream));
+    if (want_energy) *out_E = c.h_out[32 * (size_t)G] + c.h_out[32 * (size_t)G + 2];
+    contract_environments(G, angles, mats.data(), adjoint_uses_mma(&A), c.h_out, out_grads);
+    return QCB_OK;
+}
+
 // adjoint-method gradient; numbers equal the reference's shift sweep.
 static int gradients_impl(const qcb_state *psi0, int nbits, int nlayers, const double *angles, int ham_kind, const double *hp,
                           int want_energy, double *out_E, double *out_grads)
 {
     QCB_REQUIRE_INIT();
     QCB_TRY(check_state(psi0));
-    if (psi0->sharded) return set_error(QCB_EUNSUPPORTED, "gradients on sharded states are not supported");
     if (psi0->n != nbits) return set_error(QCB_EINVAL, "circuit has %d qubits, state has %d", nbits, psi0->n);
     if (ham_kind != QCB_HAM_TFIM && ham_kind != QCB_HAM_EAST) return set_error(QCB_EINVAL, "unknown Hamiltonian kind %d", ham_kind);
+    if (psi0->sharded) return gradients_sharded_impl(psi0, nbits, nlayers, angles, ham_kind, hp, want_energy, out_E, out_grads);
     Ctx &c = ctx();
     const std::vector<int> pos = brickwork_positions(nbits, nlayers);
     const int G = (int)pos.size();
@@ -273,17 +365,7 @@ static int gradients_impl(const qcb_state *psi0, int nbits, int nlayers, const d
     QCB_CUDA(cudaMemcpyAsync(c.h_out, c.d_out, sizeof(double) * (32 * (size_t)G + 2), cudaMemcpyDeviceToHost, c.stream));
     QCB_CUDA(cudaStreamSynchronize(c.stream));
     if (want_energy) *out_E = c.h_out[32 * (size_t)G];
-    // grads[k, g] = 2 Re sum_{r,c} env_g[r,c] dU_g/dtheta_k [r,c]
-    for (int g = 0; g < G; g++) {
-        double *env = c.h_out + 32 * (size_t)g;
-        if (env_post) adjm_env_from_post(mats.data() + 32 * (size_t)g, env);
-        for (int k = 0; k < 15; k++) {
-            const M4 dU = general_unitary(angles + 15 * (size_t)g, k);
-            double s = 0;
-            for (int i = 0; i < 16; i++) s += env[2 * i] * dU.m[i].real() - env[2 * i + 1] * dU.m[i].imag();
-            out_grads[k + 15 * (size_t)g] = 2 * s;
-        }
-    }
+    contract_environments(G, angles, mats.data(), env_post, c.h_out, out_grads);
     c.st_passes = fw_passes + bw_passes; c.st_stages = fw_stages + bw_stages; c.st_launches += fw_launches; c.st_gates = 4.0 * G;
     return QCB_OK;
 }

@@ -169,6 +169,46 @@ int dist_run_gate_list(qcb_state *s, const std::vector<GateOp> &gates, const dou
     return rc;
 }
 
+// ---- sharded adjoint gradients: the backward sweep runs on psi and lambda = H psi together ---------------------------
+// Both states share one layout; a planned gate pass becomes one fused backward pass on the pair (passes.cu:
+// launch_adjoint_plan, environments accumulated per rank), a bit-permuting pass and a qubit swap are applied to both.
+struct PairShardExec : ShardExecutor {
+    qcb_state *psi, *lam;
+    double *d_env;
+    PairShardExec(qcb_state *a, qcb_state *b, double *env) : psi(a), lam(b), d_env(env) {}
+    int run_pass(const PassPlan &pl, const std::vector<GateOp> &gates, const double *mats, bool) override
+    {
+        if (!pl.stages.empty()) return launch_adjoint_plan(psi, lam, pl, gates, mats, d_env);
+        QCB_TRY(launch_plan(psi, pl, gates, mats, true)); // no gates: a pure bit permutation
+        QCB_TRY(launch_plan(lam, pl, gates, mats, true));
+        ctx().st_passes += 2;
+        return QCB_OK;
+    }
+    int swap_top() override
+    {
+        QCB_TRY(swap_top_device(psi));
+        return swap_top_device(lam);
+    }
+};
+
+int dist_run_adjoint_pair(qcb_state *psi, qcb_state *lam, const std::vector<GateOp> &rev, const double *mats, double *d_env)
+{
+    if (!ctx().nccl_comm) return set_error(QCB_ENCCL, "qcb_dist_init has not been called");
+    if (psi->phys != lam->phys) return set_error(QCB_EINVAL, "psi and lambda must share one layout");
+    PairShardExec ex(psi, lam, d_env);
+    ShardLayout L = layout_of(psi);
+    int rc;
+    try {
+        rc = run_gates_sharded(ex, L, rev, mats, true, adjoint_sched_options(psi), nullptr);
+    } catch (const std::exception &e) {
+        return set_error(QCB_EINVAL, "sharded scheduler: %s", e.what());
+    }
+    psi->phys = L.phys;
+    lam->phys = L.phys;
+    if (rc < 0) return set_error(QCB_EINVAL, "sharded scheduler could not make progress (code %d)", rc);
+    return rc;
+}
+
 int dist_swap_top_now(qcb_state *s)
 {
     if (!ctx().nccl_comm) return set_error(QCB_ENCCL, "qcb_dist_init has not been called");

@@ -93,29 +93,38 @@ __global__ void __launch_bounds__(256) k_set_zero_state(typename Vec2<R>::type *
 // ---- Hamiltonian diagonal / off-diagonal pieces -----------------------------------
 // C is the full logical configuration.  diag(C): coefficient of |psi[C]|^2 ; the off-diagonal
 // part is coef * sum_i w_i(C) psi[C ^ 2^i].
+QCB_HD int popc64(unsigned long long x)
+{
+#if defined(__CUDA_ARCH__)
+    return __popcll(x);
+#else
+    return __builtin_popcountll(x);
+#endif
+}
+
 struct HamEval {
     int kind, n;          // 0 TFIM (p0 = J, p1 = h, p2 = g); 1 East (p0 = c, p1 = A, p2 = B)
     double p0, p1, p2;
-    __device__ __forceinline__ double diag(unsigned long long C) const
+    QCB_HD double diag(unsigned long long C) const
     {
         if (kind == 0) { // -J (zz + h z)        tfim.jl:25-32,48-52
             const unsigned long long pairmask = (n >= 2) ? ((1ull << (n - 1)) - 1ull) : 0ull;
-            const int eq = __popcll(~(C ^ (C >> 1)) & pairmask);
+            const int eq = popc64(~(C ^ (C >> 1)) & pairmask);
             const int zz = 2 * eq - (n - 1);
-            const int z = n - 2 * __popcll(C);
+            const int z = n - 2 * popc64(C);
             return -p0 * ((double)zz + p1 * (double)z);
         }
         // East: B * (n_0 + sum_{i>=1} n_{i-1} n_i + c n_{i-1}) + c       east_model.jl:38-50
         const unsigned long long all = (n >= 64) ? ~0ull : ((1ull << n) - 1ull);
         const unsigned long long zero = ~C & all; // bit i set iff n_i = 1
         const unsigned long long prev = zero & ((n >= 2) ? ((1ull << (n - 1)) - 1ull) : 0ull); // n_{i-1}, i = 1..n-1
-        const int nn = __popcll(prev & (zero >> 1));
-        const int np = __popcll(prev);
+        const int nn = popc64(prev & (zero >> 1));
+        const int np = popc64(prev);
         return p2 * ((double)(zero & 1ull) + (double)nn + p0 * (double)np) + p0;
     }
-    __device__ __forceinline__ double offdiag_coef() const { return kind == 0 ? -p0 * p2 : p1; }
+    QCB_HD double offdiag_coef() const { return kind == 0 ? -p0 * p2 : p1; }
     // weight of the flip of bit i at configuration C
-    __device__ __forceinline__ bool flip_on(unsigned long long C, int i) const
+    QCB_HD bool flip_on(unsigned long long C, int i) const
     {
         if (kind == 0 || i == 0) return true;
         return ((C >> (i - 1)) & 1ull) == 0ull; // n_{i-1}
@@ -211,6 +220,67 @@ __global__ void __launch_bounds__(kRedThreads) k_measure_csr(const typename Vec2
     block_sum<2>(acc, out);
     if (threadIdx.x == 0) partial[blockIdx.x] = make_double2(out[0], out[1]);
 }
+
+// ---- lambda = H psi on a sharded state ------------------------------------------------------------------------------
+// Layout of a shard: local index bit phys[q] (< nloc) or rank bit phys[q] - nloc holds logical qubit q.  A flip of logical
+// qubit i pairs amplitudes of the same shard only while phys[i] < nloc, so lambda is built in two sweeps with one qubit
+// swap between them (canonical layout: the qubits below nloc; after swap_top: the others); `mask` selects the logical
+// qubits whose flips this sweep adds, `first` also writes the diagonal term (otherwise lambda is accumulated).
+struct ShardMap {
+    unsigned char phys[40];
+    int n, nloc;
+    unsigned long long hi; // rank << nloc
+};
+QCB_HD unsigned long long logical_config(const ShardMap &M, unsigned long long x)
+{
+    const unsigned long long X = x | M.hi;
+    unsigned long long C = 0;
+    for (int q = 0; q < M.n; q++) C |= ((X >> M.phys[q]) & 1ull) << q;
+    return C;
+}
+// one amplitude; adds conj(psi[x]) * (this sweep's contribution to lambda[x]) to (er, ei)
+template <typename V>
+QCB_HD void ham_sharded_amp(V *lam, const V *psi, unsigned long long x, const ShardMap &M, const HamEval &H, unsigned long long mask,
+                            bool first, double &er, double &ei)
+{
+    const unsigned long long C = logical_config(M, x);
+    const V p = psi[x];
+    double xr = 0, xi = 0;
+    for (int i = 0; i < H.n; i++) {
+        if (!((mask >> i) & 1ull) || !H.flip_on(C, i)) continue;
+        const V o = psi[x ^ (1ull << M.phys[i])];
+        xr += (double)o.x;
+        xi += (double)o.y;
+    }
+    const double oc = H.offdiag_coef();
+    double lr = oc * xr, li = oc * xi;
+    if (first) {
+        const double d = H.diag(C);
+        lr += d * (double)p.x;
+        li += d * (double)p.y;
+    }
+    er += (double)p.x * lr + (double)p.y * li;
+    ei += (double)p.x * li - (double)p.y * lr;
+    V r = first ? V{} : lam[x];
+    r.x = (decltype(r.x))((double)r.x + lr);
+    r.y = (decltype(r.y))((double)r.y + li);
+    lam[x] = r;
+}
+#if defined(__CUDACC__)
+template <typename R>
+__global__ void __launch_bounds__(kRedThreads) k_apply_ham_sharded(typename Vec2<R>::type *lam, const typename Vec2<R>::type *__restrict__ psi,
+                                                                   unsigned long long namps, const __grid_constant__ ShardMap M, HamEval H,
+                                                                   unsigned long long mask, int first, double2 *partial)
+{
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    double acc[2] = {0.0, 0.0};
+    for (unsigned long long x = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; x < namps; x += stride)
+        ham_sharded_amp(lam, psi, x, M, H, mask, first != 0, acc[0], acc[1]);
+    __shared__ double out[2];
+    block_sum<2>(acc, out);
+    if (threadIdx.x == 0) partial[blockIdx.x] = make_double2(out[0], out[1]);
+}
+#endif
 
 // generic fixed-order final reduction: out[v] = sum_b partial[b * nv + v]
 static __global__ void k_final_sum(const double *__restrict__ partial, int nblocks, int nv, double *out)

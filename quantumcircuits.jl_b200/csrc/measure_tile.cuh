@@ -35,15 +35,6 @@ template <typename R> struct MeasParams {
     unsigned long long c_hi; // index bits above the local shard (rank << nloc), 0 for unsharded states
 };
 
-QCB_HD int popc64(unsigned long long x)
-{
-#if defined(__CUDA_ARCH__)
-    return __popcll(x);
-#else
-    return __builtin_popcountll(x);
-#endif
-}
-
 QCB_HD double ham_diag(const HamEval &h, unsigned long long C)
 {
     const int n = h.n;

@@ -342,14 +342,55 @@ template <> int launch_adjoint_any<double>(qcb_state *psi, qcb_state *lam, int T
     }
 }
 
+// one planned backward pass on (psi, lambda): un-apply its gates on both, environments into d_env rows (GateOp.mat)
+template <typename R>
+static int launch_adjoint_plan_t(qcb_state *psi, qcb_state *lam, const PassPlan &pl, const std::vector<GateOp> &rev, const double *mats, double *d_env, bool mma)
+{
+    Ctx &c = ctx();
+    static thread_local AdjParams<R> A;
+    try {
+        fill_params<R>(pl, psi->nloc, rev, mats, true, A.P);
+    } catch (const std::exception &e) {
+        return set_error(QCB_EINVAL, "pass parameters: %s", e.what());
+    }
+    EnvIds ids;
+    ids.n = 0;
+    std::memset(A.slot_gate, 0, sizeof A.slot_gate);
+    for (size_t st = 0; st < pl.stages.size(); st++)
+        for (int slot = 0; slot < kSlots; slot++) {
+            const int g = pl.stages[st].gate[slot];
+            if (g < 0) continue;
+            if (ids.n >= kAdjMaxGates) return set_error(QCB_EINVAL, "too many gates in a backward pass");
+            A.slot_gate[st * kSlots + slot] = (uint8_t)ids.n;
+            ids.id[ids.n++] = rev[g].mat;
+        }
+    A.ngates = ids.n;
+    QCB_TRY(launch_adjoint_any<R>(psi, lam, pl.TB, mma, A, ids, d_env));
+    c.st_passes += 1;
+    c.st_stages += (double)pl.stages.size();
+    return QCB_OK;
+}
+
+// (sharded gradients, dist.cu: the planner hands out one pass at a time)
+bool adjoint_uses_mma(const qcb_state *psi) { return psi->dtype == QCB_C128 && ctx().adjoint_mma != 0; }
+SchedOptions adjoint_sched_options(const qcb_state *psi)
+{
+    // two tiles per CTA: smaller tiles than the forward pass keep more CTAs per SM resident
+    SchedOptions opt = current_sched_options(psi);
+    opt.max_gates_per_pass = std::min(opt.max_gates_per_pass, kAdjMaxGates);
+    opt.tile_bits = ctx().adjoint_tile_bits ? (int)ctx().adjoint_tile_bits : std::min(opt.tile_bits, psi->dtype == QCB_C128 ? 10 : 11);
+    return opt;
+}
+int launch_adjoint_plan(qcb_state *psi, qcb_state *lam, const PassPlan &pl, const std::vector<GateOp> &rev, const double *mats, double *d_env)
+{
+    if (psi->dtype == QCB_C128) return launch_adjoint_plan_t<double>(psi, lam, pl, rev, mats, d_env, adjoint_uses_mma(psi));
+    return launch_adjoint_plan_t<float>(psi, lam, pl, rev, mats, d_env, false);
+}
+
 template <typename R> static int run_adjoint_fused_t(qcb_state *psi, qcb_state *lam, const std::vector<GateOp> &rev, const double *mats, double *d_env, bool mma)
 {
     Ctx &c = ctx();
-    SchedOptions opt = current_sched_options(psi);
-    opt.max_gates_per_pass = std::min(opt.max_gates_per_pass, kAdjMaxGates);
-    // two tiles + accumulators per CTA: smaller tiles than the forward pass keep 6 (double) / 3-6 (float) CTAs per SM
-    // resident, which is what hides the tile loads of this persistent kernel
-    opt.tile_bits = c.adjoint_tile_bits ? (int)c.adjoint_tile_bits : std::min(opt.tile_bits, sizeof(R) == 8 ? 10 : 11);
+    const SchedOptions opt = adjoint_sched_options(psi);
     // (cached like the forward plans: planning costs 0.2-0.4 ms, a fifth of a 20-qubit gradient)
     const std::string key = "adj:" + plan_key(psi, rev, opt);
     auto it = c.plan_cache.find(key);
@@ -366,29 +407,7 @@ template <typename R> static int run_adjoint_fused_t(qcb_state *psi, qcb_state *
         if (c.plan_cache.size() > 64) c.plan_cache.clear();
         it = c.plan_cache.emplace(key, std::move(plans)).first;
     }
-    static thread_local AdjParams<R> A;
-    for (const PassPlan &pl : it->second) {
-        try {
-            fill_params<R>(pl, psi->nloc, rev, mats, true, A.P);
-        } catch (const std::exception &e) {
-            return set_error(QCB_EINVAL, "pass parameters: %s", e.what());
-        }
-        EnvIds ids;
-        ids.n = 0;
-        std::memset(A.slot_gate, 0, sizeof A.slot_gate);
-        for (size_t st = 0; st < pl.stages.size(); st++)
-            for (int slot = 0; slot < kSlots; slot++) {
-                const int g = pl.stages[st].gate[slot];
-                if (g < 0) continue;
-                if (ids.n >= kAdjMaxGates) return set_error(QCB_EINVAL, "too many gates in a backward pass");
-                A.slot_gate[st * kSlots + slot] = (uint8_t)ids.n;
-                ids.id[ids.n++] = rev[g].mat;
-            }
-        A.ngates = ids.n;
-        QCB_TRY(launch_adjoint_any<R>(psi, lam, pl.TB, mma, A, ids, d_env));
-        c.st_passes += 1;
-        c.st_stages += (double)pl.stages.size();
-    }
+    for (const PassPlan &pl : it->second) QCB_TRY(launch_adjoint_plan_t<R>(psi, lam, pl, rev, mats, d_env, mma));
     return QCB_OK;
 }
 

@@ -92,6 +92,9 @@ inline void count_launch(int k = 1)
 // gate-list execution (passes.cu)
 int run_gate_list(qcb_state *s, const std::vector<GateOp> &gates, const double *mats, bool adjoint);
 int run_adjoint_fused(qcb_state *psi, qcb_state *lam, const std::vector<GateOp> &rev, const double *mats, double *d_env, bool *env_post);
+int launch_adjoint_plan(qcb_state *psi, qcb_state *lam, const PassPlan &plan, const std::vector<GateOp> &rev, const double *mats, double *d_env);
+bool adjoint_uses_mma(const qcb_state *psi);
+SchedOptions adjoint_sched_options(const qcb_state *psi);
 int launch_plan(qcb_state *s, const PassPlan &plan, const std::vector<GateOp> &gates, const double *mats, bool adjoint);
 int launch_plan_peer(qcb_state *s, const PeerSrc &src, void *dst, const PassPlan &plan, const std::vector<GateOp> &gates, const double *mats, bool adjoint);
 SchedOptions current_sched_options(const qcb_state *s);
@@ -102,5 +105,7 @@ int dist_run_gate_list(qcb_state *s, const std::vector<GateOp> &gates, const dou
 int dist_alloc_alt(qcb_state *s);
 int dist_swap_top_now(qcb_state *s);                 // NCCL exchange of the rank bits with the top local bits + layout update
 int dist_allreduce_sum(double *device_buf, int count); // in place, over all ranks, on the work stream
+// backward sweep of the adjoint gradient on a pair of sharded states in the same layout (qubit swaps move both)
+int dist_run_adjoint_pair(qcb_state *psi, qcb_state *lam, const std::vector<GateOp> &rev, const double *mats, double *d_env);
 
 } // namespace qcb

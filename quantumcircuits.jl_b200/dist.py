@@ -124,6 +124,14 @@ class ShardedState:
 
         return _measure_state(H, self)
 
+    def gradients(self, H, circuit, calculate_energy=False):
+        """gradients(H, psi, circuit; calculate_energy) on the sharded state (collective; every rank gets E and the full
+        15 x G gradient): forward circuit with qubit swaps, lambda = H psi in two sweeps around one swap, backward sweep on
+        the (psi, lambda) pair, one all-reduce."""
+        from .gradients import gradients
+
+        return gradients(H, self, circuit, calculate_energy=calculate_energy)
+
     def norm2(self):
         import torch
         import torch.distributed as dist

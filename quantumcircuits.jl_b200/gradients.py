@@ -29,7 +29,8 @@ def gradients_(cache, psi_p, psi_pp, psi, H, psi0, circuit, calculate_energy=Fal
     """gradients!(cache, psi', psi'', psi, H, psi0, circuit; calculate_energy) -- src/gradients.jl:88-152."""
     if not isinstance(H, AbstractKernelHamiltonian):
         raise TypeError("only kernel Hamiltonians are accelerated")
-    st0 = psi0 if isinstance(psi0, B200State) else B200State(psi0)
+    # (a dist.ShardedState works too: collective call, every rank receives the energy and the full gradient)
+    st0 = psi0 if isinstance(psi0, B200State) or hasattr(psi0, "_handle") else B200State(psi0)
     a = circuit.angles_abi()
     hp = H.params()
     E = C.c_double(0.0)
@@ -60,7 +61,8 @@ def optimise_(circuit, H, psi0, epochs, lr, use_progress=False):
     """optimise!(circuit, H, psi0, epochs, lr) -- src/gradients.jl:1-17, with quirk Q1 resolved to the intended
     semantics (calculate_energy=true, theta <- theta - lr * grad).  circuit.gate_angles is updated in place;
     returns `energies` laid out like the reference's (length epochs+1, [0] never written, [-1] = final measure)."""
-    st0 = psi0 if isinstance(psi0, B200State) else B200State(psi0)
+    # (a dist.ShardedState works too: collective call, every rank receives the energy and the full gradient)
+    st0 = psi0 if isinstance(psi0, B200State) or hasattr(psi0, "_handle") else B200State(psi0)
     a = circuit.angles_abi().copy()
     hp = H.params()
     energies = np.zeros(epochs + 1, dtype=np.float64)

@@ -93,6 +93,46 @@ def main():
         if rank == 0:
             print(f"{'PASS' if good else 'FAIL'} round-trip n={n} err={rt:.2e}", flush=True)
         st.close()
+    # ---- adjoint gradients on the sharded state vs the single-GPU gradient of the same circuit (both Hamiltonians, both
+    # dtypes; the ComplexF64 backward pass runs on the tensor cores, the scalar pass is checked with adjoint_mma = 0) and,
+    # at a size the oracle handles, vs the oracle's restatement of the reference's shift sweep ----------------------------
+    gcases = [(20, 4, qc.TFIMHamiltonian(1.0, 0.1, 0.5), 1, np.complex128), (21, 3, qc.EastModelHamiltonian(0.1, -0.1), 1, np.complex128),
+              (20, 3, qc.TFIMHamiltonian(1.0, 0.9045, 1.4), 0, np.complex128), (21, 4, qc.TFIMHamiltonian(1.0, 0.1, 0.5), 1, np.complex64),
+              (14, 3, qc.TFIMHamiltonian(1.0, 0.1, 0.5), 1, np.complex128)]
+    for n, layers, Hq, mma, dt in gcases:
+        if n - int(np.log2(world)) < 9:
+            continue
+        qc.set_option("adjoint_mma", mma)
+        rng = np.random.default_rng(400 + n + layers)
+        c = qc.GenericBrickworkCircuit(n, layers)
+        c.gate_angles[...] = rng.uniform(0, 2 * np.pi, c.gate_angles.shape)
+        v = rng.standard_normal(2 ** n) + 1j * rng.standard_normal(2 ** n)
+        psi0 = (v / np.linalg.norm(v)).astype(dt)
+        E_ref, g_ref = qc.gradients(Hq, qc.B200State(psi0), c, calculate_energy=True)  # every rank, on its own GPU
+        if n <= 14:
+            E_o, g_o = oracle.gradients_brickwork(psi0.astype(np.complex128), n, layers, c.gate_angles, Hq.kind, Hq.params())
+            E_ref, g_ref = E_o, g_o
+        st = qdist.ShardedState(n, dt)
+        per = 1 << st.local_qubits
+        st.upload_shard(psi0[rank * per:(rank + 1) * per])
+        E_sh, g_sh = st.gradients(Hq, c, calculate_energy=True)
+        tol = 1e-12 if dt == np.complex128 else 1e-5
+        scale = max(1.0, float(np.max(np.abs(g_ref))))
+        dE, dg = abs(E_sh - E_ref), float(np.max(np.abs(g_sh - g_ref)))
+        good = dE < tol * max(1.0, abs(E_ref)) and dg < tol * scale
+        g_again = st.gradients(Hq, c)  # the input state is untouched: same numbers again
+        good = good and float(np.max(np.abs(g_again - g_sh))) == 0.0
+        back = st.download_shard()
+        good = good and float(np.max(np.abs(back - psi0[rank * per:(rank + 1) * per]))) == 0.0
+        t = torch.tensor([0 if good else 1], device="cuda")
+        dist.all_reduce(t)
+        good = t.item() == 0
+        ok = ok and good
+        if rank == 0:
+            print(f"{'PASS' if good else 'FAIL'} sharded gradients n={n} layers={layers} {type(Hq).__name__} {np.dtype(dt).name} mma={mma} "
+                  f"dE={dE:.2e} dgrad={dg:.2e}", flush=True)
+        st.close()
+    qc.set_option("adjoint_mma", 1)
     flag = torch.tensor([0 if ok else 1], device="cuda")
     dist.all_reduce(flag)
     dist.barrier()

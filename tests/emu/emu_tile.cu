@@ -527,3 +527,126 @@ extern "C" int emu_sharded_measure(int n, int g, const void *psi_, int kind, dou
         return 1;
     }
 }
+
+// ---- sharded adjoint gradients with simulated ranks: lambda = H psi in two sweeps around one qubit swap (kernels.cuh:
+// ham_sharded_amp), then the backward sweep on the (psi, lambda) pair through the sharded planner (what
+// gradients_sharded_impl / PairShardExec do on the GPUs with NCCL swaps) -------------------------------------------------
+struct EmuPairShards : ShardExecutor {
+    int nloc = 0, g = 0;
+    std::vector<std::vector<double2>> psi, lam; // [rank][2^nloc]
+    std::vector<double> env;                    // [gate][32], summed over the ranks
+    int nswap = 0, npass = 0;
+    static void exchange(std::vector<std::vector<double2>> &sh, int nloc, int g)
+    {
+        const int P = (int)sh.size();
+        const size_t blk = (size_t)1 << (nloc - g);
+        std::vector<std::vector<double2>> out = sh;
+        for (int r = 0; r < P; r++)
+            for (int j = 0; j < P; j++) std::copy(sh[r].begin() + j * blk, sh[r].begin() + (j + 1) * blk, out[j].begin() + r * blk);
+        sh.swap(out);
+    }
+    int run_pass(const PassPlan &pl, const std::vector<GateOp> &gates, const double *mats, bool) override
+    {
+        npass++;
+        if (pl.stages.empty()) { // bit permutation of both states
+            PassParams<double> *P = new PassParams<double>;
+            fill_params<double>(pl, nloc, gates, mats, true, *P);
+            for (size_t r = 0; r < psi.size(); r++)
+                switch (pl.TB) {
+#define CASE(T) case T: ::run_pass<double, T>(psi[r].data(), nloc, *P); ::run_pass<double, T>(lam[r].data(), nloc, *P); break;
+                CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(11) CASE(12) CASE(13)
+#undef CASE
+                default: delete P; return 3;
+                }
+            delete P;
+            return 0;
+        }
+        AdjParams<double> *A = new AdjParams<double>;
+        fill_params<double>(pl, nloc, gates, mats, true, A->P);
+        int ids[kAdjMaxGates], nid = 0;
+        std::memset(A->slot_gate, 0, sizeof A->slot_gate);
+        for (size_t st = 0; st < pl.stages.size(); st++)
+            for (int slot = 0; slot < kSlots; slot++) {
+                const int gi = pl.stages[st].gate[slot];
+                if (gi < 0) continue;
+                A->slot_gate[st * kSlots + slot] = (uint8_t)nid;
+                ids[nid++] = gates[gi].mat;
+            }
+        A->ngates = nid;
+        int rc = 0;
+        for (size_t r = 0; r < psi.size() && !rc; r++) {
+            std::vector<double> acc(kAdjMaxGates * 32, 0.0);
+            switch (pl.TB) {
+#define CASE(T) case T: run_adjoint_pass<double, T>(psi[r].data(), lam[r].data(), nloc, *A, acc.data()); break;
+            CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(11) CASE(12)
+#undef CASE
+            default: rc = 3;
+            }
+            for (int k = 0; k < nid; k++)
+                for (int i = 0; i < 32; i++) env[(size_t)ids[k] * 32 + i] += acc[k * 32 + i];
+        }
+        delete A;
+        return rc;
+    }
+    int swap_top() override
+    {
+        nswap++;
+        exchange(psi, nloc, g);
+        exchange(lam, nloc, g);
+        return 0;
+    }
+};
+
+// psi_: full canonical state psi_G (complex128).  env_out[G][32]: sum conj(lam_g[r]) psi_{g-1}[c]; E_out[2]: <psi|H|psi>.
+extern "C" int emu_sharded_gradient_env(int n, int g, const void *psi_, int kind, double p0, double p1, double p2, int ngates, const int *q,
+                                        const double *mats, int tile_bits, int low_bits, double *env_out, double *E_out, int *stats)
+{
+    try {
+        EmuPairShards ex;
+        ex.nloc = n - g; ex.g = g;
+        const int P = 1 << g;
+        const size_t per = (size_t)1 << ex.nloc;
+        const double2 *psi = (const double2 *)psi_;
+        ex.psi.resize(P); ex.lam.resize(P);
+        for (int r = 0; r < P; r++) { ex.psi[r].assign(psi + r * per, psi + (r + 1) * per); ex.lam[r].assign(per, double2{0.0, 0.0}); }
+        ex.env.assign((size_t)ngates * 32, 0.0);
+        ShardLayout L;
+        L.n = n; L.nloc = ex.nloc; L.g = g;
+        L.phys.resize(n);
+        for (int i = 0; i < n; i++) L.phys[i] = i;
+        HamEval H{kind, n, p0, p1, p2};
+        double er = 0, ei = 0;
+        auto sweep = [&](unsigned long long mask, bool first) {
+            for (int r = 0; r < P; r++) {
+                ShardMap M;
+                std::memset(&M, 0, sizeof M);
+                M.n = n; M.nloc = ex.nloc; M.hi = (unsigned long long)r << ex.nloc;
+                for (int i = 0; i < n; i++) M.phys[i] = (unsigned char)L.phys[i];
+                // (out of place on the host: every amplitude reads psi only, lambda[x] is its own)
+                for (unsigned long long x = 0; x < per; x++) ham_sharded_amp(ex.lam[r].data(), ex.psi[r].data(), x, M, H, mask, first, er, ei);
+            }
+        };
+        unsigned long long local_mask = 0;
+        for (int i = 0; i < n; i++)
+            if (L.phys[i] < L.nloc) local_mask |= 1ull << i;
+        sweep(local_mask, true);
+        if (g > 0) {
+            ex.swap_top();
+            swap_top_layout(L);
+            sweep(((1ull << n) - 1ull) & ~local_mask, false);
+        }
+        E_out[0] = er; E_out[1] = ei;
+        std::vector<GateOp> rev(ngates);
+        for (int i = 0; i < ngates; i++) rev[i] = GateOp{q[ngates - 1 - i], ngates - 1 - i};
+        SchedOptions opt;
+        opt.tile_bits = tile_bits; opt.low_bits = low_bits; opt.max_gates_per_pass = kAdjMaxGates;
+        const int rc = run_gates_sharded(ex, L, rev, mats, true, opt, nullptr);
+        if (rc) return 10 + (rc < 0 ? -rc : rc);
+        std::copy(ex.env.begin(), ex.env.end(), env_out);
+        if (stats) { stats[0] = ex.npass; stats[1] = ex.nswap; }
+        return 0;
+    } catch (const std::exception &e) {
+        std::fprintf(stderr, "emu sharded gradient: %s\n", e.what());
+        return 1;
+    }
+}

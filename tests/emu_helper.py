@@ -115,6 +115,25 @@ def adjoint_sweep_mma(psi, lam, q0, mats, tile_bits, low_bits, nwarps):
     return psi, lam, envc, (int(conf[0]), int(conf[1]))
 
 
+def sharded_gradient_env(psiG, g, kind, params, q0, mats, tile_bits, low_bits):
+    """Sharded adjoint gradient with 2^g simulated ranks, from the full canonical psi_G: returns (env[G, 4, 4], E, stats)."""
+    psi = np.ascontiguousarray(psiG, dtype=np.complex128)
+    n = int(psi.size).bit_length() - 1
+    q0 = np.ascontiguousarray(q0, dtype=np.int32)
+    m = np.ascontiguousarray(np.stack([np.asarray(M, dtype=np.complex128).reshape(-1, order="F") for M in mats]))
+    env = np.zeros((len(q0), 32), dtype=np.float64)
+    E = np.zeros(2, dtype=np.float64)
+    stats = np.zeros(4, dtype=np.int32)
+    rc = lib().emu_sharded_gradient_env(C.c_int(n), C.c_int(g), psi.ctypes.data_as(C.c_void_p), C.c_int(kind), C.c_double(params[0]),
+                                        C.c_double(params[1]), C.c_double(params[2]), C.c_int(len(q0)), q0.ctypes.data_as(C.c_void_p),
+                                        m.ctypes.data_as(C.c_void_p), C.c_int(tile_bits), C.c_int(low_bits), env.ctypes.data_as(C.c_void_p),
+                                        E.ctypes.data_as(C.c_void_p), stats.ctypes.data_as(C.c_void_p))
+    if rc:
+        raise RuntimeError(f"emu_sharded_gradient_env rc={rc}")
+    envc = (env[:, 0::2] + 1j * env[:, 1::2]).reshape(len(q0), 4, 4).transpose(0, 2, 1)
+    return envc, complex(E[0], E[1]), dict(passes=int(stats[0]), swaps=int(stats[1]))
+
+
 def measure(psi, kind, params, tile_bits, low_bits):
     """Tiled expectation value replay.  kind 0: TFIM (J, h, g); 1: East (c, A, B).  Returns (E, number of passes)."""
     psi = np.ascontiguousarray(psi)

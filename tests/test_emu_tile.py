@@ -231,6 +231,40 @@ def test_emu_adjoint_sweep_mma(emu, oracle, n, layers, tb, nw):
     assert wf == wf_min, f"{wf - wf_min} bank-conflict wavefronts out of {wf_min}"
 
 
+@pytest.mark.parametrize("n,layers,g,tb,ham", [(12, 5, 1, 9, "tfim"), (13, 6, 2, 9, "east"), (13, 4, 3, 10, "tfim"), (12, 6, 2, 10, "east")])
+def test_emu_sharded_gradients(emu, oracle, n, layers, g, tb, ham):
+    """Sharded adjoint gradients on 2^g simulated ranks: lambda = H psi in two sweeps around one qubit swap, backward sweep on
+    the (psi, lambda) pair through the sharded planner -> the reference's parameter-shift gradients and energy."""
+    import ctypes as C
+
+    from qcb200 import _lib
+
+    rng = np.random.default_rng(n * 13 + layers + g)
+    G = onp.brickwork_num_gates(n, layers)
+    angles = rng.uniform(0, 2 * np.pi, (15, G))
+    q0 = np.array(onp.brickwork_gate_positions(n, layers)) - 1
+    mats = [oracle.build_general_unitary_gate(angles[:, k]) for k in range(G)]
+    psi0 = rand_state(rng, n)
+    if ham == "tfim":
+        kind, hp = 0, (1.0, 0.1, 0.5)
+    else:
+        A, B = onp.east_params(0.1, -0.1)
+        kind, hp = 1, (0.1, A, B)
+    psiG = oracle.apply_brickwork(psi0, n, layers, angles)
+    env, E, st = emu.sharded_gradient_env(psiG, g, kind, hp, q0, mats, tb, 3)
+    E_ref, g_ref = oracle.gradients_brickwork(psi0, n, layers, angles, kind, hp)
+    assert abs(E.real - E_ref) < 1e-12 * max(1.0, abs(E_ref)) and abs(E.imag) < 1e-12
+    grads = np.zeros((15, G))
+    for k in range(G):
+        a = np.ascontiguousarray(angles[:, k])
+        for j in range(15):
+            d = np.empty(16, dtype=np.complex128)
+            _lib.check(_lib.lib().qcb_general_unitary_gate_derivative(a.ctypes.data_as(C.c_void_p), C.c_int(j), d.ctypes.data_as(C.c_void_p)))
+            grads[j, k] = 2 * np.real(np.sum(env[k] * d.reshape(4, 4, order="F")))
+    assert np.max(np.abs(grads - g_ref)) < 1e-12 * max(1.0, np.max(np.abs(g_ref)))
+    assert st["swaps"] >= 1  # the top qubits' gates needed at least one more exchange after the Hamiltonian's
+
+
 # ---- tiled expectation value -----------------------------------------------------------------------------
 @pytest.mark.parametrize("n,tb,c", [(10, 8, 3), (13, 9, 3), (14, 12, 3), (15, 13, 3), (16, 10, 4), (17, 12, 3)])
 def test_emu_tiled_measure(emu, oracle, n, tb, c):
