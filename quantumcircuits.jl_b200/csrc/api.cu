@@ -215,9 +215,30 @@ static int gradients_sharded_impl(const qcb_state *psi0, int nbits, int nlayers,
     const int g = psi0->n - psi0->nloc;
     QCB_TRY(ensure_scratch(0, psi0->bytes));
     QCB_TRY(ensure_scratch(1, psi0->bytes));
+    // a third buffer lets the qubit swaps of the pair run out of place (NCCL straight into it, then the buffers rotate);
+    // without the memory for it they go through the bounded staging buffer in place
+    {
+        size_t free_b = 0, total_b = 0;
+        if (c.scratch_bytes[3] < psi0->bytes && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && free_b > psi0->bytes + ((size_t)6 << 30)) {
+            if (ensure_scratch(3, psi0->bytes) != QCB_OK) cudaGetLastError();
+        }
+    }
+    void *spare = c.scratch_bytes[3] >= psi0->bytes ? c.scratch[3] : nullptr;
+    struct Buf { void *p; size_t bytes; } pool[3] = {{c.scratch[0], c.scratch_bytes[0]}, {c.scratch[1], c.scratch_bytes[1]}, {spare, spare ? c.scratch_bytes[3] : 0}};
     qcb_state A = *psi0, B = *psi0;
     A.d = c.scratch[0]; A.owned = false; A.alt = nullptr; A.peer_d.clear(); A.peer_alt.clear();
     B.d = c.scratch[1]; B.owned = false; B.alt = nullptr; B.peer_d.clear(); B.peer_alt.clear();
+    // (whatever happens below, the scratch slots must own the three buffers again, in their rotated order)
+    struct Restore {
+        Ctx &c; qcb_state &A, &B; void *&spare; Buf (&pool)[3];
+        ~Restore()
+        {
+            auto bytes_of = [&](void *p) { for (const Buf &b : pool) if (b.p == p) return b.bytes; return (size_t)0; };
+            c.scratch[0] = A.d; c.scratch_bytes[0] = bytes_of(A.d);
+            c.scratch[1] = B.d; c.scratch_bytes[1] = bytes_of(B.d);
+            if (spare) { c.scratch[3] = spare; c.scratch_bytes[3] = bytes_of(spare); }
+        }
+    } restore{c, A, B, spare, pool};
     QCB_TRY(copy_state_raw(A.d, psi0->d, psi0->bytes));
     std::vector<GateOp> gates;
     std::vector<double> mats;
@@ -262,14 +283,13 @@ static int gradients_sharded_impl(const qcb_state *psi0, int nbits, int nlayers,
         if (A.phys[q] < A.nloc) local_mask |= 1ull << q;
     QCB_TRY(sweep(local_mask, 1, 0));
     if (g > 0) {
-        QCB_TRY(dist_swap_top_now(&A));
-        QCB_TRY(dist_swap_top_now(&B));
+        QCB_TRY(dist_swap_top_pair(&A, &B, &spare));
         const unsigned long long all = nbits >= 64 ? ~0ull : ((1ull << nbits) - 1ull);
         QCB_TRY(sweep(all & ~local_mask, 0, 1));
     }
     std::vector<GateOp> rev(G);
     for (int i = 0; i < G; i++) rev[i] = GateOp{pos[G - 1 - i], G - 1 - i};
-    QCB_TRY(dist_run_adjoint_pair(&A, &B, rev, mats.data(), c.d_out));
+    QCB_TRY(dist_run_adjoint_pair(&A, &B, &spare, rev, mats.data(), c.d_out));
     QCB_TRY(dist_allreduce_sum(c.d_out, 32 * G + 4));
     QCB_CUDA(cudaMemcpyAsync(c.h_out, c.d_out, sizeof(double) * (32 * (size_t)G + 4), cudaMemcpyDeviceToHost, c.stream));
     QCB_CUDA(cudaStreamSynchronize(c.stream));
@@ -421,7 +441,7 @@ int qcb_finalize(void)
     Ctx &c = ctx();
     if (!c.inited) return QCB_OK;
     cudaStreamSynchronize(c.stream);
-    for (int i = 0; i < 3; i++) { if (c.scratch[i]) cudaFree(c.scratch[i]); c.scratch[i] = nullptr; c.scratch_bytes[i] = 0; }
+    for (int i = 0; i < 4; i++) { if (c.scratch[i]) cudaFree(c.scratch[i]); c.scratch[i] = nullptr; c.scratch_bytes[i] = 0; }
     if (c.d_partial) cudaFree(c.d_partial);
     if (c.d_out) cudaFree(c.d_out);
     if (c.h_out) cudaFreeHost(c.h_out);
@@ -443,7 +463,7 @@ int qcb_trim(void)
     if (!c.inited) return QCB_OK;
     QCB_CUDA(cudaStreamSynchronize(c.stream));
     QCB_CUDA(cudaStreamSynchronize(c.copy_stream));
-    for (int i = 0; i < 3; i++) {
+    for (int i = 0; i < 4; i++) {
         if (c.scratch[i]) cudaFree(c.scratch[i]);
         c.scratch[i] = nullptr;
         c.scratch_bytes[i] = 0;

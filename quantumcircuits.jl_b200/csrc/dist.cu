@@ -172,10 +172,24 @@ int dist_run_gate_list(qcb_state *s, const std::vector<GateOp> &gates, const dou
 // ---- sharded adjoint gradients: the backward sweep runs on psi and lambda = H psi together ---------------------------
 // Both states share one layout; a planned gate pass becomes one fused backward pass on the pair (passes.cu:
 // launch_adjoint_plan, environments accumulated per rank), a bit-permuting pass and a qubit swap are applied to both.
+static int swap_top_pair_device(qcb_state *psi, qcb_state *lam, void **spare)
+{
+    // with a spare buffer: psi <-> spare out of place (its old buffer becomes the spare), then lambda the same way
+    for (qcb_state *s : {psi, lam}) {
+        s->alt = spare ? *spare : nullptr;
+        const int rc = swap_top_device(s); // exchanges s->d and s->alt when alt exists
+        if (spare) *spare = s->alt;
+        s->alt = nullptr;
+        if (rc != QCB_OK) return rc;
+    }
+    return QCB_OK;
+}
+
 struct PairShardExec : ShardExecutor {
     qcb_state *psi, *lam;
+    void **spare;
     double *d_env;
-    PairShardExec(qcb_state *a, qcb_state *b, double *env) : psi(a), lam(b), d_env(env) {}
+    PairShardExec(qcb_state *a, qcb_state *b, void **sp, double *env) : psi(a), lam(b), spare(sp), d_env(env) {}
     int run_pass(const PassPlan &pl, const std::vector<GateOp> &gates, const double *mats, bool) override
     {
         if (!pl.stages.empty()) return launch_adjoint_plan(psi, lam, pl, gates, mats, d_env);
@@ -184,18 +198,14 @@ struct PairShardExec : ShardExecutor {
         ctx().st_passes += 2;
         return QCB_OK;
     }
-    int swap_top() override
-    {
-        QCB_TRY(swap_top_device(psi));
-        return swap_top_device(lam);
-    }
+    int swap_top() override { return swap_top_pair_device(psi, lam, spare); }
 };
 
-int dist_run_adjoint_pair(qcb_state *psi, qcb_state *lam, const std::vector<GateOp> &rev, const double *mats, double *d_env)
+int dist_run_adjoint_pair(qcb_state *psi, qcb_state *lam, void **spare, const std::vector<GateOp> &rev, const double *mats, double *d_env)
 {
     if (!ctx().nccl_comm) return set_error(QCB_ENCCL, "qcb_dist_init has not been called");
     if (psi->phys != lam->phys) return set_error(QCB_EINVAL, "psi and lambda must share one layout");
-    PairShardExec ex(psi, lam, d_env);
+    PairShardExec ex(psi, lam, spare, d_env);
     ShardLayout L = layout_of(psi);
     int rc;
     try {
@@ -207,6 +217,18 @@ int dist_run_adjoint_pair(qcb_state *psi, qcb_state *lam, const std::vector<Gate
     lam->phys = L.phys;
     if (rc < 0) return set_error(QCB_EINVAL, "sharded scheduler could not make progress (code %d)", rc);
     return rc;
+}
+
+int dist_swap_top_pair(qcb_state *psi, qcb_state *lam, void **spare)
+{
+    if (!ctx().nccl_comm) return set_error(QCB_ENCCL, "qcb_dist_init has not been called");
+    if (psi->phys != lam->phys) return set_error(QCB_EINVAL, "psi and lambda must share one layout");
+    QCB_TRY(swap_top_pair_device(psi, lam, spare));
+    ShardLayout L = layout_of(psi);
+    swap_top_layout(L);
+    psi->phys = L.phys;
+    lam->phys = L.phys;
+    return QCB_OK;
 }
 
 int dist_swap_top_now(qcb_state *s)

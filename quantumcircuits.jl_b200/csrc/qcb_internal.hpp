@@ -48,8 +48,8 @@ struct Ctx {
     double *d_out = nullptr;     // small device result buffer
     size_t out_cap = 0;
     double *h_out = nullptr;     // pinned mirror
-    void *scratch[3] = {nullptr, nullptr, nullptr};
-    size_t scratch_bytes[3] = {0, 0, 0};
+    void *scratch[4] = {nullptr, nullptr, nullptr, nullptr}; // 0, 1: gradient work states; 2: host-call state / swap staging; 3: spare shard
+    size_t scratch_bytes[4] = {0, 0, 0, 0};
     std::map<std::string, std::vector<PassPlan>> plan_cache;
     // distributed
     int rank = 0, nranks = 1;
@@ -106,6 +106,8 @@ int dist_alloc_alt(qcb_state *s);
 int dist_swap_top_now(qcb_state *s);                 // NCCL exchange of the rank bits with the top local bits + layout update
 int dist_allreduce_sum(double *device_buf, int count); // in place, over all ranks, on the work stream
 // backward sweep of the adjoint gradient on a pair of sharded states in the same layout (qubit swaps move both)
-int dist_run_adjoint_pair(qcb_state *psi, qcb_state *lam, const std::vector<GateOp> &rev, const double *mats, double *d_env);
+// *spare: a third buffer of the shards' size (or nullptr): qubit swaps then run out of place, the three buffers rotate
+int dist_run_adjoint_pair(qcb_state *psi, qcb_state *lam, void **spare, const std::vector<GateOp> &rev, const double *mats, double *d_env);
+int dist_swap_top_pair(qcb_state *psi, qcb_state *lam, void **spare); // swap_top on both states + layout update
 
 } // namespace qcb

@@ -98,9 +98,9 @@ def main():
     # at a size the oracle handles, vs the oracle's restatement of the reference's shift sweep ----------------------------
     gcases = [(20, 4, qc.TFIMHamiltonian(1.0, 0.1, 0.5), 1, np.complex128), (21, 3, qc.EastModelHamiltonian(0.1, -0.1), 1, np.complex128),
               (20, 3, qc.TFIMHamiltonian(1.0, 0.9045, 1.4), 0, np.complex128), (21, 4, qc.TFIMHamiltonian(1.0, 0.1, 0.5), 1, np.complex64),
-              (14, 3, qc.TFIMHamiltonian(1.0, 0.1, 0.5), 1, np.complex128)]
+              (15, 3, qc.TFIMHamiltonian(1.0, 0.1, 0.5), 1, np.complex128)]
     for n, layers, Hq, mma, dt in gcases:
-        if n - int(np.log2(world)) < 9:
+        if n - int(np.log2(world)) < 14:  # qcb_state_create_sharded: at least 14 local qubits
             continue
         qc.set_option("adjoint_mma", mma)
         rng = np.random.default_rng(400 + n + layers)
@@ -109,7 +109,7 @@ def main():
         v = rng.standard_normal(2 ** n) + 1j * rng.standard_normal(2 ** n)
         psi0 = (v / np.linalg.norm(v)).astype(dt)
         E_ref, g_ref = qc.gradients(Hq, qc.B200State(psi0), c, calculate_energy=True)  # every rank, on its own GPU
-        if n <= 14:
+        if n <= 15:
             E_o, g_o = oracle.gradients_brickwork(psi0.astype(np.complex128), n, layers, c.gate_angles, Hq.kind, Hq.params())
             E_ref, g_ref = E_o, g_o
         st = qdist.ShardedState(n, dt)
