@@ -133,7 +133,8 @@ int qcb_measure_csr(const qcb_state *s, long long nrows, const long long *rowptr
 
 /* ---- gradients!(cache, psi', psi'', psi, H, psi0, circuit; calculate_energy)  src/gradients.jl:88-152 ----
  * Same numbers as the reference's parameter-shift sweep, computed by the O(G) adjoint sweep
- * (SURVEY.md appendix A).  psi0 is not modified.  out_grads is 15 x G column-major. */
+ * (SURVEY.md appendix A).  psi0 is not modified.  out_grads is 15 x G column-major.
+ * Sharded states: collective call (every rank), every rank receives the energy and the full gradient. */
 int qcb_gradients_brickwork(const qcb_state *psi0, int nbits, int nlayers, const double *angles, int ham_kind,
                             const double *ham_params3, int want_energy, double *out_E, double *out_grads);
 /* optimise!(circuit, H, psi0, epochs, lr)  src/gradients.jl:1-17 with quirk Q1 resolved
