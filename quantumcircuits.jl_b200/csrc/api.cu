@@ -202,7 +202,8 @@ static void contract_environments(int G, const double *angles, const double *mat
 }
 
 // Sharded states (collective call): forward circuit with qubit swaps, lambda = H psi in two sweeps around one swap (the
-// flips of the qubits that live in the rank bits pair amplitudes of different ranks), backward sweep on the pair
+// flips of the qubits that live in the rank bits pair amplitudes of different ranks; in the layout the forward circuit
+// ended in), backward sweep on the pair
 // (dist.cu: PairShardExec), one all-reduce of the per-rank environments and energy parts.
 static int gradients_sharded_impl(const qcb_state *psi0, int nbits, int nlayers, const double *angles, int ham_kind, const double *hp,
                                   int want_energy, double *out_E, double *out_grads)
@@ -252,7 +253,7 @@ static int gradients_sharded_impl(const qcb_state *psi0, int nbits, int nlayers,
         }
         return QCB_OK;
     }
-    QCB_TRY(dist_state_canonicalize(&A));
+    // (no canonicalisation: the two sweeps below work in any layout -- every logical qubit is local either now or after swap_top)
     B.phys = A.phys;
     const unsigned long long namps = 1ull << A.nloc;
     HamEval H{ham_kind, nbits, hp[0], hp[1], hp[2]};

@@ -536,6 +536,7 @@ struct EmuPairShards : ShardExecutor {
     std::vector<std::vector<double2>> psi, lam; // [rank][2^nloc]
     std::vector<double> env;                    // [gate][32], summed over the ranks
     int nswap = 0, npass = 0;
+    bool forward = false; // forward circuit: plain gate passes and swaps on psi alone
     static void exchange(std::vector<std::vector<double2>> &sh, int nloc, int g)
     {
         const int P = (int)sh.size();
@@ -548,12 +549,12 @@ struct EmuPairShards : ShardExecutor {
     int run_pass(const PassPlan &pl, const std::vector<GateOp> &gates, const double *mats, bool) override
     {
         npass++;
-        if (pl.stages.empty()) { // bit permutation of both states
+        if (pl.stages.empty() || forward) { // bit permutation of both states / forward gate pass on psi
             PassParams<double> *P = new PassParams<double>;
-            fill_params<double>(pl, nloc, gates, mats, true, *P);
+            fill_params<double>(pl, nloc, gates, mats, !forward, *P);
             for (size_t r = 0; r < psi.size(); r++)
                 switch (pl.TB) {
-#define CASE(T) case T: ::run_pass<double, T>(psi[r].data(), nloc, *P); ::run_pass<double, T>(lam[r].data(), nloc, *P); break;
+#define CASE(T) case T: ::run_pass<double, T>(psi[r].data(), nloc, *P); if (!forward) ::run_pass<double, T>(lam[r].data(), nloc, *P); break;
                 CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(11) CASE(12) CASE(13)
 #undef CASE
                 default: delete P; return 3;
@@ -592,12 +593,13 @@ struct EmuPairShards : ShardExecutor {
     {
         nswap++;
         exchange(psi, nloc, g);
-        exchange(lam, nloc, g);
+        if (!forward) exchange(lam, nloc, g);
         return 0;
     }
 };
 
-// psi_: full canonical state psi_G (complex128).  env_out[G][32]: sum conj(lam_g[r]) psi_{g-1}[c]; E_out[2]: <psi|H|psi>.
+// psi_: full canonical input state psi_0 (complex128); the forward circuit runs sharded first and leaves whatever layout it
+// ends in.  env_out[G][32]: sum conj(lam_g[r]) psi_{g-1}[c]; E_out[2]: <psi|H|psi>.
 extern "C" int emu_sharded_gradient_env(int n, int g, const void *psi_, int kind, double p0, double p1, double p2, int ngates, const int *q,
                                         const double *mats, int tile_bits, int low_bits, double *env_out, double *E_out, int *stats)
 {
@@ -614,6 +616,17 @@ extern "C" int emu_sharded_gradient_env(int n, int g, const void *psi_, int kind
         L.n = n; L.nloc = ex.nloc; L.g = g;
         L.phys.resize(n);
         for (int i = 0; i < n; i++) L.phys[i] = i;
+        SchedOptions fopt;
+        fopt.tile_bits = tile_bits; fopt.low_bits = low_bits;
+        {
+            std::vector<GateOp> fwd(ngates);
+            for (int i = 0; i < ngates; i++) fwd[i] = GateOp{q[i], i};
+            ex.forward = true;
+            const int rc = run_gates_sharded(ex, L, fwd, mats, false, fopt, nullptr);
+            ex.forward = false;
+            if (rc) return 30 + (rc < 0 ? -rc : rc);
+            if (stats) stats[2] = L.canonical() ? 1 : 0;
+        }
         HamEval H{kind, n, p0, p1, p2};
         double er = 0, ei = 0;
         auto sweep = [&](unsigned long long mask, bool first) {

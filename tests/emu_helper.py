@@ -115,9 +115,10 @@ def adjoint_sweep_mma(psi, lam, q0, mats, tile_bits, low_bits, nwarps):
     return psi, lam, envc, (int(conf[0]), int(conf[1]))
 
 
-def sharded_gradient_env(psiG, g, kind, params, q0, mats, tile_bits, low_bits):
-    """Sharded adjoint gradient with 2^g simulated ranks, from the full canonical psi_G: returns (env[G, 4, 4], E, stats)."""
-    psi = np.ascontiguousarray(psiG, dtype=np.complex128)
+def sharded_gradient_env(psi0, g, kind, params, q0, mats, tile_bits, low_bits):
+    """Sharded adjoint gradient with 2^g simulated ranks, from the full canonical input state psi_0 (forward circuit, lambda =
+    H psi, backward sweep: all sharded): returns (env[G, 4, 4], E, stats)."""
+    psi = np.ascontiguousarray(psi0, dtype=np.complex128)
     n = int(psi.size).bit_length() - 1
     q0 = np.ascontiguousarray(q0, dtype=np.int32)
     m = np.ascontiguousarray(np.stack([np.asarray(M, dtype=np.complex128).reshape(-1, order="F") for M in mats]))
@@ -131,7 +132,7 @@ def sharded_gradient_env(psiG, g, kind, params, q0, mats, tile_bits, low_bits):
     if rc:
         raise RuntimeError(f"emu_sharded_gradient_env rc={rc}")
     envc = (env[:, 0::2] + 1j * env[:, 1::2]).reshape(len(q0), 4, 4).transpose(0, 2, 1)
-    return envc, complex(E[0], E[1]), dict(passes=int(stats[0]), swaps=int(stats[1]))
+    return envc, complex(E[0], E[1]), dict(passes=int(stats[0]), swaps=int(stats[1]), canonical_after_forward=bool(stats[2]))
 
 
 def measure(psi, kind, params, tile_bits, low_bits):

@@ -250,8 +250,8 @@ def test_emu_sharded_gradients(emu, oracle, n, layers, g, tb, ham):
     else:
         A, B = onp.east_params(0.1, -0.1)
         kind, hp = 1, (0.1, A, B)
-    psiG = oracle.apply_brickwork(psi0, n, layers, angles)
-    env, E, st = emu.sharded_gradient_env(psiG, g, kind, hp, q0, mats, tb, 3)
+    env, E, st = emu.sharded_gradient_env(psi0, g, kind, hp, q0, mats, tb, 3)
+    assert not st["canonical_after_forward"]  # lambda = H psi is built in whatever layout the forward circuit ends in
     E_ref, g_ref = oracle.gradients_brickwork(psi0, n, layers, angles, kind, hp)
     assert abs(E.real - E_ref) < 1e-12 * max(1.0, abs(E_ref)) and abs(E.imag) < 1e-12
     grads = np.zeros((15, G))
