@@ -153,37 +153,48 @@ inline void fill_adj_mma(AdjMmaParams &M, int TB, int NW)
     }
 }
 // ... and the threads' programs, prog[ordinal * 32 NW + thread], gates in processing order (stage by stage, slot by slot =
-// the ordinals of A.slot_gate)
-template <int TB, int NW> inline void build_adj_mma_prog(const AdjMmaParams &M, AdjmLaneProg *prog)
+// the ordinals of A.slot_gate).  One record (host + device: the GPU builds the table with k_build_adj_mma_prog from the
+// kernel parameters -- no host-to-device copy, which from pageable memory would synchronise the stream once per pass; the
+// CPU replay and the `adjoint_prog_host` cross-check option build it on the host):
+template <int TB, int NW> QCB_HD AdjmLaneProg adj_mma_prog_record(const AdjMmaParams &M, int s, int slot, uint32_t warp, uint32_t lane)
 {
     constexpr int WPW = (1 << (TB - kRegBits)) / NW;
     constexpr int WB = Log2<WPW>::value;
     static_assert(WB >= 1 && WB <= 4, "2 to 16 windows per warp");
-    for (int s = 0; s < M.A.P.nstages; s++) {
-        const StageDesc &S = M.A.P.stage[s];
-        int last_slot = -1;
-        for (int slot = 0; slot < kSlots; slot++)
-            if ((S.mask >> slot) & 1) last_slot = slot;
-        for (int slot = 0; slot < kSlots; slot++) {
-            if (!((S.mask >> slot) & 1)) continue;
-            const int ord = M.A.slot_gate[s * kSlots + slot];
-            for (uint32_t warp = 0; warp < (uint32_t)NW; warp++) {
-                const AdjmStage<TB, WB> C = adjm_stage_consts<TB, WB>(S, warp);
-                for (uint32_t ln = 0; ln < 32; ln++) {
-                    const AdjmGate<TB, WB> G = adjm_gate_consts<TB, WB>(C, S, slot_lo(slot), M.sel[s * kSlots + slot], ln);
-                    AdjmLaneProg &p = prog[(size_t)ord * (32 * NW) + warp * 32 + ln];
-                    std::memset(&p, 0, sizeof p);
-                    adjm_gate_operand(M.A.P.U[s * kSlots + slot], ln, p.a_re, p.a_im);
-                    p.ld = (uint16_t)G.L.ld;
-                    p.st[0] = (uint16_t)G.L.st[0];
-                    p.st[1] = (uint16_t)G.L.st[1];
-                    for (int j = 0; j + 1 < WB; j++) p.cg[j] = (uint16_t)G.cg[j];
-                    p.flags = slot == last_slot ? 1 : 0;
-                }
-            }
-        }
-    }
+    const StageDesc &S = M.A.P.stage[s];
+    const AdjmStage<TB, WB> C = adjm_stage_consts<TB, WB>(S, warp);
+    const AdjmGate<TB, WB> G = adjm_gate_consts<TB, WB>(C, S, slot_lo(slot), M.sel[s * kSlots + slot], lane);
+    AdjmLaneProg p;
+    adjm_gate_operand(M.A.P.U[s * kSlots + slot], lane, p.a_re, p.a_im);
+    p.ld = (uint16_t)G.L.ld;
+    p.st[0] = (uint16_t)G.L.st[0];
+    p.st[1] = (uint16_t)G.L.st[1];
+    p.cg[0] = p.cg[1] = p.cg[2] = 0;
+#pragma unroll
+    for (int j = 0; j + 1 < WB; j++) p.cg[j] = (uint16_t)G.cg[j];
+    p.flags = (S.mask >> (slot + 1)) == 0 ? 1 : 0; // last active slot of its stage
+    p.pad = 0;
+    return p;
 }
+template <int TB, int NW> inline void build_adj_mma_prog(const AdjMmaParams &M, AdjmLaneProg *prog)
+{
+    for (int s = 0; s < M.A.P.nstages; s++)
+        for (int slot = 0; slot < kSlots; slot++) {
+            if (!((M.A.P.stage[s].mask >> slot) & 1)) continue;
+            const int ord = M.A.slot_gate[s * kSlots + slot];
+            for (uint32_t t = 0; t < 32u * NW; t++) prog[(size_t)ord * (32 * NW) + t] = adj_mma_prog_record<TB, NW>(M, s, slot, t >> 5, t & 31u);
+        }
+}
+#if defined(__CUDACC__)
+// grid = (stage, slot) pairs = kMaxStages * kSlots blocks of 32 NW threads; inactive slots exit
+template <int TB, int NW> __global__ void k_build_adj_mma_prog(const __grid_constant__ AdjMmaParams M, AdjmLaneProg *prog)
+{
+    const int s = blockIdx.x / kSlots, slot = blockIdx.x % kSlots;
+    if (s >= M.A.P.nstages || !((M.A.P.stage[s].mask >> slot) & 1)) return;
+    const int ord = M.A.slot_gate[s * kSlots + slot];
+    prog[(size_t)ord * (32 * NW) + threadIdx.x] = adj_mma_prog_record<TB, NW>(M, s, slot, threadIdx.x >> 5, threadIdx.x & 31u);
+}
+#endif
 
 // raw[j * 32 + lane] = E[g][2t + j] (lane = 4g + t; rows m = (r', Re/Im of lambda), columns n = (c, Re/Im of psi)) ->
 // M[r', c] in the layout of the environments, out32[2 (r' + 4c)] = Re, + 1 = Im:

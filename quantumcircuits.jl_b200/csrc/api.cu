@@ -524,6 +524,8 @@ int qcb_set_option(const char *key, long value)
         c.adjoint_tile_bits = value;
     } else if (k == "adjoint_mma") {
         c.adjoint_mma = value ? 1 : 0;
+    } else if (k == "adjoint_prog_host") {
+        c.adjoint_prog_host = value ? 1 : 0;
     } else if (k == "adjoint_warps") {
         if (value != 0 && value != 4 && value != 8) return set_error(QCB_EINVAL, "adjoint_warps must be 0 (auto), 4 or 8");
         c.adjoint_warps = value;

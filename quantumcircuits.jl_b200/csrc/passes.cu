@@ -279,17 +279,22 @@ template <int TB, int NW> static int launch_adjoint_mma(qcb_state *psi, qcb_stat
     const unsigned long long ntiles = 1ull << (psi->nloc - TB);
     const unsigned grid = (unsigned)std::min<unsigned long long>(ntiles, (unsigned long long)ctx().sm_count * ctas_per_sm);
     // device work area: [accumulator rows of every warp | their sums | the threads' per-gate programs]
-    static thread_local std::vector<AdjmLaneProg> prog;
-    prog.resize((size_t)kAdjMaxGates * NT);
-    build_adj_mma_prog<TB, NW>(M, prog.data());
     const size_t nrows = (size_t)grid * NW;
     const size_t rows_doubles = nrows * kAdjMaxGates * kAdjmRow, raw_doubles = (size_t)kAdjMaxGates * kAdjmRow;
-    const size_t prog_bytes = (size_t)M.A.ngates * NT * sizeof(AdjmLaneProg);
     QCB_TRY(ensure_partial(rows_doubles + raw_doubles + (size_t)kAdjMaxGates * 16 * 32 * sizeof(AdjmLaneProg) / sizeof(double)));
     double *d_rows = ctx().d_partial, *d_raw = d_rows + rows_doubles, *d_prog = d_raw + raw_doubles;
     QCB_CUDA(cudaMemsetAsync(d_rows, 0, rows_doubles * sizeof(double), ctx().stream));
-    // (stream-ordered upload from pageable memory: the driver stages the source, so it may be reused at once)
-    QCB_CUDA(cudaMemcpyAsync(d_prog, prog.data(), prog_bytes, cudaMemcpyHostToDevice, ctx().stream));
+    if (ctx().adjoint_prog_host) {
+        // cross-check path: the table built on the host (what the CPU replay runs) and uploaded
+        static thread_local std::vector<AdjmLaneProg> prog;
+        prog.resize((size_t)kAdjMaxGates * NT);
+        build_adj_mma_prog<TB, NW>(M, prog.data());
+        QCB_CUDA(cudaMemcpyAsync(d_prog, prog.data(), (size_t)M.A.ngates * NT * sizeof(AdjmLaneProg), cudaMemcpyHostToDevice, ctx().stream));
+    } else {
+        k_build_adj_mma_prog<TB, NW><<<kMaxStages * kSlots, NT, 0, ctx().stream>>>(M, (AdjmLaneProg *)d_prog);
+        QCB_CUDA(cudaGetLastError());
+        count_launch();
+    }
     kern<<<grid, NT, smem, ctx().stream>>>((double2 *)psi->d, (double2 *)lam->d, M.A.P, M.A.ngates, (const uint4 *)d_prog, ntiles, d_rows);
     QCB_CUDA(cudaGetLastError());
     k_env_reduce_raw<<<ids.n * kAdjmRow, 128, 0, ctx().stream>>>(d_rows, (int)nrows, d_raw);

@@ -49,6 +49,7 @@ def _defaults():
     qc.set_option("max_gates_per_pass", 1 << 30)
     qc.set_option("adjoint_mma", 1)
     qc.set_option("adjoint_tile_bits", 0)
+    qc.set_option("adjoint_prog_host", 0)
     yield
 
 
@@ -332,6 +333,11 @@ def test_gradients_tensor_core_pass_equals_scalar_pass(oracle, n, layers, atb):
     if n <= 13:
         _, g_ref = oracle.gradients_brickwork(psi0.to_numpy(), n, layers, c.gate_angles, 0 if n % 2 else 1, H.params())
         assert np.max(np.abs(g1 - g_ref)) < 1e-12 * max(scale_g, 1.0)
+    # the per-thread gate programs built on the device == the table the CPU replay builds on the host (uploaded): same kernel,
+    # same inputs, so the numbers must be identical
+    qc.set_option("adjoint_prog_host", 1)
+    E2, g2 = qc.gradients(H, psi0, c, calculate_energy=True)
+    assert E2 == E1 and np.array_equal(g2, g1)
 
 
 def test_gradients_c2_shape_against_shift_subset(oracle):
