@@ -99,6 +99,9 @@ int qcb_brickwork_num_gates(int nbits, int nlayers);
 /* Partial derivative of the 15-angle gate with respect to angle k (0-based); the factor the
  * reference differentiates implicitly with its +-pi/2 shifts (src/gradients.jl:120-139). */
 int qcb_general_unitary_gate_derivative(const double *angles15, int k, double *out_u32);
+/* out15[k] = 2 Re sum_{r,c} env[r,c] (dU/dangle_k)[r,c], k = 0..14, for a 4x4 environment env (column-major r + 4c, (re, im)
+ * pairs): the contraction the adjoint gradient applies to each gate's environment, all 15 angles from shared partial products. */
+int qcb_general_unitary_gate_gradient(const double *angles15, const double *env32, double *out15);
 
 /* ---- gate application (in place; the shim keeps the (psi', psi) signature) -------- */
 /* apply!(psi', psi, ::Localised1SpinGate)  src/apply.jl:20-38 */

@@ -192,12 +192,7 @@ static void contract_environments(int G, const double *angles, const double *mat
     for (int g = 0; g < G; g++) {
         double *env = env_rows + 32 * (size_t)g;
         if (env_post) adjm_env_from_post(mats + 32 * (size_t)g, env);
-        for (int k = 0; k < 15; k++) {
-            const M4 dU = general_unitary(angles + 15 * (size_t)g, k);
-            double s = 0;
-            for (int i = 0; i < 16; i++) s += env[2 * i] * dU.m[i].real() - env[2 * i + 1] * dU.m[i].imag();
-            out_grads[k + 15 * (size_t)g] = 2 * s;
-        }
+        general_unitary_gradient(angles + 15 * (size_t)g, env, out_grads + 15 * (size_t)g);
     }
 }
 
@@ -719,6 +714,12 @@ int qcb_general_unitary_gate_derivative(const double *angles15, int k, double *o
 {
     if (!angles15 || !out_u32 || k < 0 || k > 14) return set_error(QCB_EINVAL, "bad arguments");
     to_doubles(general_unitary(angles15, k), out_u32);
+    return QCB_OK;
+}
+int qcb_general_unitary_gate_gradient(const double *angles15, const double *env32, double *out15)
+{
+    if (!angles15 || !env32 || !out15) return set_error(QCB_EINVAL, "null pointer");
+    general_unitary_gradient(angles15, env32, out15);
     return QCB_OK;
 }
 int qcb_brickwork_num_gates(int nbits, int nlayers) { return (int)brickwork_positions(nbits, nlayers).size(); }

@@ -12,6 +12,7 @@
 #pragma once
 #include <cmath>
 #include <complex>
+#include <utility>
 
 namespace qcb {
 
@@ -20,11 +21,15 @@ using cd = std::complex<double>;
 struct M2 { cd m[4]; };
 struct M4 { cd m[16]; };
 
+// complex product without std::complex's operator* (which goes through the NaN-recovering __muldc3: 10x slower, and this
+// algebra runs 15 G times per gradient on the host)
+inline cd cmul(const cd &x, const cd &y) { return cd(x.real() * y.real() - x.imag() * y.imag(), x.real() * y.imag() + x.imag() * y.real()); }
+
 inline M2 mul(const M2 &a, const M2 &b)
 {
     M2 o;
     for (int c = 0; c < 2; c++)
-        for (int r = 0; r < 2; r++) o.m[r + 2 * c] = a.m[r] * b.m[2 * c] + a.m[r + 2] * b.m[1 + 2 * c];
+        for (int r = 0; r < 2; r++) o.m[r + 2 * c] = cmul(a.m[r], b.m[2 * c]) + cmul(a.m[r + 2], b.m[1 + 2 * c]);
     return o;
 }
 inline M4 mul(const M4 &a, const M4 &b)
@@ -32,9 +37,13 @@ inline M4 mul(const M4 &a, const M4 &b)
     M4 o;
     for (int c = 0; c < 4; c++)
         for (int r = 0; r < 4; r++) {
-            cd s = 0;
-            for (int k = 0; k < 4; k++) s += a.m[r + 4 * k] * b.m[k + 4 * c];
-            o.m[r + 4 * c] = s;
+            double sr = 0, si = 0;
+            for (int k = 0; k < 4; k++) {
+                const cd &x = a.m[r + 4 * k], &y = b.m[k + 4 * c];
+                sr += x.real() * y.real() - x.imag() * y.imag();
+                si += x.real() * y.imag() + x.imag() * y.real();
+            }
+            o.m[r + 4 * c] = cd(sr, si);
         }
     return o;
 }
@@ -45,7 +54,7 @@ inline M4 kron(const M2 &hi, const M2 &lo)
     for (int ch = 0; ch < 2; ch++)
         for (int cl = 0; cl < 2; cl++)
             for (int rh = 0; rh < 2; rh++)
-                for (int rl = 0; rl < 2; rl++) o.m[(2 * rh + rl) + 4 * (2 * ch + cl)] = hi.m[rh + 2 * ch] * lo.m[rl + 2 * cl];
+                for (int rl = 0; rl < 2; rl++) o.m[(2 * rh + rl) + 4 * (2 * ch + cl)] = cmul(hi.m[rh + 2 * ch], lo.m[rl + 2 * cl]);
     return o;
 }
 
@@ -115,6 +124,67 @@ inline M4 general_unitary(const double *a, int dk = -1)
     const M4 l4 = kron(r2, mul(r1, rzm));
     const M4 rc = rcnot4(), cn = cnot4();
     return mul(mul(mul(l4, rc), mul(l3, cn)), mul(mul(l2, rc), l1));
+}
+
+inline M4 transpose(const M4 &a)
+{
+    M4 o;
+    for (int c = 0; c < 4; c++)
+        for (int r = 0; r < 4; r++) o.m[r + 4 * c] = a.m[c + 4 * r];
+    return o;
+}
+
+// out15[k] = 2 Re sum_{r,c} env[r,c] dU/dtheta_k [r,c] for all 15 angles of the general gate at once.
+// U = l4 rc l3 cn l2 rc l1 and every angle sits in one Kronecker factor of one l_j, so with dU = X_j dl_j Y_j
+//     sum env .* dU = sum_{a,b} dl_j[a,b] W_j[a,b],   W_j = X_j^T env Y_j^T :
+// four W matrices (shared prefix / suffix products) and one 16-term contraction per angle, instead of 15 full products of
+// seven 4x4 matrices (the per-angle form, general_unitary(a, k), costs 1 us per angle on the host: 0.6 ms of a 0.9 ms
+// 20-qubit gradient).  Same numbers up to the association order of the products.
+inline void general_unitary_gradient(const double *a, const double *env32, double *out15)
+{
+    M2 r[4], dr[4][3];
+    for (int i = 0; i < 4; i++) { // (one set of sines and cosines per rotation: the trigonometry is most of this function's time)
+        const double c = std::cos(a[3 * i] / 2), sn = std::sin(a[3 * i] / 2);
+        const cd p1(std::cos(a[3 * i + 2]), std::sin(a[3 * i + 2])), p2(std::cos(a[3 * i + 1]), std::sin(a[3 * i + 1]));
+        const cd p3 = cmul(p1, p2), I(0, 1);
+        r[i] = M2{{c, p2 * sn, -p1 * sn, c * p3}};
+        dr[i][0] = M2{{-0.5 * sn, 0.5 * p2 * c, -0.5 * p1 * c, -0.5 * sn * p3}};
+        dr[i][1] = M2{{0, cmul(I, p2) * sn, 0, cmul(I, p3) * c}};
+        dr[i][2] = M2{{0, 0, -cmul(I, p1) * sn, cmul(I, p3) * c}};
+    }
+    const M2 rzm = rz(-M_PI / 2), id = identity2();
+    const M2 z13 = rz(a[12]), y14 = ry(a[13]), y15 = ry(a[14]);
+    // d/da exp(-i a P / 2) = R(a + pi) / 2, and cos((a + pi) / 2) = -sin(a / 2), sin((a + pi) / 2) = cos(a / 2): no new trigonometry
+    const M2 dz13 = M2{{0.5 * cd(-z13.m[3].imag(), -z13.m[3].real()), 0, 0, 0.5 * cd(-z13.m[3].imag(), z13.m[3].real())}};
+    auto dry_of = [](const M2 &y) { return M2{{-0.5 * y.m[1], 0.5 * y.m[0], -0.5 * y.m[0], -0.5 * y.m[1]}}; };
+    const M2 hi1 = mul(rzm, r[3]), lo4 = mul(r[0], rzm);
+    const M4 l1 = kron(hi1, r[2]), l2 = kron(y14, z13), l3 = kron(y15, id), l4 = kron(r[1], lo4);
+    M4 E;
+    for (int i = 0; i < 16; i++) E.m[i] = cd(env32[2 * i], env32[2 * i + 1]);
+    // suffixes Y_j (everything to the right of l_j) and prefixes X_j (everything to its left).  The CNOTs are permutation
+    // matrices: rcnot swaps index 2 <-> 3, cnot swaps 1 <-> 3 (rows when applied from the left, columns from the right)
+    auto rows = [](M4 m, int i, int j) { for (int c = 0; c < 4; c++) std::swap(m.m[i + 4 * c], m.m[j + 4 * c]); return m; };
+    auto cols = [](M4 m, int i, int j) { for (int r = 0; r < 4; r++) std::swap(m.m[r + 4 * i], m.m[r + 4 * j]); return m; };
+    const M4 Y2 = rows(l1, 2, 3), Y3 = rows(mul(l2, Y2), 1, 3), Y4 = rows(mul(l3, Y3), 2, 3);
+    const M4 X3 = cols(l4, 2, 3), X2 = cols(mul(X3, l3), 1, 3), X1 = cols(mul(X2, l2), 2, 3);
+    const M4 W4 = mul(E, transpose(Y4));                        // X_4 = 1
+    const M4 W3 = mul(mul(transpose(X3), E), transpose(Y3));
+    const M4 W2 = mul(mul(transpose(X2), E), transpose(Y2));
+    const M4 W1 = mul(transpose(X1), E);                        // Y_1 = 1
+    auto dot = [](const M4 &d, const M4 &w) {
+        double s = 0;
+        for (int i = 0; i < 16; i++) s += d.m[i].real() * w.m[i].real() - d.m[i].imag() * w.m[i].imag();
+        return 2 * s;
+    };
+    for (int w = 0; w < 3; w++) {
+        out15[w] = dot(kron(r[1], mul(dr[0][w], rzm)), W4);      // angles 1-3: r1 in l4 (qubit K)
+        out15[3 + w] = dot(kron(dr[1][w], lo4), W4);             // angles 4-6: r2 in l4 (qubit K+1)
+        out15[6 + w] = dot(kron(hi1, dr[2][w]), W1);             // angles 7-9: r3 in l1 (qubit K)
+        out15[9 + w] = dot(kron(mul(rzm, dr[3][w]), r[2]), W1);  // angles 10-12: r4 in l1 (qubit K+1)
+    }
+    out15[12] = dot(kron(y14, dz13), W2);                        // theta: RZ in l2 (qubit K)
+    out15[13] = dot(kron(dry_of(y14), z13), W2);                 // phi: RY in l2 (qubit K+1)
+    out15[14] = dot(kron(dry_of(y15), id), W3);                  // lambda: RY in l3 (qubit K+1)
 }
 
 inline void to_doubles(const M4 &u, double *out32)

@@ -132,3 +132,21 @@ def test_find_tfim_ground_state():
     w, V = np.linalg.eigh(onp.dense_tfim(n, J, h, g))
     assert abs(E - w[0]) < 1e-10
     assert abs(abs(np.vdot(V[:, 0], v)) - 1) < 1e-8
+
+
+def test_general_unitary_gradient_matches_per_angle_derivatives():
+    """qcb_general_unitary_gate_gradient (15 angles from shared partial products) == contraction with each
+    qcb_general_unitary_gate_derivative, which the oracle pins by finite differences elsewhere in this file."""
+    rng = np.random.default_rng(15)
+    L = _lib.lib()
+    for _ in range(20):
+        a = np.ascontiguousarray(rng.uniform(-2 * np.pi, 2 * np.pi, 15))
+        env = rng.standard_normal((4, 4)) + 1j * rng.standard_normal((4, 4))
+        env_abi = np.ascontiguousarray(env.reshape(-1, order="F"))
+        out = np.zeros(15)
+        _lib.check(L.qcb_general_unitary_gate_gradient(a.ctypes.data_as(C.c_void_p), env_abi.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p)))
+        for k in range(15):
+            d = np.empty(16, dtype=np.complex128)
+            _lib.check(L.qcb_general_unitary_gate_derivative(a.ctypes.data_as(C.c_void_p), C.c_int(k), d.ctypes.data_as(C.c_void_p)))
+            ref = 2 * np.real(np.sum(env * d.reshape(4, 4, order="F")))
+            assert abs(out[k] - ref) < 1e-13 * max(1.0, abs(ref))
