@@ -72,20 +72,15 @@ QCB_HD void measure_stage(const MeasParams<R> &P, int s, const typename Vec2<R>:
 #pragma unroll
         for (int k = 0; k < TB; k++) C0 |= (unsigned long long)((e >> P.ld_lpos[k]) & 1u) << P.ld_phys[k];
     }
-    // (four partial sums each: one accumulator would be a chain of 16 / 32 dependent DFMAs per stage -- ncu showed the
-    // kernel waiting on exactly that, `wait` stalls on top at 48 % issue utilisation)
     if (S.diag) {
-        double d[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
         for (int r = 0; r < kRegAmps; r++) {
             unsigned long long C = C0;
 #pragma unroll
             for (int b = 0; b < kRegBits; b++) C |= (unsigned long long)((r >> b) & 1) << S.wphys[b];
-            d[r & 3] += ham_diag(P.H, C) * ((double)a[r].x * (double)a[r].x + (double)a[r].y * (double)a[r].y);
+            acc_diag += ham_diag(P.H, C) * ((double)a[r].x * (double)a[r].x + (double)a[r].y * (double)a[r].y);
         }
-        acc_diag += (d[0] + d[1]) + (d[2] + d[3]);
     }
-    double f[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
     for (int b = 0; b < kRegBits; b++) {
         if (!((S.active >> b) & 1)) continue;
@@ -102,11 +97,9 @@ QCB_HD void measure_stage(const MeasParams<R> &P, int s, const typename Vec2<R>:
             if ((r >> b) & 1) continue;
             if (KIND == 1 && !((allowed >> r) & 1u)) continue;
             const V x0 = a[r], x1 = a[r | (1 << b)];
-            const int j = ((r >> (b + 1)) << b) | (r & ((1 << b) - 1)); // ordinal of the pair (compile time after unrolling)
-            f[j & 3] += (double)x0.x * (double)x1.x + (double)x0.y * (double)x1.y;
+            acc_flip += 2.0 * ((double)x0.x * (double)x1.x + (double)x0.y * (double)x1.y);
         }
     }
-    acc_flip += 2.0 * ((f[0] + f[1]) + (f[2] + f[3]));
 }
 
 template <typename R, int TB>
