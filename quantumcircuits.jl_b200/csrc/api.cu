@@ -4,6 +4,7 @@
 #include <cstring>
 
 #include "adjoint_mma.cuh"
+#include "gates_hd.cuh"
 #include "gates_host.hpp"
 #include "kernels.cuh"
 #include "measure_plan.hpp"
@@ -186,14 +187,39 @@ static int copy_state_raw(void *dst, const void *src, size_t bytes)
     return QCB_OK;
 }
 
-// grads[k, g] = 2 Re sum_{r,c} env_g[r,c] dU_g/dtheta_k [r,c]   (env: G rows of 32 doubles on the host, modified in place)
-static void contract_environments(int G, const double *angles, const double *mats, bool env_post, double *env_rows, double *out_grads)
+// Result area of a gradient on the device (c.d_out) and its pinned mirror (c.h_out), in doubles:
+//   [ environments 32 G | energy parts 4 | gradients 15 G | angles 15 G ]
+// The angles go up first (the stream is idle then, so the staging of a pageable source costs nothing), the backward sweep
+// fills the environments, k_contract_env (gates_hd.cuh) turns them into the gradients next to them, and one download of
+// [energy parts | gradients] with one synchronisation ends the call.
+struct GradArea {
+    size_t G;
+    size_t env() const { return 0; }
+    size_t energy() const { return 32 * G; }
+    size_t grads() const { return 32 * G + 4; }
+    size_t angles() const { return 32 * G + 4 + 15 * G; }
+    size_t total() const { return 32 * G + 4 + 30 * G; }
+};
+static int grad_area_begin(const GradArea &ar, const double *angles)
 {
-    for (int g = 0; g < G; g++) {
-        double *env = env_rows + 32 * (size_t)g;
-        if (env_post) adjm_env_from_post(mats + 32 * (size_t)g, env);
-        general_unitary_gradient(angles + 15 * (size_t)g, env, out_grads + 15 * (size_t)g);
-    }
+    Ctx &c = ctx();
+    QCB_TRY(ensure_out(ar.total()));
+    QCB_CUDA(cudaMemcpyAsync(c.d_out + ar.angles(), angles, sizeof(double) * 15 * ar.G, cudaMemcpyHostToDevice, c.stream));
+    QCB_CUDA(cudaMemsetAsync(c.d_out + ar.energy(), 0, 4 * sizeof(double), c.stream));
+    return QCB_OK;
+}
+// grads[k, g] = 2 Re sum_{r,c} env_g[r,c] dU_g/dtheta_k [r,c] on the device, download, energy = sum of its two parts
+static int grad_area_finish(const GradArea &ar, bool env_post, int want_energy, double *out_E, double *out_grads)
+{
+    Ctx &c = ctx();
+    k_contract_env<<<(unsigned)((4 * ar.G + 63) / 64), 64, 0, c.stream>>>(c.d_out + ar.angles(), c.d_out + ar.env(), (int)ar.G, env_post ? 1 : 0, c.d_out + ar.grads());
+    QCB_CUDA(cudaGetLastError());
+    count_launch();
+    QCB_CUDA(cudaMemcpyAsync(c.h_out + ar.energy(), c.d_out + ar.energy(), sizeof(double) * (4 + 15 * ar.G), cudaMemcpyDeviceToHost, c.stream));
+    QCB_CUDA(cudaStreamSynchronize(c.stream));
+    if (want_energy) *out_E = c.h_out[ar.energy()] + c.h_out[ar.energy() + 2];
+    std::memcpy(out_grads, c.h_out + ar.grads(), sizeof(double) * 15 * ar.G);
+    return QCB_OK;
 }
 
 // Sharded states (collective call): forward circuit with qubit swaps, lambda = H psi in two sweeps around one swap (the
@@ -254,8 +280,8 @@ static int gradients_sharded_impl(const qcb_state *psi0, int nbits, int nlayers,
     HamEval H{ham_kind, nbits, hp[0], hp[1], hp[2]};
     const unsigned blocks = grid_for(namps, kRedThreads, 8);
     QCB_TRY(ensure_partial((size_t)blocks * 2));
-    QCB_TRY(ensure_out((size_t)32 * G + 4)); // [environments | E part 1 | E part 2]
-    QCB_CUDA(cudaMemsetAsync(c.d_out + 32 * (size_t)G, 0, 4 * sizeof(double), c.stream));
+    const GradArea ar{(size_t)G};
+    QCB_TRY(grad_area_begin(ar, angles));
     auto sweep = [&](unsigned long long mask, int first, int slot) -> int {
         ShardMap M;
         std::memset(&M, 0, sizeof M);
@@ -286,12 +312,8 @@ static int gradients_sharded_impl(const qcb_state *psi0, int nbits, int nlayers,
     std::vector<GateOp> rev(G);
     for (int i = 0; i < G; i++) rev[i] = GateOp{pos[G - 1 - i], G - 1 - i};
     QCB_TRY(dist_run_adjoint_pair(&A, &B, &spare, rev, mats.data(), c.d_out));
-    QCB_TRY(dist_allreduce_sum(c.d_out, 32 * G + 4));
-    QCB_CUDA(cudaMemcpyAsync(c.h_out, c.d_out, sizeof(double) * (32 * (size_t)G + 4), cudaMemcpyDeviceToHost, c.stream));
-    QCB_CUDA(cudaStreamSynchronize(c.stream));
-    if (want_energy) *out_E = c.h_out[32 * (size_t)G] + c.h_out[32 * (size_t)G + 2];
-    contract_environments(G, angles, mats.data(), adjoint_uses_mma(&A), c.h_out, out_grads);
-    return QCB_OK;
+    QCB_TRY(dist_allreduce_sum(c.d_out, 32 * G + 4)); // environments and energy parts of all ranks
+    return grad_area_finish(ar, adjoint_uses_mma(&A), want_energy, out_E, out_grads);
 }
 
 // adjoint-method gradient; numbers equal the reference's shift sweep.
@@ -325,13 +347,14 @@ static int gradients_impl(const qcb_state *psi0, int nbits, int nlayers, const d
         }
         return QCB_OK;
     }
+    const GradArea ar{(size_t)G};
+    QCB_TRY(grad_area_begin(ar, angles));
     // lambda = H psi_G, and E = <psi_G|lambda> from the same sweep (gradients.jl:104)
     const unsigned long long namps = 1ull << nbits;
     HamEval H{ham_kind, nbits, hp[0], hp[1], hp[2]};
     {
         const unsigned blocks = grid_for(namps, kRedThreads, 8);
         QCB_TRY(ensure_partial((size_t)blocks * 2));
-        QCB_TRY(ensure_out((size_t)32 * G + 2)); // [environments | E]: one download, one synchronisation at the end
         if (psi0->dtype == QCB_C128)
             k_apply_ham<double><<<blocks, kRedThreads, 0, c.stream>>>((double2 *)B.d, (const double2 *)A.d, namps, H, (double2 *)c.d_partial);
         else
@@ -339,7 +362,7 @@ static int gradients_impl(const qcb_state *psi0, int nbits, int nlayers, const d
         QCB_CUDA(cudaGetLastError());
         count_launch();
         if (want_energy) {
-            k_final_sum<<<2, 256, 0, c.stream>>>(c.d_partial, (int)blocks, 2, c.d_out + 32 * (size_t)G);
+            k_final_sum<<<2, 256, 0, c.stream>>>(c.d_partial, (int)blocks, 2, c.d_out + ar.energy());
             QCB_CUDA(cudaGetLastError());
             count_launch();
         }
@@ -378,10 +401,7 @@ static int gradients_impl(const qcb_state *psi0, int nbits, int nlayers, const d
         }
         bw_passes = G;
     }
-    QCB_CUDA(cudaMemcpyAsync(c.h_out, c.d_out, sizeof(double) * (32 * (size_t)G + 2), cudaMemcpyDeviceToHost, c.stream));
-    QCB_CUDA(cudaStreamSynchronize(c.stream));
-    if (want_energy) *out_E = c.h_out[32 * (size_t)G];
-    contract_environments(G, angles, mats.data(), env_post, c.h_out, out_grads);
+    QCB_TRY(grad_area_finish(ar, env_post, want_energy, out_E, out_grads));
     c.st_passes = fw_passes + bw_passes; c.st_stages = fw_stages + bw_stages; c.st_launches += fw_launches; c.st_gates = 4.0 * G;
     return QCB_OK;
 }

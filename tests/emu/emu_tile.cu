@@ -663,3 +663,21 @@ extern "C" int emu_sharded_gradient_env(int n, int g, const void *psi_, int kind
         return 1;
     }
 }
+
+// ---- gates_hd.cuh on the host: the per-gate contraction the GPU runs in k_contract_env ----------------------------------
+#include "../../quantumcircuits.jl_b200/csrc/gates_hd.cuh"
+extern "C" int emu_contract_env_gate(const double *angles15, const double *env32, int post, double *out15, double *u32_out)
+{
+    for (int layer = 1; layer <= 4; layer++) hd::contract_env_gate(angles15, env32, post, out15, layer); // as the GPU threads do
+    double all[15];
+    hd::contract_env_gate(angles15, env32, post, all, 0);
+    for (int k = 0; k < 15; k++)
+        if (all[k] != out15[k]) return 1;
+    if (u32_out) {
+        hd::GeneralGate G;
+        hd::general_gate_setup(angles15, G);
+        const hd::M4 U = hd::general_unitary_of(G);
+        for (int i = 0; i < 16; i++) { u32_out[2 * i] = U.m[i].re; u32_out[2 * i + 1] = U.m[i].im; }
+    }
+    return 0;
+}

@@ -12,7 +12,7 @@ _lib = None
 
 
 def build(force=False):
-    srcs = [os.path.join(_HERE, "emu_tile.cu"), os.path.join(_CSRC, "tile.cuh"), os.path.join(_CSRC, "schedule.hpp"), os.path.join(_CSRC, "dist_plan.hpp"), os.path.join(_CSRC, "adjoint.cuh"), os.path.join(_CSRC, "adjoint_mma.cuh"), os.path.join(_CSRC, "measure_tile.cuh"), os.path.join(_CSRC, "measure_plan.hpp"), os.path.join(_CSRC, "kernels.cuh")]
+    srcs = [os.path.join(_HERE, "emu_tile.cu"), os.path.join(_CSRC, "tile.cuh"), os.path.join(_CSRC, "schedule.hpp"), os.path.join(_CSRC, "dist_plan.hpp"), os.path.join(_CSRC, "adjoint.cuh"), os.path.join(_CSRC, "adjoint_mma.cuh"), os.path.join(_CSRC, "gates_hd.cuh"), os.path.join(_CSRC, "measure_tile.cuh"), os.path.join(_CSRC, "measure_plan.hpp"), os.path.join(_CSRC, "kernels.cuh")]
     if force or not os.path.exists(_SO) or any(os.path.getmtime(_SO) < os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["nvcc", "-O2", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler",
                                "-fPIC", "-shared", "-o", _SO, srcs[0]], cwd=_HERE)
@@ -159,3 +159,16 @@ def sharded_measure(psi, g, kind, params, tile_bits, low_bits):
     if rc:
         raise RuntimeError(f"emu_sharded_measure rc={rc}")
     return E.value
+
+
+def contract_env_gate(angles15, env, post):
+    """gates_hd.cuh (the algebra of k_contract_env) on the host: returns (out15, U as 4x4)."""
+    a = np.ascontiguousarray(angles15, dtype=np.float64)
+    e = np.ascontiguousarray(np.asarray(env, dtype=np.complex128).reshape(-1, order="F"))
+    out = np.zeros(15)
+    u = np.zeros(16, dtype=np.complex128)
+    rc = lib().emu_contract_env_gate(a.ctypes.data_as(C.c_void_p), e.ctypes.data_as(C.c_void_p), C.c_int(1 if post else 0), out.ctypes.data_as(C.c_void_p),
+                                     u.ctypes.data_as(C.c_void_p))
+    if rc:
+        raise RuntimeError("per-layer and whole-gate contraction differ")
+    return out, u.reshape(4, 4, order="F")

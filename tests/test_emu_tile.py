@@ -345,3 +345,28 @@ def test_emu_sharded_measure(emu, oracle, n, g, tb, c):
                           (1, (0.1, A, B), oracle.measure_east(psi, 0.1, A, B).real)]:
         E = emu.sharded_measure(psi, g, kind, hp, tb, c)
         assert abs(E - ref) < 1e-12 * max(1.0, abs(ref))
+
+
+def test_device_gate_algebra_matches_host(emu, oracle):
+    """gates_hd.cuh (runs on the GPU in k_contract_env; compiled for the host here) == gates_host.hpp through the ABI: the
+    gate itself, the 15-angle contraction, and the env = conj(U) M step of the tensor-core backward pass."""
+    import ctypes as C
+
+    from qcb200 import _lib
+
+    rng = np.random.default_rng(2718)
+    L = _lib.lib()
+    for _ in range(10):
+        a = np.ascontiguousarray(rng.uniform(-2 * np.pi, 2 * np.pi, 15))
+        env = rng.standard_normal((4, 4)) + 1j * rng.standard_normal((4, 4))
+        out, U = emu.contract_env_gate(a, env, False)
+        U_ref = np.asarray(oracle.build_general_unitary_gate(a)).reshape(4, 4)
+        assert np.max(np.abs(U - U_ref)) < 1e-14
+        ref = np.zeros(15)
+        e = np.ascontiguousarray(env.reshape(-1, order="F"))
+        _lib.check(L.qcb_general_unitary_gate_gradient(a.ctypes.data_as(C.c_void_p), e.ctypes.data_as(C.c_void_p), ref.ctypes.data_as(C.c_void_p)))
+        assert np.max(np.abs(out - ref)) < 1e-13 * max(1.0, np.max(np.abs(ref)))
+        out_post, _ = emu.contract_env_gate(a, env, True)
+        e2 = np.ascontiguousarray((np.conj(U_ref) @ env).reshape(-1, order="F"))
+        _lib.check(L.qcb_general_unitary_gate_gradient(a.ctypes.data_as(C.c_void_p), e2.ctypes.data_as(C.c_void_p), ref.ctypes.data_as(C.c_void_p)))
+        assert np.max(np.abs(out_post - ref)) < 1e-13 * max(1.0, np.max(np.abs(ref)))
