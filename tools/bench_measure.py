@@ -17,6 +17,9 @@ def main():
 
     qc.init(0)
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 30
+    if os.environ.get("MEASURE_CTAS"):
+        qc.set_option("measure_ctas", int(os.environ["MEASURE_CTAS"]))
+        print("measure_ctas", os.environ["MEASURE_CTAS"])
     c = qc.GenericBrickworkCircuit(n, 2)
     c.gate_angles[...] = np.random.default_rng(n).uniform(0, 2 * np.pi, c.gate_angles.shape)
     print(f"== measure {n}q")
