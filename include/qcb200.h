@@ -141,6 +141,11 @@ int qcb_measure_csr(const qcb_state *s, long long nrows, const long long *rowptr
  * Sharded states: collective call (every rank), every rank receives the energy and the full gradient. */
 int qcb_gradients_brickwork(const qcb_state *psi0, int nbits, int nlayers, const double *angles, int ham_kind,
                             const double *ham_params3, int want_energy, double *out_E, double *out_grads);
+/* gradients(H::AbstractMatrix, psi0, circuit; calculate_energy): the same sweep for an explicit Hermitian Hamiltonian in CSR
+ * form (layout as qcb_measure_csr) -- the reference's generic gradients! over measure!(psi', H::AbstractMatrix, psi)
+ * (src/circuits.jl:56-58; examples/test_gradients.jl:25).  Not for sharded states. */
+int qcb_gradients_brickwork_csr(const qcb_state *psi0, int nbits, int nlayers, const double *angles, long long nrows, const long long *rowptr,
+                                const long long *colidx, const double *vals_reim, int want_energy, double *out_E, double *out_grads);
 /* optimise!(circuit, H, psi0, epochs, lr)  src/gradients.jl:1-17 with quirk Q1 resolved
  * (energy + full gradient each epoch).  energies_out has epochs+1 entries laid out like the reference's. */
 int qcb_optimise_brickwork(const qcb_state *psi0, int nbits, int nlayers, double *angles_inout, int ham_kind,

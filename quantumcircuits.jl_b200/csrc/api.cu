@@ -191,6 +191,58 @@ static int copy_state_raw(void *dst, const void *src, size_t bytes)
     return QCB_OK;
 }
 
+// An explicit Hamiltonian in CSR form, uploaded for the duration of one call (measure / gradients with H::AbstractMatrix)
+struct DeviceCsr {
+    char *base = nullptr;
+    long long nrows = 0;
+    long long *rowptr = nullptr, *colidx = nullptr;
+    double2 *vals = nullptr;
+    ~DeviceCsr() { if (base) cudaFree(base); }
+};
+static int upload_csr(DeviceCsr &D, int nqubits, long long nrows, const long long *rowptr, const long long *colidx, const double *vals_reim)
+{
+    if (!rowptr) return set_error(QCB_EINVAL, "null pointer");
+    if (nrows != (1ll << nqubits)) return set_error(QCB_EINVAL, "H must be 2^n x 2^n with n = %d", nqubits);
+    const long long nnz = rowptr[nrows];
+    if (rowptr[0] != 0 || nnz < 0 || (nnz > 0 && (!colidx || !vals_reim))) return set_error(QCB_EINVAL, "bad CSR arrays");
+    for (long long r = 0; r < nrows; r++)
+        if (rowptr[r + 1] < rowptr[r]) return set_error(QCB_EINVAL, "rowptr must be non-decreasing");
+    for (long long k = 0; k < nnz; k++)
+        if (colidx[k] < 0 || colidx[k] >= nrows) return set_error(QCB_EINVAL, "column index out of range");
+    Ctx &c = ctx();
+    const size_t b_ptr = sizeof(long long) * (size_t)(nrows + 1), b_col = sizeof(long long) * (size_t)nnz, b_val = 16 * (size_t)nnz;
+    QCB_CUDA(cudaMalloc(&D.base, b_ptr + b_col + b_val + 64));
+    D.nrows = nrows;
+    D.rowptr = (long long *)D.base;
+    D.colidx = (long long *)(D.base + b_ptr);
+    D.vals = (double2 *)(D.base + b_ptr + b_col + ((16 - (b_ptr + b_col) % 16) % 16));
+    QCB_CUDA(cudaMemcpyAsync(D.rowptr, rowptr, b_ptr, cudaMemcpyHostToDevice, c.stream));
+    if (nnz > 0) {
+        QCB_CUDA(cudaMemcpyAsync(D.colidx, colidx, b_col, cudaMemcpyHostToDevice, c.stream));
+        QCB_CUDA(cudaMemcpyAsync(D.vals, vals_reim, b_val, cudaMemcpyHostToDevice, c.stream));
+    }
+    return QCB_OK;
+}
+
+static int measure_csr_device(const qcb_state *s, const DeviceCsr &D, double *out_E2)
+{
+    Ctx &c = ctx();
+    const unsigned blocks = grid_for((unsigned long long)D.nrows, kRedThreads, 8);
+    QCB_TRY(ensure_partial((size_t)blocks * 2));
+    QCB_TRY(ensure_out(64));
+    if (s->dtype == QCB_C128) k_measure_csr<double><<<blocks, kRedThreads, 0, c.stream>>>((const double2 *)s->d, D.nrows, D.rowptr, D.colidx, D.vals, (double2 *)c.d_partial);
+    else k_measure_csr<float><<<blocks, kRedThreads, 0, c.stream>>>((const float2 *)s->d, D.nrows, D.rowptr, D.colidx, D.vals, (double2 *)c.d_partial);
+    QCB_CUDA(cudaGetLastError());
+    k_final_sum<<<2, 256, 0, c.stream>>>(c.d_partial, (int)blocks, 2, c.d_out);
+    QCB_CUDA(cudaGetLastError());
+    count_launch(2);
+    QCB_CUDA(cudaMemcpyAsync(c.h_out, c.d_out, 2 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    QCB_CUDA(cudaStreamSynchronize(c.stream));
+    out_E2[0] = c.h_out[0];
+    out_E2[1] = c.h_out[1];
+    return QCB_OK;
+}
+
 // Result area of a gradient on the device (c.d_out) and its pinned mirror (c.h_out), in doubles:
 //   [ environments 32 G | energy parts 4 | gradients 15 G | angles 15 G ]
 // The angles go up first (the stream is idle then, so the staging of a pageable source costs nothing), the backward sweep
@@ -321,13 +373,15 @@ static int gradients_sharded_impl(const qcb_state *psi0, int nbits, int nlayers,
 }
 
 // adjoint-method gradient; numbers equal the reference's shift sweep.
+// csr != nullptr: explicit Hamiltonian (ham_kind / hp unused)
 static int gradients_impl(const qcb_state *psi0, int nbits, int nlayers, const double *angles, int ham_kind, const double *hp,
-                          int want_energy, double *out_E, double *out_grads)
+                          int want_energy, double *out_E, double *out_grads, const DeviceCsr *csr = nullptr)
 {
     QCB_REQUIRE_INIT();
     QCB_TRY(check_state(psi0));
     if (psi0->n != nbits) return set_error(QCB_EINVAL, "circuit has %d qubits, state has %d", nbits, psi0->n);
-    if (ham_kind != QCB_HAM_TFIM && ham_kind != QCB_HAM_EAST) return set_error(QCB_EINVAL, "unknown Hamiltonian kind %d", ham_kind);
+    if (!csr && ham_kind != QCB_HAM_TFIM && ham_kind != QCB_HAM_EAST) return set_error(QCB_EINVAL, "unknown Hamiltonian kind %d", ham_kind);
+    if (psi0->sharded && csr) return set_error(QCB_EUNSUPPORTED, "matrix Hamiltonians are not supported on sharded states");
     if (psi0->sharded) return gradients_sharded_impl(psi0, nbits, nlayers, angles, ham_kind, hp, want_energy, out_E, out_grads);
     Ctx &c = ctx();
     const std::vector<int> pos = brickwork_positions(nbits, nlayers);
@@ -346,7 +400,8 @@ static int gradients_impl(const qcb_state *psi0, int nbits, int nlayers, const d
     if (G == 0) {
         if (want_energy) {
             double E2[2];
-            QCB_TRY(measure_impl(&A, ham_kind, hp[0], hp[1], hp[2], E2)); // gradients.jl:104
+            if (csr) QCB_TRY(measure_csr_device(&A, *csr, E2));
+            else QCB_TRY(measure_impl(&A, ham_kind, hp[0], hp[1], hp[2], E2)); // gradients.jl:104
             *out_E = E2[0];
         }
         return QCB_OK;
@@ -355,11 +410,15 @@ static int gradients_impl(const qcb_state *psi0, int nbits, int nlayers, const d
     QCB_TRY(grad_area_begin(ar, angles));
     // lambda = H psi_G, and E = <psi_G|lambda> from the same sweep (gradients.jl:104)
     const unsigned long long namps = 1ull << nbits;
-    HamEval H{ham_kind, nbits, hp[0], hp[1], hp[2]};
+    HamEval H{ham_kind, nbits, csr ? 0.0 : hp[0], csr ? 0.0 : hp[1], csr ? 0.0 : hp[2]};
     {
         const unsigned blocks = grid_for(namps, kRedThreads, 8);
         QCB_TRY(ensure_partial((size_t)blocks * 2));
-        if (psi0->dtype == QCB_C128)
+        if (csr && psi0->dtype == QCB_C128)
+            k_apply_csr<double><<<blocks, kRedThreads, 0, c.stream>>>((double2 *)B.d, (const double2 *)A.d, csr->nrows, csr->rowptr, csr->colidx, csr->vals, (double2 *)c.d_partial);
+        else if (csr)
+            k_apply_csr<float><<<blocks, kRedThreads, 0, c.stream>>>((float2 *)B.d, (const float2 *)A.d, csr->nrows, csr->rowptr, csr->colidx, csr->vals, (double2 *)c.d_partial);
+        else if (psi0->dtype == QCB_C128)
             k_apply_ham<double><<<blocks, kRedThreads, 0, c.stream>>>((double2 *)B.d, (const double2 *)A.d, namps, H, (double2 *)c.d_partial);
         else
             k_apply_ham<float><<<blocks, kRedThreads, 0, c.stream>>>((float2 *)B.d, (const float2 *)A.d, namps, H, (double2 *)c.d_partial);
@@ -937,42 +996,26 @@ int qcb_measure_csr(const qcb_state *s, long long nrows, const long long *rowptr
 {
     QCB_REQUIRE_INIT();
     QCB_TRY(check_state(s));
-    if (!rowptr || !out_E2) return set_error(QCB_EINVAL, "null pointer");
+    if (!out_E2) return set_error(QCB_EINVAL, "null pointer");
     if (s->sharded) return set_error(QCB_EUNSUPPORTED, "matrix Hamiltonians are not supported on sharded states");
-    if (nrows != (1ll << s->n)) return set_error(QCB_EINVAL, "H must be 2^n x 2^n with n = %d", s->n);
-    const long long nnz = rowptr[nrows];
-    if (rowptr[0] != 0 || nnz < 0 || (nnz > 0 && (!colidx || !vals_reim))) return set_error(QCB_EINVAL, "bad CSR arrays");
-    for (long long r = 0; r < nrows; r++)
-        if (rowptr[r + 1] < rowptr[r]) return set_error(QCB_EINVAL, "rowptr must be non-decreasing");
-    for (long long k = 0; k < nnz; k++)
-        if (colidx[k] < 0 || colidx[k] >= nrows) return set_error(QCB_EINVAL, "column index out of range");
-    Ctx &c = ctx();
-    const size_t b_ptr = sizeof(long long) * (size_t)(nrows + 1), b_col = sizeof(long long) * (size_t)nnz, b_val = 16 * (size_t)nnz;
-    char *d = nullptr;
-    QCB_CUDA(cudaMalloc(&d, b_ptr + b_col + b_val + 64));
-    long long *d_ptr = (long long *)d, *d_col = (long long *)(d + b_ptr);
-    double2 *d_val = (double2 *)(d + b_ptr + b_col + ((16 - (b_ptr + b_col) % 16) % 16));
-    int rc = QCB_OK;
-    auto upload = [&](void *dst, const void *src, size_t n) { return n == 0 || cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, c.stream) == cudaSuccess; };
-    if (!upload(d_ptr, rowptr, b_ptr) || !upload(d_col, colidx, b_col) || !upload(d_val, vals_reim, b_val))
-        rc = set_error(QCB_ECUDA, "upload of the CSR arrays failed");
-    const unsigned blocks = grid_for((unsigned long long)nrows, kRedThreads, 8);
-    if (rc == QCB_OK) rc = ensure_partial((size_t)blocks * 2);
-    if (rc == QCB_OK) rc = ensure_out(64);
-    if (rc == QCB_OK) {
-        if (s->dtype == QCB_C128) k_measure_csr<double><<<blocks, kRedThreads, 0, c.stream>>>((const double2 *)s->d, nrows, d_ptr, d_col, d_val, (double2 *)c.d_partial);
-        else k_measure_csr<float><<<blocks, kRedThreads, 0, c.stream>>>((const float2 *)s->d, nrows, d_ptr, d_col, d_val, (double2 *)c.d_partial);
-        k_final_sum<<<2, 256, 0, c.stream>>>(c.d_partial, (int)blocks, 2, c.d_out);
-        count_launch(2);
-        if (cudaGetLastError() != cudaSuccess || cudaMemcpyAsync(c.h_out, c.d_out, 2 * sizeof(double), cudaMemcpyDeviceToHost, c.stream) != cudaSuccess ||
-            cudaStreamSynchronize(c.stream) != cudaSuccess)
-            rc = set_error(QCB_ECUDA, "matrix expectation value failed: %s", cudaGetErrorString(cudaGetLastError()));
-    }
-    cudaFree(d);
-    if (rc != QCB_OK) return rc;
-    out_E2[0] = c.h_out[0];
-    out_E2[1] = c.h_out[1];
-    return QCB_OK;
+    DeviceCsr D;
+    QCB_TRY(upload_csr(D, s->n, nrows, rowptr, colidx, vals_reim));
+    return measure_csr_device(s, D, out_E2);
+}
+
+// gradients(H::AbstractMatrix, psi0, circuit; calculate_energy): the reference reaches this through the generic
+// gradients! + measure!(psi', H::AbstractMatrix, psi) (src/gradients.jl:88-152, src/circuits.jl:56-58;
+// examples/test_gradients.jl:25).  Same adjoint sweep as for the kernel Hamiltonians with lambda = H psi as a CSR product;
+// H must be Hermitian (the reference asserts a real expectation value).
+int qcb_gradients_brickwork_csr(const qcb_state *psi0, int nbits, int nlayers, const double *angles, long long nrows, const long long *rowptr,
+                                const long long *colidx, const double *vals_reim, int want_energy, double *out_E, double *out_grads)
+{
+    QCB_REQUIRE_INIT();
+    QCB_TRY(check_state(psi0));
+    if (!angles || !out_grads || (want_energy && !out_E)) return set_error(QCB_EINVAL, "null pointer");
+    DeviceCsr D;
+    QCB_TRY(upload_csr(D, psi0->n, nrows, rowptr, colidx, vals_reim));
+    return gradients_impl(psi0, nbits, nlayers, angles, 0, nullptr, want_energy, out_E, out_grads, &D);
 }
 
 // ---- polar-optimiser building blocks -----------------------------------------------------------------------------

@@ -282,6 +282,37 @@ __global__ void __launch_bounds__(kRedThreads) k_apply_ham_sharded(typename Vec2
 }
 #endif
 
+// lambda = H psi for an explicit CSR Hamiltonian (and E = <psi|lambda> partials): the adjoint gradient with a matrix
+// Hamiltonian (the reference's gradients!(..., H::AbstractMatrix, ...) through measure!, examples/test_gradients.jl:25)
+template <typename R>
+__global__ void __launch_bounds__(kRedThreads) k_apply_csr(typename Vec2<R>::type *lam, const typename Vec2<R>::type *__restrict__ psi, long long nrows,
+                                                           const long long *__restrict__ rowptr, const long long *__restrict__ colidx,
+                                                           const double2 *__restrict__ vals, double2 *partial)
+{
+    using V = typename Vec2<R>::type;
+    double acc[2] = {0.0, 0.0};
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += stride) {
+        double hr = 0, hi = 0;
+        for (long long k = rowptr[r]; k < rowptr[r + 1]; k++) {
+            const double2 v = vals[k];
+            const V x = psi[colidx[k]];
+            hr += v.x * (double)x.x - v.y * (double)x.y;
+            hi += v.x * (double)x.y + v.y * (double)x.x;
+        }
+        const V p = psi[r];
+        V o;
+        o.x = (R)hr;
+        o.y = (R)hi;
+        lam[r] = o;
+        acc[0] += (double)p.x * hr + (double)p.y * hi;
+        acc[1] += (double)p.x * hi - (double)p.y * hr;
+    }
+    __shared__ double out[2];
+    block_sum<2>(acc, out);
+    if (threadIdx.x == 0) partial[blockIdx.x] = make_double2(out[0], out[1]);
+}
+
 // generic fixed-order final reduction: out[v] = sum_b partial[b * nv + v]
 static __global__ void k_final_sum(const double *__restrict__ partial, int nblocks, int nv, double *out)
 {

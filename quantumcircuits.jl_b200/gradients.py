@@ -12,7 +12,7 @@ import numpy as np
 
 from . import _lib
 from .apply import B200ApplyCache, _apply_circuit_inplace, construct_apply_cache
-from .hamiltonians import AbstractKernelHamiltonian
+from .hamiltonians import AbstractKernelHamiltonian, _csr_arrays, _is_matrix
 from .state import B200State
 
 
@@ -27,14 +27,24 @@ def construct_grads_cache(psi):
 
 def gradients_(cache, psi_p, psi_pp, psi, H, psi0, circuit, calculate_energy=False):
     """gradients!(cache, psi', psi'', psi, H, psi0, circuit; calculate_energy) -- src/gradients.jl:88-152."""
-    if not isinstance(H, AbstractKernelHamiltonian):
-        raise TypeError("only kernel Hamiltonians are accelerated")
     # (a dist.ShardedState works too: collective call, every rank receives the energy and the full gradient)
     st0 = psi0 if isinstance(psi0, B200State) or hasattr(psi0, "_handle") else B200State(psi0)
     a = circuit.angles_abi()
-    hp = H.params()
     E = C.c_double(0.0)
     grads = np.zeros(15 * circuit.ngates, dtype=np.float64)
+    if _is_matrix(H):
+        # H::AbstractMatrix (dense or sparse, Hermitian): the reference's generic gradients! over measure!(psi', H, psi),
+        # src/circuits.jl:56-58, examples/test_gradients.jl:25
+        n, rowptr, colidx, vals = _csr_arrays(H)
+        _lib.check(_lib.lib().qcb_gradients_brickwork_csr(st0._handle, C.c_int(circuit.nbits), C.c_int(circuit.nlayers),
+                                                          a.ctypes.data_as(C.c_void_p), C.c_longlong(n), rowptr.ctypes.data_as(C.c_void_p),
+                                                          colidx.ctypes.data_as(C.c_void_p), vals.ctypes.data_as(C.c_void_p),
+                                                          C.c_int(1 if calculate_energy else 0), C.byref(E), grads.ctypes.data_as(C.c_void_p)))
+        grads = grads.reshape(15, circuit.ngates, order="F")
+        return (E.value, grads) if calculate_energy else grads
+    if not isinstance(H, AbstractKernelHamiltonian):
+        raise TypeError(f"gradients: unsupported Hamiltonian type {type(H)}")
+    hp = H.params()
     _lib.check(_lib.lib().qcb_gradients_brickwork(st0._handle, C.c_int(circuit.nbits), C.c_int(circuit.nlayers),
                                                   a.ctypes.data_as(C.c_void_p), C.c_int(H.kind),
                                                   hp.ctypes.data_as(C.c_void_p), C.c_int(1 if calculate_energy else 0),

@@ -63,11 +63,13 @@ def _is_matrix(H):
     return isinstance(H, np.ndarray) or (hasattr(H, "tocsr") and hasattr(H, "shape"))
 
 
-def _measure_matrix(H, st):
-    """measure(H::AbstractMatrix, psi) = real(dot(psi, H, psi)) -- src/circuits.jl:49-55, on the device through
-    qcb_measure_csr (dense matrices travel as the CSR that holds every entry)."""
-    if len(H.shape) != 2:  # @assert ndims(H) == 2   :50
+def _csr_arrays(H):
+    """(nrows, rowptr, colidx, vals) of a numpy / scipy-sparse matrix as the ABI wants them (0-based, int64, complex128);
+    a dense matrix travels as the CSR that holds every entry."""
+    if len(H.shape) != 2:  # @assert ndims(H) == 2   src/circuits.jl:50
         raise AssertionError("ndims(H) == 2")
+    if H.shape[0] != H.shape[1]:
+        raise ValueError("H must be square")
     if isinstance(H, np.ndarray):
         n = H.shape[0]
         vals = np.ascontiguousarray(H, dtype=np.complex128).reshape(-1)
@@ -79,8 +81,13 @@ def _measure_matrix(H, st):
         vals = np.ascontiguousarray(M.data, dtype=np.complex128)
         rowptr = np.ascontiguousarray(M.indptr, dtype=np.int64)
         colidx = np.ascontiguousarray(M.indices, dtype=np.int64)
-    if H.shape[0] != H.shape[1]:
-        raise ValueError("H must be square")
+    return n, rowptr, colidx, vals
+
+
+def _measure_matrix(H, st):
+    """measure(H::AbstractMatrix, psi) = real(dot(psi, H, psi)) -- src/circuits.jl:49-55, on the device through
+    qcb_measure_csr."""
+    n, rowptr, colidx, vals = _csr_arrays(H)
     E = np.zeros(2, dtype=np.float64)
     _lib.check(_lib.lib().qcb_measure_csr(st._handle, C.c_longlong(n), rowptr.ctypes.data_as(C.c_void_p), colidx.ctypes.data_as(C.c_void_p),
                                           vals.ctypes.data_as(C.c_void_p), E.ctypes.data_as(C.c_void_p)))

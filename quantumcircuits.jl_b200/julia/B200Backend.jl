@@ -231,6 +231,21 @@ end
 gradients(H::AbstractKernelHamiltonian, psi::B200State, circuit::GenericBrickworkCircuit; kwargs...) =
     gradients!(construct_grads_cache(psi)..., H, psi, circuit; kwargs...)
 
+# the same sweep for an explicit (dense or sparse, Hermitian) Hamiltonian: examples/test_gradients.jl:25
+function gradients!(::B200ApplyCache, _psi_p, _psi_pp, _psi, H::AbstractMatrix, psi0::B200State,
+                    circuit::GenericBrickworkCircuit; calculate_energy::Bool=false)
+    grads = similar(circuit.gate_angles, Float64)
+    angles = Matrix{Float64}(circuit.gate_angles)
+    rowptr, cols, vals = _csr(H)
+    E = Ref{Cdouble}(0)
+    check(ccall((:qcb_gradients_brickwork_csr, LIB), Cint,
+                (Ptr{Cvoid}, Cint, Cint, Ptr{Cdouble}, Clonglong, Ptr{Int64}, Ptr{Int64}, Ptr{ComplexF64}, Cint, Ptr{Cdouble}, Ptr{Cdouble}),
+                psi0.handle, circuit.nbits, circuit.nlayers, angles, size(H, 1), rowptr, cols, vals, calculate_energy ? 1 : 0, E, grads))
+    return calculate_energy ? (E[], grads) : grads
+end
+gradients(H::AbstractMatrix, psi::B200State, circuit::GenericBrickworkCircuit; kwargs...) =
+    gradients!(construct_grads_cache(psi)..., H, psi, circuit; kwargs...)
+
 function propagate_forwards!(::B200ApplyCache, psi_p::B200State, psi::B200State, circuit::GenericBrickworkCircuit,
                              start_layer::Int, layer_gate_idx::Int, gate_idx::Int)
     copyto!(psi_p, psi)

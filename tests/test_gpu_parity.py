@@ -340,6 +340,34 @@ def test_gradients_tensor_core_pass_equals_scalar_pass(oracle, n, layers, atb):
     assert E2 == E1 and np.array_equal(g2, g1)
 
 
+# ---- examples/test_gradients.jl:10-28 : gradients with the Hamiltonian as an explicit (sparse) matrix == kernel Hamiltonian
+@pytest.mark.parametrize("n,layers,dtype", [(8, 4, np.complex128), (5, 3, np.complex128), (10, 3, np.complex128), (11, 2, np.complex64)])
+def test_gradients_matrix_hamiltonian(oracle, n, layers, dtype):
+    rng = np.random.default_rng(25 * n + layers)
+    c = circuit(n, layers, rng, 0.01 if n == 8 else None)
+    J, h, g = 1.0, 0.1, 0.5
+    Hs, Heff = qc.build_sparse_tfim_hamiltonian(n, J, h, g), qc.TFIMHamiltonian(J, h, g)
+    psi0 = qc.zero_state_tensor(n).astype(dtype) if n == 8 else rand_state(rng, n).astype(dtype)
+    tol = 1e-12 if dtype == np.complex128 else 1e-5
+    E, grads = qc.gradients(Heff, psi0, c, calculate_energy=True)
+    E_m, grads_m = qc.gradients(Hs, psi0, c, calculate_energy=True)
+    assert abs(E - E_m) < tol * max(1.0, abs(E))  # @test E ≈ E_m
+    assert np.max(np.abs(grads - grads_m)) < tol * max(1.0, np.max(np.abs(grads)))  # @test grads ≈ grads_m
+    if n <= 8:  # dense form, and a Hermitian matrix that is no kernel Hamiltonian, against the shift rule on the oracle
+        np.testing.assert_allclose(qc.gradients(Hs.toarray(), psi0, c), grads_m, atol=1e-13)
+        A = rng.standard_normal((2 ** n, 2 ** n)) + 1j * rng.standard_normal((2 ** n, 2 ** n))
+        A = (A + A.conj().T) / 2 ** n
+        gA = qc.gradients(A, psi0, c)
+        v0 = psi0.reshape(-1, order="F").astype(np.complex128)
+        flat = c.gate_angles.reshape(-1, order="F")
+        for idx in rng.choice(flat.size, 5, replace=False):
+            es = []
+            for sh in (np.pi / 2, -np.pi / 2):
+                cc = qc.reconstruct(c, int(idx), sh)
+                es.append(onp.measure_matrix(A, oracle.apply_brickwork(v0, n, layers, cc.gate_angles)))
+            assert abs((es[0] - es[1]) / 2 - gA.reshape(-1, order="F")[idx]) < 1e-12
+
+
 def test_gradients_c2_shape_against_shift_subset(oracle):
     """20-qubit TFIM config (BASELINE C2): adjoint gradient vs the shift rule evaluated on the GPU for a few angles,
     and vs the oracle's forward energy."""
