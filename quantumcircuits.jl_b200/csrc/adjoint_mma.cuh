@@ -227,18 +227,24 @@ __device__ __forceinline__ void dmma(double &d0, double &d1, double a, double b)
 struct AdjmCarry {
     double e0, e1; // pending accumulators E[g][2t], E[g][2t+1]
     double *row;   // their row: [2][32] doubles (column parity, lane)
+    bool first;    // they are the row's first contribution (the CTA's first tile): stored, not added -- the rows need no zeroing
     uint4 prog[2]; // AdjmLaneProg of the next gate
 };
 
 __device__ __forceinline__ void adjm_flush(const AdjmCarry &C, uint32_t lane)
 {
-    asm volatile("red.global.add.f64 [%0], %1;" ::"l"(C.row + lane), "d"(C.e0) : "memory");
-    asm volatile("red.global.add.f64 [%0], %1;" ::"l"(C.row + 32 + lane), "d"(C.e1) : "memory");
+    if (C.first) {
+        C.row[lane] = C.e0;
+        C.row[32 + lane] = C.e1;
+    } else {
+        asm volatile("red.global.add.f64 [%0], %1;" ::"l"(C.row + lane), "d"(C.e0) : "memory");
+        asm volatile("red.global.add.f64 [%0], %1;" ::"l"(C.row + 32 + lane), "d"(C.e1) : "memory");
+    }
 }
 
 // one gate of the pass on the warp's windows; returns the program's flags
 template <int TB, int NW>
-__device__ __forceinline__ uint32_t adjoint_gate_mma(double2 *smP, double2 *smL, double *row, uint32_t lane, AdjmCarry &carry,
+__device__ __forceinline__ uint32_t adjoint_gate_mma(double2 *smP, double2 *smL, double *row, bool first_tile, uint32_t lane, AdjmCarry &carry,
                                                      const uint4 *__restrict__ next_prog)
 {
     constexpr int WPW = (1 << (TB - kRegBits)) / NW; // windows per warp
@@ -288,6 +294,7 @@ __device__ __forceinline__ uint32_t adjoint_gate_mma(double2 *smP, double2 *smL,
     }
     carry.e0 = e0; carry.e1 = e1;
     carry.row = row;
+    carry.first = first_tile;
     return w1.w & 0xffffu;
 }
 
@@ -342,7 +349,7 @@ template <int TB, int NW, int MINB>
 __global__ void __launch_bounds__(32 * NW, MINB)
 adjoint_pass_mma_kernel(double2 *psi, double2 *lam, const __grid_constant__ PassParams<double> P, int ngates,
                         const uint4 *__restrict__ prog /* AdjmLaneProg [ngates][32 NW] */, unsigned long long ntiles,
-                        double *rows /* [gridDim.x][NW][kAdjMaxGates][kAdjmRow], zeroed */)
+                        double *rows /* [gridDim.x][NW][kAdjMaxGates][kAdjmRow], need not be initialised */)
 {
     constexpr int NT = 32 * NW;
     extern __shared__ __align__(16) unsigned char qcb_smem_raw[];
@@ -352,8 +359,9 @@ adjoint_pass_mma_kernel(double2 *psi, double2 *lam, const __grid_constant__ Pass
     double *rows_warp = rows + ((size_t)blockIdx.x * NW + warp) * (kAdjMaxGates * kAdjmRow);
     const uint4 *my_prog = prog + 2 * tid;
     AdjmCarry carry;
-    carry.e0 = carry.e1 = 0.0; // nothing pending: the first flush adds zeros to row 0
-    carry.row = rows_warp;
+    carry.e0 = carry.e1 = 0.0; // nothing pending: the first flush adds zeros to row 0 (whatever it holds: gate 0's own
+    carry.row = rows_warp;     // first contribution is stored over it afterwards, same thread, same address)
+    carry.first = false;
     carry.prog[0] = __ldg(my_prog);
     carry.prog[1] = __ldg(my_prog + 1);
     const AdjmTileIo<TB, NT> io(P, tid);
@@ -368,7 +376,7 @@ adjoint_pass_mma_kernel(double2 *psi, double2 *lam, const __grid_constant__ Pass
 #pragma unroll 1
         for (int gi = 0; gi < ngates; gi++) {
             const int gn = gi + 1 < ngates ? gi + 1 : 0; // (the next tile runs the same program)
-            const uint32_t flags = adjoint_gate_mma<TB, NW>(smP, smL, rows_warp + kAdjmRow * gi, lane, carry, my_prog + (size_t)gn * (2 * NT));
+            const uint32_t flags = adjoint_gate_mma<TB, NW>(smP, smL, rows_warp + kAdjmRow * gi, tile == blockIdx.x, lane, carry, my_prog + (size_t)gn * (2 * NT));
             if (flags & 1u) __syncthreads(); // gates of the next stage regroup the tile's windows over the warps
             else __syncwarp();
         }

@@ -239,8 +239,23 @@ template <typename R, int TB> static int launch_adjoint(qcb_state *psi, qcb_stat
 }
 
 // ComplexF64: the tensor-core form (adjoint_mma.cuh); env rows hold the post-gate matrix M, see run_adjoint_fused.
-// Final reduction of its raw accumulator rows: block = (gate ordinal, raw element); fixed-order sum over all warps' rows.
-static __global__ void k_env_reduce_raw(const double *__restrict__ rows, int nrows /* CTAs x warps */, double *raw_out /* [ngates][64] */)
+// Final reduction of its raw accumulator rows, fixed summation order.  Few rows (small states: a handful of CTAs): one
+// block per gate sums and combines in one launch.  Many rows: one block per (gate, raw element) so that the whole GPU
+// reads the rows, then a second tiny launch turns the 64 raw sums of each gate into its complex 4x4 matrix.
+static __global__ void __launch_bounds__(256) k_env_reduce_raw(const double *__restrict__ rows, int nrows /* CTAs x warps */, EnvIds ids, double *env_out)
+{
+    __shared__ double part[4][kAdjmRow];
+    __shared__ double raw[kAdjmRow];
+    const int ord = blockIdx.x, el = threadIdx.x & (kAdjmRow - 1), q = threadIdx.x >> 6;
+    double s = 0;
+    for (int r = q; r < nrows; r += 4) s += rows[((size_t)r * kAdjMaxGates + ord) * kAdjmRow + el];
+    part[q][el] = s;
+    __syncthreads();
+    if (threadIdx.x < kAdjmRow) raw[el] = (part[0][el] + part[1][el]) + (part[2][el] + part[3][el]);
+    __syncthreads();
+    if (threadIdx.x == 0) adjm_combine_raw(raw, env_out + (size_t)ids.id[ord] * 32);
+}
+static __global__ void k_env_reduce_raw_wide(const double *__restrict__ rows, int nrows, double *raw_out /* [ngates][64] */)
 {
     const int ord = blockIdx.x >> 6, el = blockIdx.x & 63;
     double s = 0;
@@ -282,8 +297,8 @@ template <int TB, int NW> static int launch_adjoint_mma(qcb_state *psi, qcb_stat
     const size_t nrows = (size_t)grid * NW;
     const size_t rows_doubles = nrows * kAdjMaxGates * kAdjmRow, raw_doubles = (size_t)kAdjMaxGates * kAdjmRow;
     QCB_TRY(ensure_partial(rows_doubles + raw_doubles + (size_t)kAdjMaxGates * 16 * 32 * sizeof(AdjmLaneProg) / sizeof(double)));
+    // (the rows need no zeroing: first contributions are stored)
     double *d_rows = ctx().d_partial, *d_raw = d_rows + rows_doubles, *d_prog = d_raw + raw_doubles;
-    QCB_CUDA(cudaMemsetAsync(d_rows, 0, rows_doubles * sizeof(double), ctx().stream));
     if (ctx().adjoint_prog_host) {
         // cross-check path: the table built on the host (what the CPU replay runs) and uploaded
         static thread_local std::vector<AdjmLaneProg> prog;
@@ -297,11 +312,17 @@ template <int TB, int NW> static int launch_adjoint_mma(qcb_state *psi, qcb_stat
     }
     kern<<<grid, NT, smem, ctx().stream>>>((double2 *)psi->d, (double2 *)lam->d, M.A.P, M.A.ngates, (const uint4 *)d_prog, ntiles, d_rows);
     QCB_CUDA(cudaGetLastError());
-    k_env_reduce_raw<<<ids.n * kAdjmRow, 128, 0, ctx().stream>>>(d_rows, (int)nrows, d_raw);
-    QCB_CUDA(cudaGetLastError());
-    k_env_combine_raw<<<1, 32, 0, ctx().stream>>>(d_raw, ids, d_env);
-    QCB_CUDA(cudaGetLastError());
-    count_launch(3);
+    if (nrows <= 128) {
+        k_env_reduce_raw<<<ids.n, 256, 0, ctx().stream>>>(d_rows, (int)nrows, ids, d_env);
+        QCB_CUDA(cudaGetLastError());
+        count_launch(2);
+    } else {
+        k_env_reduce_raw_wide<<<ids.n * kAdjmRow, 128, 0, ctx().stream>>>(d_rows, (int)nrows, d_raw);
+        QCB_CUDA(cudaGetLastError());
+        k_env_combine_raw<<<1, 32, 0, ctx().stream>>>(d_raw, ids, d_env);
+        QCB_CUDA(cudaGetLastError());
+        count_launch(3);
+    }
     return QCB_OK;
 }
 
