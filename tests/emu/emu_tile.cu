@@ -681,3 +681,116 @@ extern "C" int emu_contract_env_gate(const double *angles15, const double *env32
     }
     return 0;
 }
+
+// ---- the same sharded gradient with ONE real process per rank (tests: torch.distributed gloo): this process holds its
+// shards of psi and lambda, qubit swaps go through the host framework's all-to-all (callback, once per state), the
+// per-rank environments / energy parts are returned for an all-reduce by the caller --------------------------------------
+struct EmuOneRankPair : ShardExecutor {
+    int nloc = 0, g = 0;
+    std::vector<double2> psi, lam;
+    std::vector<double> env;
+    emu_swap_cb cb = nullptr;
+    bool forward = false;
+    int run_pass(const PassPlan &pl, const std::vector<GateOp> &gates, const double *mats, bool) override
+    {
+        if (pl.stages.empty() || forward) {
+            PassParams<double> *P = new PassParams<double>;
+            fill_params<double>(pl, nloc, gates, mats, !forward, *P);
+            switch (pl.TB) {
+#define CASE(T) case T: ::run_pass<double, T>(psi.data(), nloc, *P); if (!forward) ::run_pass<double, T>(lam.data(), nloc, *P); break;
+            CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(11) CASE(12) CASE(13)
+#undef CASE
+            default: delete P; return 3;
+            }
+            delete P;
+            return 0;
+        }
+        AdjParams<double> *A = new AdjParams<double>;
+        fill_params<double>(pl, nloc, gates, mats, true, A->P);
+        int ids[kAdjMaxGates], nid = 0;
+        std::memset(A->slot_gate, 0, sizeof A->slot_gate);
+        for (size_t st = 0; st < pl.stages.size(); st++)
+            for (int slot = 0; slot < kSlots; slot++) {
+                const int gi = pl.stages[st].gate[slot];
+                if (gi < 0) continue;
+                A->slot_gate[st * kSlots + slot] = (uint8_t)nid;
+                ids[nid++] = gates[gi].mat;
+            }
+        A->ngates = nid;
+        std::vector<double> acc(kAdjMaxGates * 32, 0.0);
+        int rc = 0;
+        switch (pl.TB) {
+#define CASE(T) case T: run_adjoint_pass<double, T>(psi.data(), lam.data(), nloc, *A, acc.data()); break;
+        CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(11) CASE(12)
+#undef CASE
+        default: rc = 3;
+        }
+        for (int k = 0; k < nid; k++)
+            for (int i = 0; i < 32; i++) env[(size_t)ids[k] * 32 + i] += acc[k * 32 + i];
+        delete A;
+        return rc;
+    }
+    int swap_top() override
+    {
+        int rc = cb(psi.data(), nloc, g);
+        if (!rc && !forward) rc = cb(lam.data(), nloc, g);
+        return rc;
+    }
+};
+
+// shard: this rank's canonical slice of psi_0 (not modified).  env_out[G][32], E_out[2]: this rank's partial sums.
+extern "C" int emu_rank_gradient_env(int n, int g, int rank, const void *shard, int kind, double p0, double p1, double p2, int ngates, const int *q,
+                                     const double *mats, int tile_bits, int low_bits, emu_swap_cb cb, double *env_out, double *E_out)
+{
+    try {
+        EmuOneRankPair ex;
+        ex.nloc = n - g; ex.g = g; ex.cb = cb;
+        const size_t per = (size_t)1 << ex.nloc;
+        ex.psi.assign((const double2 *)shard, (const double2 *)shard + per);
+        ex.lam.assign(per, double2{0.0, 0.0});
+        ex.env.assign((size_t)ngates * 32, 0.0);
+        ShardLayout L;
+        L.n = n; L.nloc = ex.nloc; L.g = g;
+        L.phys.resize(n);
+        for (int i = 0; i < n; i++) L.phys[i] = i;
+        SchedOptions fopt;
+        fopt.tile_bits = tile_bits; fopt.low_bits = low_bits;
+        std::vector<GateOp> fwd(ngates);
+        for (int i = 0; i < ngates; i++) fwd[i] = GateOp{q[i], i};
+        ex.forward = true;
+        int rc = run_gates_sharded(ex, L, fwd, mats, false, fopt, nullptr);
+        ex.forward = false;
+        if (rc) return 30 + (rc < 0 ? -rc : rc);
+        HamEval H{kind, n, p0, p1, p2};
+        double er = 0, ei = 0;
+        auto sweep = [&](unsigned long long mask, bool first) {
+            ShardMap M;
+            std::memset(&M, 0, sizeof M);
+            M.n = n; M.nloc = ex.nloc; M.hi = (unsigned long long)rank << ex.nloc;
+            for (int i = 0; i < n; i++) M.phys[i] = (unsigned char)L.phys[i];
+            for (unsigned long long x = 0; x < per; x++) ham_sharded_amp(ex.lam.data(), ex.psi.data(), x, M, H, mask, first, er, ei);
+        };
+        unsigned long long local_mask = 0;
+        for (int i = 0; i < n; i++)
+            if (L.phys[i] < L.nloc) local_mask |= 1ull << i;
+        sweep(local_mask, true);
+        if (g > 0) {
+            rc = ex.swap_top();
+            if (rc) return 40 + rc;
+            swap_top_layout(L);
+            sweep(((1ull << n) - 1ull) & ~local_mask, false);
+        }
+        E_out[0] = er; E_out[1] = ei;
+        std::vector<GateOp> rev(ngates);
+        for (int i = 0; i < ngates; i++) rev[i] = GateOp{q[ngates - 1 - i], ngates - 1 - i};
+        SchedOptions opt;
+        opt.tile_bits = tile_bits; opt.low_bits = low_bits; opt.max_gates_per_pass = kAdjMaxGates;
+        rc = run_gates_sharded(ex, L, rev, mats, true, opt, nullptr);
+        if (rc) return 10 + (rc < 0 ? -rc : rc);
+        std::copy(ex.env.begin(), ex.env.end(), env_out);
+        return 0;
+    } catch (const std::exception &e) {
+        std::fprintf(stderr, "emu rank gradient: %s\n", e.what());
+        return 1;
+    }
+}

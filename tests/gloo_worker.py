@@ -66,10 +66,46 @@ def main():
     ref = oracle.apply_brickwork(psi0, n, layers, angles)[rank * per:(rank + 1) * per]
     err = float(np.linalg.norm(shard - ref))
     ok = rc == 0 and err < 1e-12 and nswaps[0] >= 1 and list(phys) == list(range(n))
+    # ---- adjoint gradients on the sharded state: forward circuit, lambda = H psi around one swap of both states, backward
+    # sweep on the pair; the per-rank environments and energy parts are all-reduced here like NCCL does on the GPUs ----------
+    n2, layers2 = 12, 5
+    G2 = onp.brickwork_num_gates(n2, layers2)
+    angles2 = rng.uniform(0, 2 * np.pi, (15, G2))
+    q2 = np.ascontiguousarray(np.array(onp.brickwork_gate_positions(n2, layers2)) - 1, dtype=np.int32)
+    mats2 = np.ascontiguousarray(np.stack([oracle.build_general_unitary_gate(angles2[:, i]).reshape(-1, order="F") for i in range(G2)]))
+    v2 = rng.standard_normal(2 ** n2) + 1j * rng.standard_normal(2 ** n2)
+    psi2 = v2 / np.linalg.norm(v2)
+    per2 = 1 << (n2 - g)
+    shard2 = np.ascontiguousarray(psi2[rank * per2:(rank + 1) * per2])
+    hp = (1.0, 0.1, 0.5)
+    env = np.zeros((G2, 32))
+    E2 = np.zeros(2)
+    swaps_before = nswaps[0]
+    rc2 = emu_helper.lib().emu_rank_gradient_env(C.c_int(n2), C.c_int(g), C.c_int(rank), shard2.ctypes.data_as(C.c_void_p), C.c_int(0),
+                                                 C.c_double(hp[0]), C.c_double(hp[1]), C.c_double(hp[2]), C.c_int(G2), q2.ctypes.data_as(C.c_void_p),
+                                                 mats2.ctypes.data_as(C.c_void_p), C.c_int(9), C.c_int(3), swap_cb, env.ctypes.data_as(C.c_void_p),
+                                                 E2.ctypes.data_as(C.c_void_p))
+    t = torch.from_numpy(np.concatenate([env.reshape(-1), E2]))
+    dist.all_reduce(t)
+    tot = t.numpy()
+    envc = (tot[:-2].reshape(G2, 32)[:, 0::2] + 1j * tot[:-2].reshape(G2, 32)[:, 1::2]).reshape(G2, 4, 4).transpose(0, 2, 1)
+    from qcb200 import _lib
+    grads = np.zeros((15, G2))
+    for k in range(G2):
+        a = np.ascontiguousarray(angles2[:, k])
+        e = np.ascontiguousarray(envc[k].reshape(-1, order="F"))
+        out = np.zeros(15)
+        _lib.check(_lib.lib().qcb_general_unitary_gate_gradient(a.ctypes.data_as(C.c_void_p), e.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p)))
+        grads[:, k] = out
+    E_ref, g_ref = oracle.gradients_brickwork(psi2, n2, layers2, angles2, 0, hp)
+    gerr = float(np.max(np.abs(grads - g_ref)))
+    ok2 = rc2 == 0 and abs(tot[-2] - E_ref) < 1e-12 * max(1.0, abs(E_ref)) and abs(tot[-1]) < 1e-12 and gerr < 1e-12 and nswaps[0] - swaps_before >= 3
+    ok = ok and ok2
     flags = [None] * world
     dist.all_gather_object(flags, ok)
     if rank == 0:
-        print(("PASS" if all(flags) else "FAIL"), f"gloo sharded world={world} rc={rc} err={err:.2e} swaps={nswaps[0]}", flush=True)
+        print(("PASS" if all(flags) else "FAIL"), f"gloo sharded world={world} rc={rc} err={err:.2e} swaps={nswaps[0]}; "
+              f"gradients rc={rc2} dE={abs(tot[-2] - E_ref):.2e} dgrad={gerr:.2e}", flush=True)
     dist.destroy_process_group()
     sys.exit(0 if all(flags) else 1)
 

@@ -1,4 +1,6 @@
-"""N>1 path on the CPU: world_size-2 (and 4) gloo processes, one shard each, real all-to-all qubit swaps."""
+"""N>1 path on the CPU: world_size-2 (and 4) gloo processes, one shard each, real all-to-all qubit swaps: gate application
+(forward circuit == oracle, canonical layout restored) and adjoint gradients (pair swaps, all-reduced environments == the
+oracle's restatement of the reference's shift sweep)."""
 import os
 import shutil
 import subprocess
@@ -23,4 +25,4 @@ def test_gloo_sharded_protocol(world):
            "--master-port", str(29610 + world), os.path.join(ROOT, "tests", "gloo_worker.py")]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-3000:]
-    assert "PASS" in res.stdout
+    assert "PASS" in res.stdout and "gradients rc=0" in res.stdout
