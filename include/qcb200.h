@@ -117,6 +117,10 @@ int qcb_apply_gates(qcb_state *s, int ngates, const int *K, const int *arity, co
 int qcb_apply_brickwork(qcb_state *s, int nbits, int nlayers, const double *angles);
 int qcb_apply_brickwork_range(qcb_state *s, int nbits, int nlayers, const double *angles, int first_gate,
                               int last_gate, int adjoint /* 1: apply U_g^dagger for g = last-1 .. first */);
+/* The same with distinct states, dst = circuit(src) and src untouched (the reference's (psi', psi) contract): the first
+ * fused pass reads src and writes dst, no copy of the state precedes it.  Unsharded states of equal size and type. */
+int qcb_apply_brickwork_from(qcb_state *dst, const qcb_state *src, int nbits, int nlayers, const double *angles, int first_gate,
+                             int last_gate, int adjoint);
 /* One-shot form with HOST buffers (apply(psi, circuit) src/circuits.jl:37-42 on an Array):
  * H2D, circuit, D2H.  psi_in may be NULL for |0...0>. */
 int qcb_apply_brickwork_host(int dtype, int nbits, int nlayers, const double *angles, const void *psi_in_host,

@@ -58,6 +58,13 @@ def _apply_circuit_inplace(state, circuit, first=0, last=None, adjoint=False):
                                                     C.c_int(1 if adjoint else 0)))
 
 
+def _apply_circuit_from(dst, src, circuit, first=0, last=None, adjoint=False):
+    last = circuit.ngates if last is None else last
+    a = circuit.angles_abi()
+    _lib.check(_lib.lib().qcb_apply_brickwork_from(dst._handle, src._handle, C.c_int(circuit.nbits), C.c_int(circuit.nlayers),
+                                                   a.ctypes.data_as(C.c_void_p), C.c_int(first), C.c_int(last), C.c_int(1 if adjoint else 0)))
+
+
 def apply_(*args):
     """apply!(psi', psi, gate) | apply!(cache, psi', psi, gate) | apply!(cache, psi', psi, circuit)
 
@@ -66,6 +73,9 @@ def apply_(*args):
         args = args[1:]
     psi_out, psi, op = args
     _check_pair(psi_out, psi)
+    if isinstance(op, GenericBrickworkCircuit) and psi_out is not psi and isinstance(psi, B200State):
+        _apply_circuit_from(psi_out, psi, op)  # psi' = circuit(psi): the first pass reads psi, no copy
+        return psi_out
     if psi_out is not psi:
         psi_out.assign(psi)
     if isinstance(op, GenericBrickworkCircuit):
@@ -82,6 +92,10 @@ def apply(psi, op):
     host = not isinstance(psi, B200State)
     if host and isinstance(op, GenericBrickworkCircuit):
         return apply_circuit_host(psi, op)
+    if not host and isinstance(op, GenericBrickworkCircuit):
+        st = psi.similar()
+        _apply_circuit_from(st, psi, op)
+        return st
     st = B200State(psi)
     if isinstance(op, GenericBrickworkCircuit):
         _apply_circuit_inplace(st, op)

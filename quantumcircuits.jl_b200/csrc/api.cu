@@ -391,11 +391,11 @@ static int gradients_impl(const qcb_state *psi0, int nbits, int nlayers, const d
     qcb_state A = *psi0, B = *psi0;
     A.d = c.scratch[0]; A.owned = false;
     B.d = c.scratch[1]; B.owned = false;
-    QCB_TRY(copy_state_raw(A.d, psi0->d, psi0->bytes)); // psi .= psi0   gradients.jl:90
     std::vector<GateOp> gates;
     std::vector<double> mats;
     QCB_TRY(brickwork_gates(nbits, nlayers, angles, 0, G, false, gates, mats));
-    QCB_TRY(run_gate_list(&A, gates, mats.data(), false)); // forward pass  gradients.jl:92-101
+    // psi .= psi0 (gradients.jl:90) and the forward pass (:92-101) in one: the first fused pass reads psi0 and writes psi
+    QCB_TRY(run_gate_list(&A, gates, mats.data(), false, psi0->d));
     const double fw_passes = c.st_passes, fw_stages = c.st_stages, fw_launches = c.st_launches;
     if (G == 0) {
         if (want_energy) {
@@ -880,6 +880,22 @@ int qcb_apply_brickwork_range(qcb_state *s, int nbits, int nlayers, const double
     std::vector<double> mats;
     QCB_TRY(brickwork_gates(nbits, nlayers, angles, first_gate, last_gate, adjoint != 0, gates, mats));
     return run_gate_list(s, gates, mats.data(), adjoint != 0);
+}
+// apply!(cache, psi', psi, circuit) with distinct states, as the reference's out-of-place contract has it (src/circuits.jl:19-31):
+// dst = circuit(src), src untouched.  The first fused pass reads src and writes dst, so no copy of the state precedes it.
+int qcb_apply_brickwork_from(qcb_state *dst, const qcb_state *src, int nbits, int nlayers, const double *angles, int first_gate, int last_gate, int adjoint)
+{
+    QCB_REQUIRE_INIT();
+    QCB_TRY(check_state(dst));
+    QCB_TRY(check_state(src));
+    if (dst == src || dst->d == src->d) return qcb_apply_brickwork_range(dst, nbits, nlayers, angles, first_gate, last_gate, adjoint);
+    if (dst->n != src->n || dst->dtype != src->dtype || dst->sharded || src->sharded) return set_error(QCB_EINVAL, "psi' must be the same size as psi.");
+    if (dst->n != nbits) return set_error(QCB_EINVAL, "circuit has %d qubits, state has %d", nbits, dst->n);
+    if (!angles && last_gate > first_gate) return set_error(QCB_EINVAL, "null angles");
+    std::vector<GateOp> gates;
+    std::vector<double> mats;
+    QCB_TRY(brickwork_gates(nbits, nlayers, angles, first_gate, last_gate, adjoint != 0, gates, mats));
+    return run_gate_list(dst, gates, mats.data(), adjoint != 0, src->d);
 }
 int qcb_apply_brickwork(qcb_state *s, int nbits, int nlayers, const double *angles)
 {

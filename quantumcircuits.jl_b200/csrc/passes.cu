@@ -12,7 +12,9 @@
 namespace qcb {
 
 
-template <typename R, int TB> static int launch_pass(qcb_state *s, const PassParams<R> &P)
+// src == nullptr: in place.  Otherwise the pass reads `src` (another state of the same size) and writes the state: every
+// amplitude is read and written exactly once per pass, so the first pass of a circuit can double as the copy of its input.
+template <typename R, int TB> static int launch_pass(qcb_state *s, const PassParams<R> &P, const void *src = nullptr)
 {
     using V = typename Vec2<R>::type;
     constexpr int NT = 1 << (TB - kRegBits);
@@ -27,7 +29,7 @@ template <typename R, int TB> static int launch_pass(qcb_state *s, const PassPar
         attr_set = true;
     }
     const unsigned long long nblocks = 1ull << (s->nloc - TB);
-    kern<<<(unsigned)nblocks, NT, smem, ctx().stream>>>((const V *)s->d, (V *)s->d, P);
+    kern<<<(unsigned)nblocks, NT, smem, ctx().stream>>>((const V *)(src ? src : s->d), (V *)s->d, P);
     QCB_CUDA(cudaGetLastError());
     count_launch();
     return QCB_OK;
@@ -64,14 +66,14 @@ template <typename R> static int launch_pass_peer_tb(qcb_state *s, int TB, const
     }
 }
 
-template <typename R> static int launch_pass_tb(qcb_state *s, int TB, const PassParams<R> &P)
+template <typename R> static int launch_pass_tb(qcb_state *s, int TB, const PassParams<R> &P, const void *src = nullptr)
 {
     switch (TB) {
-    case 9: return launch_pass<R, 9>(s, P);
-    case 10: return launch_pass<R, 10>(s, P);
-    case 11: return launch_pass<R, 11>(s, P);
-    case 12: return launch_pass<R, 12>(s, P);
-    case 13: return launch_pass<R, 13>(s, P);
+    case 9: return launch_pass<R, 9>(s, P, src);
+    case 10: return launch_pass<R, 10>(s, P, src);
+    case 11: return launch_pass<R, 11>(s, P, src);
+    case 12: return launch_pass<R, 12>(s, P, src);
+    case 13: return launch_pass<R, 13>(s, P, src);
     default: return set_error(QCB_EINVAL, "unsupported tile size %d", TB);
     }
 }
@@ -157,7 +159,7 @@ static std::string plan_key(const qcb_state *s, const std::vector<GateOp> &gates
     return ss.str();
 }
 
-template <typename R> static int run_fused(qcb_state *s, const std::vector<GateOp> &gates, const double *mats, bool adjoint)
+template <typename R> static int run_fused(qcb_state *s, const std::vector<GateOp> &gates, const double *mats, bool adjoint, const void *first_src)
 {
     Ctx &c = ctx();
     const SchedOptions opt = current_sched_options(s);
@@ -183,7 +185,8 @@ template <typename R> static int run_fused(qcb_state *s, const std::vector<GateO
         } catch (const std::exception &e) {
             return set_error(QCB_EINVAL, "pass parameters: %s", e.what());
         }
-        QCB_TRY(launch_pass_tb<R>(s, pl.TB, P));
+        QCB_TRY(launch_pass_tb<R>(s, pl.TB, P, first_src));
+        first_src = nullptr; // only the first pass reads the input state
         c.st_passes += 1;
         c.st_stages += (double)pl.stages.size();
     }
@@ -448,20 +451,26 @@ int run_adjoint_fused(qcb_state *psi, qcb_state *lam, const std::vector<GateOp> 
     return run_adjoint_fused_t<float>(psi, lam, rev, mats, d_env, false);
 }
 
-int run_gate_list(qcb_state *s, const std::vector<GateOp> &gates, const double *mats, bool adjoint)
+// first_src != nullptr: the state's storage is uninitialised and the circuit's input is the device buffer `first_src`
+// (same size and type): the first fused pass reads it directly; paths without such a pass copy it first.
+int run_gate_list(qcb_state *s, const std::vector<GateOp> &gates, const double *mats, bool adjoint, const void *first_src)
 {
     Ctx &c = ctx();
     c.st_passes = c.st_stages = c.st_launches = c.st_swaps = c.st_fused_swaps = 0;
     c.st_gates = (double)gates.size();
-    if (gates.empty()) return QCB_OK;
     for (const GateOp &g : gates)
         if (g.q < 0 || g.q + 1 >= s->n)
             return set_error(QCB_EINVAL, "The gate cannot be applied as it sits outside the qubit space.");
-    if (s->sharded) return dist_run_gate_list(s, gates, mats, adjoint);
     const bool simple = c.force_simple || s->nloc < kMinTB;
+    if (first_src && (gates.empty() || s->sharded || simple)) {
+        QCB_CUDA(cudaMemcpyAsync(s->d, first_src, s->bytes, cudaMemcpyDeviceToDevice, c.stream));
+        first_src = nullptr;
+    }
+    if (gates.empty()) return QCB_OK;
+    if (s->sharded) return dist_run_gate_list(s, gates, mats, adjoint);
     if (s->dtype == QCB_C128)
-        return simple ? run_simple<double>(s, gates, mats, adjoint) : run_fused<double>(s, gates, mats, adjoint);
-    return simple ? run_simple<float>(s, gates, mats, adjoint) : run_fused<float>(s, gates, mats, adjoint);
+        return simple ? run_simple<double>(s, gates, mats, adjoint) : run_fused<double>(s, gates, mats, adjoint, first_src);
+    return simple ? run_simple<float>(s, gates, mats, adjoint) : run_fused<float>(s, gates, mats, adjoint, first_src);
 }
 
 } // namespace qcb

@@ -90,7 +90,7 @@ inline void count_launch(int k = 1)
 }
 
 // gate-list execution (passes.cu)
-int run_gate_list(qcb_state *s, const std::vector<GateOp> &gates, const double *mats, bool adjoint);
+int run_gate_list(qcb_state *s, const std::vector<GateOp> &gates, const double *mats, bool adjoint, const void *first_src = nullptr);
 int run_adjoint_fused(qcb_state *psi, qcb_state *lam, const std::vector<GateOp> &rev, const double *mats, double *d_env, bool *env_post);
 int launch_adjoint_plan(qcb_state *psi, qcb_state *lam, const PassPlan &plan, const std::vector<GateOp> &rev, const double *mats, double *d_env);
 bool adjoint_uses_mma(const qcb_state *psi);

@@ -113,8 +113,14 @@ def measure(H, psi, circuit=None):
     (numpy arrays, scipy sparse matrices): src/circuits.jl:49-62."""
     if circuit is None:
         return measure_(None, H, psi)
-    st = B200State(psi)  # copy: the input is not modified (:19)
-    _apply_circuit_inplace(st, circuit)
+    if isinstance(psi, B200State):  # the input is not modified (:19): psi' = circuit(psi) out of place, no copy
+        from .apply import _apply_circuit_from
+
+        st = psi.similar()
+        _apply_circuit_from(st, psi, circuit)
+    else:
+        st = B200State(psi)
+        _apply_circuit_inplace(st, circuit)
     return measure_(None, H, st)
 
 

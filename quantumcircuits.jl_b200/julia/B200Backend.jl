@@ -148,12 +148,18 @@ function _apply_circuit!(s::B200State, c::GenericBrickworkCircuit, first::Intege
                 s.handle, c.nbits, c.nlayers, angles, first, last, adj ? 1 : 0))
     return s
 end
+# psi' = circuit(psi) out of place: the first fused pass reads psi and writes psi' (no copy of the state)
+function _apply_circuit_from!(dst::B200State, src::B200State, c::GenericBrickworkCircuit, first::Integer, last::Integer, adj::Bool)
+    angles = Matrix{Float64}(c.gate_angles)
+    check(ccall((:qcb_apply_brickwork_from, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Cint, Ptr{Cdouble}, Cint, Cint, Cint),
+                dst.handle, src.handle, c.nbits, c.nlayers, angles, first, last, adj ? 1 : 0))
+    return dst
+end
 function apply!(::B200ApplyCache, psi_out::B200State, psi::B200State, circuit::GenericBrickworkCircuit)
     _check_pair(psi_out, psi)
-    psi_out === psi || copyto!(psi_out, psi)
-    return _apply_circuit!(psi_out, circuit, 0, circuit.ngates, false)
+    return _apply_circuit_from!(psi_out, psi, circuit, 0, circuit.ngates, false)
 end
-apply(psi::B200State, circuit::GenericBrickworkCircuit) = _apply_circuit!(copy(psi), circuit, 0, circuit.ngates, false)
+apply(psi::B200State, circuit::GenericBrickworkCircuit) = _apply_circuit_from!(similar(psi), psi, circuit, 0, circuit.ngates, false)
 
 # ------------------------------------------------------------------------------------------------
 # hamiltonians.jl seam: measure! (src/hamiltonians/hamiltonians.jl:31-50)
@@ -248,8 +254,7 @@ gradients(H::AbstractMatrix, psi::B200State, circuit::GenericBrickworkCircuit; k
 
 function propagate_forwards!(::B200ApplyCache, psi_p::B200State, psi::B200State, circuit::GenericBrickworkCircuit,
                              start_layer::Int, layer_gate_idx::Int, gate_idx::Int)
-    copyto!(psi_p, psi)
-    _apply_circuit!(psi_p, circuit, gate_idx - 1, circuit.ngates, false)
+    _apply_circuit_from!(psi_p, psi, circuit, gate_idx - 1, circuit.ngates, false)
     return psi_p, psi
 end
 

@@ -251,6 +251,31 @@ def test_measure_with_circuit(oracle):
     np.testing.assert_array_equal(st.to_numpy(), onp.zero_state(n))  # input not modified
 
 
+# ---- src/circuits.jl:19-42 : apply!(cache, psi', psi, circuit) with distinct states -- psi' = circuit(psi), psi untouched;
+# the first fused pass reads psi and writes psi' (no copy); small states and empty circuits fall back to a copy
+@pytest.mark.parametrize("n,layers,dtype", [(4, 3, np.complex128), (9, 2, np.complex128), (13, 5, np.complex128), (16, 7, np.complex64), (12, 0, np.complex128)])
+def test_out_of_place_circuit_apply(oracle, n, layers, dtype):
+    rng = np.random.default_rng(19 * n + layers)
+    c = circuit(n, max(layers, 1), rng)
+    if layers == 0:
+        c = qc.GenericBrickworkCircuit(n, 0)
+    psi_host = rand_state(rng, n).astype(dtype)
+    psi, out = qc.B200State(psi_host), qc.B200State(n, dtype)
+    res = qc.apply_(qc.construct_apply_cache(psi), out, psi, c)
+    assert res is out
+    np.testing.assert_array_equal(psi.to_numpy(), psi_host)  # the input is untouched
+    ref = oracle.apply_brickwork(psi_host.astype(np.complex128), n, c.nlayers, c.gate_angles) if c.ngates else psi_host.astype(np.complex128)
+    tol = 1e-12 if dtype == np.complex128 else 1e-5
+    assert rel(out.to_numpy().astype(np.complex128), ref) < tol
+    inplace = qc.B200State(psi_host)
+    qc.apply_(inplace, inplace, c)
+    np.testing.assert_array_equal(out.to_numpy(), inplace.to_numpy())  # same passes, same arithmetic
+    st = qc.apply(psi, c)  # apply(psi, circuit) on a device state
+    assert st is not psi
+    np.testing.assert_array_equal(st.to_numpy(), out.to_numpy())
+    np.testing.assert_array_equal(psi.to_numpy(), psi_host)
+
+
 # ---- src/circuits.jl:49-62 : measure(H::AbstractMatrix, psi[, circuit]) on the device (CSR sweep)
 @pytest.mark.parametrize("n", [1, 3, 5, 8, 11])
 @pytest.mark.parametrize("dtype", [np.complex128, np.complex64])
