@@ -268,7 +268,10 @@ static int grad_area_begin(const GradArea &ar, const double *angles)
 static int grad_area_finish(const GradArea &ar, bool env_post, int want_energy, double *out_E, double *out_grads)
 {
     Ctx &c = ctx();
-    k_contract_env<<<(unsigned)((4 * ar.G + 63) / 64), 64, 0, c.stream>>>(c.d_out + ar.angles(), c.d_out + ar.env(), (int)ar.G, env_post ? 1 : 0, c.d_out + ar.grads());
+    if (c.contract_coop)
+        k_contract_env_coop<<<(unsigned)((ar.G + 7) / 8), 128, 0, c.stream>>>(c.d_out + ar.angles(), c.d_out + ar.env(), (int)ar.G, env_post ? 1 : 0, c.d_out + ar.grads());
+    else
+        k_contract_env<<<(unsigned)((4 * ar.G + 63) / 64), 64, 0, c.stream>>>(c.d_out + ar.angles(), c.d_out + ar.env(), (int)ar.G, env_post ? 1 : 0, c.d_out + ar.grads());
     QCB_CUDA(cudaGetLastError());
     count_launch();
     QCB_CUDA(cudaMemcpyAsync(c.h_out + ar.energy(), c.d_out + ar.energy(), sizeof(double) * (4 + 15 * ar.G), cudaMemcpyDeviceToHost, c.stream));
@@ -602,6 +605,8 @@ int qcb_set_option(const char *key, long value)
         c.adjoint_tile_bits = value;
     } else if (k == "adjoint_mma") {
         c.adjoint_mma = value ? 1 : 0;
+    } else if (k == "contract_coop") {
+        c.contract_coop = value ? 1 : 0;
     } else if (k == "measure_ctas") {
         if (value != 0 && value != 2 && value != 3) return set_error(QCB_EINVAL, "measure_ctas must be 0 (auto), 2 or 3");
         c.measure_ctas = value;

@@ -190,11 +190,117 @@ QCB_HD void contract_env_gate(const double *angles15, const double *env32, int p
 } // namespace hd
 
 #if defined(__CUDACC__)
-// grads[15 g + k] for all gates; one thread per (gate, layer of the gate) -- tiny: G is tens to thousands
+// grads[15 g + k] for all gates; one thread per (gate, layer of the gate) -- the plain form (cross-check of the cooperative
+// kernel below: option "contract_coop" = 0)
 static __global__ void k_contract_env(const double *__restrict__ angles, const double *__restrict__ env, int ngates, int post, double *grads)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x, g = i >> 2;
     if (g < ngates) hd::contract_env_gate(angles + 15 * (size_t)g, env + 32 * (size_t)g, post, grads + 15 * (size_t)g, 1 + (i & 3));
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// The same contraction with 16 lanes per gate: every 4x4 matrix lives as ONE element per lane (lane e = r + 4c), products
+// fetch their operands with shuffles inside the half warp, the 2x2 factors are recomputed by every lane.  No matrix ever
+// sits in local memory: ~7 us instead of ~60 us per launch, which is 10 % of a 12-qubit gradient.  The lane algebra
+// (which lane a shuffle reads for a product, a transpose, a CNOT permutation) was prototyped lane by lane against
+// gates_host.hpp before it was written down here; tests/test_gpu_parity.py compares it with the plain form above.
+namespace coop {
+using hd::Cx;
+using hd::cx;
+using hd::M2;
+
+__device__ __forceinline__ Cx m2_elem(const M2 &a, uint32_t i, uint32_t j)
+{
+    const Cx c0 = i ? a.m[1] : a.m[0], c1 = i ? a.m[3] : a.m[2];
+    return j ? c1 : c0;
+}
+// element (r, c) of kron(hi, lo)
+__device__ __forceinline__ Cx kron_elem(const M2 &hi, const M2 &lo, uint32_t r, uint32_t c) { return m2_elem(hi, r >> 1, c >> 1) * m2_elem(lo, r & 1u, c & 1u); }
+__device__ __forceinline__ uint32_t s23(uint32_t x) { return x ^ ((x >> 1) & 1u); } // rcnot: 2 <-> 3
+__device__ __forceinline__ uint32_t s13(uint32_t x) { return x ^ ((x & 1u) << 1); } // cnot:  1 <-> 3
+__device__ __forceinline__ Cx shfl_cx(Cx v, uint32_t src) { return cx(__shfl_sync(0xffffffffu, v.re, (int)src, 16), __shfl_sync(0xffffffffu, v.im, (int)src, 16)); }
+// lane (r, c): sum_k A'(r, k) B'(k, c) with A' = A^T if TA (A(k, r) sits on lane k + 4r), B' = B^T if TB
+template <bool TA, bool TB> __device__ __forceinline__ Cx mm(Cx A, Cx B, uint32_t r, uint32_t c)
+{
+    double sr = 0, si = 0;
+#pragma unroll
+    for (uint32_t k = 0; k < 4; k++) {
+        const Cx a = shfl_cx(A, TA ? (k + 4 * r) : (r + 4 * k)), b = shfl_cx(B, TB ? (c + 4 * k) : (k + 4 * c));
+        sr += a.re * b.re - a.im * b.im;
+        si += a.re * b.im + a.im * b.re;
+    }
+    return cx(sr, si);
+}
+// 2 Re sum over the 16 lanes of d .* w (valid on every lane)
+__device__ __forceinline__ double dot_re(Cx d, Cx w)
+{
+    double v = d.re * w.re - d.im * w.im;
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o, 16);
+    return 2 * v;
+}
+} // namespace coop
+
+// blockDim.x = 128: 8 gates per block, one per half warp
+static __global__ void __launch_bounds__(128) k_contract_env_coop(const double *__restrict__ angles, const double *__restrict__ env, int ngates, int post,
+                                                                  double *grads)
+{
+    using namespace coop;
+    const uint32_t e = threadIdx.x & 15u, r = e & 3u, c = e >> 2;
+    const int gid = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 4);
+    const int g = gid < ngates ? gid : ngates - 1; // whole warps stay active for the shuffles; surplus half warps do not write
+    const double *a = angles + 15 * (size_t)g;
+    M2 rot[4], unused3[3], rzm, z13, dz13, y14, dy14, y15, dy15, unused;
+#pragma unroll
+    for (int i = 0; i < 4; i++) hd::rotation_all(a[3 * i], a[3 * i + 1], a[3 * i + 2], rot[i], unused3);
+    hd::rz_all(-3.14159265358979323846 / 2, rzm, unused);
+    hd::rz_all(a[12], z13, dz13);
+    hd::ry_all(a[13], y14, dy14);
+    hd::ry_all(a[14], y15, dy15);
+    const M2 hi1 = hd::mul(rzm, rot[3]), lo4 = hd::mul(rot[0], rzm), id = hd::identity2();
+    // this lane's element of the four layers and of their CNOT-permuted forms
+    const Cx l1 = kron_elem(hi1, rot[2], r, c), l2 = kron_elem(y14, z13, r, c), l3 = kron_elem(y15, id, r, c);
+    const Cx Y2 = kron_elem(hi1, rot[2], s23(r), c);  // rcnot l1
+    const Cx X3 = kron_elem(rot[1], lo4, r, s23(c));  // l4 rcnot
+    const Cx D12 = kron_elem(y14, dz13, r, c), D13 = kron_elem(dy14, z13, r, c), D14 = kron_elem(dy15, id, r, c);
+    Cx E = cx(env[32 * (size_t)g + 2 * e], env[32 * (size_t)g + 2 * e + 1]);
+    if (post) { // env = conj(U) M,  U = (l4 rc) (l3 cn) ((l2 rc) l1)
+        const Cx L3c = kron_elem(y15, id, r, s13(c)), L2c = kron_elem(y14, z13, r, s23(c));
+        Cx U = mm<false, false>(mm<false, false>(X3, L3c, r, c), mm<false, false>(L2c, l1, r, c), r, c);
+        U.im = -U.im;
+        E = mm<false, false>(U, E, r, c);
+    }
+    // suffixes Y_j and prefixes X_j of the layers; a CNOT on a product is a shuffle
+    const Cx Y3 = shfl_cx(mm<false, false>(l2, Y2, r, c), s13(r) + 4 * c);
+    const Cx Y4 = shfl_cx(mm<false, false>(l3, Y3, r, c), s23(r) + 4 * c);
+    const Cx X2 = shfl_cx(mm<false, false>(X3, l3, r, c), r + 4 * s13(c));
+    const Cx X1 = shfl_cx(mm<false, false>(X2, l2, r, c), r + 4 * s23(c));
+    const Cx W4 = mm<false, true>(E, Y4, r, c);                            // X_4 = 1
+    const Cx W1 = mm<true, false>(X1, E, r, c);                            // Y_1 = 1
+    const Cx W2 = mm<false, true>(mm<true, false>(X2, E, r, c), Y2, r, c);
+    const Cx W3 = mm<false, true>(mm<true, false>(X3, E, r, c), Y3, r, c);
+    double out[15];
+    out[12] = dot_re(D12, W2);
+    out[13] = dot_re(D13, W2);
+    out[14] = dot_re(D14, W3);
+#pragma unroll
+    for (int i = 0; i < 4; i++) { // the rotations' derivatives (trigonometry recomputed: cheaper than keeping 12 more 2x2 matrices alive)
+        M2 ri, d[3];
+        hd::rotation_all(a[3 * i], a[3 * i + 1], a[3 * i + 2], ri, d);
+#pragma unroll
+        for (int w = 0; w < 3; w++) {
+            Cx D;
+            if (i == 0) D = kron_elem(rot[1], hd::mul(d[w], rzm), r, c);      // angles 1-3: r1 in l4 (qubit K)
+            else if (i == 1) D = kron_elem(d[w], lo4, r, c);                  // angles 4-6: r2 in l4 (qubit K+1)
+            else if (i == 2) D = kron_elem(hi1, d[w], r, c);                  // angles 7-9: r3 in l1 (qubit K)
+            else D = kron_elem(hd::mul(rzm, d[w]), rot[2], r, c);             // angles 10-12: r4 in l1 (qubit K+1)
+            out[3 * i + w] = dot_re(D, i < 2 ? W4 : W1);
+        }
+    }
+    if (gid < ngates && e == 0) {
+#pragma unroll
+        for (int k = 0; k < 15; k++) grads[15 * (size_t)g + k] = out[k];
+    }
 }
 #endif
 

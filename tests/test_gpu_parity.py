@@ -50,6 +50,7 @@ def _defaults():
     qc.set_option("adjoint_mma", 1)
     qc.set_option("adjoint_tile_bits", 0)
     qc.set_option("adjoint_prog_host", 0)
+    qc.set_option("contract_coop", 1)
     yield
 
 
@@ -363,6 +364,17 @@ def test_gradients_tensor_core_pass_equals_scalar_pass(oracle, n, layers, atb):
     qc.set_option("adjoint_prog_host", 1)
     E2, g2 = qc.gradients(H, psi0, c, calculate_energy=True)
     assert E2 == E1 and np.array_equal(g2, g1)
+    # the 16-lane cooperative contraction of the environments (default) == one thread per gate layer (gates_hd.cuh on
+    # both sides: the same algebra the CPU tests check against gates_host.hpp)
+    qc.set_option("contract_coop", 0)
+    E3, g3 = qc.gradients(H, psi0, c, calculate_energy=True)
+    assert E3 == E1 and np.max(np.abs(g3 - g1)) < 1e-13 * max(scale_g, 1.0)
+    for dt in (np.complex64,):  # and for the scalar backward pass (environments, not post-gate matrices)
+        psi32 = qc.B200State(psi0.to_numpy().astype(dt))
+        ga = qc.gradients(H, psi32, c)
+        qc.set_option("contract_coop", 1)
+        gb = qc.gradients(H, psi32, c)
+        assert np.max(np.abs(ga - gb)) < 1e-13 * max(scale_g, 1.0)
 
 
 # ---- examples/test_gradients.jl:10-28 : gradients with the Hamiltonian as an explicit (sparse) matrix == kernel Hamiltonian
