@@ -70,7 +70,7 @@ int qcb_timer_start(void);
 int qcb_timer_stop(float *out_ms);
 /* Tunables: "tile_bits", "low_bits", "max_gates_per_pass", "adjoint_tile_bits" (0 = auto), "adjoint_mma" (1 = ComplexF64 backward pass on the FP64
  * tensor cores, default; 0 = scalar-FMA pass), "adjoint_warps" (0 = auto, 4, 8: warps per CTA of that pass), "adjoint_prog_host" (1 = build that pass's
- * per-thread gate programs on the host and upload them: cross-check of the device-built table), "measure_ctas" (0 = auto, 2, 3: CTAs per SM of the tiled expectation-value kernel), "contract_coop" (1 = 16-lane cooperative
+ * per-thread gate programs on the host and upload them: cross-check of the device-built table), "measure_ctas" (0 = auto, 2, 3: CTAs per SM of the tiled expectation-value kernel), "measure_persistent" (1 = persistent form of that kernel, 0 = one tile per CTA, default), "contract_coop" (1 = 16-lane cooperative
  * contraction of the environments with the gate derivatives, default; 0 = one thread per gate layer), "force_simple" (1 = one
  * unfused launch per gate). */
 int qcb_set_option(const char *key, long value);

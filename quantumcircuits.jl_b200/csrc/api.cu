@@ -136,6 +136,72 @@ template <typename R> static int measure_tiled(qcb_state *s, const HamEval &H, d
     return QCB_OK;
 }
 
+// ---- persistent form of the tiled expectation value (measure_tile_persistent_kernel; option "measure_persistent") ------
+template <typename R, int TB, int MINB, int KIND>
+static int launch_measure_pass_persistent(const qcb_state *s, const MeasParams<R> &P, double2 *partial, unsigned *grid_out)
+{
+    using V = typename Vec2<R>::type;
+    auto kern = measure_tile_persistent_kernel<R, TB, MINB, KIND>;
+    const size_t smem = sizeof(V) << TB;
+    static bool attr_set = false;
+    static int ctas_per_sm = 1;
+    if (!attr_set) {
+        QCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        QCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, 1 << (TB - kRegBits), smem));
+        if (ctas_per_sm < 1) ctas_per_sm = 1;
+        attr_set = true;
+    }
+    const unsigned long long ntiles = 1ull << (s->nloc - TB);
+    const unsigned grid = (unsigned)std::min<unsigned long long>(ntiles, (unsigned long long)ctx().sm_count * ctas_per_sm);
+    kern<<<grid, 1 << (TB - kRegBits), smem, ctx().stream>>>((const V *)s->d, P, ntiles, partial);
+    QCB_CUDA(cudaGetLastError());
+    count_launch();
+    *grid_out = grid;
+    return QCB_OK;
+}
+
+template <typename R> static int measure_tiled_persistent(qcb_state *s, const HamEval &H, double *out2)
+{
+    Ctx &c = ctx();
+    constexpr int TB = 12;
+    const int g = s->n - s->nloc;
+    unsigned long long c_hi = 0;
+    if (s->sharded) {
+        QCB_TRY(dist_state_canonicalize(s));
+        c_hi = (unsigned long long)c.rank << s->nloc;
+    }
+    const std::vector<MeasParams<R>> passes = plan_measure<R>(s->nloc, TB, (int)c.low_bits, H, c_hi);
+    const size_t npass = passes.size() + (g > 0 ? 1 : 0);
+    const size_t max_grid = (size_t)c.sm_count * 8; // upper bound of the persistent grid
+    QCB_TRY(ensure_partial(2 * max_grid * npass));
+    QCB_TRY(ensure_out(64));
+    size_t filled = 0; // partial sums written so far (passes are packed back to back)
+    auto launch = [&](const MeasParams<R> &P) -> int {
+        unsigned grid = 0;
+        double2 *part = (double2 *)c.d_partial + filled;
+        const int rc = H.kind == 0 ? launch_measure_pass_persistent<R, TB, 2, 0>(s, P, part, &grid) : launch_measure_pass_persistent<R, TB, 2, 1>(s, P, part, &grid);
+        filled += grid;
+        return rc;
+    };
+    for (size_t p = 0; p < passes.size(); p++) QCB_TRY(launch(passes[p]));
+    if (g > 0) {
+        QCB_TRY(dist_swap_top_now(s));
+        QCB_TRY(launch(plan_measure_top<R>(s->nloc, g, TB, (int)c.low_bits, H, c_hi)));
+    }
+    if (filled > max_grid * npass) return set_error(QCB_ECUDA, "internal: persistent grid larger than its bound");
+    k_final_sum<<<2, 256, 0, c.stream>>>(c.d_partial, (int)filled, 2, c.d_out);
+    QCB_CUDA(cudaGetLastError());
+    count_launch();
+    if (g > 0) QCB_TRY(dist_allreduce_sum(c.d_out, 2));
+    QCB_CUDA(cudaMemcpyAsync(c.h_out, c.d_out, 2 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    QCB_CUDA(cudaStreamSynchronize(c.stream));
+    const double oc = H.kind == 0 ? -H.p0 * H.p2 : H.p1;
+    out2[0] = c.h_out[0] + oc * c.h_out[1];
+    out2[1] = 0.0;
+    c.st_passes = (double)npass;
+    return QCB_OK;
+}
+
 static int measure_impl(const qcb_state *s, int kind, double p0, double p1, double p2, double *out2)
 {
     QCB_REQUIRE_INIT();
@@ -145,6 +211,7 @@ static int measure_impl(const qcb_state *s, int kind, double p0, double p1, doub
     if (s->sharded || (!c.force_simple && s->nloc >= 13)) {
         // (a sharded state may be re-laid-out: the handle is logically const, the amplitudes it represents do not change)
         qcb_state *ms = const_cast<qcb_state *>(s);
+        if (c.measure_persistent) return s->dtype == QCB_C128 ? measure_tiled_persistent<double>(ms, H, out2) : measure_tiled_persistent<float>(ms, H, out2);
         return s->dtype == QCB_C128 ? measure_tiled<double>(ms, H, out2) : measure_tiled<float>(ms, H, out2);
     }
     const unsigned long long namps = 1ull << s->nloc;
@@ -605,6 +672,8 @@ int qcb_set_option(const char *key, long value)
         c.adjoint_tile_bits = value;
     } else if (k == "adjoint_mma") {
         c.adjoint_mma = value ? 1 : 0;
+    } else if (k == "measure_persistent") {
+        c.measure_persistent = value ? 1 : 0;
     } else if (k == "contract_coop") {
         c.contract_coop = value ? 1 : 0;
     } else if (k == "measure_ctas") {

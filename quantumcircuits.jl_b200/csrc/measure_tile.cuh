@@ -131,6 +131,136 @@ QCB_HD void measure_tile_load(const typename Vec2<R>::type *__restrict__ src, co
     for (int i = 0; i < kRegAmps; i++) sm[e ^ P.ld_eoff[i]] = tmp[i];
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Persistent form (option "measure_persistent", off by default until it has been measured on a GPU).  ncu on the kernel
+// below (one tile per CTA) shows it bound by instruction issue, not by HBM: 93-126 warp instructions per amplitude and
+// pass, a third of them in the tile load (segment loops, per-thread index deposits) and another third in the stage
+// prologues (window offsets, physical index) -- all of it work that does not depend on the tile.  Here a CTA walks many
+// tiles and keeps the tile-independent part in registers: its share of the global index and its load offset, and per
+// stage the swizzled window offset and the thread's share of the physical index.  Same arithmetic, same summation order
+// per thread; the partial sums are per persistent CTA instead of per tile.
+template <typename R, int TB> struct MeasThread {
+    unsigned long long gthread;               // this thread's bits of the global index (tile load)
+    uint32_t e_load;                          // swizzled tile-local offset of its element 0 (tile load)
+    uint32_t es[kMeasMaxStages];              // per stage: swizzled offset of its window
+    unsigned long long cth[kMeasMaxStages];   // per stage: its bits of the physical index (without tile base and c_hi)
+};
+template <typename R, int TB> QCB_HD MeasThread<R, TB> measure_thread_consts(const MeasParams<R> &P, uint32_t tid)
+{
+    constexpr int SWB = Vec2<R>::SWB;
+    constexpr int TBITS = TB - kRegBits;
+    MeasThread<R, TB> T;
+    T.gthread = 0;
+    uint32_t e = 0;
+#pragma unroll
+    for (int k = 0; k < TBITS; k++) {
+        const uint32_t bit = (tid >> k) & 1u;
+        T.gthread |= (unsigned long long)bit << P.ld_phys[k];
+        e |= bit << P.ld_lpos[k];
+    }
+    T.e_load = swz<SWB>(e);
+#pragma unroll
+    for (int s = 0; s < kMeasMaxStages; s++) {
+        uint32_t es = 0;
+        if (s < P.nstages) {
+#pragma unroll
+            for (int k = 0; k < TBITS; k++) es |= ((tid >> k) & 1u) << P.stage[s].sd.tpos[k];
+        }
+        unsigned long long cth = 0;
+#pragma unroll
+        for (int k = 0; k < TB; k++) cth |= (unsigned long long)((es >> P.ld_lpos[k]) & 1u) << P.ld_phys[k];
+        T.es[s] = swz<SWB>(es);
+        T.cth[s] = cth;
+    }
+    return T;
+}
+// global index bits of tile `bid` (the non-tile bits, segment by segment)
+template <typename R> QCB_HD unsigned long long measure_tile_base(const MeasParams<R> &P, unsigned long long bid)
+{
+    unsigned long long g = 0;
+    for (int s = 0; s < P.nseg; s++) {
+        const int len = P.seg_len[s];
+        g |= (bid & ((1ull << len) - 1ull)) << P.seg_start[s];
+        bid >>= len;
+    }
+    return g;
+}
+template <typename R, int TB>
+QCB_HD void measure_tile_load_pre(const typename Vec2<R>::type *__restrict__ src, const MeasParams<R> &P, typename Vec2<R>::type *sm,
+                                  const MeasThread<R, TB> &T, unsigned long long tile_base)
+{
+    using V = typename Vec2<R>::type;
+    const unsigned long long g = tile_base | T.gthread;
+    V tmp[kRegAmps];
+#pragma unroll
+    for (int i = 0; i < kRegAmps; i++) tmp[i] = src[g | P.ld_goff[i]];
+#pragma unroll
+    for (int i = 0; i < kRegAmps; i++) sm[T.e_load ^ P.ld_eoff[i]] = tmp[i];
+}
+// measure_stage with the thread's window offset `es` (swizzled) and physical index C0 given
+template <typename R, int TB, int KIND>
+QCB_HD void measure_stage_pre(const MeasParams<R> &P, int s, const typename Vec2<R>::type *sm, uint32_t es, unsigned long long C0,
+                              double &acc_diag, double &acc_flip)
+{
+    using V = typename Vec2<R>::type;
+    const MeasStage &S = P.stage[s];
+    V a[kRegAmps];
+#pragma unroll
+    for (int r = 0; r < kRegAmps; r++) a[r] = sm[es ^ S.sd.roff[r]];
+    if (S.diag) {
+#pragma unroll
+        for (int r = 0; r < kRegAmps; r++) {
+            unsigned long long C = C0;
+#pragma unroll
+            for (int b = 0; b < kRegBits; b++) C |= (unsigned long long)((r >> b) & 1) << S.wphys[b];
+            acc_diag += ham_diag(P.H, C) * ((double)a[r].x * (double)a[r].x + (double)a[r].y * (double)a[r].y);
+        }
+    }
+#pragma unroll
+    for (int b = 0; b < kRegBits; b++) {
+        if (!((S.active >> b) & 1)) continue;
+        uint32_t allowed = 0xffffu;
+        if (KIND == 1 && S.ctl[b] >= 0) {
+            const int ctl = S.ctl[b];
+            if (b > 0 && S.wphys[b - 1] == ctl) allowed = b == 1 ? 0x5555u : (b == 2 ? 0x3333u : 0x0f0fu);
+            else allowed = ((C0 >> ctl) & 1ull) ? 0u : 0xffffu;
+        }
+#pragma unroll
+        for (int r = 0; r < kRegAmps; r++) {
+            if ((r >> b) & 1) continue;
+            if (KIND == 1 && !((allowed >> r) & 1u)) continue;
+            const V x0 = a[r], x1 = a[r | (1 << b)];
+            acc_flip += 2.0 * ((double)x0.x * (double)x1.x + (double)x0.y * (double)x1.y);
+        }
+    }
+}
+
+#if defined(__CUDACC__)
+template <typename R, int TB, int MINB, int KIND>
+__global__ void __launch_bounds__(1 << (TB - kRegBits), MINB)
+measure_tile_persistent_kernel(const typename Vec2<R>::type *psi, const __grid_constant__ MeasParams<R> P, unsigned long long ntiles,
+                               double2 *partial /* [gridDim.x] */)
+{
+    using V = typename Vec2<R>::type;
+    extern __shared__ __align__(16) unsigned char qcb_smem_raw[];
+    V *sm = reinterpret_cast<V *>(qcb_smem_raw);
+    const MeasThread<R, TB> T = measure_thread_consts<R, TB>(P, threadIdx.x);
+    double acc[2] = {0.0, 0.0};
+    for (unsigned long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const unsigned long long base = measure_tile_base(P, tile);
+        measure_tile_load_pre<R, TB>(psi, P, sm, T, base);
+        __syncthreads();
+#pragma unroll
+        for (int s = 0; s < kMeasMaxStages; s++)
+            if (s < P.nstages) measure_stage_pre<R, TB, KIND>(P, s, sm, T.es[s], base | P.c_hi | T.cth[s], acc[0], acc[1]);
+        __syncthreads(); // the next tile's stores overwrite what other threads still read
+    }
+    __shared__ double out[2];
+    block_sum_n<2, (1 << (TB - kRegBits)) / 32>(acc, out);
+    if (threadIdx.x == 0) partial[blockIdx.x] = make_double2(out[0], out[1]);
+}
+#endif
+
 #if defined(__CUDACC__)
 template <typename R, int TB, int MINB, int KIND>
 __global__ void __launch_bounds__(1 << (TB - kRegBits), MINB)

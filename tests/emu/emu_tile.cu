@@ -794,3 +794,60 @@ extern "C" int emu_rank_gradient_env(int n, int g, int rank, const void *shard, 
         return 1;
     }
 }
+
+// ---- persistent form of the tiled expectation value (measure_tile_persistent_kernel) replayed on the CPU: `grid` CTAs walk
+// the tiles with their tile-independent constants hoisted; also the sharded top-bits pass through c_hi is reachable ---------
+template <typename R, int TB>
+static void emu_measure_pass_persistent(const typename Vec2<R>::type *psi, int n, const MeasParams<R> &P, int grid, double *acc)
+{
+    using V = typename Vec2<R>::type;
+    const int kind = P.H.kind;
+    const uint32_t NT = 1u << (TB - kRegBits);
+    const unsigned long long ntiles = 1ull << (n - TB);
+    std::vector<V> sm(1u << TB);
+    for (int b = 0; b < grid; b++) {
+        std::vector<MeasThread<R, TB>> T(NT);
+        for (uint32_t t = 0; t < NT; t++) T[t] = measure_thread_consts<R, TB>(P, t);
+        for (unsigned long long tile = (unsigned long long)b; tile < ntiles; tile += (unsigned long long)grid) {
+            const unsigned long long base = measure_tile_base(P, tile);
+            for (uint32_t t = 0; t < NT; t++) measure_tile_load_pre<R, TB>(psi, P, sm.data(), T[t], base);
+            for (int s = 0; s < kMeasMaxStages; s++) {
+                if (s >= P.nstages) continue;
+                for (uint32_t t = 0; t < NT; t++) {
+                    if (kind == 0) measure_stage_pre<R, TB, 0>(P, s, sm.data(), T[t].es[s], base | P.c_hi | T[t].cth[s], acc[0], acc[1]);
+                    else measure_stage_pre<R, TB, 1>(P, s, sm.data(), T[t].es[s], base | P.c_hi | T[t].cth[s], acc[0], acc[1]);
+                }
+            }
+        }
+    }
+}
+
+extern "C" int emu_measure_persistent(int dtype, int n, const void *psi, int kind, double p0, double p1, double p2, int tile_bits, int low_bits,
+                                      int grid, double *out_E)
+{
+    HamEval H{kind, n, p0, p1, p2};
+    double acc[2] = {0.0, 0.0};
+    try {
+        if (dtype) {
+            for (auto &P : plan_measure<double>(n, tile_bits, low_bits, H)) switch (tile_bits) {
+#define CASE(T) case T: emu_measure_pass_persistent<double, T>((const double2 *)psi, n, P, grid, acc); break;
+                CASE(8) CASE(9) CASE(10) CASE(11) CASE(12) CASE(13)
+#undef CASE
+                default: return 3;
+            }
+        } else {
+            for (auto &P : plan_measure<float>(n, tile_bits, low_bits, H)) switch (tile_bits) {
+#define CASE(T) case T: emu_measure_pass_persistent<float, T>((const float2 *)psi, n, P, grid, acc); break;
+                CASE(8) CASE(9) CASE(10) CASE(11) CASE(12) CASE(13)
+#undef CASE
+                default: return 3;
+            }
+        }
+    } catch (const std::exception &e) {
+        std::fprintf(stderr, "emu measure persistent: %s\n", e.what());
+        return 1;
+    }
+    const double oc = kind == 0 ? -p0 * p2 : p1;
+    *out_E = acc[0] + oc * acc[1];
+    return 0;
+}

@@ -149,6 +149,19 @@ def measure(psi, kind, params, tile_bits, low_bits):
     return E.value, npass.value
 
 
+def measure_persistent(psi, kind, params, tile_bits, low_bits, grid):
+    """Persistent form of the tiled expectation value (grid CTAs walking the tiles)."""
+    psi = np.ascontiguousarray(psi)
+    n = int(psi.size).bit_length() - 1
+    E = C.c_double(0)
+    rc = lib().emu_measure_persistent(C.c_int(1 if psi.dtype == np.complex128 else 0), C.c_int(n), psi.ctypes.data_as(C.c_void_p), C.c_int(kind),
+                                      C.c_double(params[0]), C.c_double(params[1]), C.c_double(params[2]), C.c_int(tile_bits), C.c_int(low_bits),
+                                      C.c_int(grid), C.byref(E))
+    if rc:
+        raise RuntimeError(f"emu_measure_persistent rc={rc}")
+    return E.value
+
+
 def sharded_measure(psi, g, kind, params, tile_bits, low_bits):
     """Expectation value of a state split over 2^g simulated ranks (canonical layout)."""
     psi = np.ascontiguousarray(psi, dtype=np.complex128)

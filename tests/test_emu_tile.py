@@ -370,3 +370,20 @@ def test_device_gate_algebra_matches_host(emu, oracle):
         e2 = np.ascontiguousarray((np.conj(U_ref) @ env).reshape(-1, order="F"))
         _lib.check(L.qcb_general_unitary_gate_gradient(a.ctypes.data_as(C.c_void_p), e2.ctypes.data_as(C.c_void_p), ref.ctypes.data_as(C.c_void_p)))
         assert np.max(np.abs(out_post - ref)) < 1e-13 * max(1.0, np.max(np.abs(ref)))
+
+
+@pytest.mark.parametrize("n,tb,c,grid", [(13, 9, 3, 5), (14, 12, 3, 3), (15, 10, 4, 7), (16, 12, 3, 1)])
+def test_emu_tiled_measure_persistent(emu, oracle, n, tb, c, grid):
+    """Persistent form of the tiled expectation value (tile-independent thread constants hoisted out of the tile loop; option
+    measure_persistent, off by default) == the one-tile-per-CTA form == the oracle."""
+    rng = np.random.default_rng(n * 37 + tb)
+    A, B = onp.east_params(0.1, -0.1)
+    for dt in (np.complex128, np.complex64):
+        psi = rand_state(rng, n).astype(dt)
+        for kind, hp, ref in [(0, (1.0, 0.1, 0.5), oracle.measure_tfim(psi.astype(np.complex128), 1.0, 0.1, 0.5).real),
+                              (1, (0.1, A, B), oracle.measure_east(psi.astype(np.complex128), 0.1, A, B).real)]:
+            E = emu.measure_persistent(psi, kind, hp, tb, c, grid)
+            E_tile, _ = emu.measure(psi, kind, hp, tb, c)
+            tol = 1e-12 if dt == np.complex128 else 1e-5
+            assert abs(E - ref) < tol * max(1.0, abs(ref))
+            assert abs(E - E_tile) < 1e-12 * max(1.0, abs(ref))

@@ -239,6 +239,22 @@ def test_measure_vs_oracle(oracle, nbits, dtype):
     assert abs(qc.measure_(None, H, z) - (H.B * (1 + (nbits - 1) * (1 + H.c)) + H.c)) < 1e-12
 
 
+@pytest.mark.parametrize("n,dtype", [(13, np.complex128), (17, np.complex64), (21, np.complex128)])
+def test_measure_persistent_option(oracle, n, dtype):
+    """Persistent form of the tiled expectation value (option measure_persistent) == the default one-tile-per-CTA form."""
+    rng = np.random.default_rng(5 * n)
+    st = qc.B200State(rand_state(rng, n).astype(dtype))
+    try:
+        for H in (qc.TFIMHamiltonian(1.0, 0.1, 0.5), qc.EastModelHamiltonian(0.1, -0.1)):
+            qc.set_option("measure_persistent", 0)
+            E0 = qc.measure(H, st)
+            qc.set_option("measure_persistent", 1)
+            E1 = qc.measure(H, st)
+            assert abs(E1 - E0) < (1e-12 if dtype == np.complex128 else 1e-6) * max(1.0, abs(E0))
+    finally:
+        qc.set_option("measure_persistent", 0)
+
+
 def test_measure_with_circuit(oracle):
     rng = np.random.default_rng(17)
     n, layers = 12, 6

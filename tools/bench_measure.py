@@ -17,6 +17,9 @@ def main():
 
     qc.init(0)
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 30
+    if os.environ.get("MEASURE_PERSISTENT"):
+        qc.set_option("measure_persistent", int(os.environ["MEASURE_PERSISTENT"]))
+        print("measure_persistent", os.environ["MEASURE_PERSISTENT"])
     if os.environ.get("MEASURE_CTAS"):
         qc.set_option("measure_ctas", int(os.environ["MEASURE_CTAS"]))
         print("measure_ctas", os.environ["MEASURE_CTAS"])
