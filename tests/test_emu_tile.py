@@ -387,3 +387,58 @@ def test_emu_tiled_measure_persistent(emu, oracle, n, tb, c, grid):
             tol = 1e-12 if dt == np.complex128 else 1e-5
             assert abs(E - ref) < tol * max(1.0, abs(ref))
             assert abs(E - E_tile) < 1e-12 * max(1.0, abs(ref))
+
+
+def test_emu_scheduler_property_random_gate_lists(emu, oracle):
+    """Property test of the pass scheduler + tile kernels on the CPU replay: ANY program-ordered list of adjacent 2-qubit
+    gates, any tile shape, with or without a cap on the gates per pass, gives the state the gate-by-gate oracle gives."""
+    from hypothesis import HealthCheck, given, settings
+    from hypothesis import strategies as st
+
+    @settings(max_examples=25, deadline=None, suppress_health_check=list(HealthCheck))
+    @given(n=st.integers(9, 12), tb=st.integers(9, 12), low=st.integers(0, 4), cap=st.sampled_from([0, 1, 3, 7]),
+           seed=st.integers(0, 2 ** 31 - 1), ngates=st.integers(1, 30))
+    def run(n, tb, low, cap, seed, ngates):
+        tb = min(tb, n)
+        rng = np.random.default_rng(seed)
+        q0 = rng.integers(0, n - 1, size=ngates)
+        mats = []
+        for _ in range(ngates):
+            u = rng.standard_normal((4, 4)) + 1j * rng.standard_normal((4, 4))
+            mats.append(u / np.linalg.norm(u) * 2.0)
+        psi0 = rand_state(rng, n)
+        ref = psi0
+        for q, M in zip(q0, mats):
+            ref = oracle.apply_2q(ref, M, int(q) + 1)
+        out, (npass, _) = emu.apply_gates(psi0, q0, mats, tb, min(low, tb - 4), max_gates=cap)
+        assert rel(out, ref) < 1e-12
+        if cap:
+            assert npass >= -(-ngates // cap)
+
+    run()
+
+
+def test_emu_adjoint_mma_property_random_gate_lists(emu, oracle):
+    """Property test of the tensor-core backward pass replay: any list of adjacent unitary 2-qubit gates (not only brickwork
+    layers), any supported tile / warp shape: same un-applied states and environments as the scalar pass, and no
+    shared-memory bank conflict in any stage (the choice of `sel` in fill_adj_mma must work for every window position)."""
+    from hypothesis import HealthCheck, given, settings
+    from hypothesis import strategies as st
+
+    shapes = [(9, 4), (9, 2), (10, 4), (10, 8), (11, 8)]
+
+    @settings(max_examples=20, deadline=None, suppress_health_check=list(HealthCheck))
+    @given(n=st.integers(11, 12), shape=st.sampled_from(shapes), seed=st.integers(0, 2 ** 31 - 1), ngates=st.integers(1, 24))
+    def run(n, shape, seed, ngates):
+        tb, nw = shape
+        rng = np.random.default_rng(seed)
+        q0 = rng.integers(0, n - 1, size=ngates)
+        mats = [oracle.build_general_unitary_gate(rng.uniform(0, 2 * np.pi, 15)) for _ in range(ngates)]
+        psi, lam = rand_state(rng, n), rand_state(rng, n)
+        p_ref, l_ref, env_ref = emu.adjoint_sweep(psi, lam, q0, mats, tb, 3)
+        p, l, env, (wf, wf_min) = emu.adjoint_sweep_mma(psi, lam, q0, mats, tb, 3, nw)
+        assert rel(p, p_ref) < 1e-12 and rel(l, l_ref) < 1e-12
+        assert np.max(np.abs(env - env_ref)) < 1e-12
+        assert wf == wf_min
+
+    run()
