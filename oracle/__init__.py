@@ -80,10 +80,13 @@ def brickwork_num_gates(nbits, nlayers):
     return lib().qco_brickwork_num_gates(C.c_int(nbits), C.c_int(nlayers))
 
 
-def apply_2q(psi, M, K, scatter=False):
-    """M: 4x4 (row = i+2j, col = a+2b) or (2,2,2,2) Julia-ordered array."""
+def apply_2q(psi, M, K, scatter=False, out=None):
+    """M: 4x4 (row = i+2j, col = a+2b) or (2,2,2,2) Julia-ordered array.  `out`: preallocated psi' (the reference's
+    apply!(psi', psi, gate) contract; bench.py ping-pongs two buffers like src/circuits.jl:19-31)."""
     psi = np.ascontiguousarray(psi).reshape(-1)
-    out = np.empty_like(psi)
+    if out is None:
+        out = np.empty_like(psi)
+    assert out.dtype == psi.dtype and out.size == psi.size and out.flags.c_contiguous and out is not psi
     M = np.asarray(M)
     u = _gate(M if M.ndim == 2 else M.reshape(4, 4, order="F"), 16)
     fn = lib().qco_apply_2q_scatter if scatter else lib().qco_apply_2q
@@ -112,21 +115,24 @@ def _angles(angles, nbits, nlayers):
     return np.ascontiguousarray(a), G
 
 
-def apply_brickwork(psi, nbits, nlayers, angles, g_begin=0, g_end=None, inplace=False):
+def apply_brickwork(psi, nbits, nlayers, angles, g_begin=0, g_end=None, inplace=False, scratch=None):
     psi = np.ascontiguousarray(psi).reshape(-1)
     if not inplace:
         psi = psi.copy()
     a, G = _angles(angles, nbits, nlayers)
-    scratch = np.empty_like(psi)
+    if scratch is None:
+        scratch = np.empty_like(psi)
+    assert scratch.dtype == psi.dtype and scratch.size == psi.size
     rc = lib().qco_apply_brickwork_range(_dt(psi), C.c_int(nbits), C.c_int(nlayers), _p(a), _p(psi), _p(scratch),
                                          C.c_int(g_begin), C.c_int(G if g_end is None else g_end))
     assert rc == 0
     return psi
 
 
-def measure_tfim(psi, J, h, g):
+def measure_tfim(psi, J, h, g, scratch=None):
     psi = np.ascontiguousarray(psi).reshape(-1)
-    scratch = np.empty_like(psi)
+    if scratch is None:
+        scratch = np.empty_like(psi)
     E = np.zeros(2)
     lib().qco_measure_tfim(_dt(psi), _nq(psi), _p(scratch), _p(psi), C.c_double(J), C.c_double(h), C.c_double(g), _p(E))
     return complex(E[0], E[1])

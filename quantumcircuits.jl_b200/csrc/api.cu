@@ -536,6 +536,7 @@ static int gradients_impl(const qcb_state *psi0, int nbits, int nlayers, const d
     }
     QCB_TRY(grad_area_finish(ar, env_post, want_energy, out_E, out_grads));
     c.st_passes = fw_passes + bw_passes; c.st_stages = fw_stages + bw_stages; c.st_launches += fw_launches; c.st_gates = 4.0 * G;
+    c.st_fw_passes = fw_passes; c.st_bw_passes = bw_passes;
     return QCB_OK;
 }
 
@@ -600,6 +601,8 @@ int qcb_finalize(void)
     for (int i = 0; i < 2; i++)
         for (int k = 0; k < 16; k++) if (c.chunk_ev[i][k]) { cudaEventDestroy(c.chunk_ev[i][k]); c.chunk_ev[i][k] = nullptr; }
     if (c.copy_stream) { cudaStreamDestroy(c.copy_stream); c.copy_stream = nullptr; }
+    for (cudaEvent_t e : c.pass_ev) cudaEventDestroy(e);
+    c.pass_ev.clear(); c.pass_ev_used = 0;
     c.stream = nullptr;
     c.plan_cache.clear();
     c.inited = false;
@@ -684,6 +687,10 @@ int qcb_set_option(const char *key, long value)
     } else if (k == "adjoint_warps") {
         if (value != 0 && value != 4 && value != 8) return set_error(QCB_EINVAL, "adjoint_warps must be 0 (auto), 4 or 8");
         c.adjoint_warps = value;
+    } else if (k == "time_passes") {
+        c.time_passes = value ? 1 : 0;
+        c.pass_ev_used = 0;
+        return QCB_OK; // (no effect on plans)
     } else if (k == "fuse_swaps") {
         c.fuse_swaps = value ? 1 : 0;
     } else if (k == "force_simple") {
@@ -706,6 +713,23 @@ int qcb_get_stat(const char *key, double *out)
     else if (k == "swaps") *out = c.st_swaps;
     else if (k == "fused_swaps") *out = c.st_fused_swaps;
     else if (k == "sm_count") *out = c.sm_count;
+    else if (k == "fw_passes") *out = c.st_fw_passes;
+    else if (k == "bw_passes") *out = c.st_bw_passes;
+    else if (k == "ham_passes") *out = c.st_ham_passes;
+    else if (k == "pass_count") *out = (double)(c.pass_ev_used / 2);
+    else if (k == "pass_ms") {
+        // sum of the event-timed durations of the gate-pass launches since the last read; resets the list
+        double tot = 0;
+        if (c.inited && c.pass_ev_used) {
+            cudaStreamSynchronize(c.stream);
+            for (size_t i = 0; i + 1 < c.pass_ev_used; i += 2) {
+                float ms = 0;
+                if (cudaEventElapsedTime(&ms, c.pass_ev[i], c.pass_ev[i + 1]) == cudaSuccess) tot += ms;
+            }
+        }
+        c.pass_ev_used = 0;
+        *out = tot;
+    }
     else return set_error(QCB_EINVAL, "unknown stat '%s'", k.c_str());
     return QCB_OK;
 }
@@ -1186,7 +1210,8 @@ int qcb_optimise_brickwork(const qcb_state *psi0, int nbits, int nlayers, double
     QCB_TRY(check_state(psi0));
     QCB_TRY(ensure_scratch(0, psi0->bytes));
     qcb_state A = *psi0;
-    A.d = c.scratch[0]; A.owned = false;
+    // (a work copy must not inherit psi0's second buffer or its peer views: a fused qubit swap would read the peers' psi0)
+    A.d = c.scratch[0]; A.owned = false; A.alt = nullptr; A.peer_d.clear(); A.peer_alt.clear();
     QCB_TRY(copy_state_raw(A.d, psi0->d, psi0->bytes));
     QCB_TRY(qcb_apply_brickwork(&A, nbits, nlayers, angles));
     double E2[2];

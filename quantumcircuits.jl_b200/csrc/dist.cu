@@ -162,8 +162,11 @@ int dist_run_gate_list(qcb_state *s, const std::vector<GateOp> &gates, const dou
     try {
         rc = run_gates_sharded(ex, L, gates, mats, adjoint, current_sched_options(s), nullptr);
     } catch (const std::exception &e) {
+        ex.flush();
+        s->phys = L.phys;
         return set_error(QCB_EINVAL, "sharded scheduler: %s", e.what());
     }
+    if (rc != QCB_OK) ex.flush(); // error return: a deferred qubit swap must still happen, the layout below says it did
     s->phys = L.phys;
     if (rc < 0) return set_error(QCB_EINVAL, "sharded scheduler could not make progress (code %d)", rc);
     return rc;
@@ -259,8 +262,11 @@ int dist_state_canonicalize(qcb_state *s)
     try {
         rc = canonicalize(ex, L, current_sched_options(s));
     } catch (const std::exception &e) {
+        ex.flush();
+        s->phys = L.phys;
         return set_error(QCB_EINVAL, "canonicalize: %s", e.what());
     }
+    if (rc != QCB_OK) ex.flush();
     s->phys = L.phys;
     return rc;
 }
@@ -325,13 +331,16 @@ int qcb_state_ipc_import(qcb_state *s, const void *all_handles /* nranks x 128 b
     Ctx &c = ctx();
     if (!s || !s->d || !all_handles) return set_error(QCB_EINVAL, "null pointer");
     if (!s->sharded || c.nranks > 8) return set_error(QCB_EINVAL, "peer mapping needs a sharded state and at most 8 ranks");
+    if (!s->peer_d.empty()) qcb_state_ipc_close(s);
+    const char zero[64] = {0};
+    // some rank has no second buffer: stay on NCCL (decided before anything is mapped)
+    for (int r = 0; r < c.nranks; r++)
+        if (!s->alt || !memcmp((const char *)all_handles + 128 * (size_t)r + 64, zero, 64)) return QCB_OK;
     s->peer_d.assign(c.nranks, nullptr);
     s->peer_alt.assign(c.nranks, nullptr);
-    const char zero[64] = {0};
     for (int r = 0; r < c.nranks; r++) {
         const char *h = (const char *)all_handles + 128 * (size_t)r;
         if (r == c.rank) { s->peer_d[r] = s->d; s->peer_alt[r] = s->alt; continue; }
-        if (!memcmp(h + 64, zero, 64) || !s->alt) { s->peer_d.clear(); s->peer_alt.clear(); return QCB_OK; } // some rank has no second buffer: stay on NCCL
         cudaIpcMemHandle_t hd, ha;
         memcpy(&hd, h, 64);
         memcpy(&ha, h + 64, 64);
@@ -339,8 +348,7 @@ int qcb_state_ipc_import(qcb_state *s, const void *all_handles /* nranks x 128 b
         cudaError_t e2 = e1 == cudaSuccess ? cudaIpcOpenMemHandle(&s->peer_alt[r], ha, cudaIpcMemLazyEnablePeerAccess) : e1;
         if (e1 != cudaSuccess || e2 != cudaSuccess) {
             cudaGetLastError();
-            s->peer_d.clear();
-            s->peer_alt.clear();
+            qcb_state_ipc_close(s); // unmaps what the lower ranks already opened
             return set_error(QCB_ECUDA, "cudaIpcOpenMemHandle(rank %d): %s", r, cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
         }
     }

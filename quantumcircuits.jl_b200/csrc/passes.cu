@@ -29,6 +29,7 @@ template <typename R, int TB> static int launch_pass(qcb_state *s, const PassPar
         attr_set = true;
     }
     const unsigned long long nblocks = 1ull << (s->nloc - TB);
+    PassTimerScope timer;
     kern<<<(unsigned)nblocks, NT, smem, ctx().stream>>>((const V *)(src ? src : s->d), (V *)s->d, P);
     QCB_CUDA(cudaGetLastError());
     count_launch();
@@ -48,6 +49,7 @@ template <typename R, int TB> static int launch_pass_peer(qcb_state *s, const Pe
         QCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
+    PassTimerScope timer;
     kern<<<(unsigned)(1ull << (s->nloc - TB)), NT, smem, ctx().stream>>>(src, (V *)dst, P);
     QCB_CUDA(cudaGetLastError());
     count_launch();
@@ -147,16 +149,16 @@ int launch_plan_peer(qcb_state *s, const PeerSrc &src, void *dst, const PassPlan
 
 static std::string plan_key(const qcb_state *s, const std::vector<GateOp> &gates, const SchedOptions &o)
 {
-    // FNV-1a over everything the plan depends on
-    unsigned long long h = 1469598103934665603ull;
-    auto mix = [&](unsigned long long v) { h ^= v; h *= 1099511628211ull; };
-    mix((unsigned long long)s->nloc); mix((unsigned long long)o.tile_bits); mix((unsigned long long)o.low_bits);
-    mix((unsigned long long)o.max_gates_per_pass); mix((unsigned long long)o.max_stages);
-    for (int p : s->phys) mix((unsigned long long)p + 17);
-    for (const GateOp &g : gates) { mix((unsigned long long)g.q + 3); mix((unsigned long long)g.mat + 5); }
-    std::ostringstream ss;
-    ss << gates.size() << ":" << h;
-    return ss.str();
+    // the whole key material, byte for byte (a hash could collide and silently reuse the plan of another gate list)
+    std::string k;
+    k.reserve(16 * 4 + s->phys.size() + gates.size() * 4);
+    auto put = [&](long long v, int bytes) { for (int i = 0; i < bytes; i++) k.push_back((char)((v >> (8 * i)) & 0xff)); };
+    put(s->nloc, 1); put(o.tile_bits, 1); put(o.low_bits, 1); put(o.max_stages, 1); put(o.max_gates_per_pass, 4);
+    put((long long)s->phys.size(), 1);
+    for (int p : s->phys) put(p, 1);
+    put((long long)gates.size(), 4);
+    for (const GateOp &g : gates) { put(g.q, 1); put(g.mat, 3); }
+    return k;
 }
 
 template <typename R> static int run_fused(qcb_state *s, const std::vector<GateOp> &gates, const double *mats, bool adjoint, const void *first_src)

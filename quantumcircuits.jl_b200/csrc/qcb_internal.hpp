@@ -41,6 +41,11 @@ struct Ctx {
     // stats
     double st_passes = 0, st_stages = 0, st_launches = 0, st_gates = 0, st_launches_total = 0, st_swaps = 0, st_fused_swaps = 0;
     long fuse_swaps = 1;
+    // per-launch device timing of the gate passes (option "time_passes"; read and reset by the stats "pass_ms" / "pass_count")
+    long time_passes = 0;
+    std::vector<cudaEvent_t> pass_ev; // pairs (start, stop)
+    size_t pass_ev_used = 0;
+    double st_fw_passes = 0, st_bw_passes = 0, st_ham_passes = 0;
     int *d_barrier = nullptr; // 1 int for stream-ordered inter-rank barriers (NCCL all-reduce)
     // scratch
     double *d_partial = nullptr; // reduction partials
@@ -83,6 +88,29 @@ inline size_t amp_bytes(int dtype) { return dtype == QCB_C128 ? 16 : 8; }
 int ensure_scratch(int slot, size_t bytes);
 int ensure_partial(size_t doubles);
 int ensure_out(size_t doubles);
+// brackets one gate-pass launch with CUDA events on the work stream when "time_passes" is on
+struct PassTimerScope {
+    cudaEvent_t stop = nullptr;
+    PassTimerScope()
+    {
+        Ctx &c = ctx();
+        if (!c.time_passes) return;
+        if (c.pass_ev_used + 2 > c.pass_ev.size()) {
+            cudaEvent_t a, b;
+            if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return;
+            c.pass_ev.push_back(a);
+            c.pass_ev.push_back(b);
+        }
+        cudaEventRecord(c.pass_ev[c.pass_ev_used], c.stream);
+        stop = c.pass_ev[c.pass_ev_used + 1];
+        c.pass_ev_used += 2;
+    }
+    ~PassTimerScope()
+    {
+        if (stop) cudaEventRecord(stop, ctx().stream);
+    }
+};
+
 inline void count_launch(int k = 1)
 {
     ctx().st_launches += k;

@@ -73,9 +73,23 @@ def optimise_(circuit, H, psi0, epochs, lr, use_progress=False):
     returns `energies` laid out like the reference's (length epochs+1, [0] never written, [-1] = final measure)."""
     # (a dist.ShardedState works too: collective call, every rank receives the energy and the full gradient)
     st0 = psi0 if isinstance(psi0, B200State) or hasattr(psi0, "_handle") else B200State(psi0)
+    energies = np.zeros(epochs + 1, dtype=np.float64)
+    if _is_matrix(H):
+        # optimise! is generic over H (src/gradients.jl:1-17); a matrix Hamiltonian runs the same loop on the host, one
+        # qcb_gradients_brickwork_csr call per epoch (the reference's small-n cross-check path)
+        from .hamiltonians import measure
+
+        for e in range(1, epochs + 1):
+            E, g = gradients_(None, None, None, None, H, st0, circuit, calculate_energy=True)
+            energies[e] = E                      # :11
+            circuit.gate_angles[...] -= lr * g   # :13
+        if epochs >= 0:
+            energies[epochs] = measure(H, st0, circuit)  # :15
+        return energies
+    if not isinstance(H, AbstractKernelHamiltonian):
+        raise TypeError(f"optimise!: unsupported Hamiltonian type {type(H)}")
     a = circuit.angles_abi().copy()
     hp = H.params()
-    energies = np.zeros(epochs + 1, dtype=np.float64)
     _lib.check(_lib.lib().qcb_optimise_brickwork(st0._handle, C.c_int(circuit.nbits), C.c_int(circuit.nlayers),
                                                  a.ctypes.data_as(C.c_void_p), C.c_int(H.kind), hp.ctypes.data_as(C.c_void_p),
                                                  C.c_int(epochs), C.c_double(lr), energies.ctypes.data_as(C.c_void_p)))

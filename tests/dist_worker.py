@@ -133,6 +133,29 @@ def main():
                   f"dE={dE:.2e} dgrad={dg:.2e}", flush=True)
         st.close()
     qc.set_option("adjoint_mma", 1)
+    # ---- optimise! on a sharded state (its final energy runs circuit + measure on a work copy that must not inherit
+    # psi0's peer views): same trajectory as on one GPU, with the swaps fused into gate passes and on NCCL only ----------
+    for fuse in (1, 0):
+        n, layers, epochs, lr = 20, 3, 3, 0.01
+        qc.set_option("fuse_swaps", fuse)
+        rng = np.random.default_rng(77)
+        a0 = rng.standard_normal((15, qc.brickwork_num_gates(n, layers))) * 0.1
+        Hq = qc.TFIMHamiltonian(1.0, 0.9045, 1.4)
+        c_ref = qc.GenericBrickworkCircuit(n, layers, gate_angles=a0.copy())
+        e_ref = qc.optimise_(c_ref, Hq, qc.B200State(n, np.complex128), epochs, lr)
+        st = qdist.ShardedState(n, np.complex128)
+        c_sh = qc.GenericBrickworkCircuit(n, layers, gate_angles=a0.copy())
+        e_sh = qc.optimise_(c_sh, Hq, st, epochs, lr)
+        de, da = float(np.max(np.abs(e_sh - e_ref))), float(np.max(np.abs(c_sh.gate_angles - c_ref.gate_angles)))
+        good = de < 1e-11 and da < 1e-12
+        t = torch.tensor([0 if good else 1], device="cuda")
+        dist.all_reduce(t)
+        good = t.item() == 0
+        ok = ok and good
+        if rank == 0:
+            print(f"{'PASS' if good else 'FAIL'} sharded optimise fuse_swaps={fuse} peers={st.peers_mapped} dE={de:.2e} dangles={da:.2e}", flush=True)
+        st.close()
+    qc.set_option("fuse_swaps", 1)
     flag = torch.tensor([0 if ok else 1], device="cuda")
     dist.all_reduce(flag)
     dist.barrier()
