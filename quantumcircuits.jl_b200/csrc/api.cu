@@ -7,6 +7,7 @@
 #include "gates_hd.cuh"
 #include "gates_host.hpp"
 #include "kernels.cuh"
+#include "flip_tile.cuh"
 #include "measure_plan.hpp"
 #include "qcb_internal.hpp"
 
@@ -202,6 +203,67 @@ template <typename R> static int measure_tiled_persistent(qcb_state *s, const Ha
     return QCB_OK;
 }
 
+// ---- TMA-fed persistent form (flip_tile.cuh; default for >= 14 / 15 local qubits) ---------------------------------------
+template <typename R, int KIND> static int launch_flip_measure(const FlipMaps &M, const FlipParams &P, double2 *partial, unsigned *grid_out)
+{
+    auto kern = flip_measure_kernel<R, KIND>;
+    const size_t smem = flip_smem_bytes();
+    static bool attr_set = false;
+    if (!attr_set) {
+        QCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    const unsigned grid = (unsigned)std::min<unsigned long long>(P.n_items, (unsigned long long)ctx().sm_count);
+    kern<<<grid, kFlipConsumers + 32, smem, ctx().stream>>>(M, P, partial);
+    QCB_CUDA(cudaGetLastError());
+    count_launch();
+    *grid_out = grid;
+    return QCB_OK;
+}
+
+template <typename R> static int measure_flip(qcb_state *s, const HamEval &H, double *out2)
+{
+    Ctx &c = ctx();
+    const int g = s->n - s->nloc;
+    unsigned long long c_hi = 0;
+    if (s->sharded) {
+        QCB_TRY(dist_state_canonicalize(s));
+        c_hi = (unsigned long long)c.rank << s->nloc;
+    }
+    FlipParams P;
+    if (!flip_plan<R>(P, s->nloc, H, c_hi)) return set_error(QCB_EINVAL, "internal: state too small for the TMA expectation kernel");
+    flip_fill_diag_table<R>(P);
+    FlipMaps M;
+    const char *why = "";
+    if (flip_make_maps<R>(M, s->d, P, &why)) return set_error(QCB_ECUDA, "tensor map: %s", why);
+    const size_t ntiles_top = g > 0 ? ((size_t)1 << (s->nloc - 12)) : 0;
+    QCB_TRY(ensure_partial(2 * ((size_t)c.sm_count + ntiles_top)));
+    QCB_TRY(ensure_out(64));
+    unsigned grid = 0;
+    QCB_TRY((H.kind == 0 ? launch_flip_measure<R, 0>(M, P, (double2 *)c.d_partial, &grid) : launch_flip_measure<R, 1>(M, P, (double2 *)c.d_partial, &grid)));
+    size_t nparts = grid;
+    if (g > 0) {
+        // the flips of the qubits that live in the rank bits: one qubit swap brings them to the top local bits for one
+        // more (non-persistent) tile pass
+        QCB_TRY(dist_swap_top_now(s));
+        const MeasParams<R> Pt = plan_measure_top<R>(s->nloc, g, 12, (int)c.low_bits, H, c_hi);
+        double2 *part = (double2 *)c.d_partial + nparts;
+        QCB_TRY((H.kind == 0 ? launch_measure_pass<R, 12, 2, 0>(s, Pt, part) : launch_measure_pass<R, 12, 2, 1>(s, Pt, part)));
+        nparts += ntiles_top;
+    }
+    k_final_sum<<<2, 256, 0, c.stream>>>(c.d_partial, (int)nparts, 2, c.d_out);
+    QCB_CUDA(cudaGetLastError());
+    count_launch();
+    if (g > 0) QCB_TRY(dist_allreduce_sum(c.d_out, 2));
+    QCB_CUDA(cudaMemcpyAsync(c.h_out, c.d_out, 2 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    QCB_CUDA(cudaStreamSynchronize(c.stream));
+    const double oc = H.kind == 0 ? -H.p0 * H.p2 : H.p1;
+    out2[0] = c.h_out[0] + oc * c.h_out[1];
+    out2[1] = 0.0; // the two orientations of every flip pair have exactly opposite imaginary parts (Hermitian kernel Hamiltonians)
+    c.st_passes = (double)P.nlevels + (g > 0 ? 1 : 0);
+    return QCB_OK;
+}
+
 static int measure_impl(const qcb_state *s, int kind, double p0, double p1, double p2, double *out2)
 {
     QCB_REQUIRE_INIT();
@@ -211,6 +273,8 @@ static int measure_impl(const qcb_state *s, int kind, double p0, double p1, doub
     if (s->sharded || (!c.force_simple && s->nloc >= 13)) {
         // (a sharded state may be re-laid-out: the handle is logically const, the amplitudes it represents do not change)
         qcb_state *ms = const_cast<qcb_state *>(s);
+        if (c.measure_tma && s->nloc >= (s->dtype == QCB_C128 ? 14 : 15))
+            return s->dtype == QCB_C128 ? measure_flip<double>(ms, H, out2) : measure_flip<float>(ms, H, out2);
         if (c.measure_persistent) return s->dtype == QCB_C128 ? measure_tiled_persistent<double>(ms, H, out2) : measure_tiled_persistent<float>(ms, H, out2);
         return s->dtype == QCB_C128 ? measure_tiled<double>(ms, H, out2) : measure_tiled<float>(ms, H, out2);
     }
@@ -675,6 +739,8 @@ int qcb_set_option(const char *key, long value)
         c.adjoint_tile_bits = value;
     } else if (k == "adjoint_mma") {
         c.adjoint_mma = value ? 1 : 0;
+    } else if (k == "measure_tma") {
+        c.measure_tma = value ? 1 : 0;
     } else if (k == "measure_persistent") {
         c.measure_persistent = value ? 1 : 0;
     } else if (k == "contract_coop") {

@@ -12,7 +12,7 @@ _lib = None
 
 
 def build(force=False):
-    srcs = [os.path.join(_HERE, "emu_tile.cu"), os.path.join(_CSRC, "tile.cuh"), os.path.join(_CSRC, "schedule.hpp"), os.path.join(_CSRC, "dist_plan.hpp"), os.path.join(_CSRC, "adjoint.cuh"), os.path.join(_CSRC, "adjoint_mma.cuh"), os.path.join(_CSRC, "gates_hd.cuh"), os.path.join(_CSRC, "measure_tile.cuh"), os.path.join(_CSRC, "measure_plan.hpp"), os.path.join(_CSRC, "kernels.cuh")]
+    srcs = [os.path.join(_HERE, "emu_tile.cu"), os.path.join(_CSRC, "tile.cuh"), os.path.join(_CSRC, "schedule.hpp"), os.path.join(_CSRC, "dist_plan.hpp"), os.path.join(_CSRC, "adjoint.cuh"), os.path.join(_CSRC, "adjoint_mma.cuh"), os.path.join(_CSRC, "gates_hd.cuh"), os.path.join(_CSRC, "measure_tile.cuh"), os.path.join(_CSRC, "measure_plan.hpp"), os.path.join(_CSRC, "kernels.cuh"), os.path.join(_CSRC, "flip_tile.cuh"), os.path.join(_CSRC, "tma.cuh")]
     if force or not os.path.exists(_SO) or any(os.path.getmtime(_SO) < os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["nvcc", "-O2", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler",
                                "-fPIC", "-shared", "-o", _SO, srcs[0]], cwd=_HERE)
@@ -147,6 +147,21 @@ def measure(psi, kind, params, tile_bits, low_bits):
     if rc:
         raise RuntimeError(f"emu_measure rc={rc}")
     return E.value, npass.value
+
+
+def flip_measure(psi, kind, params, grid=3, n_total=None, c_hi=0):
+    """TMA-fed persistent expectation value (flip_tile.cuh) with emulated tile loads.  psi: the local amplitudes; for a
+    simulated shard pass n_total and c_hi = rank << nloc.  Returns (diagonal sum, flip sum, levels); E = diag + coef * flips."""
+    psi = np.ascontiguousarray(psi)
+    nloc = int(psi.size).bit_length() - 1
+    out = np.zeros(2)
+    nl = C.c_int(0)
+    rc = lib().emu_flip_measure(C.c_int(1 if psi.dtype == np.complex128 else 0), C.c_int(nloc), C.c_int(nloc if n_total is None else n_total),
+                                psi.ctypes.data_as(C.c_void_p), C.c_int(kind), C.c_double(params[0]), C.c_double(params[1]), C.c_double(params[2]),
+                                C.c_ulonglong(c_hi), C.c_int(grid), out.ctypes.data_as(C.c_void_p), C.byref(nl))
+    if rc:
+        raise RuntimeError(f"emu_flip_measure rc={rc}")
+    return out[0], out[1], nl.value
 
 
 def measure_persistent(psi, kind, params, tile_bits, low_bits, grid):

@@ -442,3 +442,46 @@ def test_emu_adjoint_mma_property_random_gate_lists(emu, oracle):
         assert wf == wf_min
 
     run()
+
+
+# ---- TMA-fed persistent expectation value (flip_tile.cuh): consumer code replayed on emulated tile loads --------------------
+@pytest.mark.parametrize("n,dt", [(14, np.complex128), (15, np.complex128), (17, np.complex128), (21, np.complex128), (22, np.complex128),
+                                  (15, np.complex64), (16, np.complex64), (19, np.complex64), (22, np.complex64), (23, np.complex64)])
+def test_emu_flip_measure(emu, oracle, n, dt):
+    rng = np.random.default_rng(700 + n)
+    psi = rand_state(rng, n).astype(dt)
+    ref_psi = psi.astype(np.complex128)
+    A, B = -np.exp(0.1) * np.sqrt(0.1 * 0.9), 0.8
+    tol = 1e-12 if dt == np.complex128 else 1e-5
+    for kind, hp, ref in [(0, (1.0, 0.1, 0.5), oracle.measure_tfim(ref_psi, 1.0, 0.1, 0.5).real),
+                          (0, (0.7, -0.3, 1.4), oracle.measure_tfim(ref_psi, 0.7, -0.3, 1.4).real),
+                          (1, (0.1, A, B), oracle.measure_east(ref_psi, 0.1, A, B).real)]:
+        d, f, nl = emu.flip_measure(psi, kind, hp, grid=5)
+        coef = -hp[0] * hp[2] if kind == 0 else hp[1]
+        E = d + coef * f
+        assert abs(E - ref) < tol * max(1.0, abs(ref)), (kind, E, ref)
+        tba = 12 if dt == np.complex128 else 13
+        assert nl == 1 + -(-(n - tba) // 9)
+
+
+def test_emu_flip_measure_simulated_shards(emu, oracle):
+    """local part of a sharded expectation value: every simulated rank sweeps its shard with c_hi = rank << nloc; the sum of
+    the diagonal parts and of the local-qubit flips equals the oracle's value minus the flips of the rank-bit qubits."""
+    n, g = 16, 2
+    nloc = n - g
+    rng = np.random.default_rng(1602)
+    psi = rand_state(rng, n)
+    for kind, hp in [(0, (1.0, 0.1, 0.5)), (1, (0.1, -0.33, 0.8))]:
+        coef = -hp[0] * hp[2] if kind == 0 else hp[1]
+        tot = 0.0
+        for r in range(1 << g):
+            d, f, _ = emu.flip_measure(psi[r << nloc:(r + 1) << nloc], kind, hp, grid=2, n_total=n, c_hi=r << nloc)
+            tot += d + coef * f
+        # flips of the qubits nloc..n-1, from the definition (src/hamiltonians/tfim.jl:39-44, east_model.jl:37-44)
+        top = 0.0
+        idx = np.arange(1 << n)
+        for i in range(nloc, n):
+            w = np.ones(1 << n) if kind == 0 else ((idx >> (i - 1)) & 1 == 0).astype(float)
+            top += float(np.sum(w * (np.conj(psi[idx ^ (1 << i)]) * psi).real))
+        ref = (oracle.measure_tfim(psi, *hp) if kind == 0 else oracle.measure_east(psi, *hp)).real
+        assert abs(tot + coef * top - ref) < 1e-12 * max(1.0, abs(ref))

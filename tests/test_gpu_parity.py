@@ -51,6 +51,7 @@ def _defaults():
     qc.set_option("adjoint_tile_bits", 0)
     qc.set_option("adjoint_prog_host", 0)
     qc.set_option("contract_coop", 1)
+    qc.set_option("measure_tma", 1)
     yield
 
 
@@ -239,9 +240,37 @@ def test_measure_vs_oracle(oracle, nbits, dtype):
     assert abs(qc.measure_(None, H, z) - (H.B * (1 + (nbits - 1) * (1 + H.c)) + H.c)) < 1e-12
 
 
+# ---- the TMA-fed persistent expectation kernel (flip_tile.cuh, default from 14 / 15 qubits) against the oracle, every
+# level structure: one window level (n <= 21 / 22), chunk-interleaved levels 0 + 1, a third level (n > 21 / 22)
+@pytest.mark.parametrize("n", [14, 15, 16, 19, 21, 22, 23, 25])
+@pytest.mark.parametrize("dtype", [np.complex128, np.complex64])
+def test_measure_tma_vs_oracle(oracle, n, dtype):
+    rng = np.random.default_rng(4100 + n)
+    psi = rand_state(rng, n, dtype)
+    st = qc.B200State(psi)
+    ref_psi = psi.astype(np.complex128)
+    tol = TOL[dtype]
+    for H, ref in [(qc.TFIMHamiltonian(1.0, 0.1, 0.5), oracle.measure_tfim(ref_psi, 1.0, 0.1, 0.5).real),
+                   (qc.TFIMHamiltonian(0.7, -0.3, 1.4), oracle.measure_tfim(ref_psi, 0.7, -0.3, 1.4).real),
+                   (qc.EastModelHamiltonian(0.1, -0.1), None)]:
+        if ref is None:
+            ref = oracle.measure_east(ref_psi, H.c, H.A, H.B).real
+        qc.set_option("measure_tma", 1)
+        E = qc.measure_(None, H, st)
+        levels = qc.get_stat("passes")
+        qc.set_option("measure_tma", 0)
+        E_old = qc.measure_(None, H, st)
+        qc.set_option("measure_tma", 1)
+        assert abs(E - ref) < tol * max(1.0, abs(ref)), (type(H).__name__, E, ref)
+        assert abs(E - E_old) < tol * max(1.0, abs(ref))
+        tba = 12 if dtype == np.complex128 else 13
+        assert levels == (1 + -(-(n - tba) // 9) if n >= tba + 2 else levels)
+
+
 @pytest.mark.parametrize("n,dtype", [(13, np.complex128), (17, np.complex64), (21, np.complex128)])
 def test_measure_persistent_option(oracle, n, dtype):
     """Persistent form of the tiled expectation value (option measure_persistent) == the default one-tile-per-CTA form."""
+    qc.set_option("measure_tma", 0)  # (the default TMA-fed kernel would take these sizes)
     rng = np.random.default_rng(5 * n)
     st = qc.B200State(rand_state(rng, n).astype(dtype))
     try:
