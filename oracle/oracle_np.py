@@ -152,6 +152,30 @@ def apply_2q(psi, M, K):
     return np.einsum("rc,pcq->prq", np.asarray(M), v).reshape(-1)
 
 
+def right_apply_gate(M, u4, K):
+    """src/apply.jl:144-182, literal: M' [pre, i, j, post] += M[pre, a, b, post] * u[a, b, i, j] on the COLUMN-index
+    dims X = K + nbits, X + 1 of the 2^n x 2^n matrix seen as a 2n-dim tensor (column-major: the first n dims are the
+    row-index bits).  u4 is the 4x4 form of the gate (row = i + 2j, col = a + 2b)."""
+    M = np.asarray(M)
+    n = int(np.log2(M.shape[0]))
+    assert M.shape == (2 ** n, 2 ** n), "Must be a square matrix with a power of two edge"
+    u = np.asarray(u4).reshape(2, 2, 2, 2, order="F")  # u[i, j, a, b]
+    T = M.reshape((2,) * (2 * n), order="F")           # dims 0..n-1: row bits, n..2n-1: column bits
+    X = K + n - 1                                       # 0-based dim of column qubit K
+    out = np.zeros_like(T, dtype=np.result_type(M.dtype, u.dtype))
+    for a in range(2):
+        for b in range(2):
+            src = [slice(None)] * (2 * n)
+            src[X], src[X + 1] = a, b
+            m = T[tuple(src)]
+            for i in range(2):
+                for j in range(2):
+                    dst = [slice(None)] * (2 * n)
+                    dst[X], dst[X + 1] = i, j
+                    out[tuple(dst)] += m * u[a, b, i, j]   # "u is reversed": indexed [contract..., i, j]
+    return out.reshape(2 ** n, 2 ** n, order="F")
+
+
 def apply_brickwork(psi, nbits, nlayers, angles):
     """src/circuits.jl:19-31 ; angles is (15, G) as in the reference."""
     angles = np.asarray(angles).reshape(15, -1, order="F") if np.ndim(angles) == 1 else np.asarray(angles)

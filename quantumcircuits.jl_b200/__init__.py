@@ -11,7 +11,7 @@ from .gates import (AbstractGate, Abstract1SpinGate, Abstract2SpinGate, XGate, Z
 from .circuits import GenericBrickworkCircuit, circuit_layer_starts, brickwork_num_gates, reconstruct  # noqa: F401
 from .state import B200State, zero_state_vec, zero_state_tensor  # noqa: F401
 from .utils import convert_gates_to_matrix, operation_tensor  # noqa: F401
-from .apply import B200ApplyCache, construct_apply_cache, apply, apply_, apply_circuit_host  # noqa: F401
+from .apply import B200ApplyCache, construct_apply_cache, apply, apply_, apply_circuit_host, right_apply_gate_  # noqa: F401
 from .hamiltonians import (AbstractKernelHamiltonian, TFIMHamiltonian, EastModelHamiltonian, measure, measure_,  # noqa: F401
                            imaginary_energy_limit, build_sparse_tfim_hamiltonian, find_tfim_ground_state, east_model_matrix)
 from . import dist  # noqa: F401

@@ -125,3 +125,37 @@ def apply_circuit_host(psi, circuit, out=None):
                                                    C.c_int(circuit.nlayers), a.ctypes.data_as(C.c_void_p),
                                                    flat.ctypes.data_as(C.c_void_p), res.ctypes.data_as(C.c_void_p)))
     return res.reshape(src.shape, order="F") if src.ndim > 1 else res
+
+
+def right_apply_gate_(M_out, M, gate):
+    """right_apply_gate!(M', M, gate::Localised2SpinAdjGate) -- src/apply.jl:144-182 (operator evolution: M' = M * U).
+
+    The reference contracts the gate into the column index of the 2^n x 2^n matrix,
+    M'[pre, i, j, post] += M[pre, a, b, post] * u[a, b, i, j] on dims K + n, K + n + 1 of the 2n-dim tensor.  Seen as a
+    2n-qubit state (column-major: row bits first), that is the 2-qubit gate v[i, j, a, b] = u[a, b, i, j] on qubits
+    (K + n, K + n + 1): one fused tile pass on the device."""
+    M = np.asarray(M)
+    if M.ndim != 2:
+        raise ValueError("Must be a matrix")
+    if M.shape[0] != M.shape[1]:
+        raise ValueError("Must be a square matrix")
+    if np.shape(M_out) != M.shape:
+        raise ValueError("M′ must be the same size as M")
+    nbits = int(M.shape[0]).bit_length() - 1
+    if M.shape[0] != 1 << nbits:
+        raise AssertionError("The matrix must have a power of two edge")
+    if not isinstance(gate, Localised2SpinAdjGate):
+        raise TypeError("gate must be a Localised2SpinAdjGate")
+    K = gate.target_gate_dim
+    if not (0 < K < nbits):
+        raise _lib.GateOutsideQubitSpace("The gate cannot be applied as it sits outside the qubit space.")
+    from .gates import Generic2SpinGate
+
+    u = np.asarray(gate.mat(), dtype=np.complex128)            # u[i, j, a, b]
+    v = np.ascontiguousarray(u.transpose(2, 3, 0, 1))          # v[i, j, a, b] = u[a, b, i, j]
+    dt = np.complex64 if M.dtype in (np.complex64, np.float32) else np.complex128
+    st = B200State(np.asarray(M, dtype=dt).reshape(-1, order="F"))
+    _apply_list_inplace(st, [Localised2SpinAdjGate(Generic2SpinGate(v), K + nbits)])
+    res = st.to_numpy().reshape(M.shape, order="F")
+    M_out[...] = res if np.iscomplexobj(M_out) else res.real
+    return M_out

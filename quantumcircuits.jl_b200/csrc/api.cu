@@ -739,6 +739,11 @@ int qcb_set_option(const char *key, long value)
         c.adjoint_tile_bits = value;
     } else if (k == "adjoint_mma") {
         c.adjoint_mma = value ? 1 : 0;
+    } else if (k == "pass_tma") {
+        if (value < 0 || value > 2) return set_error(QCB_EINVAL, "pass_tma must be 0 (off), 1 (every eligible pass) or 2 (HBM-bound passes only)");
+        c.pass_tma = value;
+    } else if (k == "pass_tma_max_stages") {
+        c.pass_tma_max_stages = value;
     } else if (k == "measure_tma") {
         c.measure_tma = value ? 1 : 0;
     } else if (k == "measure_persistent") {
@@ -779,6 +784,7 @@ int qcb_get_stat(const char *key, double *out)
     else if (k == "swaps") *out = c.st_swaps;
     else if (k == "fused_swaps") *out = c.st_fused_swaps;
     else if (k == "sm_count") *out = c.sm_count;
+    else if (k == "tma_passes") *out = c.st_tma_passes;
     else if (k == "fw_passes") *out = c.st_fw_passes;
     else if (k == "bw_passes") *out = c.st_bw_passes;
     else if (k == "ham_passes") *out = c.st_ham_passes;

@@ -5,9 +5,12 @@
 // one synchronize per gate (src/apply.jl:134-142).
 #include <sstream>
 
+#include <type_traits>
+
 #include "adjoint_mma.cuh"
 #include "kernels.cuh"
 #include "qcb_internal.hpp"
+#include "tile_tma.cuh"
 
 namespace qcb {
 
@@ -34,6 +37,46 @@ template <typename R, int TB> static int launch_pass(qcb_state *s, const PassPar
     QCB_CUDA(cudaGetLastError());
     count_launch();
     return QCB_OK;
+}
+
+// the same pass on the TMA-fed persistent kernel (tile_tma.cuh); P was filled with the hardware swizzle (fill_params<double, -3>)
+static int launch_pass_tma(qcb_state *s, const PassParams<double> &P, const TmaPassGeom &g, const void *src)
+{
+    auto kern = tile_pass_tma_kernel<3>;
+    const size_t smem = tma_pass_smem_bytes();
+    static bool attr_set = false;
+    static int ctas_per_sm = 1;
+    if (!attr_set) {
+        QCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        QCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, kTmaStageThreads + 32, smem));
+        if (ctas_per_sm < 1) ctas_per_sm = 1;
+        attr_set = true;
+    }
+    CUtensorMap map_ld, map_st;
+    const char *why = "";
+    if (tma_pass_map(&map_st, s->d, g, &why)) return set_error(QCB_ECUDA, "tensor map: %s", why);
+    if (src && src != s->d) {
+        if (tma_pass_map(&map_ld, src, g, &why)) return set_error(QCB_ECUDA, "tensor map: %s", why);
+    } else
+        map_ld = map_st;
+    const unsigned long long ntiles = 1ull << (s->nloc - kTmaTB);
+    const unsigned grid = (unsigned)std::min<unsigned long long>(ntiles, (unsigned long long)ctx().sm_count * ctas_per_sm);
+    PassTimerScope timer;
+    kern<<<grid, kTmaStageThreads + 32, smem, ctx().stream>>>(map_ld, map_st, P, g.a2 - g.b1, ntiles);
+    QCB_CUDA(cudaGetLastError());
+    count_launch();
+    ctx().st_tma_passes += 1;
+    return QCB_OK;
+}
+
+// does this pass go to the TMA kernel?  ("pass_tma": 0 never, 1 every eligible pass, 2 eligible passes with at most
+// `pass_tma_max_stages` register stages, i.e. the HBM-bound ones)
+static bool use_tma_pass(const qcb_state *s, const PassPlan &pl, TmaPassGeom &g)
+{
+    const Ctx &c = ctx();
+    if (!c.pass_tma || s->dtype != QCB_C128) return false;
+    if (c.pass_tma == 2 && (long)pl.stages.size() > c.pass_tma_max_stages) return false;
+    return tma_pass_eligible(pl, s->nloc, g);
 }
 
 template <typename R, int TB> static int launch_pass_peer(qcb_state *s, const PeerSrc &src, void *dst, const PassParams<R> &P)
@@ -120,6 +163,11 @@ int launch_plan(qcb_state *s, const PassPlan &pl, const std::vector<GateOp> &gat
     try {
         if (s->dtype == QCB_C128) {
             static thread_local PassParams<double> P;
+            TmaPassGeom g;
+            if (use_tma_pass(s, pl, g)) {
+                fill_params<double, -3>(pl, s->nloc, gates, mats, adjoint, P);
+                return launch_pass_tma(s, P, g, nullptr);
+            }
             fill_params<double>(pl, s->nloc, gates, mats, adjoint, P);
             return launch_pass_tb<double>(s, pl.TB, P);
         }
@@ -182,12 +230,21 @@ template <typename R> static int run_fused(qcb_state *s, const std::vector<GateO
     }
     static thread_local PassParams<R> P; // ~13 KB, reused
     for (const PassPlan &pl : it->second) {
+        TmaPassGeom g;
+        bool tma_pass = false;
         try {
-            fill_params<R>(pl, s->nloc, gates, mats, adjoint, P);
+            if constexpr (std::is_same<R, double>::value) {
+                tma_pass = use_tma_pass(s, pl, g);
+                if (tma_pass) fill_params<double, -3>(pl, s->nloc, gates, mats, adjoint, P);
+            }
+            if (!tma_pass) fill_params<R>(pl, s->nloc, gates, mats, adjoint, P);
         } catch (const std::exception &e) {
             return set_error(QCB_EINVAL, "pass parameters: %s", e.what());
         }
-        QCB_TRY(launch_pass_tb<R>(s, pl.TB, P, first_src));
+        if constexpr (std::is_same<R, double>::value) {
+            if (tma_pass) QCB_TRY(launch_pass_tma(s, P, g, first_src));
+        }
+        if (!tma_pass) QCB_TRY(launch_pass_tb<R>(s, pl.TB, P, first_src));
         first_src = nullptr; // only the first pass reads the input state
         c.st_passes += 1;
         c.st_stages += (double)pl.stages.size();
@@ -458,7 +515,7 @@ int run_adjoint_fused(qcb_state *psi, qcb_state *lam, const std::vector<GateOp> 
 int run_gate_list(qcb_state *s, const std::vector<GateOp> &gates, const double *mats, bool adjoint, const void *first_src)
 {
     Ctx &c = ctx();
-    c.st_passes = c.st_stages = c.st_launches = c.st_swaps = c.st_fused_swaps = 0;
+    c.st_passes = c.st_stages = c.st_launches = c.st_swaps = c.st_fused_swaps = c.st_tma_passes = 0;
     c.st_gates = (double)gates.size();
     for (const GateOp &g : gates)
         if (g.q < 0 || g.q + 1 >= s->n)

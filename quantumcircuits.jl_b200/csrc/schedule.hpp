@@ -236,8 +236,9 @@ template <int SWB> inline void fill_stage_desc(StageDesc &S, int p0, int TB)
     std::vector<int> order;
     std::vector<char> used(TB, 0);
     std::vector<uint32_t> basis; // reduced basis of the chosen vectors
+    const int nlane = SWB < 0 ? -SWB : SWB; // thread bits that select the bank group of a quarter / half warp
     for (int p : freepos) {
-        if ((int)order.size() >= SWB) break;
+        if ((int)order.size() >= nlane) break;
         uint32_t v = bank_vector<SWB>(p);
         for (uint32_t bvec : basis) v = std::min(v, v ^ bvec);
         if (v) { basis.push_back(v); order.push_back(p); used[p] = 1; }
@@ -248,11 +249,10 @@ template <int SWB> inline void fill_stage_desc(StageDesc &S, int p0, int TB)
     for (int r = 0; r < kRegAmps; r++) S.roff[r] = (uint16_t)swz<SWB>((uint32_t)r << p0);
 }
 
-template <typename R>
+template <typename R, int SWB = Vec2<R>::SWB>
 inline void fill_params(const PassPlan &plan, int nloc, const std::vector<GateOp> &gates, const double *mats /*32 doubles per matrix*/,
                         bool adjoint, PassParams<R> &P)
 {
-    constexpr int SWB = Vec2<R>::SWB;
     const int TB = plan.TB;
     const int TBITS = TB - kRegBits;
     std::memset(&P, 0, sizeof(P));

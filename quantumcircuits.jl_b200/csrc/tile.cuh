@@ -61,12 +61,17 @@ QCB_HD constexpr int slot_lo(int slot) { return slot == 1 ? 0 : (slot == 2 ? 2 :
 //   SWB = 3 (16 B chunks, 8 groups): the columns repeat with period 4 as 001, 010, 100, 111, so that ANY three of
 //            four consecutive index bits are linearly independent: a quarter warp that varies three bits of a 4-bit
 //            register window (stage loads, and the MMA operand loads of the backward pass) is conflict free.
+//   SWB = -3 (ComplexF64 tiles written by TMA with the 128-byte hardware swizzle, tile_tma.cuh): 16 B chunk index ^= row & 7,
+//            i.e. index bit b in {3,4,5} toggles group bit b - 3, higher bits toggle nothing: a register window at
+//            p0 >= 3 leaves the lane bits {0,1,2} (conflict free), windows at p0 < 3 see 2-way conflicts.
 template <int SWB> QCB_HD constexpr uint32_t bank_vector(int b)
 {
-    return SWB == 4 ? (1u << (b & 3)) : ((b & 3) == 3 ? 7u : (1u << (b & 3)));
+    return SWB == -3 ? (b < 3 ? (1u << b) : (b < 6 ? (1u << (b - 3)) : 0u))
+                     : SWB == 4 ? (1u << (b & 3)) : ((b & 3) == 3 ? 7u : (1u << (b & 3)));
 }
 template <int SWB> QCB_HD uint32_t swz(uint32_t e)
 {
+    if (SWB == -3) return e ^ ((e >> 3) & 7u);
     if (SWB == 3) {
         // index bits 3.. : fold in groups of 4 (bit i of h is index bit i + 3, i.e. column (i + 3) mod 4)
         const uint32_t h = e >> 3;
@@ -291,11 +296,10 @@ QCB_HD void tile_store(typename Vec2<R>::type *__restrict__ dst, const PassParam
     for (int i = 0; i < kRegAmps; i++) dst[g | P.ld_goff[i]] = sm[e ^ P.st_eoff[i]];
 }
 
-template <typename R, int TB>
+template <typename R, int TB, int SWB = Vec2<R>::SWB>
 QCB_HD void tile_stage(const PassParams<R> &P, int s, typename Vec2<R>::type *sm, uint32_t tid)
 {
     using V = typename Vec2<R>::type;
-    constexpr int SWB = Vec2<R>::SWB;
     constexpr int TBITS = TB - kRegBits;
     const StageDesc &S = P.stage[s];
     uint32_t e = 0;

@@ -892,3 +892,53 @@ extern "C" int emu_flip_measure(int dtype, int nloc, int n_total, const void *ps
     *nlevels = P.nlevels;
     return 0;
 }
+
+// ---- the fused gate pass on the TMA-fed kernel (tile_tma.cuh): the box load / store is emulated (ascending tile bits, 128-byte
+// hardware swizzle), the stage code is the device code with the stage programs fill_params<double, -3> builds ----------------
+#include "../../quantumcircuits.jl_b200/csrc/tile_tma.cuh"
+
+extern "C" int emu_apply_gates_tma(int nloc, void *psi_, int ngates, const int *q, const double *mats, int low_bits, int max_gates, int adjoint, int *stats)
+{
+    try {
+        std::vector<int> phys(nloc);
+        for (int i = 0; i < nloc; i++) phys[i] = i;
+        std::vector<GateOp> gates(ngates);
+        for (int g = 0; g < ngates; g++) gates[g] = GateOp{q[g], g};
+        SchedOptions opt;
+        opt.tile_bits = kTmaTB;
+        opt.low_bits = low_bits;
+        if (max_gates > 0) opt.max_gates_per_pass = max_gates;
+        std::vector<char> done;
+        std::vector<PassPlan> passes = plan_passes(nloc, phys, gates, opt, &done);
+        for (char d : done)
+            if (!d) return 2;
+        double2 *psi = (double2 *)psi_;
+        std::vector<double2> sm(1u << kTmaTB);
+        PassParams<double> *P = new PassParams<double>;
+        int ntma = 0;
+        for (const PassPlan &pl : passes) {
+            TmaPassGeom g;
+            if (!tma_pass_eligible(pl, nloc, g)) { delete P; return 4; } // every pass of a canonical state must be eligible
+            ntma++;
+            fill_params<double, -3>(pl, nloc, gates, mats, adjoint != 0, *P);
+            const int gap_bits = g.a2 - g.b1;
+            for (unsigned long long t = 0; t < (1ull << (nloc - kTmaTB)); t++) {
+                const unsigned long long base = ((t & ((1ull << gap_bits) - 1ull)) << g.b1) | ((t >> gap_bits) << g.b2);
+                auto gidx = [&](uint32_t e) { // box order: [0, b1) then [a2, b2)
+                    const unsigned long long lo = e & ((1u << g.b1) - 1u), hi = e >> g.b1;
+                    return base | lo | (hi << g.a2);
+                };
+                for (uint32_t e = 0; e < (1u << kTmaTB); e++) sm[swz<-3>(e)] = psi[gidx(e)];
+                for (int s = 0; s < P->nstages; s++)
+                    for (uint32_t tid = 0; tid < (uint32_t)kTmaStageThreads; tid++) tile_stage<double, kTmaTB, -3>(*P, s, sm.data(), tid);
+                for (uint32_t e = 0; e < (1u << kTmaTB); e++) psi[gidx(e)] = sm[swz<-3>(e)];
+            }
+        }
+        delete P;
+        if (stats) { stats[0] = (int)passes.size(); stats[1] = ntma; }
+        return 0;
+    } catch (const std::exception &e) {
+        std::fprintf(stderr, "emu tma: %s\n", e.what());
+        return 1;
+    }
+}

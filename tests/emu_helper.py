@@ -12,7 +12,7 @@ _lib = None
 
 
 def build(force=False):
-    srcs = [os.path.join(_HERE, "emu_tile.cu"), os.path.join(_CSRC, "tile.cuh"), os.path.join(_CSRC, "schedule.hpp"), os.path.join(_CSRC, "dist_plan.hpp"), os.path.join(_CSRC, "adjoint.cuh"), os.path.join(_CSRC, "adjoint_mma.cuh"), os.path.join(_CSRC, "gates_hd.cuh"), os.path.join(_CSRC, "measure_tile.cuh"), os.path.join(_CSRC, "measure_plan.hpp"), os.path.join(_CSRC, "kernels.cuh"), os.path.join(_CSRC, "flip_tile.cuh"), os.path.join(_CSRC, "tma.cuh")]
+    srcs = [os.path.join(_HERE, "emu_tile.cu"), os.path.join(_CSRC, "tile.cuh"), os.path.join(_CSRC, "schedule.hpp"), os.path.join(_CSRC, "dist_plan.hpp"), os.path.join(_CSRC, "adjoint.cuh"), os.path.join(_CSRC, "adjoint_mma.cuh"), os.path.join(_CSRC, "gates_hd.cuh"), os.path.join(_CSRC, "measure_tile.cuh"), os.path.join(_CSRC, "measure_plan.hpp"), os.path.join(_CSRC, "kernels.cuh"), os.path.join(_CSRC, "flip_tile.cuh"), os.path.join(_CSRC, "tma.cuh"), os.path.join(_CSRC, "tile_tma.cuh")]
     if force or not os.path.exists(_SO) or any(os.path.getmtime(_SO) < os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["nvcc", "-O2", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler",
                                "-fPIC", "-shared", "-o", _SO, srcs[0]], cwd=_HERE)
@@ -43,6 +43,21 @@ def apply_gates(psi, q0, mats, tile_bits, low_bits, phys=None, nloc=None, max_ga
                                stats.ctypes.data_as(C.c_void_p))
     if rc:
         raise RuntimeError(f"emu_apply_gates rc={rc}")
+    return psi, (int(stats[0]), int(stats[1]))
+
+
+def apply_gates_tma(psi, q0, mats, low_bits=3, max_gates=0, adjoint=False):
+    """The TMA-fed gate pass (tile_tma.cuh) on a canonical ComplexF64 state with emulated box loads / stores."""
+    psi = np.ascontiguousarray(psi, dtype=np.complex128).copy()
+    n = int(psi.size).bit_length() - 1
+    q0 = np.ascontiguousarray(q0, dtype=np.int32)
+    m = np.ascontiguousarray(np.stack([np.asarray(M, dtype=np.complex128).reshape(-1, order="F") for M in mats]))
+    stats = np.zeros(4, dtype=np.int32)
+    rc = lib().emu_apply_gates_tma(C.c_int(n), psi.ctypes.data_as(C.c_void_p), C.c_int(len(q0)), q0.ctypes.data_as(C.c_void_p),
+                                   m.ctypes.data_as(C.c_void_p), C.c_int(low_bits), C.c_int(max_gates), C.c_int(1 if adjoint else 0),
+                                   stats.ctypes.data_as(C.c_void_p))
+    if rc:
+        raise RuntimeError(f"emu_apply_gates_tma rc={rc}")
     return psi, (int(stats[0]), int(stats[1]))
 
 

@@ -485,3 +485,24 @@ def test_emu_flip_measure_simulated_shards(emu, oracle):
             top += float(np.sum(w * (np.conj(psi[idx ^ (1 << i)]) * psi).real))
         ref = (oracle.measure_tfim(psi, *hp) if kind == 0 else oracle.measure_east(psi, *hp)).real
         assert abs(tot + coef * top - ref) < 1e-12 * max(1.0, abs(ref))
+
+
+# ---- TMA-fed gate pass (tile_tma.cuh): stage programs with the hardware swizzle, emulated box loads / stores ------------------
+@pytest.mark.parametrize("n,layers,maxg", [(11, 6, 0), (12, 9, 0), (13, 12, 3), (14, 7, 0), (15, 5, 2), (16, 4, 0)])
+def test_emu_tma_gate_pass(emu, oracle, n, layers, maxg):
+    rng = np.random.default_rng(9000 + 31 * n + layers)
+    q0 = [j - 1 for l in range(1, layers + 1) for j in range(1 + (l - 1) % 2, n, 2)]
+    mats = []
+    for _ in q0:
+        u = rng.standard_normal((4, 4)) + 1j * rng.standard_normal((4, 4))
+        mats.append(u / np.linalg.det(u) ** 0.25)  # non-unitary "unitaries", as in test/correctness_tests.jl:90-98
+    psi0 = rand_state(rng, n)
+    ref = psi0
+    for q, M in zip(q0, mats):
+        ref = oracle.apply_2q(ref, M, int(q) + 1)
+    out, (npass, ntma) = emu.apply_gates_tma(psi0, q0, mats, max_gates=maxg)
+    assert ntma == npass and npass >= 1
+    assert rel(out, ref) < 1e-12
+    # the LDG form of the same plan gives the same numbers bit for bit (same stage programs, same arithmetic order)
+    out2, _ = emu.apply_gates(psi0, q0, mats, 11, 3, max_gates=maxg)
+    assert np.array_equal(out, out2)

@@ -52,6 +52,7 @@ def _defaults():
     qc.set_option("adjoint_prog_host", 0)
     qc.set_option("contract_coop", 1)
     qc.set_option("measure_tma", 1)
+    qc.set_option("pass_tma", 1)
     yield
 
 
@@ -495,6 +496,53 @@ def test_propagate_forwards_and_adjoint_range(oracle):
 
     _apply_circuit_inplace(res, c, first=gate_idx - 1, adjoint=True)  # undo
     assert rel(res.to_numpy(), psi0) < 1e-12
+
+
+# ---- src/apply.jl:144-182 : right_apply_gate!(M', M, gate) (operator evolution M' = M U) as one gate pass on the 2n-qubit tensor
+@pytest.mark.parametrize("nbits", [2, 3, 6, 9])
+@pytest.mark.parametrize("dtype", [np.complex128, np.complex64])
+def test_right_apply_gate(nbits, dtype):
+    rng = np.random.default_rng(1440 + nbits)
+    M = (rng.standard_normal((2 ** nbits, 2 ** nbits)) + 1j * rng.standard_normal((2 ** nbits, 2 ** nbits))).astype(dtype)
+    for K in sorted({1, nbits - 1, max(1, nbits // 2)}):
+        u4 = rand_nonunitary(rng, 4)
+        gate = qc.Localised2SpinAdjGate(qc.Generic2SpinGate(u4.reshape(2, 2, 2, 2, order="F")), K)
+        out = np.empty_like(M)
+        res = qc.right_apply_gate_(out, M, gate)
+        assert res is out
+        ref = onp.right_apply_gate(M.astype(np.complex128), u4, K)
+        assert np.linalg.norm(out - ref) / np.linalg.norm(ref) < TOL[dtype]
+    with pytest.raises(ValueError):
+        qc.right_apply_gate_(np.empty((4, 2), dtype=dtype), M, gate)  # "M′ must be the same size as M"
+    with pytest.raises(AssertionError):
+        qc.right_apply_gate_(np.empty_like(M), M, qc.Localised2SpinAdjGate(qc.Generic2SpinGate(u4.reshape(2, 2, 2, 2, order="F")), nbits))
+
+
+# ---- the TMA-fed persistent form of the gate pass (tile_tma.cuh, default for ComplexF64) == the LDG / STS form, bit for bit
+# (same stage programs and arithmetic order; only the tile movement and the shared-memory swizzle differ), and == oracle
+@pytest.mark.parametrize("n,layers,cap", [(11, 8, 0), (12, 20, 0), (14, 9, 3), (17, 12, 0), (20, 6, 2), (22, 10, 0), (24, 5, 4)])
+def test_tma_gate_pass_equals_ldg_pass(oracle, n, layers, cap):
+    rng = np.random.default_rng(1100 + 7 * n + layers)
+    c = circuit(n, layers, rng)
+    psi0 = rand_state(rng, n)
+    if cap:
+        qc.set_option("max_gates_per_pass", cap)
+    outs = {}
+    for mode in (1, 0):
+        qc.set_option("pass_tma", mode)
+        st = qc.B200State(psi0)
+        qc.apply_(st, st, c)
+        assert (qc.get_stat("tma_passes") == qc.get_stat("passes")) if mode else (qc.get_stat("tma_passes") == 0)
+        outs[mode] = st.to_numpy()
+        # out of place: the first pass reads psi and writes psi' through two tensor maps
+        dst = st.similar()
+        src = qc.B200State(psi0)
+        qc.apply_(dst, src, c)
+        assert np.array_equal(dst.to_numpy(), outs[mode]) and np.array_equal(src.to_numpy(), psi0)
+    qc.set_option("pass_tma", 1)
+    assert np.array_equal(outs[0], outs[1])
+    if n <= 22:
+        assert rel(outs[1], oracle.apply_brickwork(psi0, n, layers, c.gate_angles)) < 1e-12
 
 
 # ---- size-independent properties at sizes the oracle cannot check in seconds

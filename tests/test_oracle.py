@@ -263,3 +263,20 @@ def test_threads_do_not_change_results(oracle):
     oracle.set_threads(0)
     b = oracle.apply_brickwork(psi0, nbits, nlayers, angles)
     np.testing.assert_array_equal(a, b)
+
+
+# ---- src/apply.jl:144-182 : right_apply_gate!(M', M, gate) is M * U (operator evolution), restated literally -----------------
+@pytest.mark.parametrize("nbits", [2, 3, 5])
+def test_right_apply_gate_is_right_multiplication(nbits):
+    rng = np.random.default_rng(144 + nbits)
+    M = rng.standard_normal((2 ** nbits, 2 ** nbits)) + 1j * rng.standard_normal((2 ** nbits, 2 ** nbits))
+    for K in range(1, nbits):
+        u4 = rng.standard_normal((4, 4)) + 1j * rng.standard_normal((4, 4))
+        got = onp.right_apply_gate(M, u4, K)
+        U = onp.convert_gates_to_matrix(nbits, [(K, u4)])
+        np.testing.assert_allclose(got, M @ U, atol=1e-12)
+    # the identity evolved through a brick layer reproduces the layer's operator (the use the reference has for it:
+    # combine_gates / build_identity, src/utils.jl)
+    I = np.eye(2 ** nbits, dtype=np.complex128)
+    u4 = rng.standard_normal((4, 4)) + 1j * rng.standard_normal((4, 4))
+    np.testing.assert_allclose(onp.right_apply_gate(I, u4, 1), onp.convert_gates_to_matrix(nbits, [(1, u4)]), atol=1e-13)
