@@ -89,6 +89,7 @@ int qcb_state_nqubits(const qcb_state *s, int *out);
 int qcb_state_dtype(const qcb_state *s, int *out);
 int qcb_state_device_ptr(const qcb_state *s, void **out);
 int qcb_state_set_zero_state(qcb_state *s);                   /* |0...0>          */
+int qcb_state_fill_zero(qcb_state *s);                        /* psi' .= 0 (apply.jl:135) */
 int qcb_state_upload(qcb_state *s, const void *host);         /* Array -> device  */
 int qcb_state_download(const qcb_state *s, void *host);       /* device -> Array  */
 int qcb_state_copy(qcb_state *dst, const qcb_state *src);     /* psi'' .= psi     */
@@ -112,6 +113,9 @@ int qcb_apply_2q(qcb_state *s, const double *u32, int K);
 /* apply(psi, gates::AbstractArray)  src/apply.jl:5-18 : mixed list, fused on chip.
  * arity[g] in {1,2}; mats holds 32 doubles per gate (a 1-qubit gate uses the first 8). */
 int qcb_apply_gates(qcb_state *s, int ngates, const int *K, const int *arity, const double *mats);
+/* The same with distinct states: dst = gates(src), src untouched -- apply!(psi', psi, gate) src/apply.jl:20,39 and
+ * apply!(cache, psi', psi, gate) :117,:121 without the copy / zero fill (:135) in front of the pass. */
+int qcb_apply_gates_from(qcb_state *dst, const qcb_state *src, int ngates, const int *K, const int *arity, const double *mats);
 /* apply!(cache, psi', psi, circuit::GenericBrickworkCircuit)  src/circuits.jl:19-31.
  * first_gate/last_gate (0-based, half-open) select a slice of the circuit: (0, G) is the
  * whole circuit; propagate_forwards! (src/gradients.jl:54-71) is (gate_idx-1, G). */

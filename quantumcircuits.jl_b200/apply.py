@@ -35,8 +35,11 @@ def _check_pair(psi_out, psi):
         raise ValueError("ψ′ must be the same size as ψ.")  # src/apply.jl:108
 
 
-def _apply_list_inplace(state, gates):
+def _apply_list_inplace(state, gates, src=None):
+    """gates on `state` in place, or (src given) state = gates(src) with src untouched: the first fused pass reads src."""
     if not gates:
+        if src is not None and src is not state:
+            state.assign(src)
         return
     G = len(gates)
     K = np.empty(G, dtype=np.int32)
@@ -46,6 +49,10 @@ def _apply_list_inplace(state, gates):
         if not isinstance(g, (Localised1SpinGate, Localised2SpinAdjGate)):
             raise TypeError("gates must be Localised1SpinGate or Localised2SpinAdjGate")
         ar[i], K[i], mats[i] = gate_abi_block(g)
+    if src is not None and src is not state:
+        _lib.check(_lib.lib().qcb_apply_gates_from(state._handle, src._handle, C.c_int(G), K.ctypes.data_as(C.c_void_p),
+                                                   ar.ctypes.data_as(C.c_void_p), mats.ctypes.data_as(C.c_void_p)))
+        return
     _lib.check(_lib.lib().qcb_apply_gates(state._handle, C.c_int(G), K.ctypes.data_as(C.c_void_p),
                                           ar.ctypes.data_as(C.c_void_p), mats.ctypes.data_as(C.c_void_p)))
 
@@ -76,12 +83,12 @@ def apply_(*args):
     if isinstance(op, GenericBrickworkCircuit) and psi_out is not psi and isinstance(psi, B200State):
         _apply_circuit_from(psi_out, psi, op)  # psi' = circuit(psi): the first pass reads psi, no copy
         return psi_out
-    if psi_out is not psi:
-        psi_out.assign(psi)
     if isinstance(op, GenericBrickworkCircuit):
+        if psi_out is not psi:
+            psi_out.assign(psi)
         _apply_circuit_inplace(psi_out, op)
     else:
-        _apply_list_inplace(psi_out, [op])
+        _apply_list_inplace(psi_out, [op], src=psi)  # psi' = gate(psi): no copy, no zero fill (src/apply.jl:135)
     return psi_out
 
 
@@ -96,13 +103,13 @@ def apply(psi, op):
         st = psi.similar()
         _apply_circuit_from(st, psi, op)
         return st
+    gates = [op] if isinstance(op, AbstractGate) else list(op)
+    if not host:
+        st = psi.similar()
+        _apply_list_inplace(st, gates, src=psi)  # the first fused pass reads psi: no copy of the state
+        return st
     st = B200State(psi)
-    if isinstance(op, GenericBrickworkCircuit):
-        _apply_circuit_inplace(st, op)
-    elif isinstance(op, AbstractGate):
-        _apply_list_inplace(st, [op])
-    else:
-        _apply_list_inplace(st, list(op))
+    _apply_list_inplace(st, gates)
     if host:
         out = st.to_numpy()
         return out.reshape(np.shape(psi), order="F") if np.ndim(psi) > 1 else out

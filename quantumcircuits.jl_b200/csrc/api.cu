@@ -885,6 +885,15 @@ int qcb_state_set_zero_state(qcb_state *s)
     return QCB_OK;
 }
 
+// psi' .= 0 (src/apply.jl:135) for callers that keep the reference's explicit zero fill
+int qcb_state_fill_zero(qcb_state *s)
+{
+    QCB_REQUIRE_INIT();
+    QCB_TRY(check_state(s));
+    QCB_CUDA(cudaMemsetAsync(s->d, 0, s->bytes, ctx().stream));
+    return QCB_OK;
+}
+
 int qcb_state_upload(qcb_state *s, const void *host)
 {
     QCB_REQUIRE_INIT();
@@ -981,14 +990,13 @@ int qcb_general_unitary_gate_gradient(const double *angles15, const double *env3
 int qcb_brickwork_num_gates(int nbits, int nlayers) { return (int)brickwork_positions(nbits, nlayers).size(); }
 
 // ---- gate application ---------------------------------------------------------------------
-int qcb_apply_gates(qcb_state *s, int ngates, const int *K, const int *arity, const double *mats_in)
+static int apply_gates_impl(qcb_state *s, const void *first_src, int ngates, const int *K, const int *arity, const double *mats_in)
 {
-    QCB_REQUIRE_INIT();
-    QCB_TRY(check_state(s));
     if (ngates < 0 || (ngates > 0 && (!K || !arity || !mats_in))) return set_error(QCB_EINVAL, "bad gate list");
     const int n = s->n;
     // a lone 1-qubit state has no pair to embed into: dedicated kernel
     if (n == 1) {
+        if (first_src) QCB_CUDA(cudaMemcpyAsync(s->d, first_src, s->bytes, cudaMemcpyDeviceToDevice, ctx().stream));
         for (int g = 0; g < ngates; g++) {
             if (arity[g] != 1 || K[g] != 1) return set_error(QCB_EINVAL, "The gate cannot be applied as it sits outside the qubit space.");
             const double *u = mats_in + 32 * (size_t)g;
@@ -1022,7 +1030,24 @@ int qcb_apply_gates(qcb_state *s, int ngates, const int *K, const int *arity, co
         } else
             return set_error(QCB_EINVAL, "gate %d: arity must be 1 or 2", g);
     }
-    return run_gate_list(s, gates, mats.data(), false);
+    return run_gate_list(s, gates, mats.data(), false, first_src);
+}
+int qcb_apply_gates(qcb_state *s, int ngates, const int *K, const int *arity, const double *mats_in)
+{
+    QCB_REQUIRE_INIT();
+    QCB_TRY(check_state(s));
+    return apply_gates_impl(s, nullptr, ngates, K, arity, mats_in);
+}
+// apply!(psi', psi, gate) / apply!(cache, psi', psi, gate) with distinct states (src/apply.jl:20,39,117,121): dst = gates(src), src
+// untouched; the first fused pass reads src and writes dst (no copy, no zero fill of psi' -- src/apply.jl:135)
+int qcb_apply_gates_from(qcb_state *dst, const qcb_state *src, int ngates, const int *K, const int *arity, const double *mats_in)
+{
+    QCB_REQUIRE_INIT();
+    QCB_TRY(check_state(dst));
+    QCB_TRY(check_state(src));
+    if (dst == src || dst->d == src->d) return apply_gates_impl(dst, nullptr, ngates, K, arity, mats_in);
+    if (dst->n != src->n || dst->dtype != src->dtype || dst->sharded || src->sharded) return set_error(QCB_EINVAL, "psi' must be the same size as psi.");
+    return apply_gates_impl(dst, src->d, ngates, K, arity, mats_in);
 }
 
 int qcb_apply_1q(qcb_state *s, const double *u8, int K)

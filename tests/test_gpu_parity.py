@@ -139,6 +139,30 @@ def test_mixed_gate_list():
     assert rel(qc.apply(psi, gl), expected) < 1e-12
 
 
+# ---- apply!(psi', psi, gate) with distinct states (src/apply.jl:20,39,117): psi' = gate(psi), psi untouched; no copy in front
+@pytest.mark.parametrize("n", [1, 3, 8, 12, 15])
+@pytest.mark.parametrize("dtype", [np.complex128, np.complex64])
+def test_out_of_place_gate_apply(n, dtype):
+    rng = np.random.default_rng(170 + n)
+    psi0 = rand_state(rng, n, dtype)
+    src = qc.B200State(psi0)
+    dst = src.similar()
+    m1 = rand_nonunitary(rng, 2)
+    res = qc.apply_(dst, src, qc.Localised1SpinGate(qc.Generic1SpinGate(m1), n))
+    assert res is dst and np.array_equal(src.to_numpy(), psi0)
+    assert rel(dst.to_numpy(), onp.apply_1q(psi0.astype(np.complex128), m1, n)) < TOL[dtype]
+    if n >= 2:
+        for K in sorted({1, n - 1}):
+            m2 = rand_nonunitary(rng, 4) / 3
+            g = qc.Localised2SpinAdjGate(qc.Generic2SpinGate(m2.reshape(2, 2, 2, 2, order="F")), K)
+            qc.apply_(qc.construct_apply_cache(src), dst, src, g)
+            assert np.array_equal(src.to_numpy(), psi0)
+            assert rel(dst.to_numpy(), onp.apply_2q(psi0.astype(np.complex128), m2, K)) < TOL[dtype]
+            out = qc.apply(src, [g, g])  # device state in -> new device state out, input untouched
+            assert np.array_equal(src.to_numpy(), psi0)
+            assert rel(out.to_numpy(), onp.apply_2q(onp.apply_2q(psi0.astype(np.complex128), m2, K), m2, K)) < TOL[dtype]
+
+
 # ---- src/apply.jl:106-115 error behaviour
 def test_error_paths():
     psi = qc.B200State(qc.zero_state_tensor(4))
