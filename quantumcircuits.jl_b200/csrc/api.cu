@@ -737,6 +737,8 @@ int qcb_set_option(const char *key, long value)
     } else if (k == "adjoint_tile_bits") {
         if (value != 0 && (value < kMinTB || value > 12)) return set_error(QCB_EINVAL, "adjoint_tile_bits must be 0 (auto) or in [%d, 12]", kMinTB);
         c.adjoint_tile_bits = value;
+    } else if (k == "adjoint_tf32") {
+        c.adjoint_tf32 = value ? 1 : 0;
     } else if (k == "adjoint_mma") {
         c.adjoint_mma = value ? 1 : 0;
     } else if (k == "pass_tma") {
@@ -744,6 +746,9 @@ int qcb_set_option(const char *key, long value)
         c.pass_tma = value;
     } else if (k == "pass_tma_max_stages") {
         c.pass_tma_max_stages = value;
+    } else if (k == "tma_l2_promotion") {
+        if (value < 0 || value > 2) return set_error(QCB_EINVAL, "tma_l2_promotion must be 0 (none), 1 (128 bytes) or 2 (256 bytes)");
+        tma_strided_promotion() = (int)value;
     } else if (k == "measure_tma") {
         c.measure_tma = value ? 1 : 0;
     } else if (k == "measure_persistent") {

@@ -454,6 +454,7 @@ template <typename R> inline int flip_make_maps(FlipMaps &M, const void *base, c
         d.dims[2] = 1ull << kFlipWin;                          d.strides[1] = (unsigned long long)sizeof(R) * 2ull << L.w0;
         d.dims[3] = 1ull << (P.n - L.w0 - kFlipWin);           d.strides[2] = (unsigned long long)sizeof(R) * 2ull << (L.w0 + kFlipWin);
         d.box[0] = inner; d.box[1] = 1; d.box[2] = 256; d.box[3] = 1;
+        d.strided_rows = true;
         if (tma_encode(&M.m[l], base, f64, d, why)) return 1;
     }
     return 0;

@@ -7,6 +7,7 @@
 
 #include <type_traits>
 
+#include "adjoint_f32.cuh"
 #include "adjoint_mma.cuh"
 #include "kernels.cuh"
 #include "qcb_internal.hpp"
@@ -300,6 +301,34 @@ template <typename R, int TB> static int launch_adjoint(qcb_state *psi, qcb_stat
     return QCB_OK;
 }
 
+// ComplexF32: windows in registers, reduction on TF32-split tensor-core MMAs (adjoint_f32.cuh); same partial layout
+template <int TB> static int launch_adjoint_f32(qcb_state *psi, qcb_state *lam, const AdjParams<float> &A, const EnvIds &ids, double *d_env)
+{
+    constexpr int NT = 1 << (TB - kRegBits);
+    constexpr int NW = NT / 32;
+    // two windows (64 registers) + operands per thread: <= 128 registers; shared memory: two tiles + accumulators
+    constexpr int MINB = TB >= 12 ? 2 : (TB == 11 ? 4 : 8);
+    auto kern = adjoint_pass_f32_kernel<TB, MINB>;
+    const size_t smem = 2 * (sizeof(float2) << TB) + sizeof(double) * NW * kAdjMaxGates * 32;
+    static bool attr_set = false;
+    static int ctas_per_sm = 1;
+    if (!attr_set) {
+        QCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        QCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, NT, smem));
+        if (ctas_per_sm < 1) ctas_per_sm = 1;
+        attr_set = true;
+    }
+    const unsigned long long ntiles = 1ull << (psi->nloc - TB);
+    const unsigned grid = (unsigned)std::min<unsigned long long>(ntiles, (unsigned long long)ctx().sm_count * ctas_per_sm);
+    QCB_TRY(ensure_partial((size_t)grid * kAdjMaxGates * 32));
+    kern<<<grid, NT, smem, ctx().stream>>>((float2 *)psi->d, (float2 *)lam->d, A, ntiles, ctx().d_partial);
+    QCB_CUDA(cudaGetLastError());
+    k_env_final<<<ids.n * 32, 128, 0, ctx().stream>>>(ctx().d_partial, (int)grid, ids, d_env);
+    QCB_CUDA(cudaGetLastError());
+    count_launch(2);
+    return QCB_OK;
+}
+
 // ComplexF64: the tensor-core form (adjoint_mma.cuh); env rows hold the post-gate matrix M, see run_adjoint_fused.
 // Final reduction of its raw accumulator rows, fixed summation order.  Few rows (small states: a handful of CTAs): one
 // block per gate sums and combines in one launch.  Many rows: one block per (gate, raw element) so that the whole GPU
@@ -392,6 +421,17 @@ template <typename R> static int launch_adjoint_any(qcb_state *psi, qcb_state *l
 
 template <> int launch_adjoint_any<float>(qcb_state *psi, qcb_state *lam, int TB, bool, AdjParams<float> &A, const EnvIds &ids, double *d_env)
 {
+    if (ctx().adjoint_tf32) {
+        for (int k = 0; k < TB; k++)
+            if (A.P.ld_lpos[k] != A.P.st_lpos[k]) return set_error(QCB_EINVAL, "the backward pass does not permute bits");
+        switch (TB) {
+        case 9: return launch_adjoint_f32<9>(psi, lam, A, ids, d_env);
+        case 10: return launch_adjoint_f32<10>(psi, lam, A, ids, d_env);
+        case 11: return launch_adjoint_f32<11>(psi, lam, A, ids, d_env);
+        case 12: return launch_adjoint_f32<12>(psi, lam, A, ids, d_env);
+        default: return set_error(QCB_EINVAL, "unsupported tile size %d for the backward pass", TB);
+        }
+    }
     switch (TB) {
     case 9: return launch_adjoint<float, 9>(psi, lam, A, ids, d_env);
     case 10: return launch_adjoint<float, 10>(psi, lam, A, ids, d_env);

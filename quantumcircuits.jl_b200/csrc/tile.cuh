@@ -296,7 +296,9 @@ QCB_HD void tile_store(typename Vec2<R>::type *__restrict__ dst, const PassParam
     for (int i = 0; i < kRegAmps; i++) dst[g | P.ld_goff[i]] = sm[e ^ P.st_eoff[i]];
 }
 
-template <typename R, int TB, int SWB = Vec2<R>::SWB>
+// FORGET: make the compiler forget the 16 element addresses between the loads and the stores (they are one XOR away from
+// `e`); the persistent kernels need those registers for their ring bookkeeping
+template <typename R, int TB, int SWB = Vec2<R>::SWB, bool FORGET = false>
 QCB_HD void tile_stage(const PassParams<R> &P, int s, typename Vec2<R>::type *sm, uint32_t tid)
 {
     using V = typename Vec2<R>::type;
@@ -314,6 +316,9 @@ QCB_HD void tile_stage(const PassParams<R> &P, int s, typename Vec2<R>::type *sm
     if (mask & 2u) apply_window_gate<0, R, V>(a, P.U[s * kSlots + 1]);
     if (mask & 4u) apply_window_gate<2, R, V>(a, P.U[s * kSlots + 2]);
     if (mask & 8u) apply_window_gate<1, R, V>(a, P.U[s * kSlots + 3]);
+#if defined(__CUDA_ARCH__)
+    if (FORGET) asm volatile("" : "+r"(e));
+#endif
 #pragma unroll
     for (int r = 0; r < kRegAmps; r++) sm[e ^ S.roff[r]] = a[r];
 }

@@ -64,11 +64,14 @@ inline int tma_pass_map(CUtensorMap *out, const void *base, const TmaPassGeom &g
     d.dims[3] = 1ull << (g.b2 - g.a2);     d.strides[2] = 16ull << g.a2;
     d.dims[4] = 1ull << (g.n - g.b2);      d.strides[3] = g.b2 < g.n ? (16ull << g.b2) : (16ull << (g.n - 1));
     d.box[0] = 16; d.box[1] = (unsigned)d.dims[1]; d.box[2] = 1; d.box[3] = (unsigned)d.dims[3]; d.box[4] = 1;
+    d.strided_rows = g.b1 < 4; // run 1 shorter than 256 bytes
     return tma_encode(out, base, true, d, why);
 }
 
+// register budget: the stage body alone fills the 128 registers tile_pass_kernel gets; the ring bookkeeping on top of it
+// spilled inside the stage loop under the launch-bound-derived cap (104 bytes of stack).  3 CTAs x 160 threads x 136 <= 64 K.
 template <int MINB>
-__global__ void __launch_bounds__(kTmaStageThreads + 32, MINB)
+__global__ void __maxnreg__(136)
 tile_pass_tma_kernel(const __grid_constant__ CUtensorMap map_ld, const __grid_constant__ CUtensorMap map_st,
                      const __grid_constant__ PassParams<double> P, int gap_bits, unsigned long long ntiles)
 {
@@ -126,7 +129,7 @@ tile_pass_tma_kernel(const __grid_constant__ CUtensorMap map_ld, const __grid_co
 #pragma unroll 1
         for (int s = 0; s < P.nstages; s++) {
             if (s) tma::named_bar_sync(1, kTmaStageThreads);
-            tile_stage<double, kTmaTB, -3>(P, s, sm, tid);
+            tile_stage<double, kTmaTB, -3, true>(P, s, sm, tid);
         }
         tma::fence_proxy_async(); // this thread's writes -> visible to the TMA store
         tma::mbar_arrive(&done[slot]);

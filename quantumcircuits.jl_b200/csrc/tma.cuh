@@ -108,7 +108,17 @@ struct TmaDims {
     unsigned long long dims[5] = {1, 1, 1, 1, 1};
     unsigned long long strides[4] = {128, 128, 128, 128}; // bytes, for dims 1..rank-1
     unsigned box[5] = {1, 1, 1, 1, 1};
+    // the 128-byte rows of a box are NOT adjacent in memory (strided window tiles): a 256-byte L2 promotion would pull a
+    // second, unwanted line out of HBM for every row.  Contiguous boxes keep the 256-byte promotion.
+    bool strided_rows = false;
 };
+
+// L2 promotion for strided boxes: 0 none, 1 = 128 bytes (default), 2 = 256 bytes (option "tma_l2_promotion")
+inline int &tma_strided_promotion()
+{
+    static int v = 1;
+    return v;
+}
 
 // returns 0 on success; on failure a short reason in *why (static string)
 inline int tma_encode(CUtensorMap *out, const void *base, bool f64, const TmaDims &d, const char **why)
@@ -130,8 +140,10 @@ inline int tma_encode(CUtensorMap *out, const void *base, bool f64, const TmaDim
     cuuint32_t bx[5], es[5];
     for (int i = 0; i < 5; i++) { gd[i] = d.dims[i]; bx[i] = d.box[i]; es[i] = 1; }
     for (int i = 0; i < 4; i++) gs[i] = d.strides[i];
+    const int pv = d.strided_rows ? tma_strided_promotion() : 2;
+    const CUtensorMapL2promotion promo = pv == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : (pv == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_NONE);
     const CUresult r = fn(out, f64 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)d.rank, const_cast<void *>(base), gd, gs, bx,
-                          es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                          es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         if (why) *why = "cuTensorMapEncodeTiled rejected the tensor description";
         return 2;

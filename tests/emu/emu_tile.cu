@@ -356,6 +356,75 @@ extern "C" int emu_adjoint_sweep(int dtype, int n, void *psi, void *lam, int nga
     }
 }
 
+// ---- ComplexF32 backward pass with windows in registers and TF32-split reduction MMAs (adjoint_f32.cuh) -----------------
+#include "../../quantumcircuits.jl_b200/csrc/adjoint_f32.cuh"
+
+template <int TB>
+static void run_adjoint_pass_f32(float2 *psi, float2 *lam, int nloc, const AdjParams<float> &A, double *acc_out)
+{
+    const uint32_t NT = 1u << (TB - kRegBits);
+    const int NW = (int)NT / 32;
+    const unsigned long long ntiles = 1ull << (nloc - TB);
+    std::vector<float2> smP(1u << TB), smL(1u << TB);
+    std::vector<double> acc((size_t)NW * kAdjMaxGates * 32, 0.0);
+    for (unsigned long long b = 0; b < ntiles; b++) {
+        for (uint32_t t = 0; t < NT; t++) { tile_load<float, TB>(psi, A.P, smP.data(), t, b); tile_load<float, TB>(lam, A.P, smL.data(), t, b); }
+        for (int s = 0; s < A.P.nstages; s++) adjoint_stage_f32_host<TB>(A, s, smP.data(), smL.data(), acc.data());
+        for (uint32_t t = 0; t < NT; t++) { tile_store<float, TB>(psi, A.P, smP.data(), t, b); tile_store<float, TB>(lam, A.P, smL.data(), t, b); }
+    }
+    for (int i = 0; i < kAdjMaxGates * 32; i++) {
+        double t = 0;
+        for (int w = 0; w < NW; w++) t += acc[(size_t)w * kAdjMaxGates * 32 + i];
+        acc_out[i] = t;
+    }
+}
+
+extern "C" int emu_adjoint_sweep_f32(int n, void *psi, void *lam, int ngates, const int *q, const double *mats, int tile_bits, int low_bits,
+                                     double *env_out)
+{
+    try {
+        std::vector<GateOp> rev(ngates);
+        for (int i = 0; i < ngates; i++) rev[i] = GateOp{q[ngates - 1 - i], ngates - 1 - i};
+        std::vector<int> phys(n);
+        for (int i = 0; i < n; i++) phys[i] = i;
+        SchedOptions opt;
+        opt.tile_bits = tile_bits; opt.low_bits = low_bits; opt.max_gates_per_pass = kAdjMaxGates;
+        std::vector<char> done;
+        std::vector<PassPlan> plans = plan_passes(n, phys, rev, opt, &done);
+        for (char d : done) if (!d) return 2;
+        AdjParams<float> *A = new AdjParams<float>;
+        int rc = 0;
+        for (const PassPlan &pl : plans) {
+            fill_params<float>(pl, n, rev, mats, true, A->P);
+            int ids[kAdjMaxGates], nid = 0;
+            std::memset(A->slot_gate, 0, sizeof A->slot_gate);
+            for (size_t st = 0; st < pl.stages.size(); st++)
+                for (int slot = 0; slot < kSlots; slot++) {
+                    const int g = pl.stages[st].gate[slot];
+                    if (g < 0) continue;
+                    A->slot_gate[st * kSlots + slot] = (uint8_t)nid;
+                    ids[nid++] = rev[g].mat;
+                }
+            A->ngates = nid;
+            std::vector<double> acc(kAdjMaxGates * 32, 0.0);
+            switch (pl.TB) {
+#define CASE(T) case T: run_adjoint_pass_f32<T>((float2 *)psi, (float2 *)lam, n, *A, acc.data()); break;
+            CASE(9) CASE(10) CASE(11) CASE(12)
+#undef CASE
+            default: rc = 3;
+            }
+            if (rc) break;
+            for (int k = 0; k < nid; k++)
+                for (int i = 0; i < 32; i++) env_out[(size_t)ids[k] * 32 + i] = acc[k * 32 + i];
+        }
+        delete A;
+        return rc;
+    } catch (const std::exception &e) {
+        std::fprintf(stderr, "emu adjoint f32: %s\n", e.what());
+        return 1;
+    }
+}
+
 // ---- the tensor-core form of the same pass (adjoint_mma.cuh): software model of the MMA fragment layout ---------------
 template <int TB, int NW>
 static void run_adjoint_pass_mma(double2 *psi, double2 *lam, int nloc, const AdjMmaParams &M, double *acc_out, long long *conflicts)

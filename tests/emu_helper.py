@@ -12,7 +12,7 @@ _lib = None
 
 
 def build(force=False):
-    srcs = [os.path.join(_HERE, "emu_tile.cu"), os.path.join(_CSRC, "tile.cuh"), os.path.join(_CSRC, "schedule.hpp"), os.path.join(_CSRC, "dist_plan.hpp"), os.path.join(_CSRC, "adjoint.cuh"), os.path.join(_CSRC, "adjoint_mma.cuh"), os.path.join(_CSRC, "gates_hd.cuh"), os.path.join(_CSRC, "measure_tile.cuh"), os.path.join(_CSRC, "measure_plan.hpp"), os.path.join(_CSRC, "kernels.cuh"), os.path.join(_CSRC, "flip_tile.cuh"), os.path.join(_CSRC, "tma.cuh"), os.path.join(_CSRC, "tile_tma.cuh")]
+    srcs = [os.path.join(_HERE, "emu_tile.cu"), os.path.join(_CSRC, "tile.cuh"), os.path.join(_CSRC, "schedule.hpp"), os.path.join(_CSRC, "dist_plan.hpp"), os.path.join(_CSRC, "adjoint.cuh"), os.path.join(_CSRC, "adjoint_mma.cuh"), os.path.join(_CSRC, "adjoint_f32.cuh"), os.path.join(_CSRC, "gates_hd.cuh"), os.path.join(_CSRC, "measure_tile.cuh"), os.path.join(_CSRC, "measure_plan.hpp"), os.path.join(_CSRC, "kernels.cuh"), os.path.join(_CSRC, "flip_tile.cuh"), os.path.join(_CSRC, "tma.cuh"), os.path.join(_CSRC, "tile_tma.cuh")]
     if force or not os.path.exists(_SO) or any(os.path.getmtime(_SO) < os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["nvcc", "-O2", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler",
                                "-fPIC", "-shared", "-o", _SO, srcs[0]], cwd=_HERE)
@@ -108,6 +108,24 @@ def adjoint_sweep(psi, lam, q0, mats, tile_bits, low_bits):
     if rc:
         raise RuntimeError(f"emu_adjoint_sweep rc={rc}")
     envc = (env[:, 0::2] + 1j * env[:, 1::2]).reshape(len(q0), 4, 4).transpose(0, 2, 1)  # stored column-major r + 4c
+    return psi, lam, envc
+
+
+def adjoint_sweep_f32(psi, lam, q0, mats, tile_bits, low_bits):
+    """ComplexF32 backward sweep with register windows and TF32-split reduction MMAs (adjoint_f32.cuh): returns
+    (psi_0, lam_0, env[G, 4, 4])."""
+    psi = np.ascontiguousarray(psi, dtype=np.complex64).copy()
+    lam = np.ascontiguousarray(lam, dtype=np.complex64).copy()
+    n = int(psi.size).bit_length() - 1
+    q0 = np.ascontiguousarray(q0, dtype=np.int32)
+    m = np.ascontiguousarray(np.stack([np.asarray(M, dtype=np.complex128).reshape(-1, order="F") for M in mats]))
+    env = np.zeros((len(q0), 32), dtype=np.float64)
+    rc = lib().emu_adjoint_sweep_f32(C.c_int(n), psi.ctypes.data_as(C.c_void_p), lam.ctypes.data_as(C.c_void_p), C.c_int(len(q0)),
+                                     q0.ctypes.data_as(C.c_void_p), m.ctypes.data_as(C.c_void_p), C.c_int(tile_bits), C.c_int(low_bits),
+                                     env.ctypes.data_as(C.c_void_p))
+    if rc:
+        raise RuntimeError(f"emu_adjoint_sweep_f32 rc={rc}")
+    envc = (env[:, 0::2] + 1j * env[:, 1::2]).reshape(len(q0), 4, 4).transpose(0, 2, 1)
     return psi, lam, envc
 
 

@@ -231,6 +231,38 @@ def test_emu_adjoint_sweep_mma(emu, oracle, n, layers, tb, nw):
     assert wf == wf_min, f"{wf - wf_min} bank-conflict wavefronts out of {wf_min}"
 
 
+@pytest.mark.parametrize("n,layers,tb", [(9, 4, 9), (11, 5, 10), (12, 6, 11), (13, 4, 11), (12, 3, 12), (14, 5, 10)])
+def test_emu_adjoint_sweep_f32(emu, oracle, n, layers, tb):
+    """ComplexF32 backward pass with the windows in registers and the reduction on TF32-split tensor-core MMAs
+    (adjoint_f32.cuh, software model of the m16n8k8 fragments): un-applied states bit-identical to the scalar pass (same
+    FFMA order), environments equal to the ComplexF64 definition at single precision -- the hi/lo split must not lose
+    the low mantissa bits (a plain TF32 product would be wrong at 1e-3)."""
+    rng = np.random.default_rng(n * 17 + layers + tb)
+    G = onp.brickwork_num_gates(n, layers)
+    angles = rng.uniform(0, 2 * np.pi, (15, G))
+    q0 = np.array(onp.brickwork_gate_positions(n, layers)) - 1
+    mats = [oracle.build_general_unitary_gate(angles[:, g]) for g in range(G)]
+    psiG, lamG = rand_state(rng, n), 3.0 * rand_state(rng, n)
+    p_ref, l_ref, env_ref = emu.adjoint_sweep(psiG.astype(np.complex64), lamG.astype(np.complex64), q0, mats, tb, 3)
+    p, l, env = emu.adjoint_sweep_f32(psiG, lamG, q0, mats, tb, 3)
+    assert np.array_equal(p, p_ref) and np.array_equal(l, l_ref)
+    # independent ComplexF64 definition: env[g][r, c] = sum conj(lam_g[r]) psi_{g-1}[c]
+    psi, lam = psiG.copy(), lamG.copy()
+    scale = np.linalg.norm(psiG) * np.linalg.norm(lamG)
+    worst = 0.0
+    for g in range(G - 1, -1, -1):
+        Ud = np.conj(mats[g].reshape(4, 4)).T
+        psi = oracle.apply_2q(psi, Ud, int(q0[g]) + 1)
+        k = int(q0[g])
+        L4 = np.moveaxis(lam.reshape(2 ** (n - k - 2), 4, 2 ** k), 1, 0).reshape(4, -1)
+        P4 = np.moveaxis(psi.reshape(2 ** (n - k - 2), 4, 2 ** k), 1, 0).reshape(4, -1)
+        worst = max(worst, np.max(np.abs(env[g] - np.conj(L4) @ P4.T)))
+        lam = oracle.apply_2q(lam, Ud, int(q0[g]) + 1)
+    assert worst < 2e-6 * scale, worst / scale
+    # no worse than the scalar ComplexF32 pass (double accumulation of exact FP32 products) by more than the split's 2^-20
+    assert np.max(np.abs(env - env_ref)) < 2e-6 * scale
+
+
 @pytest.mark.parametrize("n,layers,g,tb,ham", [(12, 5, 1, 9, "tfim"), (13, 6, 2, 9, "east"), (13, 4, 3, 10, "tfim"), (12, 6, 2, 10, "east")])
 def test_emu_sharded_gradients(emu, oracle, n, layers, g, tb, ham):
     """Sharded adjoint gradients on 2^g simulated ranks: lambda = H psi in two sweeps around one qubit swap, backward sweep on

@@ -53,6 +53,8 @@ def _defaults():
     qc.set_option("contract_coop", 1)
     qc.set_option("measure_tma", 1)
     qc.set_option("pass_tma", 1)
+    qc.set_option("adjoint_tf32", 1)
+    qc.set_option("tma_l2_promotion", 1)
     yield
 
 
@@ -260,9 +262,12 @@ def test_measure_vs_oracle(oracle, nbits, dtype):
     ref = oracle.measure_east(psi.astype(np.complex128), H.c, H.A, H.B).real
     assert abs(qc.measure(H, psi) - ref) < tol * max(1.0, abs(ref))
     # closed forms
+    # (ComplexF32 states: the TMA-fed kernel multiplies |psi|^2 by a single-precision diagonal -- 6e-8 relative)
     z = qc.B200State(qc.zero_state_tensor(dtype, nbits))
-    assert abs(qc.measure_(None, qc.TFIMHamiltonian(1.0, 0.1, 0.5), z) + ((nbits - 1) + 0.1 * nbits)) < 1e-12
-    assert abs(qc.measure_(None, H, z) - (H.B * (1 + (nbits - 1) * (1 + H.c)) + H.c)) < 1e-12
+    cf_tol = 1e-12 if dtype == np.complex128 else 1e-6
+    e_tfim, e_east = -((nbits - 1) + 0.1 * nbits), H.B * (1 + (nbits - 1) * (1 + H.c)) + H.c
+    assert abs(qc.measure_(None, qc.TFIMHamiltonian(1.0, 0.1, 0.5), z) - e_tfim) < cf_tol * max(1.0, abs(e_tfim))
+    assert abs(qc.measure_(None, H, z) - e_east) < cf_tol * max(1.0, abs(e_east))
 
 
 # ---- the TMA-fed persistent expectation kernel (flip_tile.cuh, default from 14 / 15 qubits) against the oracle, every
@@ -408,6 +413,34 @@ def test_gradients_vs_reference_algorithm(oracle, n, layers, scale, ham):
     E32, g32 = qc.gradients(H, psi0.astype(np.complex64), c, calculate_energy=True)
     assert abs(E32 - E_ref) < 1e-5 * max(1.0, abs(E_ref))
     assert np.max(np.abs(g32 - g_ref)) < 1e-5 * max(scale_g, 1.0)
+
+
+@pytest.mark.parametrize("n,layers,atb", [(9, 3, 0), (12, 4, 0), (13, 5, 9), (16, 6, 10), (18, 4, 11), (19, 7, 12), (22, 4, 0)])
+def test_gradients_f32_tensor_core_pass(oracle, n, layers, atb):
+    """ComplexF32 backward pass with register windows and TF32-split reduction MMAs (adjoint_f32.cuh, default) vs the scalar pass
+    (adjoint.cuh, option adjoint_tf32 = 0), vs the ComplexF64 gradient of the same circuit, and at n <= 13 vs the oracle's
+    restatement of the reference's shift sweep.  Tolerance: BASELINE.json's 1e-5 relative to the gradient's max-norm; the
+    hi/lo split keeps the two ComplexF32 passes within 2e-6 of each other."""
+    rng = np.random.default_rng(2000 * n + layers)
+    c = circuit(n, layers, rng)
+    H = qc.TFIMHamiltonian(1.0, 0.9045, 1.4) if n % 2 else qc.EastModelHamiltonian(0.1, -0.1)
+    v = rand_state(rng, n)
+    E64, g64 = qc.gradients(H, qc.B200State(v), c, calculate_energy=True)
+    psi32 = qc.B200State(v.astype(np.complex64))
+    qc.set_option("adjoint_tile_bits", atb)
+    qc.set_option("adjoint_tf32", 0)
+    E0, g0 = qc.gradients(H, psi32, c, calculate_energy=True)
+    qc.set_option("adjoint_tf32", 1)
+    E1, g1 = qc.gradients(H, psi32, c, calculate_energy=True)
+    scale_g = max(np.max(np.abs(g64)), 1.0)
+    assert E1 == E0  # the forward pass and H psi do not depend on the option
+    assert np.max(np.abs(g1 - g0)) < 2e-6 * scale_g
+    assert abs(E1 - E64) < 1e-5 * max(1.0, abs(E64))
+    assert np.max(np.abs(g1 - g64)) < 1e-5 * scale_g
+    if n <= 13:
+        _, g_ref = oracle.gradients_brickwork(v, n, layers, c.gate_angles, 0 if n % 2 else 1, H.params())
+        assert np.max(np.abs(g1 - g_ref)) < 1e-5 * scale_g
+    qc.set_option("adjoint_tf32", 1)
 
 
 @pytest.mark.parametrize("n,layers,atb", [(13, 5, 0), (16, 6, 9), (18, 4, 10), (18, 7, 11), (20, 3, 12), (22, 4, 0)])
