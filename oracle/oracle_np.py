@@ -239,6 +239,91 @@ def zero_state(n, dtype=np.complex128):
 
 
 # ------------------------------------------------ statevector polar optimiser
+# ---- ext/MPSExt/polar_optimise.jl restated LITERALLY on 2x2x...x2 tensors (checker of the flat-vector restatement below) ----
+def mps_contract(A, B, dimsA, dimsB, free_first="A"):
+    """MatrixProductStates.contract(A, B, dimsA, dimsB) (1-based dims).  The package is not vendored; its convention is
+    pinned by the reference's own call sites: every `contract` is followed by `permutedims(., perm_idxs(site, N))`
+    (polar_optimise.jl:31-33,63-65,85-86,97-98), which puts result dims 1, 2 at (site, site+1) and result dims 3.. at the
+    other positions in order.  That restores the qubit order -- so that e.g. an all-identity circuit maps a state to
+    itself -- only if the free dims of A come first, then the free dims of B in their original order (numpy.tensordot's
+    convention).  free_first="B" is the other conceivable reading, kept so that the test can show it is inconsistent."""
+    out = np.tensordot(A, B, axes=([d - 1 for d in dimsA], [d - 1 for d in dimsB]))
+    if free_first == "B":
+        na = A.ndim - len(dimsA)
+        out = np.moveaxis(out, list(range(na)), list(range(out.ndim - na, out.ndim)))
+    return out
+
+
+def perm_idxs(site, N):
+    """polar_optimise.jl:5-13 (1-based)."""
+    perm = list(range(1, N + 1))
+    for i in range(1, site):
+        perm[i - 1] = i + 2
+    perm[site - 1] = 1
+    perm[site] = 2
+    return perm
+
+
+def _permutedims(A, perm):
+    """Julia's permutedims(A, perm): result dim i is A's dim perm[i]."""
+    return np.transpose(A, [p - 1 for p in perm])
+
+
+def _gate_tensor(g):
+    g = np.asarray(g, dtype=np.complex128)
+    return g if g.ndim == 4 else g.reshape(2, 2, 2, 2, order="F")
+
+
+def circuit_to_state_literal(circuit, N, free_first="A"):
+    """polar_optimise.jl:22-46, statement by statement; returns the flat column-major state."""
+    psi = np.zeros(2 ** N, dtype=np.complex128)
+    psi[0] = 1
+    psi = psi.reshape((2,) * N, order="F")
+    for layer in circuit:
+        for idx in list(range(1, N // 2 + 1)) + list(range(N // 2 + 1, N)):
+            site = 2 * idx - 1 if idx <= N // 2 else 2 * idx - N
+            psi = mps_contract(_gate_tensor(layer[idx - 1]), psi, [3, 4], [site, site + 1], free_first)
+            psi = _permutedims(psi, perm_idxs(site, N))
+    return psi.reshape(-1, order="F")
+
+
+def create_upper_state_literal(circuit, phi, N, free_first="A"):
+    """polar_optimise.jl:52-78, statement by statement."""
+    psi = np.conj(np.asarray(phi, dtype=np.complex128)).reshape((2,) * N, order="F")
+    for layer in reversed(circuit):
+        for idx in list(range(N - 1, N // 2, -1)) + list(range(N // 2, 0, -1)):
+            site = 2 * idx - N if idx > N // 2 else 2 * idx - 1
+            psi = mps_contract(_gate_tensor(layer[idx - 1]), psi, [1, 2], [site, site + 1], free_first)
+            psi = _permutedims(psi, perm_idxs(site, N))
+    return psi.reshape(-1, order="F")
+
+
+def polar_optimise_literal(circuit, psi_GS, energy_fn, N, iterations=100):
+    """polar_optimise.jl:83-147 on tensors with `mps_contract` / `permutedims`, statement by statement (slow: checker only)."""
+    circuit = [[_gate_tensor(g).copy() for g in layer] for layer in circuit]
+    overlaps, energies = [], []
+    gs = np.asarray(psi_GS, dtype=np.complex128).reshape(-1)
+    for _ in range(iterations):
+        lower = np.zeros(2 ** N, dtype=np.complex128)
+        lower[0] = 1
+        lower = lower.reshape((2,) * N, order="F")
+        upper = create_upper_state_literal(circuit, gs, N).reshape((2,) * N, order="F")
+        for layer in circuit:
+            for idx in range(1, N):
+                site = 2 * idx - 1 if idx <= N // 2 else 2 * idx - N
+                upper = _permutedims(mps_contract(np.conj(layer[idx - 1]), upper, [3, 4], [site, site + 1]), perm_idxs(site, N))
+                cd = [i for i in range(1, N + 1) if i not in (site, site + 1)]
+                E = mps_contract(upper, lower, cd, cd).reshape(4, 4, order="F")
+                U_, _, Vt = np.linalg.svd(E)
+                U = np.conj(U_ @ Vt).reshape(2, 2, 2, 2, order="F")
+                layer[idx - 1] = U
+                lower = _permutedims(mps_contract(U, lower, [3, 4], [site, site + 1]), perm_idxs(site, N))
+        flat = lower.reshape(-1, order="F")
+        overlaps.append(abs(np.vdot(gs, flat)))
+        energies.append(energy_fn(flat))
+    return [[g.reshape(4, 4, order="F") for g in layer] for layer in circuit], np.array(overlaps), np.array(energies)
+
+
 def polar_optimise(circuit, psi_GS, energy_fn, N, iterations=100):
     """ext/MPSExt/polar_optimise.jl:105-147 restated on flat state vectors.
 
@@ -246,9 +331,10 @@ def polar_optimise(circuit, psi_GS, energy_fn, N, iterations=100):
     the reference's 2x2x2x2 arrays); gates 1..N/2 of a layer sit on sites 1,3,5,.. and gates N/2+1..N-1 on sites 2,4,..
     (:124-137).  `MatrixProductStates.contract(gate, psi, [3,4], [site,site+1])` + `permutedims(perm_idxs)` (:31-33) is
     the ordinary application of the gate on (site, site+1); with [1,2] (:63-65) it is the application of the transpose.
-    NOTE: MatrixProductStates.jl is not vendored in the reference tree, so this reading of `contract` (contract the listed
-    dimensions, free dimensions of the first argument first) is inferred from the call sites: parity for this row is
-    unpinned.  Returns (circuit, overlaps, energies)."""
+    NOTE: MatrixProductStates.jl is not vendored in the reference tree; the reading of `contract` (contract the listed
+    dimensions, free dimensions of the first argument first) is the only one consistent with the `permutedims` that
+    follows every call (see mps_contract; tests/test_oracle.py checks this function against the statement-by-statement
+    tensor form `polar_optimise_literal`, and that the other reading breaks identity circuits).  Returns (circuit, overlaps, energies)."""
     assert N % 2 == 0
     circuit = [[np.array(g, dtype=np.complex128) for g in layer] for layer in circuit]
     sites = [2 * idx - 1 for idx in range(1, N // 2 + 1)] + [2 * idx - N for idx in range(N // 2 + 1, N)]

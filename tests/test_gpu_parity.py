@@ -716,6 +716,34 @@ def test_polar_optimise_statevector(N, nl):
             np.testing.assert_allclose(m @ m.conj().T, np.eye(4), atol=1e-12)
 
 
+def test_polar_optimise_invariants():
+    """The GPU path on an exactly representable target (the reference's algorithm guarantees these whatever the data): the
+    exact circuit is a fixed point with overlap 1, and from the identity start the overlap never decreases."""
+    from qcb200.polar import polar_optimise
+
+    rng = np.random.default_rng(92)
+    N, nl = 8, 2
+    sites = [2 * idx - 1 for idx in range(1, N // 2 + 1)] + [2 * idx - N for idx in range(N // 2 + 1, N)]
+
+    def rand_u():
+        q, r = np.linalg.qr(rng.standard_normal((4, 4)) + 1j * rng.standard_normal((4, 4)))
+        return q * (np.diag(r) / np.abs(np.diag(r)))
+    exact = [[rand_u() for _ in range(N - 1)] for _ in range(nl)]
+    target = onp.zero_state(N)
+    for layer in exact:
+        for g, site in zip(layer, sites):
+            target = onp.apply_2q(target, g, site)
+    H = qc.TFIMHamiltonian(1.0, 0.9045, 1.4)
+    _, ov, en = polar_optimise(exact, target, H, N, 2)
+    np.testing.assert_allclose(ov, 1.0, atol=1e-12)
+    np.testing.assert_allclose(en, onp.measure_tfim(target, 1.0, 0.9045, 1.4).real, atol=1e-11)
+    ident = [[np.eye(4, dtype=np.complex128) for _ in range(N - 1)] for _ in range(nl)]
+    _, ov, _ = polar_optimise(ident, target, H, N, 10)
+    _, ov_ref, _ = onp.polar_optimise(ident, target, lambda s: 0.0, N, 10)
+    assert np.all(np.diff(ov) > -1e-12) and ov[-1] > ov[0]
+    np.testing.assert_allclose(ov, ov_ref, atol=1e-9)
+
+
 def test_trim_releases_and_reallocates_work_buffers(oracle):
     import torch
 

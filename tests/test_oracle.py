@@ -280,3 +280,85 @@ def test_right_apply_gate_is_right_multiplication(nbits):
     I = np.eye(2 ** nbits, dtype=np.complex128)
     u4 = rng.standard_normal((4, 4)) + 1j * rng.standard_normal((4, 4))
     np.testing.assert_allclose(onp.right_apply_gate(I, u4, 1), onp.convert_gates_to_matrix(nbits, [(1, u4)]), atol=1e-13)
+
+
+# ---- ext/MPSExt/polar_optimise.jl: the convention of the un-vendored MatrixProductStates.contract, pinned by its call sites ----
+def test_polar_contract_convention_is_pinned_by_the_call_sites():
+    rng = np.random.default_rng(88)
+    N = 6
+    phi = rng.standard_normal(2 ** N) + 1j * rng.standard_normal(2 ** N)
+    ident = [[np.eye(4, dtype=np.complex128) for _ in range(N - 1)] for _ in range(2)]
+    # an all-identity circuit must hand back conj(phi) (polar_optimise.jl:52-78) -- true for "free dims of A first" only
+    np.testing.assert_allclose(onp.create_upper_state_literal(ident, phi, N), np.conj(phi), atol=0)
+    # the other conceivable reading (free dims of the state first) scrambles the qubit order already at a single call site:
+    # contract with the identity gate + permutedims(perm_idxs) must be the identity map on the state
+    T = phi.reshape((2,) * N, order="F")
+    I4 = np.eye(4, dtype=np.complex128).reshape(2, 2, 2, 2, order="F")
+    for site in range(1, N):
+        ok = onp._permutedims(onp.mps_contract(I4, T, [3, 4], [site, site + 1], "A"), onp.perm_idxs(site, N))
+        bad = onp._permutedims(onp.mps_contract(I4, T, [3, 4], [site, site + 1], "B"), onp.perm_idxs(site, N))
+        assert np.array_equal(ok, T)
+        assert np.linalg.norm(bad - T) > 0.5
+    # with that reading, contract(gate, psi, [3,4], [site, site+1]) + permutedims(perm_idxs) IS apply!(psi', psi, gate) of
+    # src/apply.jl on (site, site+1), and [1,2] applies the transposed gate
+    gates = [[rng.standard_normal((4, 4)) + 1j * rng.standard_normal((4, 4)) for _ in range(N - 1)] for _ in range(2)]
+    sites = [2 * idx - 1 for idx in range(1, N // 2 + 1)] + [2 * idx - N for idx in range(N // 2 + 1, N)]
+    ref = onp.zero_state(N)
+    for layer in gates:
+        for g, site in zip(layer, sites):
+            ref = onp.apply_2q(ref, g, site)
+    np.testing.assert_allclose(onp.circuit_to_state_literal(gates, N), ref, atol=1e-9 * np.linalg.norm(ref))
+    up = np.conj(phi)
+    for layer in reversed(gates):
+        for g, site in reversed(list(zip(layer, sites))):
+            up = onp.apply_2q(up, g.T, site)
+    np.testing.assert_allclose(onp.create_upper_state_literal(gates, phi, N), up, atol=1e-9 * np.linalg.norm(up))
+
+
+@pytest.mark.parametrize("N,nl", [(4, 1), (6, 2)])
+def test_polar_optimise_restatement_equals_literal_tensor_form(N, nl):
+    """the flat-vector restatement the GPU path is checked against == the statement-by-statement tensor form"""
+    hp = (1.0, 0.9045, 1.4)
+    w, v = np.linalg.eigh(onp.dense_tfim(N, *hp))
+    gs = v[:, 0].astype(np.complex128)
+    ident = [[np.eye(4, dtype=np.complex128) for _ in range(N - 1)] for _ in range(nl)]
+    en = lambda s: onp.measure_matrix(onp.dense_tfim(N, *hp), s)  # noqa: E731
+    c1, ov1, e1 = onp.polar_optimise(ident, gs, en, N, 4)
+    c2, ov2, e2 = onp.polar_optimise_literal(ident, gs, en, N, 4)
+    np.testing.assert_allclose(ov1, ov2, atol=1e-12)
+    np.testing.assert_allclose(e1, e2, atol=1e-11)
+    for la, lb in zip(c1, c2):
+        for a, b in zip(la, lb):
+            np.testing.assert_allclose(a, b, atol=1e-10)
+
+
+def test_polar_optimise_invariants():
+    """What the algorithm guarantees whatever the data: every polar update maximises Re tr(E U) over unitaries, so the
+    overlap with the target never decreases along a sweep sequence; a target that the circuit represents exactly is a fixed
+    point (overlap 1 from the first sweep on, gates unchanged up to the sweep's gauge)."""
+    rng = np.random.default_rng(91)
+    N, nl = 6, 2
+    sites = [2 * idx - 1 for idx in range(1, N // 2 + 1)] + [2 * idx - N for idx in range(N // 2 + 1, N)]
+
+    def rand_u():
+        q, r = np.linalg.qr(rng.standard_normal((4, 4)) + 1j * rng.standard_normal((4, 4)))
+        return q * (np.diag(r) / np.abs(np.diag(r)))
+    exact = [[rand_u() for _ in range(N - 1)] for _ in range(nl)]
+    target = onp.zero_state(N)
+    for layer in exact:
+        for g, site in zip(layer, sites):
+            target = onp.apply_2q(target, g, site)
+    en = lambda s: 0.0  # noqa: E731
+    # fixed point
+    c, ov, _ = onp.polar_optimise(exact, target, en, N, 3)
+    np.testing.assert_allclose(ov, 1.0, atol=1e-12)
+    out = onp.zero_state(N)
+    for layer in c:
+        for g, site in zip(layer, sites):
+            out = onp.apply_2q(out, g, site)
+    assert abs(abs(np.vdot(target, out)) - 1.0) < 1e-12
+    # monotone from the identity start, and from a random start
+    for start in ([[np.eye(4, dtype=np.complex128) for _ in range(N - 1)] for _ in range(nl)], [[rand_u() for _ in range(N - 1)] for _ in range(nl)]):
+        _, ov, _ = onp.polar_optimise(start, target, en, N, 12)
+        assert np.all(np.diff(ov) > -1e-12), ov
+        assert ov[-1] > ov[0]
