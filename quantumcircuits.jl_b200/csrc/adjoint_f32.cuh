@@ -8,26 +8,25 @@
 // trips per gate (psi, the operand fetch of the reduction, lambda), and the reduction itself on the FP64 tensor cores
 // after converting every operand to double (F2F + DMMA at the FP64 rate for a single-precision state).
 //
-// Here:
+// Here everything between two stage boundaries happens in registers:
 //   * the 16-amplitude register windows of BOTH states stay in registers for all (up to 4) gates of a stage, exactly as
-//     in the forward pass (tile.cuh); a gate is un-applied with packed FFMA2 on registers;
-//   * after a gate, the thread writes its updated window back in place (the write the stage needs anyway at its end),
-//     and the warp reduces its 128 quads with single-precision tensor-core MMAs (mma.sync.m16n8k8, TF32 inputs, FP32
-//     accumulate) whose operands come straight from the tile: each element is read exactly once;
-//   * single-precision accuracy is kept by the split x = hi + lo (hi = the upper 19 bits = an exact TF32 number, lo = x - hi
-//     exact in FP32): ONE m16n8k8 MMA contracts 4 quads and produces all four hi/lo cross terms:
-//         rows  m = (amplitude j of lambda, plain / "tilde", hi / lo)      16 = 4 x 2 x 2
-//         k       = (quad q, Re / Im)                                        8 = 4 x 2
-//         cols  n = (amplitude c of psi, hi / lo)                            8 = 4 x 2
-//     A[(j, plain)][(q, Re / Im)] = (Re, Im) lambda_j,   A[(j, tilde)][..] = (-Im, Re) lambda_j,   B[(q, Re / Im)][c] = (Re, Im) psi_c
-//     so that  D[(j, plain)][c] = Re conj(lambda_j) psi_c  and  D[(j, tilde)][c] = Im conj(lambda_j) psi_c  summed over the
-//     quads.  Lane (g, t) loads ONE float2 of each state per MMA (amplitude g & 3 of quad t) and builds its 4 + 2 operand
-//     registers from it; no shuffle, no double conversion, nothing on the FP64 pipe;
-//   * FP32 accumulation runs over the 128 quads a warp owns in one tile only; the per-tile sums go to double accumulators
-//     in shared memory (one row per gate and warp), as in adjoint.cuh.
+//     in the forward pass (tile.cuh); a gate is un-applied with packed FFMA2;
+//   * the thread accumulates the 4x4 complex outer products conj(lambda_r) psi_c of its own 4 quads with packed FFMA2
+//     (16 float2 accumulators: 32 FFMA2 per quad, the same issue cost as one un-application);
+//   * per gate and tile, the warp sums its 32 x 32 partial values with two transpose-reductions of 16 values (32 shuffles
+//     and adds per lane instead of 160 for 32 butterfly reductions): every lane ends up with one component of the warp's
+//     sum, which it adds to the double accumulators in shared memory (one row per gate and warp, as in adjoint.cuh).
+// Shared memory is touched once per stage (load both windows, store both windows); nothing runs on the FP64 pipe
+// except 32 DADDs per warp, gate and tile.  FP32 accumulation covers the 128 quads a warp owns in one tile only.
 //
-// The index algebra is __host__ __device__ and replayed on the CPU by tests/emu with a software model of the m16n8k8
-// fragment layout (adjoint_stage_f32_host).
+// A variant that fed the reduction to the single-precision tensor cores (mma.sync.m16n8k8 TF32 with a hi/lo operand
+// split to keep FP32 accuracy: one MMA = 4 quads x all four hi/lo cross terms) was built first and measured slower than
+// adjoint.cuh (28 q gradient 81.9 ms vs 66.2 ms): ~20 issue slots of operand preparation per MMA, 672 of the 1225
+// instructions per warp and gate, instruction-cache misses on top (ncu: no_instruction the top stall, ALU pipe 42 %,
+// tensor pipe 12 %), and the legacy MMA path takes issue bandwidth from FFMA2 (tools/fp64_peak.cu: FFMA2 drops from
+// 62.5 to 39.2 TFLOP/s with one TF32 MMA per 8 FFMA2).  profiles/r02_adjoint_f32_tf32_variant_ncu.txt keeps the numbers.
+//
+// The index algebra is __host__ __device__ and replayed on the CPU by tests/emu (adjoint_stage_f32_host).
 #pragma once
 #include <cstring>
 
@@ -35,63 +34,82 @@
 
 namespace qcb {
 
-QCB_HD uint32_t adjf_bits(float x)
-{
-#if defined(__CUDA_ARCH__)
-    return __float_as_uint(x);
-#else
-    uint32_t u;
-    std::memcpy(&u, &x, 4);
-    return u;
-#endif
-}
-QCB_HD float adjf_float(uint32_t u)
-{
-#if defined(__CUDA_ARCH__)
-    return __uint_as_float(u);
-#else
-    float x;
-    std::memcpy(&x, &u, 4);
-    return x;
-#endif
-}
-// upper 19 bits of x: exactly representable as TF32 (sign, 8 exponent bits, 10 mantissa bits)
-QCB_HD float adjf_hi(float x) { return adjf_float(adjf_bits(x) & 0xffffe000u); }
-
 // the two bits of q spread over the window bits other than LO, LO+1 (as apply_window_gate does)
 QCB_HD constexpr int adjf_other(int LO, int q) { return LO == 0 ? (q << 2) : (LO == 1 ? ((q & 1) | ((q & 2) << 2)) : q); }
 
-// operand registers of lane (g, t) for one reduction MMA, from lambda_j and psi_j (j = g & 3) of quad t
-struct AdjfFrag {
-    uint32_t a[4]; // A[g][t], A[g+8][t], A[g][t+4], A[g+8][t+4]:  (hi, lo) of the Re-slot value, (hi, lo) of the Im-slot value
-    uint32_t b[2]; // B[t][g], B[t+4][g]
-};
-QCB_HD AdjfFrag adjf_operands(float2 lv, float2 pv, uint32_t lane)
+// acc[r + 4 (c - C0)] += conj(l_r) x_c for the columns c = C0, C0 + 1 over the 4 quads of a window, gate on window bits
+// (LO, LO+1).  The 16 floats of acc are v[2 k] = Re, v[2 k + 1] = Im, k = r + 4 (c - C0): half an environment row
+// (adjoint.cuh: env_accumulate); two rounds (C0 = 0, 2) keep 16 instead of 32 accumulators live next to the two windows.
+template <int LO, int C0> QCB_HD void adjf_outer(const float2 (&l)[kRegAmps], const float2 (&x)[kRegAmps], float2 (&acc)[8])
 {
-    const bool upper = ((lane >> 4) & 1u) != 0; // g >= 4: the "tilde" rows of A, the lo columns of B
-    const float u = upper ? -lv.y : lv.x, v = upper ? lv.x : lv.y;
-    const float uh = adjf_hi(u), vh = adjf_hi(v);
-    const float ph = adjf_hi(pv.x), qh = adjf_hi(pv.y);
-    AdjfFrag F;
-    F.a[0] = adjf_bits(uh);
-    F.a[1] = adjf_bits(u - uh);
-    F.a[2] = adjf_bits(vh);
-    F.a[3] = adjf_bits(v - vh);
-    F.b[0] = adjf_bits(upper ? pv.x - ph : ph);
-    F.b[1] = adjf_bits(upper ? pv.y - qh : qh);
-    return F;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const int other = adjf_other(LO, q);
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 1000
+        float2 lx[4], ly[4], xs[2], sw[2];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const float2 lv = l[other | (j << LO)];
+            lx[j] = make_float2(lv.x, lv.x);
+            ly[j] = make_float2(lv.y, -lv.y);
+        }
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+            const float2 xv = x[other | ((C0 + c) << LO)];
+            xs[c] = xv;
+            sw[c] = make_float2(xv.y, xv.x);
+        }
+#pragma unroll
+        for (int c = 0; c < 2; c++)
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                float2 a = acc[r + 4 * c];
+                a = __ffma2_rn(lx[r], xs[c], a); // (Re, Im) += l.re * (x.re, x.im)
+                a = __ffma2_rn(ly[r], sw[c], a); //            + (l.im, -l.im) * (x.im, x.re)
+                acc[r + 4 * c] = a;
+            }
+#else
+#pragma unroll
+        for (int c = 0; c < 2; c++)
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                const float2 lv = l[other | (r << LO)], xv = x[other | ((C0 + c) << LO)];
+                float2 a = acc[r + 4 * c];
+                a.x = fmaf(lv.x, xv.x, a.x); a.y = fmaf(lv.x, xv.y, a.y);
+                a.x = fmaf(lv.y, xv.y, a.x); a.y = fmaf(-lv.y, xv.x, a.y);
+                acc[r + 4 * c] = a;
+            }
+#endif
+    }
 }
 
-// where lane (g, t) adds its two sums after the MMAs of a gate: s0 = C[g][2t] + C[g+8][2t], s1 = C[g][2t+1] + C[g+8][2t+1],
-// each summed with lane t ^ 2 (the lo columns); lanes with t < 2 own env element (j = g & 3, c = 2t, 2t+1), Re (g < 4) or Im
-QCB_HD int adjf_acc_index(uint32_t lane, int which)
+// Transpose-reduction of 16 values per lane over a warp: step s = 16, 8, 4, 2 halves the number of live components (a lane
+// whose bit s is set keeps the upper half and sends the lower half to lane ^ s, and vice versa), a last plain exchange
+// with lane ^ 1 completes the sum: lanes 2i and 2i + 1 both end up with component i of the warp's sum in v[0].
+// (16 shuffles and adds per lane and round instead of 80 for 16 butterfly reductions.)  Host form: all 32 lanes at once.
+inline void adjf_transpose_reduce_host(float (*v)[16] /* [32 lanes][16] */)
 {
-    const uint32_t g = lane >> 2, t = lane & 3u;
-    const int j = (int)(g & 3u), c = (int)(2u * t) + which;
-    return 2 * (j + 4 * c) + (int)(g >> 2);
+    for (int s = 16, n = 16; s >= 2; s >>= 1, n >>= 1) {
+        float nv[32][16];
+        for (int lane = 0; lane < 32; lane++) {
+            const bool up = (lane & s) != 0;
+            for (int i = 0; i < n / 2; i++) {
+                const float keep = up ? v[lane][i + n / 2] : v[lane][i];
+                const float recv = up ? v[lane ^ s][i + n / 2] : v[lane ^ s][i]; // the partner sends its half of the kind I keep
+                nv[lane][i] = keep + recv;
+            }
+        }
+        for (int lane = 0; lane < 32; lane++)
+            for (int i = 0; i < n / 2; i++) v[lane][i] = nv[lane][i];
+    }
+    float last[32];
+    for (int lane = 0; lane < 32; lane++) last[lane] = v[lane][0] + v[lane ^ 1][0];
+    for (int lane = 0; lane < 32; lane++) v[lane][0] = last[lane];
 }
+// where a lane adds its value after the two rounds: even lanes own round 0 (columns 0, 1), odd lanes round 1 (columns 2, 3)
+QCB_HD int adjf_acc_index(uint32_t lane) { return (int)((lane & 1u) * 16u + (lane >> 1)); }
 
-// swizzled tile-local offset of thread `geom`'s window origin (XOR-linear in geom)
+// swizzled tile-local offset of thread `geom`'s window origin
 template <int TB> QCB_HD uint32_t adjf_win_base(const StageDesc &S, uint32_t geom)
 {
     uint32_t e = 0;
@@ -99,39 +117,8 @@ template <int TB> QCB_HD uint32_t adjf_win_base(const StageDesc &S, uint32_t geo
     for (int k = 0; k < TB - kRegBits; k++) e |= ((geom >> k) & 1u) << S.tpos[k];
     return swz<4>(e);
 }
-// swizzled offset of register element r of a window at p0 (= StageDesc::roff[r], recomputed: a per-lane index into the
-// kernel-parameter bank would be a divergent constant fetch)
-QCB_HD uint32_t adjf_roff(int p0, int r) { return swz<4>((uint32_t)r << p0); }
 
-// ---- software model of mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 (CPU replay) ----------------------------------------
-// a[lane][4], b[lane][2], c[lane][4]; lane = 4 g + t.  TF32 inputs: the low 13 bits are dropped.
-inline void adjf_mma_host(const uint32_t (*a)[4], const uint32_t (*b)[2], float (*c)[4])
-{
-    float A[16][8], B[8][8];
-    for (int lane = 0; lane < 32; lane++) {
-        const int g = lane >> 2, t = lane & 3;
-        A[g][t] = adjf_float(a[lane][0] & 0xffffe000u);
-        A[g + 8][t] = adjf_float(a[lane][1] & 0xffffe000u);
-        A[g][t + 4] = adjf_float(a[lane][2] & 0xffffe000u);
-        A[g + 8][t + 4] = adjf_float(a[lane][3] & 0xffffe000u);
-        B[t][g] = adjf_float(b[lane][0] & 0xffffe000u);
-        B[t + 4][g] = adjf_float(b[lane][1] & 0xffffe000u);
-    }
-    for (int lane = 0; lane < 32; lane++) {
-        const int g = lane >> 2, t = lane & 3;
-        for (int i = 0; i < 4; i++) {
-            const int m = g + 8 * (i >> 1), n = 2 * t + (i & 1);
-            double s = c[lane][i];
-            for (int k = 0; k < 8; k++) s += (double)A[m][k] * (double)B[k][n];
-            c[lane][i] = (float)s;
-        }
-    }
-}
-
-template <int LO> inline void adjf_apply_window_host(float2 (&a)[kRegAmps], const GateMat<float> &U) { apply_window_gate<LO, float, float2>(a, U); }
-
-// CPU replay of one stage of one tile: warp by warp, phase by phase, with the device's address algebra.
-// acc: [warps][kAdjMaxGates][32] doubles
+// CPU replay of one stage of one tile: warp by warp with the device's arithmetic.  acc: [warps][kAdjMaxGates][32] doubles
 template <int TB>
 inline void adjoint_stage_f32_host(const AdjParams<float> &A, int s, float2 *smP, float2 *smL, double *acc)
 {
@@ -139,91 +126,69 @@ inline void adjoint_stage_f32_host(const AdjParams<float> &A, int s, float2 *smP
     static_assert(NT >= 32, "a warp of windows");
     const StageDesc &S = A.P.stage[s];
     for (int warp = 0; warp < NT / 32; warp++) {
+        float2 x[32][kRegAmps], l[32][kRegAmps];
+        uint32_t e[32];
+        for (uint32_t lane = 0; lane < 32; lane++) {
+            e[lane] = adjf_win_base<TB>(S, (uint32_t)warp * 32u + lane);
+            for (int r = 0; r < kRegAmps; r++) { x[lane][r] = smP[e[lane] ^ S.roff[r]]; l[lane][r] = smL[e[lane] ^ S.roff[r]]; }
+        }
         for (int slot = 0; slot < kSlots; slot++) {
             if (!((S.mask >> slot) & 1u)) continue;
             const int LO = slot_lo(slot);
             const GateMat<float> &Ud = A.P.U[s * kSlots + slot];
             double *acc_gate = acc + ((size_t)warp * kAdjMaxGates + A.slot_gate[s * kSlots + slot]) * 32;
-            auto window = [&](float2 *sm, uint32_t lane) {
-                const uint32_t e = adjf_win_base<TB>(S, (uint32_t)warp * 32u + lane);
-                float2 w[kRegAmps];
-                for (int r = 0; r < kRegAmps; r++) w[r] = sm[e ^ S.roff[r]];
-                if (LO == 0) adjf_apply_window_host<0>(w, Ud);
-                else if (LO == 1) adjf_apply_window_host<1>(w, Ud);
-                else adjf_apply_window_host<2>(w, Ud);
-                for (int r = 0; r < kRegAmps; r++) sm[e ^ S.roff[r]] = w[r];
-            };
-            for (uint32_t lane = 0; lane < 32; lane++) window(smP, lane);      // psi <- U^dagger psi
-            float c[32][4];
-            for (int lane = 0; lane < 32; lane++) c[lane][0] = c[lane][1] = c[lane][2] = c[lane][3] = 0.f;
-            for (uint32_t d = 0; d < 32; d++) {                                  // MMA d contracts the 4 quads of lane d's window
-                uint32_t a[32][4], b[32][2];
-                const uint32_t ed = adjf_win_base<TB>(S, (uint32_t)warp * 32u + d);
-                for (uint32_t lane = 0; lane < 32; lane++) {
-                    const uint32_t g = lane >> 2, t = lane & 3u;
-                    const uint32_t idx = ed ^ adjf_roff(S.p0, adjf_other(LO, (int)t) | (int)((g & 3u) << LO));
-                    const AdjfFrag F = adjf_operands(smL[idx], smP[idx], lane);
-                    for (int i = 0; i < 4; i++) a[lane][i] = F.a[i];
-                    b[lane][0] = F.b[0]; b[lane][1] = F.b[1];
-                }
-                adjf_mma_host(a, b, c);
-            }
+            float v[2][32][16];
             for (uint32_t lane = 0; lane < 32; lane++) {
-                if ((lane & 3u) >= 2) continue;
-                const float s0 = (c[lane][0] + c[lane][2]) + (c[lane ^ 2][0] + c[lane ^ 2][2]);
-                const float s1 = (c[lane][1] + c[lane][3]) + (c[lane ^ 2][1] + c[lane ^ 2][3]);
-                acc_gate[adjf_acc_index(lane, 0)] += (double)s0;
-                acc_gate[adjf_acc_index(lane, 1)] += (double)s1;
+                float2 a0[8], a1[8];
+                for (int i = 0; i < 8; i++) a0[i] = a1[i] = float2{0.f, 0.f};
+                if (LO == 0) { apply_window_gate<0, float, float2>(x[lane], Ud); adjf_outer<0, 0>(l[lane], x[lane], a0); adjf_outer<0, 2>(l[lane], x[lane], a1); apply_window_gate<0, float, float2>(l[lane], Ud); }
+                else if (LO == 1) { apply_window_gate<1, float, float2>(x[lane], Ud); adjf_outer<1, 0>(l[lane], x[lane], a0); adjf_outer<1, 2>(l[lane], x[lane], a1); apply_window_gate<1, float, float2>(l[lane], Ud); }
+                else { apply_window_gate<2, float, float2>(x[lane], Ud); adjf_outer<2, 0>(l[lane], x[lane], a0); adjf_outer<2, 2>(l[lane], x[lane], a1); apply_window_gate<2, float, float2>(l[lane], Ud); }
+                for (int i = 0; i < 8; i++) { v[0][lane][2 * i] = a0[i].x; v[0][lane][2 * i + 1] = a0[i].y; v[1][lane][2 * i] = a1[i].x; v[1][lane][2 * i + 1] = a1[i].y; }
             }
-            for (uint32_t lane = 0; lane < 32; lane++) window(smL, lane);      // lambda <- U^dagger lambda
+            adjf_transpose_reduce_host(v[0]);
+            adjf_transpose_reduce_host(v[1]);
+            for (uint32_t lane = 0; lane < 32; lane++) acc_gate[adjf_acc_index(lane)] += (double)v[lane & 1u][lane][0];
         }
+        for (uint32_t lane = 0; lane < 32; lane++)
+            for (int r = 0; r < kRegAmps; r++) { smP[e[lane] ^ S.roff[r]] = x[lane][r]; smL[e[lane] ^ S.roff[r]] = l[lane][r]; }
     }
 }
 
 #if defined(__CUDACC__)
-__device__ __forceinline__ void adjf_mma(float (&c)[4], const AdjfFrag &F)
+// one round of the reduction: columns C0, C0 + 1 of the outer products, transpose-reduced over the warp
+template <int LO, int C0>
+__device__ __forceinline__ float adjf_round(const float2 (&l)[kRegAmps], const float2 (&x)[kRegAmps], uint32_t lane)
 {
-    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-                 : "r"(F.a[0]), "r"(F.a[1]), "r"(F.a[2]), "r"(F.a[3]), "r"(F.b[0]), "r"(F.b[1]));
-}
-
-// one gate slot of a stage: x, l = the thread's psi / lambda windows (registers), e = swizzled origin of its window
-template <int TB, int LO>
-__device__ __forceinline__ void adjf_slot(const StageDesc &S, const GateMat<float> &Ud, float2 (&x)[kRegAmps], float2 (&l)[kRegAmps], float2 *smP,
-                                          float2 *smL, uint32_t e, uint32_t ewarp, const uint32_t (&cbit)[5], uint32_t lane, double *acc_gate)
-{
-    // (1) psi <- U^dagger psi on registers; write the window back in place
-    apply_window_gate<LO, float, float2>(x, Ud);
+    float2 acc[8];
 #pragma unroll
-    for (int r = 0; r < kRegAmps; r++) smP[e ^ S.roff[r]] = x[r];
-    __syncwarp();
-    // (2) env += conj(lambda) psi^T over the warp's 32 windows: MMA d takes the 4 quads of lane d's window
-    const uint32_t g = lane >> 2, t = lane & 3u;
-    const uint32_t mine = ewarp ^ adjf_roff(S.p0, adjf_other(LO, (int)t) | (int)((g & 3u) << LO));
-    float c[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int i = 0; i < 8; i++) acc[i] = make_float2(0.f, 0.f);
+    adjf_outer<LO, C0>(l, x, acc);
+    float v[16];
 #pragma unroll
-    for (int d = 0; d < 32; d++) {
-        uint32_t ed = 0; // window origin of lane d relative to the warp's: XOR of the lane-bit constants (uniform)
+    for (int i = 0; i < 8; i++) { v[2 * i] = acc[i].x; v[2 * i + 1] = acc[i].y; }
 #pragma unroll
-        for (int k = 0; k < 5; k++) ed ^= ((d >> k) & 1) ? cbit[k] : 0u;
-        const uint32_t idx = mine ^ ed;
-        adjf_mma(c, adjf_operands(smL[idx], smP[idx], lane));
-    }
-    {
-        float s0 = c[0] + c[2], s1 = c[1] + c[3];
-        s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
-        s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
-        if (t < 2u) {
-            acc_gate[adjf_acc_index(lane, 0)] += (double)s0;
-            acc_gate[adjf_acc_index(lane, 1)] += (double)s1;
+    for (int s = 16, n = 16; s >= 2; s >>= 1, n >>= 1) {
+        const bool up = (lane & (uint32_t)s) != 0;
+#pragma unroll
+        for (int i = 0; i < n / 2; i++) {
+            const float keep = up ? v[i + n / 2] : v[i];
+            const float send = up ? v[i] : v[i + n / 2];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
         }
     }
-    __syncwarp();
-    // (3) lambda <- U^dagger lambda
-    apply_window_gate<LO, float, float2>(l, Ud);
-#pragma unroll
-    for (int r = 0; r < kRegAmps; r++) smL[e ^ S.roff[r]] = l[r];
+    return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
+// one gate slot of a stage: x, l = the thread's psi / lambda windows (registers)
+template <int LO>
+__device__ __forceinline__ void adjf_slot(const GateMat<float> &Ud, float2 (&x)[kRegAmps], float2 (&l)[kRegAmps], uint32_t lane, double *acc_gate)
+{
+    apply_window_gate<LO, float, float2>(x, Ud); // psi_{g-1} = U^dagger psi_g
+    const float r0 = adjf_round<LO, 0>(l, x, lane); // conj(lambda_g) psi_{g-1}^T, summed over the warp's 128 quads
+    const float r1 = adjf_round<LO, 2>(l, x, lane);
+    apply_window_gate<LO, float, float2>(l, Ud); // lambda_{g-1} = U^dagger lambda_g
+    acc_gate[adjf_acc_index(lane)] += (double)((lane & 1u) ? r1 : r0);
 }
 
 template <int TB>
@@ -231,22 +196,18 @@ __device__ __forceinline__ void adjoint_stage_f32(const AdjParams<float> &A, int
 {
     const StageDesc &S = A.P.stage[s];
     const uint32_t lane = tid & 31u;
-    const uint32_t ewarp = adjf_win_base<TB>(S, tid & ~31u);
-    uint32_t cbit[5];
-#pragma unroll
-    for (int k = 0; k < 5; k++) cbit[k] = swz<4>(1u << S.tpos[k]);
-    uint32_t e = ewarp;
-#pragma unroll
-    for (int k = 0; k < 5; k++) e ^= ((lane >> k) & 1u) ? cbit[k] : 0u;
+    const uint32_t e = adjf_win_base<TB>(S, tid);
     float2 x[kRegAmps], l[kRegAmps];
 #pragma unroll
     for (int r = 0; r < kRegAmps; r++) { x[r] = smP[e ^ S.roff[r]]; l[r] = smL[e ^ S.roff[r]]; }
     const uint32_t mask = S.mask;
     const uint8_t *sg = A.slot_gate + s * kSlots;
-    if (mask & 1u) adjf_slot<TB, 1>(S, A.P.U[s * kSlots + 0], x, l, smP, smL, e, ewarp, cbit, lane, acc_warp + 32 * sg[0]);
-    if (mask & 2u) adjf_slot<TB, 0>(S, A.P.U[s * kSlots + 1], x, l, smP, smL, e, ewarp, cbit, lane, acc_warp + 32 * sg[1]);
-    if (mask & 4u) adjf_slot<TB, 2>(S, A.P.U[s * kSlots + 2], x, l, smP, smL, e, ewarp, cbit, lane, acc_warp + 32 * sg[2]);
-    if (mask & 8u) adjf_slot<TB, 1>(S, A.P.U[s * kSlots + 3], x, l, smP, smL, e, ewarp, cbit, lane, acc_warp + 32 * sg[3]);
+    if (mask & 1u) adjf_slot<1>(A.P.U[s * kSlots + 0], x, l, lane, acc_warp + 32 * sg[0]);
+    if (mask & 2u) adjf_slot<0>(A.P.U[s * kSlots + 1], x, l, lane, acc_warp + 32 * sg[1]);
+    if (mask & 4u) adjf_slot<2>(A.P.U[s * kSlots + 2], x, l, lane, acc_warp + 32 * sg[2]);
+    if (mask & 8u) adjf_slot<1>(A.P.U[s * kSlots + 3], x, l, lane, acc_warp + 32 * sg[3]);
+#pragma unroll
+    for (int r = 0; r < kRegAmps; r++) { smP[e ^ S.roff[r]] = x[r]; smL[e ^ S.roff[r]] = l[r]; }
 }
 
 // persistent CTAs; partial: [gridDim.x][kAdjMaxGates][32] (the layout adjoint_pass_kernel writes: k_env_final sums it)

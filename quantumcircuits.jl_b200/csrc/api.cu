@@ -1,6 +1,8 @@
 // api.cu -- the extern "C" surface of libqcb200.so (include/qcb200.h) and the host drivers
 // behind it.  Each entry point replaces the reference interface named in the header.
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "adjoint_mma.cuh"
@@ -214,7 +216,7 @@ template <typename R, int KIND> static int launch_flip_measure(const FlipMaps &M
         attr_set = true;
     }
     const unsigned grid = (unsigned)std::min<unsigned long long>(P.n_items, (unsigned long long)ctx().sm_count);
-    kern<<<grid, kFlipConsumers + 32, smem, ctx().stream>>>(M, P, partial);
+    kern<<<grid, kFlipGroups * kFlipConsumers + 32, smem, ctx().stream>>>(M, P, partial);
     QCB_CUDA(cudaGetLastError());
     count_launch();
     *grid_out = grid;
@@ -737,8 +739,8 @@ int qcb_set_option(const char *key, long value)
     } else if (k == "adjoint_tile_bits") {
         if (value != 0 && (value < kMinTB || value > 12)) return set_error(QCB_EINVAL, "adjoint_tile_bits must be 0 (auto) or in [%d, 12]", kMinTB);
         c.adjoint_tile_bits = value;
-    } else if (k == "adjoint_tf32") {
-        c.adjoint_tf32 = value ? 1 : 0;
+    } else if (k == "adjoint_f32") {
+        c.adjoint_f32 = value ? 1 : 0;
     } else if (k == "adjoint_mma") {
         c.adjoint_mma = value ? 1 : 0;
     } else if (k == "pass_tma") {
@@ -766,6 +768,7 @@ int qcb_set_option(const char *key, long value)
     } else if (k == "time_passes") {
         c.time_passes = value ? 1 : 0;
         c.pass_ev_used = 0;
+        c.pass_meta.clear();
         return QCB_OK; // (no effect on plans)
     } else if (k == "fuse_swaps") {
         c.fuse_swaps = value ? 1 : 0;
@@ -799,12 +802,20 @@ int qcb_get_stat(const char *key, double *out)
         double tot = 0;
         if (c.inited && c.pass_ev_used) {
             cudaStreamSynchronize(c.stream);
+            const char *log = std::getenv("QCB_PASS_LOG");
+            FILE *f = log && c.pass_meta.size() == c.pass_ev_used / 2 ? std::fopen(log, "a") : nullptr;
             for (size_t i = 0; i + 1 < c.pass_ev_used; i += 2) {
                 float ms = 0;
                 if (cudaEventElapsedTime(&ms, c.pass_ev[i], c.pass_ev[i + 1]) == cudaSuccess) tot += ms;
+                if (f) {
+                    const Ctx::PassMeta &m = c.pass_meta[i / 2];
+                    std::fprintf(f, "%zu %.4f stages=%d gates=%d window_bit=%d tma=%d\n", i / 2, ms, m.stages, m.gates, m.first_window_bit, m.tma);
+                }
             }
+            if (f) std::fclose(f);
         }
         c.pass_ev_used = 0;
+        c.pass_meta.clear();
         *out = tot;
     }
     else return set_error(QCB_EINVAL, "unknown stat '%s'", k.c_str());

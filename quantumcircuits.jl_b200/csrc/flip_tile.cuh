@@ -30,7 +30,9 @@ constexpr int kFlipUnitBits = 12;                       // units per tile
 constexpr int kFlipTileBytes = 16 << kFlipUnitBits;     // 64 KiB
 constexpr int kFlipWin = 9;                             // window bits of a level >= 1 tile
 constexpr int kFlipRing = 3;                            // tiles in flight per CTA
-constexpr int kFlipConsumers = 256;                     // consumer threads (8 warps); warp 8 is the producer
+constexpr int kFlipConsumers = 256;                     // consumer threads per tile (8 warps: 16 units per thread and stage)
+constexpr int kFlipGroups = 2;                          // consumer groups per CTA, each on its own tile (tile k -> group k mod 2);
+                                                        // the warp after the last group is the producer
 constexpr int kFlipMaxLevels = 5;
 
 template <typename R> struct FlipGeom;
@@ -358,7 +360,7 @@ inline void flip_emulate_tile_load(const typename Vec2<R>::type *psi, const Flip
 
 #if defined(__CUDACC__)
 // ---------------------------------------------------------------------------------------------------------------------
-// the kernel: one CTA per SM, warp 8 lane 0 = TMA producer, warps 0..7 = consumers
+// the kernel: one CTA per SM, warps 0..15 = two consumer groups, warp 16 lane 0 = TMA producer
 // ---------------------------------------------------------------------------------------------------------------------
 struct FlipMaps {
     CUtensorMap m[kFlipMaxLevels];
@@ -379,25 +381,28 @@ template <typename R> __device__ __forceinline__ void flip_issue_tile(const Flip
     }
 }
 
+// Two consumer groups: with one group (8 warps per SM) the kernel was latency bound -- ncu at 28 qubits: issue slots 41 %
+// busy, top stalls `wait` and `long_scoreboard`, DRAM at 62 % of its peak with two reads of the state.
 template <typename R, int KIND>
-__global__ void __launch_bounds__(kFlipConsumers + 32, 1)
+__global__ void __maxnreg__(120) // 17 warps x 32 x 120 registers = 65 280 of the SM's 65 536 (launch bounds alone make ptxas stop at 96)
 flip_measure_kernel(const __grid_constant__ FlipMaps M, const __grid_constant__ FlipParams P, double2 *partial /* [gridDim.x] */)
 {
     extern __shared__ unsigned char flip_smem_raw[];
     unsigned char *ring = reinterpret_cast<unsigned char *>(((uintptr_t)flip_smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t *full = reinterpret_cast<uint64_t *>(ring + kFlipRing * kFlipTileBytes);
     uint64_t *empty = full + kFlipRing;
-    double *red = reinterpret_cast<double *>(empty + kFlipRing); // [8 warps][2]
+    double *red = reinterpret_cast<double *>(empty + kFlipRing); // [16 warps][2]
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr uint32_t kWarpsPerGroup = kFlipConsumers / 32, kConsumerWarps = kFlipGroups * kWarpsPerGroup;
     if (tid == 0) {
         for (int i = 0; i < kFlipRing; i++) {
             tma::mbar_init(&full[i], 1);
-            tma::mbar_init(&empty[i], kFlipConsumers / 32);
+            tma::mbar_init(&empty[i], kWarpsPerGroup); // a tile is consumed by one group
         }
         tma::fence_barrier_init();
     }
     __syncthreads();
-    if (warp == kFlipConsumers / 32) {
+    if (warp == kConsumerWarps) {
         if (lane == 0) {
             for (int l = 0; l < P.nlevels; l++) tma::prefetch_map(&M.m[l]);
             uint32_t k = 0;
@@ -410,26 +415,27 @@ flip_measure_kernel(const __grid_constant__ FlipMaps M, const __grid_constant__ 
         return;
     }
     double acc_diag = 0.0, acc_flip = 0.0;
-    uint32_t k = 0;
-    for (unsigned long long j = blockIdx.x; j < P.n_items; j += gridDim.x, k++) {
+    const uint32_t group = warp / kWarpsPerGroup, gtid = tid % kFlipConsumers;
+    uint32_t k = group;
+    for (unsigned long long j = blockIdx.x + (unsigned long long)group * gridDim.x; j < P.n_items; j += (unsigned long long)kFlipGroups * gridDim.x, k += kFlipGroups) {
         const uint32_t slot = k % kFlipRing, round = k / kFlipRing;
         tma::mbar_wait(&full[slot], round & 1u);
-        flip_tile_consume<R, KIND>(ring + (size_t)slot * kFlipTileBytes, tid, P, flip_decode(P, j), acc_diag, acc_flip);
+        flip_tile_consume<R, KIND>(ring + (size_t)slot * kFlipTileBytes, gtid, P, flip_decode(P, j), acc_diag, acc_flip);
         __syncwarp();
         if (lane == 0) tma::mbar_arrive(&empty[slot]);
     }
     acc_diag = warp_sum(acc_diag);
     acc_flip = warp_sum(acc_flip);
     if (lane == 0) { red[2 * warp] = acc_diag; red[2 * warp + 1] = acc_flip; }
-    tma::named_bar_sync(1, kFlipConsumers);
+    tma::named_bar_sync(1, kFlipGroups * kFlipConsumers);
     if (tid == 0) {
         double d = 0, f = 0;
-        for (int w = 0; w < kFlipConsumers / 32; w++) { d += red[2 * w]; f += red[2 * w + 1]; }
+        for (uint32_t w = 0; w < kConsumerWarps; w++) { d += red[2 * w]; f += red[2 * w + 1]; } // fixed order: reproducible
         partial[blockIdx.x] = make_double2(d, f);
     }
 }
 
-inline size_t flip_smem_bytes() { return (size_t)kFlipRing * kFlipTileBytes + 1024 + 2 * kFlipRing * sizeof(uint64_t) + 16 * sizeof(double); }
+inline size_t flip_smem_bytes() { return (size_t)kFlipRing * kFlipTileBytes + 1024 + 2 * kFlipRing * sizeof(uint64_t) + 2 * kFlipGroups * (kFlipConsumers / 32) * sizeof(double); }
 
 // host: tensor maps of all levels for a state at `base`
 template <typename R> inline int flip_make_maps(FlipMaps &M, const void *base, const FlipParams &P, const char **why)

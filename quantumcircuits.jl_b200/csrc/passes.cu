@@ -242,6 +242,11 @@ template <typename R> static int run_fused(qcb_state *s, const std::vector<GateO
         } catch (const std::exception &e) {
             return set_error(QCB_EINVAL, "pass parameters: %s", e.what());
         }
+        if (c.time_passes) {
+            int fw = s->nloc;
+            for (int b : pl.phys) if (b >= opt.low_bits) { fw = b; break; }
+            c.pass_meta.push_back(Ctx::PassMeta{(int)pl.stages.size(), pl.ngates, fw, tma_pass ? 1 : 0});
+        }
         if constexpr (std::is_same<R, double>::value) {
             if (tma_pass) QCB_TRY(launch_pass_tma(s, P, g, first_src));
         }
@@ -301,12 +306,12 @@ template <typename R, int TB> static int launch_adjoint(qcb_state *psi, qcb_stat
     return QCB_OK;
 }
 
-// ComplexF32: windows in registers, reduction on TF32-split tensor-core MMAs (adjoint_f32.cuh); same partial layout
+// ComplexF32: windows of both states in registers, FFMA2 outer products, warp transpose-reduction (adjoint_f32.cuh); same partial layout
 template <int TB> static int launch_adjoint_f32(qcb_state *psi, qcb_state *lam, const AdjParams<float> &A, const EnvIds &ids, double *d_env)
 {
     constexpr int NT = 1 << (TB - kRegBits);
     constexpr int NW = NT / 32;
-    // two windows (64 registers) + operands per thread: <= 128 registers; shared memory: two tiles + accumulators
+    // two windows (64 registers) + 16 packed accumulators per thread: <= 128 registers; shared memory: two tiles + accumulators
     constexpr int MINB = TB >= 12 ? 2 : (TB == 11 ? 4 : 8);
     auto kern = adjoint_pass_f32_kernel<TB, MINB>;
     const size_t smem = 2 * (sizeof(float2) << TB) + sizeof(double) * NW * kAdjMaxGates * 32;
@@ -421,7 +426,7 @@ template <typename R> static int launch_adjoint_any(qcb_state *psi, qcb_state *l
 
 template <> int launch_adjoint_any<float>(qcb_state *psi, qcb_state *lam, int TB, bool, AdjParams<float> &A, const EnvIds &ids, double *d_env)
 {
-    if (ctx().adjoint_tf32) {
+    if (ctx().adjoint_f32) {
         for (int k = 0; k < TB; k++)
             if (A.P.ld_lpos[k] != A.P.st_lpos[k]) return set_error(QCB_EINVAL, "the backward pass does not permute bits");
         switch (TB) {

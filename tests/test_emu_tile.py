@@ -233,10 +233,9 @@ def test_emu_adjoint_sweep_mma(emu, oracle, n, layers, tb, nw):
 
 @pytest.mark.parametrize("n,layers,tb", [(9, 4, 9), (11, 5, 10), (12, 6, 11), (13, 4, 11), (12, 3, 12), (14, 5, 10)])
 def test_emu_adjoint_sweep_f32(emu, oracle, n, layers, tb):
-    """ComplexF32 backward pass with the windows in registers and the reduction on TF32-split tensor-core MMAs
-    (adjoint_f32.cuh, software model of the m16n8k8 fragments): un-applied states bit-identical to the scalar pass (same
-    FFMA order), environments equal to the ComplexF64 definition at single precision -- the hi/lo split must not lose
-    the low mantissa bits (a plain TF32 product would be wrong at 1e-3)."""
+    """ComplexF32 backward pass with both windows in registers, per-thread outer products and the warp transpose-reduction
+    (adjoint_f32.cuh, all 32 lanes replayed): un-applied states bit-identical to the quad-per-thread pass (same FMA order),
+    environments equal to the ComplexF64 definition at single precision."""
     rng = np.random.default_rng(n * 17 + layers + tb)
     G = onp.brickwork_num_gates(n, layers)
     angles = rng.uniform(0, 2 * np.pi, (15, G))
@@ -259,7 +258,7 @@ def test_emu_adjoint_sweep_f32(emu, oracle, n, layers, tb):
         worst = max(worst, np.max(np.abs(env[g] - np.conj(L4) @ P4.T)))
         lam = oracle.apply_2q(lam, Ud, int(q0[g]) + 1)
     assert worst < 2e-6 * scale, worst / scale
-    # no worse than the scalar ComplexF32 pass (double accumulation of exact FP32 products) by more than the split's 2^-20
+    # FP32 accumulation over one warp and tile only: within rounding of the pass that accumulates every product in double
     assert np.max(np.abs(env - env_ref)) < 2e-6 * scale
 
 

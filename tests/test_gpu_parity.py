@@ -53,7 +53,7 @@ def _defaults():
     qc.set_option("contract_coop", 1)
     qc.set_option("measure_tma", 1)
     qc.set_option("pass_tma", 1)
-    qc.set_option("adjoint_tf32", 1)
+    qc.set_option("adjoint_f32", 1)
     qc.set_option("tma_l2_promotion", 1)
     yield
 
@@ -417,10 +417,10 @@ def test_gradients_vs_reference_algorithm(oracle, n, layers, scale, ham):
 
 @pytest.mark.parametrize("n,layers,atb", [(9, 3, 0), (12, 4, 0), (13, 5, 9), (16, 6, 10), (18, 4, 11), (19, 7, 12), (22, 4, 0)])
 def test_gradients_f32_tensor_core_pass(oracle, n, layers, atb):
-    """ComplexF32 backward pass with register windows and TF32-split reduction MMAs (adjoint_f32.cuh, default) vs the scalar pass
-    (adjoint.cuh, option adjoint_tf32 = 0), vs the ComplexF64 gradient of the same circuit, and at n <= 13 vs the oracle's
-    restatement of the reference's shift sweep.  Tolerance: BASELINE.json's 1e-5 relative to the gradient's max-norm; the
-    hi/lo split keeps the two ComplexF32 passes within 2e-6 of each other."""
+    """ComplexF32 backward pass with both register windows resident, FFMA2 outer products and a warp transpose-reduction
+    (adjoint_f32.cuh, default) vs the quad-per-thread pass (adjoint.cuh, option adjoint_f32 = 0), vs the ComplexF64 gradient of
+    the same circuit, and at n <= 13 vs the oracle's restatement of the reference's shift sweep.  Tolerance: BASELINE.json's
+    1e-5 relative to the gradient's max-norm; the two ComplexF32 passes differ only by FP32 summation order (2e-6)."""
     rng = np.random.default_rng(2000 * n + layers)
     c = circuit(n, layers, rng)
     H = qc.TFIMHamiltonian(1.0, 0.9045, 1.4) if n % 2 else qc.EastModelHamiltonian(0.1, -0.1)
@@ -428,9 +428,9 @@ def test_gradients_f32_tensor_core_pass(oracle, n, layers, atb):
     E64, g64 = qc.gradients(H, qc.B200State(v), c, calculate_energy=True)
     psi32 = qc.B200State(v.astype(np.complex64))
     qc.set_option("adjoint_tile_bits", atb)
-    qc.set_option("adjoint_tf32", 0)
+    qc.set_option("adjoint_f32", 0)
     E0, g0 = qc.gradients(H, psi32, c, calculate_energy=True)
-    qc.set_option("adjoint_tf32", 1)
+    qc.set_option("adjoint_f32", 1)
     E1, g1 = qc.gradients(H, psi32, c, calculate_energy=True)
     scale_g = max(np.max(np.abs(g64)), 1.0)
     assert E1 == E0  # the forward pass and H psi do not depend on the option
@@ -440,7 +440,7 @@ def test_gradients_f32_tensor_core_pass(oracle, n, layers, atb):
     if n <= 13:
         _, g_ref = oracle.gradients_brickwork(v, n, layers, c.gate_angles, 0 if n % 2 else 1, H.params())
         assert np.max(np.abs(g1 - g_ref)) < 1e-5 * scale_g
-    qc.set_option("adjoint_tf32", 1)
+    qc.set_option("adjoint_f32", 1)
 
 
 @pytest.mark.parametrize("n,layers,atb", [(13, 5, 0), (16, 6, 9), (18, 4, 10), (18, 7, 11), (20, 3, 12), (22, 4, 0)])
