@@ -12,7 +12,8 @@
 //   * the 16-amplitude register windows of BOTH states stay in registers for all (up to 4) gates of a stage, exactly as
 //     in the forward pass (tile.cuh); a gate is un-applied with packed FFMA2;
 //   * the thread accumulates the 4x4 complex outer products conj(lambda_r) psi_c of its own 4 quads with packed FFMA2
-//     (16 float2 accumulators: 32 FFMA2 per quad, the same issue cost as one un-application);
+//     (32 FFMA2 per quad, the same issue cost as one un-application; the operands are the amplitudes as they sit in the
+//     registers -- see adjf_outer);
 //   * per gate and tile, the warp sums its 32 x 32 partial values with two transpose-reductions of 16 values (32 shuffles
 //     and adds per lane instead of 160 for 32 butterfly reductions): every lane ends up with one component of the warp's
 //     sum, which it adds to the double accumulators in shared memory (one row per gate and warp, as in adjoint.cuh).
@@ -37,49 +38,41 @@ namespace qcb {
 // the two bits of q spread over the window bits other than LO, LO+1 (as apply_window_gate does)
 QCB_HD constexpr int adjf_other(int LO, int q) { return LO == 0 ? (q << 2) : (LO == 1 ? ((q & 1) | ((q & 2) << 2)) : q); }
 
-// acc[r + 4 (c - C0)] += conj(l_r) x_c for the columns c = C0, C0 + 1 over the 4 quads of a window, gate on window bits
-// (LO, LO+1).  The 16 floats of acc are v[2 k] = Re, v[2 k + 1] = Im, k = r + 4 (c - C0): half an environment row
-// (adjoint.cuh: env_accumulate); two rounds (C0 = 0, 2) keep 16 instead of 32 accumulators live next to the two windows.
-template <int LO, int C0> QCB_HD void adjf_outer(const float2 (&l)[kRegAmps], const float2 (&x)[kRegAmps], float2 (&acc)[8])
+// Outer products conj(l_r) x_c for the columns c = C0, C0 + 1 over the 4 quads of a window, gate on window bits (LO, LO+1).
+// No operand is broadcast or negated: with P = (l.re x.re, l.im x.im) and Q = (l.re x.im, l.im x.re) accumulated as packed
+// pairs (two FFMA2 whose operands are the amplitudes as they sit in the registers; the swap is an operand modifier),
+//     Re conj(l) x = P.lo + P.hi,     Im conj(l) x = Q.lo - Q.hi
+// are two scalar adds per matrix element, once per gate instead of once per quad.  accP / accQ index: r + 4 (c - C0).
+template <int LO, int C0> QCB_HD void adjf_outer(const float2 (&l)[kRegAmps], const float2 (&x)[kRegAmps], float2 (&accP)[8], float2 (&accQ)[8])
 {
 #pragma unroll
     for (int q = 0; q < 4; q++) {
         const int other = adjf_other(LO, q);
-#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 1000
-        float2 lx[4], ly[4], xs[2], sw[2];
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const float2 lv = l[other | (j << LO)];
-            lx[j] = make_float2(lv.x, lv.x);
-            ly[j] = make_float2(lv.y, -lv.y);
-        }
 #pragma unroll
         for (int c = 0; c < 2; c++) {
             const float2 xv = x[other | ((C0 + c) << LO)];
-            xs[c] = xv;
-            sw[c] = make_float2(xv.y, xv.x);
-        }
-#pragma unroll
-        for (int c = 0; c < 2; c++)
+            const float2 xs = float2{xv.y, xv.x};
 #pragma unroll
             for (int r = 0; r < 4; r++) {
-                float2 a = acc[r + 4 * c];
-                a = __ffma2_rn(lx[r], xs[c], a); // (Re, Im) += l.re * (x.re, x.im)
-                a = __ffma2_rn(ly[r], sw[c], a); //            + (l.im, -l.im) * (x.im, x.re)
-                acc[r + 4 * c] = a;
-            }
+                const float2 lv = l[other | (r << LO)];
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 1000
+                accP[r + 4 * c] = __ffma2_rn(lv, xv, accP[r + 4 * c]);
+                accQ[r + 4 * c] = __ffma2_rn(lv, xs, accQ[r + 4 * c]);
 #else
-#pragma unroll
-        for (int c = 0; c < 2; c++)
-#pragma unroll
-            for (int r = 0; r < 4; r++) {
-                const float2 lv = l[other | (r << LO)], xv = x[other | ((C0 + c) << LO)];
-                float2 a = acc[r + 4 * c];
-                a.x = fmaf(lv.x, xv.x, a.x); a.y = fmaf(lv.x, xv.y, a.y);
-                a.x = fmaf(lv.y, xv.y, a.x); a.y = fmaf(-lv.y, xv.x, a.y);
-                acc[r + 4 * c] = a;
-            }
+                accP[r + 4 * c].x = fmaf(lv.x, xv.x, accP[r + 4 * c].x); accP[r + 4 * c].y = fmaf(lv.y, xv.y, accP[r + 4 * c].y);
+                accQ[r + 4 * c].x = fmaf(lv.x, xs.x, accQ[r + 4 * c].x); accQ[r + 4 * c].y = fmaf(lv.y, xs.y, accQ[r + 4 * c].y);
 #endif
+            }
+        }
+    }
+}
+// v[2 k] = Re, v[2 k + 1] = Im, k = r + 4 (c - C0): half an environment row (adjoint.cuh: env_accumulate)
+QCB_HD void adjf_combine(const float2 (&accP)[8], const float2 (&accQ)[8], float (&v)[16])
+{
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        v[2 * k] = accP[k].x + accP[k].y;
+        v[2 * k + 1] = accQ[k].x - accQ[k].y;
     }
 }
 
@@ -139,12 +132,13 @@ inline void adjoint_stage_f32_host(const AdjParams<float> &A, int s, float2 *smP
             double *acc_gate = acc + ((size_t)warp * kAdjMaxGates + A.slot_gate[s * kSlots + slot]) * 32;
             float v[2][32][16];
             for (uint32_t lane = 0; lane < 32; lane++) {
-                float2 a0[8], a1[8];
-                for (int i = 0; i < 8; i++) a0[i] = a1[i] = float2{0.f, 0.f};
-                if (LO == 0) { apply_window_gate<0, float, float2>(x[lane], Ud); adjf_outer<0, 0>(l[lane], x[lane], a0); adjf_outer<0, 2>(l[lane], x[lane], a1); apply_window_gate<0, float, float2>(l[lane], Ud); }
-                else if (LO == 1) { apply_window_gate<1, float, float2>(x[lane], Ud); adjf_outer<1, 0>(l[lane], x[lane], a0); adjf_outer<1, 2>(l[lane], x[lane], a1); apply_window_gate<1, float, float2>(l[lane], Ud); }
-                else { apply_window_gate<2, float, float2>(x[lane], Ud); adjf_outer<2, 0>(l[lane], x[lane], a0); adjf_outer<2, 2>(l[lane], x[lane], a1); apply_window_gate<2, float, float2>(l[lane], Ud); }
-                for (int i = 0; i < 8; i++) { v[0][lane][2 * i] = a0[i].x; v[0][lane][2 * i + 1] = a0[i].y; v[1][lane][2 * i] = a1[i].x; v[1][lane][2 * i + 1] = a1[i].y; }
+                float2 p0[8], q0[8], p1[8], q1[8];
+                for (int i = 0; i < 8; i++) p0[i] = q0[i] = p1[i] = q1[i] = float2{0.f, 0.f};
+                if (LO == 0) { apply_window_gate<0, float, float2>(x[lane], Ud); adjf_outer<0, 0>(l[lane], x[lane], p0, q0); adjf_outer<0, 2>(l[lane], x[lane], p1, q1); apply_window_gate<0, float, float2>(l[lane], Ud); }
+                else if (LO == 1) { apply_window_gate<1, float, float2>(x[lane], Ud); adjf_outer<1, 0>(l[lane], x[lane], p0, q0); adjf_outer<1, 2>(l[lane], x[lane], p1, q1); apply_window_gate<1, float, float2>(l[lane], Ud); }
+                else { apply_window_gate<2, float, float2>(x[lane], Ud); adjf_outer<2, 0>(l[lane], x[lane], p0, q0); adjf_outer<2, 2>(l[lane], x[lane], p1, q1); apply_window_gate<2, float, float2>(l[lane], Ud); }
+                adjf_combine(p0, q0, v[0][lane]);
+                adjf_combine(p1, q1, v[1][lane]);
             }
             adjf_transpose_reduce_host(v[0]);
             adjf_transpose_reduce_host(v[1]);
@@ -160,13 +154,12 @@ inline void adjoint_stage_f32_host(const AdjParams<float> &A, int s, float2 *smP
 template <int LO, int C0>
 __device__ __forceinline__ float adjf_round(const float2 (&l)[kRegAmps], const float2 (&x)[kRegAmps], uint32_t lane)
 {
-    float2 acc[8];
+    float2 accP[8], accQ[8];
 #pragma unroll
-    for (int i = 0; i < 8; i++) acc[i] = make_float2(0.f, 0.f);
-    adjf_outer<LO, C0>(l, x, acc);
+    for (int i = 0; i < 8; i++) accP[i] = accQ[i] = make_float2(0.f, 0.f);
+    adjf_outer<LO, C0>(l, x, accP, accQ);
     float v[16];
-#pragma unroll
-    for (int i = 0; i < 8; i++) { v[2 * i] = acc[i].x; v[2 * i + 1] = acc[i].y; }
+    adjf_combine(accP, accQ, v);
 #pragma unroll
     for (int s = 16, n = 16; s >= 2; s >>= 1, n >>= 1) {
         const bool up = (lane & (uint32_t)s) != 0;

@@ -739,6 +739,8 @@ int qcb_set_option(const char *key, long value)
     } else if (k == "adjoint_tile_bits") {
         if (value != 0 && (value < kMinTB || value > 12)) return set_error(QCB_EINVAL, "adjoint_tile_bits must be 0 (auto) or in [%d, 12]", kMinTB);
         c.adjoint_tile_bits = value;
+    } else if (k == "adjoint_ctas") {
+        c.adjoint_ctas = value;
     } else if (k == "adjoint_f32") {
         c.adjoint_f32 = value ? 1 : 0;
     } else if (k == "adjoint_mma") {

@@ -384,7 +384,8 @@ template <typename R> __device__ __forceinline__ void flip_issue_tile(const Flip
 // Two consumer groups: with one group (8 warps per SM) the kernel was latency bound -- ncu at 28 qubits: issue slots 41 %
 // busy, top stalls `wait` and `long_scoreboard`, DRAM at 62 % of its peak with two reads of the state.
 template <typename R, int KIND>
-__global__ void __maxnreg__(120) // 17 warps x 32 x 120 registers = 65 280 of the SM's 65 536 (launch bounds alone make ptxas stop at 96)
+__global__ void __maxnreg__(112) // 17 warps x 32 x 112 registers (a warp's registers are allocated in units of 512: 120 would need 4096 per warp
+                                 // and the launch fails); launch bounds alone make ptxas stop at 96
 flip_measure_kernel(const __grid_constant__ FlipMaps M, const __grid_constant__ FlipParams P, double2 *partial /* [gridDim.x] */)
 {
     extern __shared__ unsigned char flip_smem_raw[];

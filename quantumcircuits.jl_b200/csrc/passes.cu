@@ -372,11 +372,12 @@ static __global__ void k_env_combine_raw(const double *__restrict__ raw, EnvIds 
     if (ord < ids.n) adjm_combine_raw(raw + ord * kAdjmRow, env_out + (size_t)ids.id[ord] * 32);
 }
 
-template <int TB, int NW> static int launch_adjoint_mma(qcb_state *psi, qcb_state *lam, const AdjMmaParams &M, const EnvIds &ids, double *d_env)
+template <int TB, int NW, int MINB_ = 0> static int launch_adjoint_mma(qcb_state *psi, qcb_state *lam, const AdjMmaParams &M, const EnvIds &ids, double *d_env)
 {
     constexpr int NT = 32 * NW;
-    // two tiles per CTA and at most 80 registers per thread: 6 CTAs = 24 warps per SM at TB = 10
-    constexpr int MINB = TB >= 12 ? 1 : (TB == 11 ? 2 : (TB == 10 ? (NW == 8 ? 3 : 6) : 6));
+    // two tiles per CTA and at most 80 registers per thread: 6 CTAs = 24 warps per SM at TB = 10 (option "adjoint_ctas" = 5:
+    // 96 registers, no spills, 20 warps)
+    constexpr int MINB = MINB_ ? MINB_ : (TB >= 12 ? 1 : (TB == 11 ? 2 : (TB == 10 ? (NW == 8 ? 3 : 6) : 6)));
     auto kern = adjoint_pass_mma_kernel<TB, NW, MINB>;
     const size_t smem = 2 * (sizeof(double2) << TB);
     static bool attr_set = false;
@@ -459,7 +460,7 @@ template <> int launch_adjoint_any<double>(qcb_state *psi, qcb_state *lam, int T
         fill_adj_mma(M, TB, NW);
         switch (TB * 100 + NW) {
         case 904: return launch_adjoint_mma<9, 4>(psi, lam, M, ids, d_env);
-        case 1004: return launch_adjoint_mma<10, 4>(psi, lam, M, ids, d_env);
+        case 1004: return ctx().adjoint_ctas == 5 ? launch_adjoint_mma<10, 4, 5>(psi, lam, M, ids, d_env) : launch_adjoint_mma<10, 4>(psi, lam, M, ids, d_env);
         case 1008: return launch_adjoint_mma<10, 8>(psi, lam, M, ids, d_env);
         case 1108: return launch_adjoint_mma<11, 8>(psi, lam, M, ids, d_env);
         case 1216: return launch_adjoint_mma<12, 16>(psi, lam, M, ids, d_env);
