@@ -19,6 +19,8 @@ namespace qcb {
 
 constexpr int kAdjMaxGates = 10; // gates per backward pass (bounds the shared-memory accumulators)
 
+struct EnvIds { int id[kAdjMaxGates]; int n; }; // accumulator row (ordinal inside the pass) -> gate index of the circuit
+
 template <typename R> struct AdjParams {
     PassParams<R> P;                          // geometry, stages, U^dagger matrices
     uint8_t slot_gate[kMaxStages * kSlots];   // ordinal of the slot's gate inside this pass (accumulator row)

@@ -206,8 +206,10 @@ __device__ __forceinline__ void adjoint_stage_f32(const AdjParams<float> &A, int
 // persistent CTAs; partial: [gridDim.x][kAdjMaxGates][32] (the layout adjoint_pass_kernel writes: k_env_final sums it)
 template <int TB, int MINB>
 __global__ void __launch_bounds__(1 << (TB - kRegBits), MINB)
-adjoint_pass_f32_kernel(float2 *psi, float2 *lam, const __grid_constant__ AdjParams<float> A, unsigned long long ntiles, double *partial)
+adjoint_pass_f32_kernel(float2 *psi, float2 *lam, const __grid_constant__ AdjParams<float> A, unsigned long long ntiles, double *partial,
+                        const __grid_constant__ EnvIds ids, int *id_row /* may be null: [kAdjMaxGates] gate index of every accumulator row */)
 {
+    if (id_row && blockIdx.x == 0 && threadIdx.x < kAdjMaxGates) id_row[threadIdx.x] = (int)threadIdx.x < ids.n ? ids.id[threadIdx.x] : -1;
     constexpr int NT = 1 << (TB - kRegBits);
     constexpr int NW = NT / 32;
     extern __shared__ __align__(16) unsigned char qcb_smem_raw[];

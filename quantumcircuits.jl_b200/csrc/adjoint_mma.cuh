@@ -187,8 +187,10 @@ template <int TB, int NW> inline void build_adj_mma_prog(const AdjMmaParams &M, 
 }
 #if defined(__CUDACC__)
 // grid = (stage, slot) pairs = kMaxStages * kSlots blocks of 32 NW threads; inactive slots exit
-template <int TB, int NW> __global__ void k_build_adj_mma_prog(const __grid_constant__ AdjMmaParams M, AdjmLaneProg *prog)
+template <int TB, int NW> __global__ void k_build_adj_mma_prog(const __grid_constant__ AdjMmaParams M, AdjmLaneProg *prog, const __grid_constant__ EnvIds ids,
+                                                               int *id_row /* may be null */)
 {
+    if (id_row && blockIdx.x == 0 && threadIdx.x < kAdjMaxGates) id_row[threadIdx.x] = (int)threadIdx.x < ids.n ? ids.id[threadIdx.x] : -1;
     const int s = blockIdx.x / kSlots, slot = blockIdx.x % kSlots;
     if (s >= M.A.P.nstages || !((M.A.P.stage[s].mask >> slot) & 1)) return;
     const int ord = M.A.slot_gate[s * kSlots + slot];

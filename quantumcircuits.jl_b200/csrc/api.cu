@@ -216,7 +216,7 @@ template <typename R, int KIND> static int launch_flip_measure(const FlipMaps &M
         attr_set = true;
     }
     const unsigned grid = (unsigned)std::min<unsigned long long>(P.n_items, (unsigned long long)ctx().sm_count);
-    kern<<<grid, kFlipGroups * kFlipConsumers + 32, smem, ctx().stream>>>(M, P, partial);
+    kern<<<grid, kFlipGroups * kFlipConsumers, smem, ctx().stream>>>(M, P, partial);
     QCB_CUDA(cudaGetLastError());
     count_launch();
     *grid_out = grid;
@@ -739,6 +739,8 @@ int qcb_set_option(const char *key, long value)
     } else if (k == "adjoint_tile_bits") {
         if (value != 0 && (value < kMinTB || value > 12)) return set_error(QCB_EINVAL, "adjoint_tile_bits must be 0 (auto) or in [%d, 12]", kMinTB);
         c.adjoint_tile_bits = value;
+    } else if (k == "adjoint_defer") {
+        c.adjoint_defer = value ? 1 : 0;
     } else if (k == "adjoint_ctas") {
         c.adjoint_ctas = value;
     } else if (k == "adjoint_f32") {

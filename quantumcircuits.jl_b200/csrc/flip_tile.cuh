@@ -5,9 +5,9 @@
 // sum(psi') pass (src/hamiltonians/hamiltonians.jl:41):
 //     E = sum_C diag(C) |psi_C|^2  +  coef * sum_i sum_{C : bit i clear} w_i(C) * 2 Re(conj(psi[C | 2^i]) psi[C])
 // (each flip pair once; the two orientations have exactly opposite imaginary parts).  The reference gathers n + 1
-// amplitudes per amplitude; here a CTA per SM walks 64 KiB tiles that one producer thread streams into a three-slot
-// shared-memory ring with TMA (cp.async.bulk.tensor, mbarrier full / empty phases), and eight consumer warps pull
-// 16-unit register windows out of the ring and do the flips in registers.
+// amplitudes per amplitude; here a CTA per SM walks 64 KiB tiles that stream into a three-slot shared-memory ring with TMA
+// (cp.async.bulk.tensor, one mbarrier per slot), and two groups of eight warps pull 16-unit register windows out of the
+// ring and do the flips in registers.
 //
 // Tile geometry (unit = 16 bytes = one ComplexF64 or two ComplexF32 amplitudes; 4096 units per tile, 12 unit bits):
 //   level 0   : 2^12 contiguous units (amplitude bits [0, 12) / [0, 13)): all flips inside the tile + the diagonal term
@@ -360,7 +360,7 @@ inline void flip_emulate_tile_load(const typename Vec2<R>::type *psi, const Flip
 
 #if defined(__CUDACC__)
 // ---------------------------------------------------------------------------------------------------------------------
-// the kernel: one CTA per SM, warps 0..15 = two consumer groups, warp 16 lane 0 = TMA producer
+// the kernel: one CTA per SM, 16 warps = two consumer groups that also issue their own TMA refills
 // ---------------------------------------------------------------------------------------------------------------------
 struct FlipMaps {
     CUtensorMap m[kFlipMaxLevels];
@@ -381,39 +381,33 @@ template <typename R> __device__ __forceinline__ void flip_issue_tile(const Flip
     }
 }
 
-// Two consumer groups: with one group (8 warps per SM) the kernel was latency bound -- ncu at 28 qubits: issue slots 41 %
-// busy, top stalls `wait` and `long_scoreboard`, DRAM at 62 % of its peak with two reads of the state.
+// Two consumer groups of 8 warps, no producer warp: with one group the kernel was latency bound (ncu at 28 qubits: issue
+// slots 41 % busy, top stalls `wait` and `long_scoreboard`, DRAM at 62 % of its peak with two reads of the state), and a 17th
+// warp would cost registers (a CTA's warps are allocated in fours: 20 x 32 x 96).  16 warps x 32 x 128 registers fill the SM.
+// Tile k of the CTA lives in ring slot k mod 3 and is consumed by group k mod 2; when a group has finished a tile (group
+// barrier), its first thread refills that very slot with tile k + 3 -- which the OTHER group will consume -- so a slot is
+// never written while it is read and no "empty" barriers are needed: only one `full` mbarrier per slot.
 template <typename R, int KIND>
-__global__ void __maxnreg__(112) // 17 warps x 32 x 112 registers (a warp's registers are allocated in units of 512: 120 would need 4096 per warp
-                                 // and the launch fails); launch bounds alone make ptxas stop at 96
+__global__ void __launch_bounds__(kFlipGroups * kFlipConsumers, 1)
 flip_measure_kernel(const __grid_constant__ FlipMaps M, const __grid_constant__ FlipParams P, double2 *partial /* [gridDim.x] */)
 {
     extern __shared__ unsigned char flip_smem_raw[];
     unsigned char *ring = reinterpret_cast<unsigned char *>(((uintptr_t)flip_smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t *full = reinterpret_cast<uint64_t *>(ring + kFlipRing * kFlipTileBytes);
-    uint64_t *empty = full + kFlipRing;
-    double *red = reinterpret_cast<double *>(empty + kFlipRing); // [16 warps][2]
+    double *red = reinterpret_cast<double *>(full + 2 * kFlipRing); // [16 warps][2]
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     constexpr uint32_t kWarpsPerGroup = kFlipConsumers / 32, kConsumerWarps = kFlipGroups * kWarpsPerGroup;
     if (tid == 0) {
-        for (int i = 0; i < kFlipRing; i++) {
-            tma::mbar_init(&full[i], 1);
-            tma::mbar_init(&empty[i], kWarpsPerGroup); // a tile is consumed by one group
-        }
+        for (int i = 0; i < kFlipRing; i++) tma::mbar_init(&full[i], 1);
         tma::fence_barrier_init();
+        for (int l = 0; l < P.nlevels; l++) tma::prefetch_map(&M.m[l]);
     }
     __syncthreads();
-    if (warp == kConsumerWarps) {
-        if (lane == 0) {
-            for (int l = 0; l < P.nlevels; l++) tma::prefetch_map(&M.m[l]);
-            uint32_t k = 0;
-            for (unsigned long long j = blockIdx.x; j < P.n_items; j += gridDim.x, k++) {
-                const uint32_t slot = k % kFlipRing, round = k / kFlipRing;
-                tma::mbar_wait(&empty[slot], (round & 1u) ^ 1u);
-                flip_issue_tile<R>(M, P, flip_decode(P, j), ring + (size_t)slot * kFlipTileBytes, &full[slot]);
-            }
+    if (tid == 0) {
+        for (uint32_t k = 0; k < (uint32_t)kFlipRing; k++) {
+            const unsigned long long j = blockIdx.x + (unsigned long long)k * gridDim.x;
+            if (j < P.n_items) flip_issue_tile<R>(M, P, flip_decode(P, j), ring + (size_t)k * kFlipTileBytes, &full[k]);
         }
-        return;
     }
     double acc_diag = 0.0, acc_flip = 0.0;
     const uint32_t group = warp / kWarpsPerGroup, gtid = tid % kFlipConsumers;
@@ -422,13 +416,16 @@ flip_measure_kernel(const __grid_constant__ FlipMaps M, const __grid_constant__ 
         const uint32_t slot = k % kFlipRing, round = k / kFlipRing;
         tma::mbar_wait(&full[slot], round & 1u);
         flip_tile_consume<R, KIND>(ring + (size_t)slot * kFlipTileBytes, gtid, P, flip_decode(P, j), acc_diag, acc_flip);
-        __syncwarp();
-        if (lane == 0) tma::mbar_arrive(&empty[slot]);
+        tma::named_bar_sync(1 + (int)group, kFlipConsumers); // every warp of the group is done with the slot
+        if (gtid == 0) {
+            const unsigned long long jn = j + (unsigned long long)kFlipRing * gridDim.x; // tile k + 3 of this CTA
+            if (jn < P.n_items) flip_issue_tile<R>(M, P, flip_decode(P, jn), ring + (size_t)slot * kFlipTileBytes, &full[slot]);
+        }
     }
     acc_diag = warp_sum(acc_diag);
     acc_flip = warp_sum(acc_flip);
     if (lane == 0) { red[2 * warp] = acc_diag; red[2 * warp + 1] = acc_flip; }
-    tma::named_bar_sync(1, kFlipGroups * kFlipConsumers);
+    __syncthreads();
     if (tid == 0) {
         double d = 0, f = 0;
         for (uint32_t w = 0; w < kConsumerWarps; w++) { d += red[2 * w]; f += red[2 * w + 1]; } // fixed order: reproducible

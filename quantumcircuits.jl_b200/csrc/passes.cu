@@ -259,8 +259,6 @@ template <typename R> static int run_fused(qcb_state *s, const std::vector<GateO
 }
 
 // ---- fused backward pass of the adjoint gradient sweep (adjoint.cuh) -------------------------------------
-struct EnvIds { int id[kAdjMaxGates]; int n; };
-
 static __global__ void k_env_final(const double *__restrict__ partial, int nblocks, EnvIds ids, double *env_out)
 {
     // block = (gate ordinal, element); fixed-order sum over the persistent CTAs' partials
@@ -276,6 +274,64 @@ static __global__ void k_env_final(const double *__restrict__ partial, int nbloc
         for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += red[w];
         env_out[(size_t)ids.id[ord] * 32 + el] = t;
     }
+}
+
+// ---- deferred reduction (Ctx::AdjDefer): d_partial = [pass areas | gate-id table (ints, kAdjMaxGates per pass) | raw sums]
+// every pass records which gates its accumulator rows belong to
+static __global__ void k_env_note_ids(EnvIds ids, int *table_row)
+{
+    if (threadIdx.x < kAdjMaxGates) table_row[threadIdx.x] = (int)threadIdx.x < ids.n ? ids.id[threadIdx.x] : -1;
+}
+// kind 2: block = (pass, gate ordinal, element); fixed-order sum over the pass's CTAs
+static __global__ void k_env_final_deferred(const double *__restrict__ areas, size_t stride, int nblocks, const int *__restrict__ table, double *env_out)
+{
+    const int el = blockIdx.x & 31, ord = (blockIdx.x >> 5) % kAdjMaxGates, pass = (blockIdx.x >> 5) / kAdjMaxGates;
+    const int gate = table[pass * kAdjMaxGates + ord];
+    if (gate < 0) return;
+    const double *partial = areas + (size_t)pass * stride;
+    double s = 0;
+    for (int b = threadIdx.x; b < nblocks; b += blockDim.x) s += partial[(size_t)b * (kAdjMaxGates * 32) + ord * 32 + el];
+    __shared__ double red[32];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += red[w];
+        env_out[(size_t)gate * 32 + el] = t;
+    }
+}
+
+static size_t adj_defer_table_doubles() { return (((size_t)ctx().adj_defer.npasses * kAdjMaxGates * sizeof(int) + 15) / 16) * 2; } // keeps what follows 16-byte aligned
+static int *adj_defer_table() { return reinterpret_cast<int *>(ctx().d_partial + (size_t)ctx().adj_defer.npasses * ctx().adj_defer.stride); }
+static double *adj_defer_raw()
+{
+    const Ctx::AdjDefer &D = ctx().adj_defer;
+    return ctx().d_partial + (size_t)D.npasses * D.stride + adj_defer_table_doubles();
+}
+// area of the current pass; the first pass of a sweep sizes the arena (nothing to preserve yet)
+static int adj_defer_area(size_t doubles_per_pass, int nrows, int kind, size_t extra_doubles, double **area)
+{
+    Ctx::AdjDefer &D = ctx().adj_defer;
+    if (D.pass == 0) {
+        D.stride = doubles_per_pass; D.nrows = nrows; D.kind = kind;
+        const size_t total = (size_t)D.npasses * D.stride + adj_defer_table_doubles() + (size_t)D.npasses * kAdjMaxGates * 64 + extra_doubles;
+        if (total * sizeof(double) > ((size_t)512 << 20)) { D.on = false; return QCB_OK; } // too many passes: reduce pass by pass
+        QCB_TRY(ensure_partial(total));
+    } else if (D.stride != doubles_per_pass || D.nrows != nrows || D.kind != kind) {
+        return set_error(QCB_EINVAL, "backward passes of one sweep differ in shape");
+    }
+    *area = ctx().d_partial + (size_t)D.pass * D.stride;
+    return QCB_OK;
+}
+static int adj_defer_note(const EnvIds &ids)
+{
+    Ctx::AdjDefer &D = ctx().adj_defer;
+    k_env_note_ids<<<1, 32, 0, ctx().stream>>>(ids, adj_defer_table() + D.pass * kAdjMaxGates);
+    QCB_CUDA(cudaGetLastError());
+    count_launch();
+    D.pass += 1;
+    return QCB_OK;
 }
 
 template <typename R, int TB> static int launch_adjoint(qcb_state *psi, qcb_state *lam, const AdjParams<R> &A, const EnvIds &ids, double *d_env)
@@ -297,12 +353,16 @@ template <typename R, int TB> static int launch_adjoint(qcb_state *psi, qcb_stat
     }
     const unsigned long long ntiles = 1ull << (psi->nloc - TB);
     const unsigned grid = (unsigned)std::min<unsigned long long>(ntiles, (unsigned long long)ctx().sm_count * ctas_per_sm);
-    QCB_TRY(ensure_partial((size_t)grid * kAdjMaxGates * 32));
-    kern<<<grid, NT, smem, ctx().stream>>>((V *)psi->d, (V *)lam->d, A, ntiles, ctx().d_partial);
+    double *area = nullptr;
+    if (ctx().adj_defer.on) QCB_TRY(adj_defer_area((size_t)grid * kAdjMaxGates * 32, (int)grid, 2, 0, &area));
+    if (!ctx().adj_defer.on) { QCB_TRY(ensure_partial((size_t)grid * kAdjMaxGates * 32)); area = ctx().d_partial; }
+    kern<<<grid, NT, smem, ctx().stream>>>((V *)psi->d, (V *)lam->d, A, ntiles, area);
     QCB_CUDA(cudaGetLastError());
-    k_env_final<<<ids.n * 32, 128, 0, ctx().stream>>>(ctx().d_partial, (int)grid, ids, d_env);
+    count_launch();
+    if (ctx().adj_defer.on) return adj_defer_note(ids);
+    k_env_final<<<ids.n * 32, 128, 0, ctx().stream>>>(area, (int)grid, ids, d_env);
     QCB_CUDA(cudaGetLastError());
-    count_launch(2);
+    count_launch();
     return QCB_OK;
 }
 
@@ -325,8 +385,18 @@ template <int TB> static int launch_adjoint_f32(qcb_state *psi, qcb_state *lam, 
     }
     const unsigned long long ntiles = 1ull << (psi->nloc - TB);
     const unsigned grid = (unsigned)std::min<unsigned long long>(ntiles, (unsigned long long)ctx().sm_count * ctas_per_sm);
+    double *area = nullptr;
+    if (ctx().adj_defer.on) QCB_TRY(adj_defer_area((size_t)grid * kAdjMaxGates * 32, (int)grid, 2, 0, &area));
+    if (ctx().adj_defer.on) {
+        // the kernel itself notes which gates its rows belong to; the rows of all passes are summed after the sweep
+        kern<<<grid, NT, smem, ctx().stream>>>((float2 *)psi->d, (float2 *)lam->d, A, ntiles, area, ids, adj_defer_table() + ctx().adj_defer.pass * kAdjMaxGates);
+        QCB_CUDA(cudaGetLastError());
+        count_launch();
+        ctx().adj_defer.pass += 1;
+        return QCB_OK;
+    }
     QCB_TRY(ensure_partial((size_t)grid * kAdjMaxGates * 32));
-    kern<<<grid, NT, smem, ctx().stream>>>((float2 *)psi->d, (float2 *)lam->d, A, ntiles, ctx().d_partial);
+    kern<<<grid, NT, smem, ctx().stream>>>((float2 *)psi->d, (float2 *)lam->d, A, ntiles, ctx().d_partial, ids, nullptr);
     QCB_CUDA(cudaGetLastError());
     k_env_final<<<ids.n * 32, 128, 0, ctx().stream>>>(ctx().d_partial, (int)grid, ids, d_env);
     QCB_CUDA(cudaGetLastError());
@@ -372,6 +442,51 @@ static __global__ void k_env_combine_raw(const double *__restrict__ raw, EnvIds 
     if (ord < ids.n) adjm_combine_raw(raw + ord * kAdjmRow, env_out + (size_t)ids.id[ord] * 32);
 }
 
+// deferred forms: block = (pass, gate ordinal, raw element); then one thread per (pass, gate ordinal)
+static __global__ void k_env_reduce_raw_deferred(const double *__restrict__ areas, size_t stride, int nrows, const int *__restrict__ table, double *raw_out)
+{
+    const int el = blockIdx.x & 63, slot = blockIdx.x >> 6, ord = slot % kAdjMaxGates, pass = slot / kAdjMaxGates;
+    if (table[slot] < 0) return;
+    const double *rows = areas + (size_t)pass * stride;
+    double s = 0;
+    for (int r = threadIdx.x; r < nrows; r += blockDim.x) s += rows[((size_t)r * kAdjMaxGates + ord) * kAdjmRow + el];
+    __shared__ double red[32];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += red[w];
+        raw_out[(size_t)slot * kAdjmRow + el] = t;
+    }
+}
+static __global__ void k_env_combine_raw_deferred(const double *__restrict__ raw, const int *__restrict__ table, int nslots, double *env_out)
+{
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot < nslots && table[slot] >= 0) adjm_combine_raw(raw + (size_t)slot * kAdjmRow, env_out + (size_t)table[slot] * 32);
+}
+
+// end of a sweep whose reductions were deferred
+static int adj_defer_finish(double *d_env)
+{
+    Ctx::AdjDefer &D = ctx().adj_defer;
+    if (!D.on || D.pass == 0) { D.on = false; return QCB_OK; }
+    const int nslots = D.pass * kAdjMaxGates;
+    if (D.kind == 1) {
+        k_env_reduce_raw_deferred<<<nslots * kAdjmRow, 128, 0, ctx().stream>>>(ctx().d_partial, D.stride, D.nrows, adj_defer_table(), adj_defer_raw());
+        QCB_CUDA(cudaGetLastError());
+        k_env_combine_raw_deferred<<<(nslots + 63) / 64, 64, 0, ctx().stream>>>(adj_defer_raw(), adj_defer_table(), nslots, d_env);
+        QCB_CUDA(cudaGetLastError());
+        count_launch(2);
+    } else {
+        k_env_final_deferred<<<nslots * 32, 128, 0, ctx().stream>>>(ctx().d_partial, D.stride, D.nrows, adj_defer_table(), d_env);
+        QCB_CUDA(cudaGetLastError());
+        count_launch();
+    }
+    D.on = false;
+    return QCB_OK;
+}
+
 template <int TB, int NW, int MINB_ = 0> static int launch_adjoint_mma(qcb_state *psi, qcb_state *lam, const AdjMmaParams &M, const EnvIds &ids, double *d_env)
 {
     constexpr int NT = 32 * NW;
@@ -393,22 +508,42 @@ template <int TB, int NW, int MINB_ = 0> static int launch_adjoint_mma(qcb_state
     // device work area: [accumulator rows of every warp | their sums | the threads' per-gate programs]
     const size_t nrows = (size_t)grid * NW;
     const size_t rows_doubles = nrows * kAdjMaxGates * kAdjmRow, raw_doubles = (size_t)kAdjMaxGates * kAdjmRow;
-    QCB_TRY(ensure_partial(rows_doubles + raw_doubles + (size_t)kAdjMaxGates * 16 * 32 * sizeof(AdjmLaneProg) / sizeof(double)));
+    const size_t prog_doubles = (size_t)kAdjMaxGates * 16 * 32 * sizeof(AdjmLaneProg) / sizeof(double);
     // (the rows need no zeroing: first contributions are stored)
-    double *d_rows = ctx().d_partial, *d_raw = d_rows + rows_doubles, *d_prog = d_raw + raw_doubles;
+    double *d_rows = nullptr, *d_raw = nullptr, *d_prog = nullptr;
+    int *id_row = nullptr;
+    if (ctx().adj_defer.on) QCB_TRY(adj_defer_area(rows_doubles, (int)nrows, 1, prog_doubles, &d_rows));
+    if (ctx().adj_defer.on) {
+        const Ctx::AdjDefer &D = ctx().adj_defer;
+        d_prog = adj_defer_raw() + (size_t)D.npasses * kAdjMaxGates * 64;
+        id_row = adj_defer_table() + D.pass * kAdjMaxGates;
+    } else {
+        QCB_TRY(ensure_partial(rows_doubles + raw_doubles + prog_doubles));
+        d_rows = ctx().d_partial; d_raw = d_rows + rows_doubles; d_prog = d_raw + raw_doubles;
+    }
     if (ctx().adjoint_prog_host) {
         // cross-check path: the table built on the host (what the CPU replay runs) and uploaded
         static thread_local std::vector<AdjmLaneProg> prog;
         prog.resize((size_t)kAdjMaxGates * NT);
         build_adj_mma_prog<TB, NW>(M, prog.data());
         QCB_CUDA(cudaMemcpyAsync(d_prog, prog.data(), (size_t)M.A.ngates * NT * sizeof(AdjmLaneProg), cudaMemcpyHostToDevice, ctx().stream));
+        if (id_row) {
+            k_env_note_ids<<<1, 32, 0, ctx().stream>>>(ids, id_row);
+            QCB_CUDA(cudaGetLastError());
+            count_launch();
+        }
     } else {
-        k_build_adj_mma_prog<TB, NW><<<kMaxStages * kSlots, NT, 0, ctx().stream>>>(M, (AdjmLaneProg *)d_prog);
+        k_build_adj_mma_prog<TB, NW><<<kMaxStages * kSlots, NT, 0, ctx().stream>>>(M, (AdjmLaneProg *)d_prog, ids, id_row);
         QCB_CUDA(cudaGetLastError());
         count_launch();
     }
     kern<<<grid, NT, smem, ctx().stream>>>((double2 *)psi->d, (double2 *)lam->d, M.A.P, M.A.ngates, (const uint4 *)d_prog, ntiles, d_rows);
     QCB_CUDA(cudaGetLastError());
+    if (ctx().adj_defer.on) {
+        count_launch();
+        ctx().adj_defer.pass += 1;
+        return QCB_OK;
+    }
     if (nrows <= 128) {
         k_env_reduce_raw<<<ids.n, 256, 0, ctx().stream>>>(d_rows, (int)nrows, ids, d_env);
         QCB_CUDA(cudaGetLastError());
@@ -541,8 +676,15 @@ template <typename R> static int run_adjoint_fused_t(qcb_state *psi, qcb_state *
         if (c.plan_cache.size() > 64) c.plan_cache.clear();
         it = c.plan_cache.emplace(key, std::move(plans)).first;
     }
-    for (const PassPlan &pl : it->second) QCB_TRY(launch_adjoint_plan_t<R>(psi, lam, pl, rev, mats, d_env, mma));
-    return QCB_OK;
+    Ctx::AdjDefer &D = c.adj_defer;
+    D = Ctx::AdjDefer();
+    D.on = c.adjoint_defer != 0 && it->second.size() > 0;
+    D.npasses = (int)it->second.size();
+    for (const PassPlan &pl : it->second) {
+        const int rc = launch_adjoint_plan_t<R>(psi, lam, pl, rev, mats, d_env, mma);
+        if (rc != QCB_OK) { D.on = false; return rc; }
+    }
+    return adj_defer_finish(d_env);
 }
 
 // rev: the circuit's gates in reverse order, GateOp.mat = original gate index (also the row of d_env, 32 doubles each).

@@ -37,7 +37,7 @@ struct Ctx {
     cudaEvent_t chunk_ev[2][16] = {};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // options
-    long tile_bits = 11, low_bits = 3, max_gates_per_pass = 1 << 30, force_simple = 0, adjoint_tile_bits = 0, adjoint_mma = 1, adjoint_warps = 0, adjoint_prog_host = 0, measure_ctas = 0, contract_coop = 1, measure_persistent = 0, measure_tma = 1, pass_tma = 0, pass_tma_max_stages = 3, adjoint_f32 = 1, adjoint_ctas = 0;
+    long tile_bits = 11, low_bits = 3, max_gates_per_pass = 1 << 30, force_simple = 0, adjoint_tile_bits = 0, adjoint_mma = 1, adjoint_warps = 0, adjoint_prog_host = 0, measure_ctas = 0, contract_coop = 1, measure_persistent = 0, measure_tma = 1, pass_tma = 0, pass_tma_max_stages = 3, adjoint_f32 = 1, adjoint_ctas = 5, adjoint_defer = 1;
     // stats
     double st_passes = 0, st_stages = 0, st_launches = 0, st_gates = 0, st_launches_total = 0, st_swaps = 0, st_fused_swaps = 0;
     long fuse_swaps = 1;
@@ -50,6 +50,15 @@ struct Ctx {
     double st_tma_passes = 0, st_fw_passes = 0, st_bw_passes = 0, st_ham_passes = 0;
     int *d_barrier = nullptr; // 1 int for stream-ordered inter-rank barriers (NCCL all-reduce)
     // scratch
+    // backward sweep of an unsharded gradient: the per-pass accumulator rows of ALL passes stay in d_partial (one area per
+    // pass) and are reduced by two launches at the end of the sweep instead of two or three per pass
+    struct AdjDefer {
+        bool on = false;
+        int pass = 0, npasses = 0;
+        size_t stride = 0;   // doubles per pass area
+        int nrows = 0;       // accumulator rows per pass (mma: CTAs x warps; else CTAs)
+        int kind = 0;        // 1: raw rows of the tensor-core pass (64 doubles per gate), 2: environment partials (32 doubles)
+    } adj_defer;
     double *d_partial = nullptr; // reduction partials
     size_t partial_cap = 0;      // in doubles
     double *d_out = nullptr;     // small device result buffer

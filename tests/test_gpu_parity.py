@@ -54,6 +54,8 @@ def _defaults():
     qc.set_option("measure_tma", 1)
     qc.set_option("pass_tma", 1)
     qc.set_option("adjoint_f32", 1)
+    qc.set_option("adjoint_ctas", 5)
+    qc.set_option("adjoint_defer", 1)
     qc.set_option("tma_l2_promotion", 1)
     yield
 
@@ -441,6 +443,36 @@ def test_gradients_f32_tensor_core_pass(oracle, n, layers, atb):
         _, g_ref = oracle.gradients_brickwork(v, n, layers, c.gate_angles, 0 if n % 2 else 1, H.params())
         assert np.max(np.abs(g1 - g_ref)) < 1e-5 * scale_g
     qc.set_option("adjoint_f32", 1)
+
+
+@pytest.mark.parametrize("n,layers", [(9, 2), (12, 20), (14, 9), (17, 5), (20, 4), (23, 3)])
+@pytest.mark.parametrize("dtype", [np.complex128, np.complex64])
+def test_gradients_deferred_reduction(n, layers, dtype):
+    """The accumulator rows of all backward passes reduced by two launches after the sweep (default) == one reduction per
+    pass (option adjoint_defer = 0); same fixed summation order, so the numbers agree to rounding of the final adds.  Every
+    backward-pass kernel: tensor-core ComplexF64 (5 and 6 CTAs per SM), scalar ComplexF64, both ComplexF32 forms."""
+    rng = np.random.default_rng(3000 + 31 * n + layers)
+    c = circuit(n, layers, rng)
+    H = qc.EastModelHamiltonian(0.1, -0.1) if n % 2 else qc.TFIMHamiltonian(1.0, 0.9045, 1.4)
+    psi0 = qc.B200State(rand_state(rng, n, dtype))
+    variants = [("adjoint_mma", 1), ("adjoint_mma", 0)] if dtype == np.complex128 else [("adjoint_f32", 1), ("adjoint_f32", 0)]
+    for key, val in variants:
+        qc.set_option(key, val)
+        for ctas in ((5, 6) if (key, val) == ("adjoint_mma", 1) else (0,)):
+            qc.set_option("adjoint_ctas", ctas)
+            qc.set_option("adjoint_defer", 0)
+            E0, g0 = qc.gradients(H, psi0, c, calculate_energy=True)
+            l0 = qc.get_stat("launches")
+            qc.set_option("adjoint_defer", 1)
+            E1, g1 = qc.gradients(H, psi0, c, calculate_energy=True)
+            l1 = qc.get_stat("launches")
+            assert E1 == E0
+            assert np.max(np.abs(g1 - g0)) < 1e-13 * max(1.0, np.max(np.abs(g0)))
+            if n >= 12:
+                assert l1 < l0  # fewer launches per gradient
+    qc.set_option("adjoint_mma", 1)
+    qc.set_option("adjoint_f32", 1)
+    qc.set_option("adjoint_ctas", 5)
 
 
 @pytest.mark.parametrize("n,layers,atb", [(13, 5, 0), (16, 6, 9), (18, 4, 10), (18, 7, 11), (20, 3, 12), (22, 4, 0)])
