@@ -203,6 +203,27 @@ __device__ __forceinline__ void adjoint_stage_f32(const AdjParams<float> &A, int
     for (int r = 0; r < kRegAmps; r++) { smP[e ^ S.roff[r]] = x[r]; smL[e ^ S.roff[r]] = l[r]; }
 }
 
+// tile_load (tile.cuh) in two halves, so that the next tile's global loads are in flight during the write-back of the current one
+template <int TB>
+__device__ __forceinline__ void adjf_fetch(const float2 *__restrict__ src, const PassParams<float> &P, uint32_t tid, unsigned long long bid, float2 (&tmp)[kRegAmps])
+{
+    unsigned long long g = cta_base(P, bid);
+#pragma unroll
+    for (int k = 0; k < TB - kRegBits; k++) g |= (unsigned long long)((tid >> k) & 1u) << P.ld_phys[k];
+#pragma unroll
+    for (int i = 0; i < kRegAmps; i++) tmp[i] = src[g | P.ld_goff[i]];
+}
+template <int TB>
+__device__ __forceinline__ void adjf_fill(const PassParams<float> &P, float2 *sm, uint32_t tid, const float2 (&tmp)[kRegAmps])
+{
+    uint32_t e = 0;
+#pragma unroll
+    for (int k = 0; k < TB - kRegBits; k++) e |= ((tid >> k) & 1u) << P.ld_lpos[k];
+    e = swz<4>(e);
+#pragma unroll
+    for (int i = 0; i < kRegAmps; i++) sm[e ^ P.ld_eoff[i]] = tmp[i];
+}
+
 // persistent CTAs; partial: [gridDim.x][kAdjMaxGates][32] (the layout adjoint_pass_kernel writes: k_env_final sums it)
 template <int TB, int MINB>
 __global__ void __launch_bounds__(1 << (TB - kRegBits), MINB)
@@ -220,19 +241,38 @@ adjoint_pass_f32_kernel(float2 *psi, float2 *lam, const __grid_constant__ AdjPar
     for (int i = tid; i < NW * kAdjMaxGates * 32; i += NT) acc[i] = 0.0;
     __syncthreads();
     double *acc_warp = acc + (tid >> 5) * (kAdjMaxGates * 32);
-    for (unsigned long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        tile_load<float, TB>(psi, A.P, smP, tid, tile);
-        tile_load<float, TB>(lam, A.P, smL, tid, tile);
+    unsigned long long tile = blockIdx.x; // (the host launches at most ntiles CTAs)
+    {
+        float2 rp[kRegAmps], rl[kRegAmps];
+        adjf_fetch<TB>(psi, A.P, tid, tile, rp);
+        adjf_fetch<TB>(lam, A.P, tid, tile, rl);
+        adjf_fill<TB>(A.P, smP, tid, rp);
+        adjf_fill<TB>(A.P, smL, tid, rl);
+    }
+    while (true) {
         __syncthreads();
 #pragma unroll 1
         for (int s = 0; s < A.P.nstages; s++) {
             adjoint_stage_f32<TB>(A, s, smP, smL, acc_warp, tid);
             __syncthreads();
         }
+        const unsigned long long next = tile + gridDim.x;
+        if (next >= ntiles) {
+            tile_store<float, TB>(psi, A.P, smP, tid, tile);
+            tile_store<float, TB>(lam, A.P, smL, tid, tile);
+            break;
+        }
+        float2 rp[kRegAmps], rl[kRegAmps];
+        adjf_fetch<TB>(psi, A.P, tid, next, rp); // in flight during the write-back
+        adjf_fetch<TB>(lam, A.P, tid, next, rl);
         tile_store<float, TB>(psi, A.P, smP, tid, tile);
         tile_store<float, TB>(lam, A.P, smL, tid, tile);
-        __syncthreads();
+        __syncthreads(); // every thread has read its part of the tile: the buffers may be overwritten
+        adjf_fill<TB>(A.P, smP, tid, rp);
+        adjf_fill<TB>(A.P, smL, tid, rl);
+        tile = next;
     }
+    __syncthreads();
     for (int i = tid; i < kAdjMaxGates * 32; i += NT) {
         double s = 0;
 #pragma unroll

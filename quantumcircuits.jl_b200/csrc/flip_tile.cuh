@@ -386,7 +386,11 @@ template <typename R> __device__ __forceinline__ void flip_issue_tile(const Flip
 // warp would cost registers (a CTA's warps are allocated in fours: 20 x 32 x 96).  16 warps x 32 x 128 registers fill the SM.
 // Tile k of the CTA lives in ring slot k mod 3 and is consumed by group k mod 2; when a group has finished a tile (group
 // barrier), its first thread refills that very slot with tile k + 3 -- which the OTHER group will consume -- so a slot is
-// never written while it is read and no "empty" barriers are needed: only one `full` mbarrier per slot.
+// never written while it is read and no "empty" barriers are needed: one `full` mbarrier per slot, plus a plain counter
+// `issued[slot]` (round of the last tile issued into the slot, + 1).  The counter is what makes the parity wait sound: a
+// parity test cannot tell "phase r has completed" from "phase r - 1 has not completed yet", and the group that waits for
+// round r of a slot did not consume round r - 1 of it.  Once it has seen issued[slot] == r + 1 it knows that the other
+// group has passed its own wait for round r - 1 (it issues only after consuming), so the barrier is in phase r.
 template <typename R, int KIND>
 __global__ void __launch_bounds__(kFlipGroups * kFlipConsumers, 1)
 flip_measure_kernel(const __grid_constant__ FlipMaps M, const __grid_constant__ FlipParams P, double2 *partial /* [gridDim.x] */)
@@ -394,11 +398,12 @@ flip_measure_kernel(const __grid_constant__ FlipMaps M, const __grid_constant__ 
     extern __shared__ unsigned char flip_smem_raw[];
     unsigned char *ring = reinterpret_cast<unsigned char *>(((uintptr_t)flip_smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t *full = reinterpret_cast<uint64_t *>(ring + kFlipRing * kFlipTileBytes);
+    volatile uint32_t *issued = reinterpret_cast<volatile uint32_t *>(full + kFlipRing); // [kFlipRing], inside the 2 * kFlipRing words reserved for barriers
     double *red = reinterpret_cast<double *>(full + 2 * kFlipRing); // [16 warps][2]
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     constexpr uint32_t kWarpsPerGroup = kFlipConsumers / 32, kConsumerWarps = kFlipGroups * kWarpsPerGroup;
     if (tid == 0) {
-        for (int i = 0; i < kFlipRing; i++) tma::mbar_init(&full[i], 1);
+        for (int i = 0; i < kFlipRing; i++) { tma::mbar_init(&full[i], 1); issued[i] = 0; }
         tma::fence_barrier_init();
         for (int l = 0; l < P.nlevels; l++) tma::prefetch_map(&M.m[l]);
     }
@@ -406,7 +411,11 @@ flip_measure_kernel(const __grid_constant__ FlipMaps M, const __grid_constant__ 
     if (tid == 0) {
         for (uint32_t k = 0; k < (uint32_t)kFlipRing; k++) {
             const unsigned long long j = blockIdx.x + (unsigned long long)k * gridDim.x;
-            if (j < P.n_items) flip_issue_tile<R>(M, P, flip_decode(P, j), ring + (size_t)k * kFlipTileBytes, &full[k]);
+            if (j < P.n_items) {
+                flip_issue_tile<R>(M, P, flip_decode(P, j), ring + (size_t)k * kFlipTileBytes, &full[k]);
+                __threadfence_block();
+                issued[k] = 1;
+            }
         }
     }
     double acc_diag = 0.0, acc_flip = 0.0;
@@ -414,12 +423,19 @@ flip_measure_kernel(const __grid_constant__ FlipMaps M, const __grid_constant__ 
     uint32_t k = group;
     for (unsigned long long j = blockIdx.x + (unsigned long long)group * gridDim.x; j < P.n_items; j += (unsigned long long)kFlipGroups * gridDim.x, k += kFlipGroups) {
         const uint32_t slot = k % kFlipRing, round = k / kFlipRing;
+        while (issued[slot] < round + 1u) { } // the tile of this round has been issued (=> the previous round of the slot has landed)
+        __threadfence_block();
         tma::mbar_wait(&full[slot], round & 1u);
         flip_tile_consume<R, KIND>(ring + (size_t)slot * kFlipTileBytes, gtid, P, flip_decode(P, j), acc_diag, acc_flip);
         tma::named_bar_sync(1 + (int)group, kFlipConsumers); // every warp of the group is done with the slot
         if (gtid == 0) {
             const unsigned long long jn = j + (unsigned long long)kFlipRing * gridDim.x; // tile k + 3 of this CTA
-            if (jn < P.n_items) flip_issue_tile<R>(M, P, flip_decode(P, jn), ring + (size_t)slot * kFlipTileBytes, &full[slot]);
+            if (jn < P.n_items) {
+                tma::fence_proxy_async(); // the group's reads of the slot come before the bulk copy that overwrites it
+                flip_issue_tile<R>(M, P, flip_decode(P, jn), ring + (size_t)slot * kFlipTileBytes, &full[slot]);
+                __threadfence_block();
+                issued[slot] = round + 2u;
+            }
         }
     }
     acc_diag = warp_sum(acc_diag);
