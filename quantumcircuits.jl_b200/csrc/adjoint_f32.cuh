@@ -195,10 +195,17 @@ __device__ __forceinline__ void adjoint_stage_f32(const AdjParams<float> &A, int
     for (int r = 0; r < kRegAmps; r++) { x[r] = smP[e ^ S.roff[r]]; l[r] = smL[e ^ S.roff[r]]; }
     const uint32_t mask = S.mask;
     const uint8_t *sg = A.slot_gate + s * kSlots;
-    if (mask & 1u) adjf_slot<1>(A.P.U[s * kSlots + 0], x, l, lane, acc_warp + 32 * sg[0]);
-    if (mask & 2u) adjf_slot<0>(A.P.U[s * kSlots + 1], x, l, lane, acc_warp + 32 * sg[1]);
-    if (mask & 4u) adjf_slot<2>(A.P.U[s * kSlots + 2], x, l, lane, acc_warp + 32 * sg[2]);
-    if (mask & 8u) adjf_slot<1>(A.P.U[s * kSlots + 3], x, l, lane, acc_warp + 32 * sg[3]);
+    // slots 0 and 3 act on the same window bits (1, 2): one copy of that code, entered twice (the kernel is bound by the FMA
+    // pipe with 16 warps per SM; ncu showed instruction-fetch stalls on the fully unrolled form)
+#pragma unroll 1
+    for (int rep = 0; rep < 2; rep++) {
+        const int sl = rep ? 3 : 0;
+        if ((mask >> sl) & 1u) adjf_slot<1>(A.P.U[s * kSlots + sl], x, l, lane, acc_warp + 32 * sg[sl]);
+        if (rep == 0) {
+            if (mask & 2u) adjf_slot<0>(A.P.U[s * kSlots + 1], x, l, lane, acc_warp + 32 * sg[1]);
+            if (mask & 4u) adjf_slot<2>(A.P.U[s * kSlots + 2], x, l, lane, acc_warp + 32 * sg[2]);
+        }
+    }
 #pragma unroll
     for (int r = 0; r < kRegAmps; r++) { smP[e ^ S.roff[r]] = x[r]; smL[e ^ S.roff[r]] = l[r]; }
 }
