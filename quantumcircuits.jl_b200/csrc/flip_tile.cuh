@@ -6,8 +6,8 @@
 //     E = sum_C diag(C) |psi_C|^2  +  coef * sum_i sum_{C : bit i clear} w_i(C) * 2 Re(conj(psi[C | 2^i]) psi[C])
 // (each flip pair once; the two orientations have exactly opposite imaginary parts).  The reference gathers n + 1
 // amplitudes per amplitude; here a CTA per SM walks 64 KiB tiles that stream into a three-slot shared-memory ring with TMA
-// (cp.async.bulk.tensor, one mbarrier per slot), and sixteen warps pull 16-unit register windows out of the ring and do the
-// flips in registers (two threads per window, each doing half of its work).
+// (cp.async.bulk.tensor, one mbarrier per slot), and two groups of eight warps pull 16-unit register windows out of the
+// ring and do the flips in registers.
 //
 // Tile geometry (unit = 16 bytes = one ComplexF64 or two ComplexF32 amplitudes; 4096 units per tile, 12 unit bits):
 //   level 0   : 2^12 contiguous units (amplitude bits [0, 12) / [0, 13)): all flips inside the tile + the diagonal term
@@ -31,7 +31,8 @@ constexpr int kFlipTileBytes = 16 << kFlipUnitBits;     // 64 KiB
 constexpr int kFlipWin = 9;                             // window bits of a level >= 1 tile
 constexpr int kFlipRing = 3;                            // tiles in flight per CTA
 constexpr int kFlipConsumers = 256;                     // consumer threads per tile (8 warps: 16 units per thread and stage)
-constexpr int kFlipGroups = 2;                          // the two halves of the CTA: both work on the same tile, each on half of every window's work
+constexpr int kFlipGroups = 2;                          // consumer groups per CTA, each on its own tile (tile k -> group k mod 2);
+                                                        // the warp after the last group is the producer
 constexpr int kFlipMaxLevels = 5;
 
 template <typename R> struct FlipGeom;
@@ -283,33 +284,24 @@ QCB_HD void flip_window_bit(const typename FlipAmp<R>::V (&a)[16 << FlipGeom<R>:
     }
 }
 
-// HALF = -1: the thread does the whole stage.  HALF = 0 / 1: two threads load the same window and share its work (window bits
-// 0, 1 / window bits 2, 3; the diagonal term by the lowest window bit) -- the kernel puts 16 warps on ONE tile that way, so
-// that a tile leaves shared memory twice as fast and two of the three ring slots are in flight.
-template <typename R, int KIND, int LV, int S, int HALF = -1>
+template <typename R, int KIND, int LV, int S>
 QCB_HD void flip_stage(const unsigned char *tile, uint32_t tid, const FlipParams &P, const FlipTileCtx &T, double &acc_diag, double &acc_flip)
 {
     using G = FlipGeom<R>;
     using V = typename FlipAmp<R>::V;
     constexpr int NR = 16 << G::SUB;
-    // skip a stage none of whose window bits (of this half) is active (upper levels of small states, row bits of window tiles)
-    constexpr uint32_t m01 = (1u << flip_win(LV, S, 0)) | (1u << flip_win(LV, S, 1)), m23 = (1u << flip_win(LV, S, 2)) | (1u << flip_win(LV, S, 3));
-    constexpr uint32_t wmask = HALF == 0 ? m01 : (HALF == 1 ? m23 : (m01 | m23));
-    constexpr uint32_t rowbits = LV == 1 ? 7u : 0u; // unit bits 0..2 of a window tile were covered by level 0
-    if (!(LV == 0 && S == 2) && !(T.active & wmask & ~rowbits)) return;
+    // skip a stage none of whose window bits is active (upper levels of small states)
+    constexpr uint32_t wmask = (1u << flip_win(LV, S, 0)) | (1u << flip_win(LV, S, 1)) | (1u << flip_win(LV, S, 2)) | (1u << flip_win(LV, S, 3));
+    if (!(LV == 0) && !(T.active & wmask)) return;
     const uint32_t u0 = flip_thread_unit<LV, S>(tid);
     V a[NR];
     flip_load_window<R, LV, S>(tile, u0, a);
-    if constexpr (HALF != 1) {
-        flip_window_bit<R, KIND, LV, S, 0>(a, u0, T, acc_flip);
-        flip_window_bit<R, KIND, LV, S, 1>(a, u0, T, acc_flip);
-    }
-    if constexpr (HALF != 0) {
-        flip_window_bit<R, KIND, LV, S, 2>(a, u0, T, acc_flip);
-        flip_window_bit<R, KIND, LV, S, 3>(a, u0, T, acc_flip);
-    }
+    flip_window_bit<R, KIND, LV, S, 0>(a, u0, T, acc_flip);
+    flip_window_bit<R, KIND, LV, S, 1>(a, u0, T, acc_flip);
+    flip_window_bit<R, KIND, LV, S, 2>(a, u0, T, acc_flip);
+    flip_window_bit<R, KIND, LV, S, 3>(a, u0, T, acc_flip);
     if constexpr (LV == 0 && S == 2) {
-        if constexpr (G::SUB == 1 && HALF != 1) acc_flip += 2.0 * (double)flip_pair_sum<R, NR, 0, -1>(a); // ComplexF32: index bit 0 lives inside the unit (no control)
+        if constexpr (G::SUB == 1) acc_flip += 2.0 * (double)flip_pair_sum<R, NR, 0, -1>(a); // ComplexF32: index bit 0 lives inside the unit (no control)
         // diagonal term: window = unit bits 8..11 (+ in-unit bit); boundary bits: unit 8, unit 11 (+ index bit 0)
         const unsigned long long C0 = T.base | ((unsigned long long)u0 << G::SUB);
         const unsigned long long lo = 1ull << (8 + G::SUB), hi = 1ull << (11 + G::SUB);
@@ -319,7 +311,6 @@ QCB_HD void flip_stage(const unsigned char *tile, uint32_t tid, const FlipParams
         typename FlipAmp<R>::Acc part = 0;
 #pragma unroll
         for (int r = 0; r < NR; r++) {
-            if (HALF >= 0 && ((r >> G::SUB) & 1) != HALF) continue; // split by the lowest window bit
             double d = d0 + P.diag_T[r];
             if ((r >> G::SUB) & 1) d += dlo;
             if ((r >> (3 + G::SUB)) & 1) d += dhi;
@@ -331,7 +322,7 @@ QCB_HD void flip_stage(const unsigned char *tile, uint32_t tid, const FlipParams
     }
 }
 
-template <typename R, int KIND, int HALF = -1>
+template <typename R, int KIND>
 QCB_HD void flip_tile_consume(const unsigned char *tile, uint32_t tid, const FlipParams &P, const FlipItem &it, double &acc_diag, double &acc_flip)
 {
     FlipTileCtx T;
@@ -339,14 +330,14 @@ QCB_HD void flip_tile_consume(const unsigned char *tile, uint32_t tid, const Fli
     T.active = P.level[it.lv].active;
     T.tile_ctl_ok = 1;
     if (it.lv == 0) {
-        flip_stage<R, KIND, 0, 0, HALF>(tile, tid, P, T, acc_diag, acc_flip);
-        flip_stage<R, KIND, 0, 1, HALF>(tile, tid, P, T, acc_diag, acc_flip);
-        flip_stage<R, KIND, 0, 2, HALF>(tile, tid, P, T, acc_diag, acc_flip);
+        flip_stage<R, KIND, 0, 0>(tile, tid, P, T, acc_diag, acc_flip);
+        flip_stage<R, KIND, 0, 1>(tile, tid, P, T, acc_diag, acc_flip);
+        flip_stage<R, KIND, 0, 2>(tile, tid, P, T, acc_diag, acc_flip);
     } else {
         if (KIND == 1) T.tile_ctl_ok = ((T.base >> (P.level[it.lv].w0 - 1)) & 1ull) ? 0 : 1;
-        flip_stage<R, KIND, 1, 0, HALF>(tile, tid, P, T, acc_diag, acc_flip);
-        flip_stage<R, KIND, 1, 1, HALF>(tile, tid, P, T, acc_diag, acc_flip);
-        flip_stage<R, KIND, 1, 2, HALF>(tile, tid, P, T, acc_diag, acc_flip);
+        flip_stage<R, KIND, 1, 0>(tile, tid, P, T, acc_diag, acc_flip);
+        flip_stage<R, KIND, 1, 1>(tile, tid, P, T, acc_diag, acc_flip);
+        flip_stage<R, KIND, 1, 2>(tile, tid, P, T, acc_diag, acc_flip);
     }
 }
 
@@ -369,7 +360,7 @@ inline void flip_emulate_tile_load(const typename Vec2<R>::type *psi, const Flip
 
 #if defined(__CUDACC__)
 // ---------------------------------------------------------------------------------------------------------------------
-// the kernel: one CTA per SM, 16 warps on one tile at a time, thread 0 issues the TMA refills
+// the kernel: one CTA per SM, 16 warps = two consumer groups that also issue their own TMA refills
 // ---------------------------------------------------------------------------------------------------------------------
 struct FlipMaps {
     CUtensorMap m[kFlipMaxLevels];
@@ -390,17 +381,18 @@ template <typename R> __device__ __forceinline__ void flip_issue_tile(const Flip
     }
 }
 
-// 16 warps on ONE tile, no producer warp.  History of the shape (ncu at 28 qubits, ComplexF64, profiles/r02_measure_ncu.txt):
-//   8 consumer warps + a producer warp          2.18 ms: the consumers are the bottleneck (issue slots 41 %, stalls `wait` /
-//                                                `long_scoreboard`), two tiles in flight
-//   2 groups of 8 warps, each on its own tile    2.11 ms: the consumers keep up, but two tiles being consumed leave ONE 64 KiB
-//                                                slot in flight per SM (3 x 64 KiB fill shared memory), and a strided tile
-//                                                takes ~3 us to land: DRAM 51 % busy
-//   16 warps on the same tile (this form)        two threads load every register window and share its work (flip_stage<HALF>):
-//                                                a tile leaves shared memory twice as fast and TWO slots are in flight.
-// A 17th warp would cost registers (a CTA's warps are allocated in fours: 20 x 32 x 96); 16 x 32 x 128 fill the SM.  Every
-// thread waits for every tile in order, so the parity waits are sound without further bookkeeping; after the CTA barrier that
-// ends a tile, thread 0 refills that very slot with tile k + 3.
+// Two consumer groups of 8 warps, no producer warp: with one group the kernel was latency bound (ncu at 28 qubits: issue
+// slots 41 % busy, top stalls `wait` and `long_scoreboard`, DRAM at 62 % of its peak with two reads of the state), and a 17th
+// warp would cost registers (a CTA's warps are allocated in fours: 20 x 32 x 96).  16 warps x 32 x 128 registers fill the SM.
+// (Also tried: all 16 warps on ONE tile, two threads per register window sharing its work, so that two slots are in flight --
+// 2.82 ms instead of 2.11 ms at 28 qubits: +36 % instructions for the redundant window loads and a CTA-wide barrier per tile.)
+// Tile k of the CTA lives in ring slot k mod 3 and is consumed by group k mod 2; when a group has finished a tile (group
+// barrier), its first thread refills that very slot with tile k + 3 -- which the OTHER group will consume -- so a slot is
+// never written while it is read and no "empty" barriers are needed: one `full` mbarrier per slot, plus a plain counter
+// `issued[slot]` (round of the last tile issued into the slot, + 1).  The counter is what makes the parity wait sound: a
+// parity test cannot tell "phase r has completed" from "phase r - 1 has not completed yet", and the group that waits for
+// round r of a slot did not consume round r - 1 of it.  Once it has seen issued[slot] == r + 1 it knows that the other
+// group has passed its own wait for round r - 1 (it issues only after consuming), so the barrier is in phase r.
 template <typename R, int KIND>
 __global__ void __launch_bounds__(kFlipGroups * kFlipConsumers, 1)
 flip_measure_kernel(const __grid_constant__ FlipMaps M, const __grid_constant__ FlipParams P, double2 *partial /* [gridDim.x] */)
@@ -408,11 +400,12 @@ flip_measure_kernel(const __grid_constant__ FlipMaps M, const __grid_constant__ 
     extern __shared__ unsigned char flip_smem_raw[];
     unsigned char *ring = reinterpret_cast<unsigned char *>(((uintptr_t)flip_smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t *full = reinterpret_cast<uint64_t *>(ring + kFlipRing * kFlipTileBytes);
+    volatile uint32_t *issued = reinterpret_cast<volatile uint32_t *>(full + kFlipRing); // [kFlipRing], inside the 2 * kFlipRing words reserved for barriers
     double *red = reinterpret_cast<double *>(full + 2 * kFlipRing); // [16 warps][2]
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    constexpr uint32_t kWarps = kFlipGroups * kFlipConsumers / 32;
+    constexpr uint32_t kWarpsPerGroup = kFlipConsumers / 32, kConsumerWarps = kFlipGroups * kWarpsPerGroup;
     if (tid == 0) {
-        for (int i = 0; i < kFlipRing; i++) tma::mbar_init(&full[i], 1);
+        for (int i = 0; i < kFlipRing; i++) { tma::mbar_init(&full[i], 1); issued[i] = 0; }
         tma::fence_barrier_init();
         for (int l = 0; l < P.nlevels; l++) tma::prefetch_map(&M.m[l]);
     }
@@ -420,24 +413,30 @@ flip_measure_kernel(const __grid_constant__ FlipMaps M, const __grid_constant__ 
     if (tid == 0) {
         for (uint32_t k = 0; k < (uint32_t)kFlipRing; k++) {
             const unsigned long long j = blockIdx.x + (unsigned long long)k * gridDim.x;
-            if (j < P.n_items) flip_issue_tile<R>(M, P, flip_decode(P, j), ring + (size_t)k * kFlipTileBytes, &full[k]);
+            if (j < P.n_items) {
+                flip_issue_tile<R>(M, P, flip_decode(P, j), ring + (size_t)k * kFlipTileBytes, &full[k]);
+                __threadfence_block();
+                issued[k] = 1;
+            }
         }
     }
     double acc_diag = 0.0, acc_flip = 0.0;
-    const uint32_t half = tid / kFlipConsumers, gtid = tid % kFlipConsumers;
-    uint32_t k = 0;
-    for (unsigned long long j = blockIdx.x; j < P.n_items; j += gridDim.x, k++) {
+    const uint32_t group = warp / kWarpsPerGroup, gtid = tid % kFlipConsumers;
+    uint32_t k = group;
+    for (unsigned long long j = blockIdx.x + (unsigned long long)group * gridDim.x; j < P.n_items; j += (unsigned long long)kFlipGroups * gridDim.x, k += kFlipGroups) {
         const uint32_t slot = k % kFlipRing, round = k / kFlipRing;
-        unsigned char *tile = ring + (size_t)slot * kFlipTileBytes;
+        while (issued[slot] < round + 1u) { } // the tile of this round has been issued (=> the previous round of the slot has landed)
+        __threadfence_block();
         tma::mbar_wait(&full[slot], round & 1u);
-        if (half == 0) flip_tile_consume<R, KIND, 0>(tile, gtid, P, flip_decode(P, j), acc_diag, acc_flip);
-        else flip_tile_consume<R, KIND, 1>(tile, gtid, P, flip_decode(P, j), acc_diag, acc_flip);
-        __syncthreads(); // every warp is done with the slot
-        if (tid == 0) {
+        flip_tile_consume<R, KIND>(ring + (size_t)slot * kFlipTileBytes, gtid, P, flip_decode(P, j), acc_diag, acc_flip);
+        tma::named_bar_sync(1 + (int)group, kFlipConsumers); // every warp of the group is done with the slot
+        if (gtid == 0) {
             const unsigned long long jn = j + (unsigned long long)kFlipRing * gridDim.x; // tile k + 3 of this CTA
             if (jn < P.n_items) {
-                tma::fence_proxy_async(); // the CTA's reads of the slot come before the bulk copy that overwrites it
-                flip_issue_tile<R>(M, P, flip_decode(P, jn), tile, &full[slot]);
+                tma::fence_proxy_async(); // the group's reads of the slot come before the bulk copy that overwrites it
+                flip_issue_tile<R>(M, P, flip_decode(P, jn), ring + (size_t)slot * kFlipTileBytes, &full[slot]);
+                __threadfence_block();
+                issued[slot] = round + 2u;
             }
         }
     }
@@ -447,7 +446,7 @@ flip_measure_kernel(const __grid_constant__ FlipMaps M, const __grid_constant__ 
     __syncthreads();
     if (tid == 0) {
         double d = 0, f = 0;
-        for (uint32_t w = 0; w < kWarps; w++) { d += red[2 * w]; f += red[2 * w + 1]; } // fixed order: reproducible
+        for (uint32_t w = 0; w < kConsumerWarps; w++) { d += red[2 * w]; f += red[2 * w + 1]; } // fixed order: reproducible
         partial[blockIdx.x] = make_double2(d, f);
     }
 }

@@ -926,7 +926,7 @@ extern "C" int emu_measure_persistent(int dtype, int n, const void *psi, int kin
 #include "../../quantumcircuits.jl_b200/csrc/flip_tile.cuh"
 
 template <typename R, int KIND>
-static void emu_flip_run(const typename Vec2<R>::type *psi, const FlipParams &P, int grid, double *acc, int split)
+static void emu_flip_run(const typename Vec2<R>::type *psi, const FlipParams &P, int grid, double *acc)
 {
     std::vector<unsigned char> tile(kFlipTileBytes + 1024);
     unsigned char *t0 = reinterpret_cast<unsigned char *>(((uintptr_t)tile.data() + 1023) & ~(uintptr_t)1023);
@@ -934,14 +934,7 @@ static void emu_flip_run(const typename Vec2<R>::type *psi, const FlipParams &P,
         for (unsigned long long j = b; j < P.n_items; j += grid) {
             const FlipItem it = flip_decode(P, j);
             flip_emulate_tile_load<R>(psi, P, it, t0);
-            // the device form: two threads per window, each half of its work (split == 0: one thread does it all)
-            for (uint32_t tid = 0; tid < (uint32_t)kFlipConsumers; tid++) {
-                if (split) {
-                    flip_tile_consume<R, KIND, 0>(t0, tid, P, it, acc[0], acc[1]);
-                    flip_tile_consume<R, KIND, 1>(t0, tid, P, it, acc[0], acc[1]);
-                } else
-                    flip_tile_consume<R, KIND>(t0, tid, P, it, acc[0], acc[1]);
-            }
+            for (uint32_t tid = 0; tid < (uint32_t)kFlipConsumers; tid++) flip_tile_consume<R, KIND>(t0, tid, P, it, acc[0], acc[1]);
         }
 }
 
@@ -949,21 +942,19 @@ static void emu_flip_run(const typename Vec2<R>::type *psi, const FlipParams &P,
 extern "C" int emu_flip_measure(int dtype, int nloc, int n_total, const void *psi, int kind, double p0, double p1, double p2,
                                 unsigned long long c_hi, int grid, double *out2 /* diagonal sum, flip sum */, int *nlevels)
 {
-    const int split = grid < 0 ? 0 : 1; // grid < 0: replay the one-thread-per-window form on |grid| CTAs
-    if (grid < 0) grid = -grid;
     HamEval H{kind, n_total, p0, p1, p2};
     FlipParams P;
     double acc[2] = {0.0, 0.0};
     if (dtype) {
         if (!flip_plan<double>(P, nloc, H, c_hi)) return 2;
         flip_fill_diag_table<double>(P);
-        if (kind == 0) emu_flip_run<double, 0>((const double2 *)psi, P, grid, acc, split);
-        else emu_flip_run<double, 1>((const double2 *)psi, P, grid, acc, split);
+        if (kind == 0) emu_flip_run<double, 0>((const double2 *)psi, P, grid, acc);
+        else emu_flip_run<double, 1>((const double2 *)psi, P, grid, acc);
     } else {
         if (!flip_plan<float>(P, nloc, H, c_hi)) return 2;
         flip_fill_diag_table<float>(P);
-        if (kind == 0) emu_flip_run<float, 0>((const float2 *)psi, P, grid, acc, split);
-        else emu_flip_run<float, 1>((const float2 *)psi, P, grid, acc, split);
+        if (kind == 0) emu_flip_run<float, 0>((const float2 *)psi, P, grid, acc);
+        else emu_flip_run<float, 1>((const float2 *)psi, P, grid, acc);
     }
     out2[0] = acc[0];
     out2[1] = acc[1];
