@@ -398,7 +398,9 @@ __global__ void __launch_bounds__(kFlipGroups * kFlipConsumers, 1)
 flip_measure_kernel(const __grid_constant__ FlipMaps M, const __grid_constant__ FlipParams P, double2 *partial /* [gridDim.x] */)
 {
     extern __shared__ unsigned char flip_smem_raw[];
-    unsigned char *ring = reinterpret_cast<unsigned char *>(((uintptr_t)flip_smem_raw + 1023) & ~(uintptr_t)1023);
+    // (pointer arithmetic on the shared array itself: a round trip through uintptr_t makes every tile access a generic LD / ST
+    // with a 64-bit address instead of LDS / STS)
+    unsigned char *ring = flip_smem_raw + ((1024u - (tma::smem_u32(flip_smem_raw) & 1023u)) & 1023u);
     uint64_t *full = reinterpret_cast<uint64_t *>(ring + kFlipRing * kFlipTileBytes);
     volatile uint32_t *issued = reinterpret_cast<volatile uint32_t *>(full + kFlipRing); // [kFlipRing], inside the 2 * kFlipRing words reserved for barriers
     double *red = reinterpret_cast<double *>(full + 2 * kFlipRing); // [16 warps][2]

@@ -49,7 +49,7 @@ static int launch_pass_tma(qcb_state *s, const PassParams<double> &P, const TmaP
     static int ctas_per_sm = 1;
     if (!attr_set) {
         QCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        QCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, kTmaStageThreads + 32, smem));
+        QCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, kTmaStageThreads, smem));
         if (ctas_per_sm < 1) ctas_per_sm = 1;
         attr_set = true;
     }
@@ -63,7 +63,7 @@ static int launch_pass_tma(qcb_state *s, const PassParams<double> &P, const TmaP
     const unsigned long long ntiles = 1ull << (s->nloc - kTmaTB);
     const unsigned grid = (unsigned)std::min<unsigned long long>(ntiles, (unsigned long long)ctx().sm_count * ctas_per_sm);
     PassTimerScope timer;
-    kern<<<grid, kTmaStageThreads + 32, smem, ctx().stream>>>(map_ld, map_st, P, g.a2 - g.b1, ntiles);
+    kern<<<grid, kTmaStageThreads, smem, ctx().stream>>>(map_ld, map_st, P, g.a2 - g.b1, ntiles);
     QCB_CUDA(cudaGetLastError());
     count_launch();
     ctx().st_tma_passes += 1;

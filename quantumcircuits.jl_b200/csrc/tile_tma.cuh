@@ -8,8 +8,7 @@
 // whose index bits are [0, b1) with b1 >= 3 plus at most one more run [a2, b2), in ascending local order, not permuting
 // (every pass of an unsharded state); everything else stays on tile_pass_kernel.
 //
-// Roles: warp 4 lane 0 = producer (loads, and the stores: it waits for "tile computed", issues the store, waits until the
-// store has read the slot, then refills it); warps 0..3 = the 128 stage threads of tile.cuh.
+// Roles: the 128 stage threads of tile.cuh; thread 0 also issues the TMA stores and loads between two tiles.
 #pragma once
 #include "tile.cuh"
 #include "tma.cuh"
@@ -68,75 +67,67 @@ inline int tma_pass_map(CUtensorMap *out, const void *base, const TmaPassGeom &g
     return tma_encode(out, base, true, d, why);
 }
 
-// register budget: the stage body alone fills the 128 registers tile_pass_kernel gets; the ring bookkeeping on top of it
-// spilled inside the stage loop under the launch-bound-derived cap (104 bytes of stack).  3 CTAs x 160 threads x 136 <= 64 K.
+// No producer warp: a CTA's warps are allocated in fours, so a fifth warp costs as many registers as four more stage warps (the
+// first form, 4 + 1 warps at 136 registers, ran 2 CTAs per SM).  Thread 0 does the TMA work between two tiles: after the CTA
+// barrier that ends tile k it issues the store of the slot, waits until the store has READ the slot (a few hundred ns; the other
+// slot's tile is already there for the other warps to start on) and refills it with tile k + 2.  Every thread waits for every
+// tile in order, so the parity waits need no further bookkeeping.
 template <int MINB>
-__global__ void __maxnreg__(136)
+__global__ void __launch_bounds__(kTmaStageThreads, MINB)
 tile_pass_tma_kernel(const __grid_constant__ CUtensorMap map_ld, const __grid_constant__ CUtensorMap map_st,
                      const __grid_constant__ PassParams<double> P, int gap_bits, unsigned long long ntiles)
 {
     extern __shared__ unsigned char tma_smem_raw[];
-    unsigned char *ring = reinterpret_cast<unsigned char *>(((uintptr_t)tma_smem_raw + 1023) & ~(uintptr_t)1023);
+    // (pointer arithmetic on the shared array itself: a round trip through uintptr_t makes every tile access a generic LD / ST
+    // with a 64-bit address instead of LDS / STS)
+    unsigned char *ring = tma_smem_raw + ((1024u - (tma::smem_u32(tma_smem_raw) & 1023u)) & 1023u);
     uint64_t *full = reinterpret_cast<uint64_t *>(ring + kTmaSlots * kTmaTileBytes);
-    uint64_t *done = full + kTmaSlots;
-    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t tid = threadIdx.x;
+    const unsigned long long gap_mask = (1ull << gap_bits) - 1ull, stride = gridDim.x;
     if (tid == 0) {
-        for (int i = 0; i < kTmaSlots; i++) {
-            tma::mbar_init(&full[i], 1);
-            tma::mbar_init(&done[i], kTmaStageThreads);
-        }
+        for (int i = 0; i < kTmaSlots; i++) tma::mbar_init(&full[i], 1);
         tma::fence_barrier_init();
-    }
-    __syncthreads();
-    const unsigned long long gap_mask = (1ull << gap_bits) - 1ull;
-    if (warp == kTmaStageThreads / 32) {
-        if (lane != 0) return;
         tma::prefetch_map(&map_ld);
         tma::prefetch_map(&map_st);
-        uint32_t k = 0;
-        const unsigned long long back = (unsigned long long)kTmaSlots * gridDim.x; // the tile a slot held before: t - back
-        for (unsigned long long t = blockIdx.x; t < ntiles; t += gridDim.x, k++) {
-            const uint32_t slot = k % kTmaSlots;
-            unsigned char *buf = ring + (size_t)slot * kTmaTileBytes;
-            if (k >= kTmaSlots) {
-                // the slot holds tile k - 2: wait until its stages are done, write it back, wait until the store has read it
-                tma::mbar_wait(&done[slot], ((k / kTmaSlots) - 1) & 1u);
-                const unsigned long long p = t - back;
-                tma::store_5d(&map_st, buf, 0, 0, (int)(p & gap_mask), 0, (int)(p >> gap_bits));
-                tma::store_commit();
-                tma::store_wait_read<0>();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (uint32_t i = 0; i < (uint32_t)kTmaSlots; i++) {
+            const unsigned long long t = blockIdx.x + i * stride;
+            if (t < ntiles) {
+                tma::mbar_expect_tx(&full[i], kTmaTileBytes);
+                tma::load_5d(ring + (size_t)i * kTmaTileBytes, &map_ld, &full[i], 0, 0, (int)(t & gap_mask), 0, (int)(t >> gap_bits));
             }
-            tma::mbar_expect_tx(&full[slot], kTmaTileBytes);
-            tma::load_5d(buf, &map_ld, &full[slot], 0, 0, (int)(t & gap_mask), 0, (int)(t >> gap_bits));
         }
-        // drain: the last min(k, 2) tiles
-        const uint32_t total = k;
-        for (uint32_t j = total > kTmaSlots ? total - kTmaSlots : 0; j < total; j++) {
-            const uint32_t slot = j % kTmaSlots;
-            tma::mbar_wait(&done[slot], (j / kTmaSlots) & 1u);
-            const unsigned long long p = blockIdx.x + (unsigned long long)j * gridDim.x;
-            tma::store_5d(&map_st, ring + (size_t)slot * kTmaTileBytes, 0, 0, (int)(p & gap_mask), 0, (int)(p >> gap_bits));
-            tma::store_commit();
-        }
-        tma::store_wait_all<0>();
-        return;
     }
     uint32_t k = 0;
-    for (unsigned long long t = blockIdx.x; t < ntiles; t += gridDim.x, k++) {
+    for (unsigned long long t = blockIdx.x; t < ntiles; t += stride, k++) {
         const uint32_t slot = k % kTmaSlots;
-        double2 *sm = reinterpret_cast<double2 *>(ring + (size_t)slot * kTmaTileBytes);
+        unsigned char *buf = ring + (size_t)slot * kTmaTileBytes;
+        double2 *sm = reinterpret_cast<double2 *>(buf);
         tma::mbar_wait(&full[slot], (k / kTmaSlots) & 1u);
 #pragma unroll 1
         for (int s = 0; s < P.nstages; s++) {
-            if (s) tma::named_bar_sync(1, kTmaStageThreads);
+            if (s) __syncthreads();
             tile_stage<double, kTmaTB, -3, true>(P, s, sm, tid);
         }
         tma::fence_proxy_async(); // this thread's writes -> visible to the TMA store
-        tma::mbar_arrive(&done[slot]);
+        __syncthreads();
+        if (tid == 0) {
+            tma::store_5d(&map_st, buf, 0, 0, (int)(t & gap_mask), 0, (int)(t >> gap_bits));
+            tma::store_commit();
+            const unsigned long long tn = t + (unsigned long long)kTmaSlots * stride;
+            if (tn < ntiles) {
+                tma::store_wait_read<0>(); // the store has read the slot: it may be refilled
+                tma::mbar_expect_tx(&full[slot], kTmaTileBytes);
+                tma::load_5d(buf, &map_ld, &full[slot], 0, 0, (int)(tn & gap_mask), 0, (int)(tn >> gap_bits));
+            }
+        }
     }
+    if (tid == 0) tma::store_wait_all<0>();
 }
 
-inline size_t tma_pass_smem_bytes() { return (size_t)kTmaSlots * kTmaTileBytes + 1024 + 2 * kTmaSlots * sizeof(uint64_t); }
+inline size_t tma_pass_smem_bytes() { return (size_t)kTmaSlots * kTmaTileBytes + 1024 + kTmaSlots * sizeof(uint64_t); }
 #endif
 
 } // namespace qcb
