@@ -10,7 +10,8 @@ import os
 import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libqcb200.so")
+# QCB200_LIB: another build of the same library (A/B timing of compile-time variants); the default is the in-tree build
+SO_PATH = os.environ.get("QCB200_LIB") or os.path.join(_HERE, "libqcb200.so")
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "qcb200.h")
 
 QCB_OK, QCB_EINVAL, QCB_ENOMEM, QCB_ECUDA, QCB_ENCCL, QCB_EUNSUPPORTED = range(6)

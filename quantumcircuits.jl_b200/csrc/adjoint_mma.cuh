@@ -126,7 +126,7 @@ QCB_HD constexpr int adjm_gray_bit(int i)
 QCB_HD void adjm_gate_operand(const GateMat<double> &Ud, uint32_t lane, double &a_re, double &a_im)
 {
     const uint32_t g = lane >> 2, t = lane & 3u, a = g >> 1;
-    const double ur = Ud.v[2 * (a + 4 * t)], ui = Ud.v[2 * (a + 4 * t) + 1];
+    const double ur = gate_re(Ud, (int)a, (int)t), ui = gate_im(Ud, (int)a, (int)t);
     a_re = (g & 1u) ? ui : ur;
     a_im = (g & 1u) ? ur : -ui;
 }

@@ -82,16 +82,20 @@ template <int SWB> QCB_HD uint32_t swz(uint32_t e)
 }
 
 // Gate matrix as the kernels consume it (r = output index, c = input index of the 4x4 form).
-//   double: v[2k] = Re u, v[2k+1] = Im u, k = r + 4c.
+//   double: with A = Re u, B = Im u: v[12r + c] = A_rc, v[12r + 4 + c] = -(A + B)_rc, v[12r + 8 + c] = (B - A)_rc -- the
+//           constants of the three-multiplication form of the complex product (apply_quad below), row by row in the
+//           order they are consumed; v[48 + r + 4c] = B_rc (A and B themselves are read by the tensor-core backward
+//           pass, adjoint_mma.cuh, through gate_re / gate_im).
 //   float : packed for FFMA2 (sm_100 fma.rn.f32x2): v[4k..4k+3] = (Re u, Re u, -Im u, Im u), so that
 //           (re, im) += (Re u, Re u) * (x.re, x.im) + (-Im u, Im u) * (x.im, x.re) is two packed FMAs.
-template <typename R> struct GateMat { R v[32]; };
-template <> struct GateMat<float> { float v[64]; };
+template <typename R> struct alignas(16) GateMat { R v[64]; };
 QCB_HD void gate_set(GateMat<double> &U, int r, int c, double re, double im)
 {
-    U.v[2 * (r + 4 * c)] = re;
-    U.v[2 * (r + 4 * c) + 1] = im;
+    U.v[12 * r + c] = re; U.v[12 * r + 4 + c] = -(re + im); U.v[12 * r + 8 + c] = im - re;
+    U.v[48 + r + 4 * c] = im;
 }
+QCB_HD double gate_re(const GateMat<double> &U, int r, int c) { return U.v[12 * r + c]; }
+QCB_HD double gate_im(const GateMat<double> &U, int r, int c) { return U.v[48 + r + 4 * c]; }
 QCB_HD void gate_set(GateMat<float> &U, int r, int c, double re, double im)
 {
     float *p = U.v + 4 * (r + 4 * c);
@@ -110,6 +114,7 @@ template <typename R> struct PassParams {
     GateMat<R> U[kMaxStages * kSlots];
     StageDesc stage[kMaxStages];
     int32_t nstages;
+    uint8_t zq[4];                     // zeros the compiler cannot see through (apply_window_gate)
     int32_t nseg;                      // the CTA index is deposited into the non-tile bits, segment by segment
     uint8_t seg_start[kMaxSeg], seg_len[kMaxSeg];
     uint8_t ld_phys[kMaxTB];           // memory-order bit k (thread bits first) -> physical index bit
@@ -123,19 +128,31 @@ template <typename R> struct PassParams {
 // ---------------------------------------------------------------------------------
 // one gate on one amplitude quad held in registers
 // ---------------------------------------------------------------------------------
+// ComplexF64: three real products per complex product (Gauss / "3M").  With u = A + iB and x = p + iq,
+//   Re(u x) = A (p + q) - (A + B) q,   Im(u x) = A (p + q) + (B - A) p,
+// the sum S_r = sum_c A_rc (p_c + q_c) is shared by both parts of output r and t_c = p_c + q_c by all four outputs:
+// 48 DFMA/DMUL + 4 DADD per quad instead of 64 on the FP64 pipe that bounds the deep passes.  Normwise error bound as
+// for the ordinary form (the component-wise one is lost: |err| <= c eps |u||x|, which is what a unitary needs).
+// QCB_F64_FORM selects the ComplexF64 arithmetic at compile time: 0 = four products per complex product (the form of
+// round 1), 1 = 3M, one quad at a time (all 48 constants fetched per quad), 2 = 3M, two quads x two output rows at a time
+// (apply_window_gate_f64 below), 3 = 3M, four quads x two output rows at a time (apply_window_gate_f64_rows; the default).
+#ifndef QCB_F64_FORM
+#define QCB_F64_FORM 3
+#endif
 QCB_HD void apply_quad(double2 &x0, double2 &x1, double2 &x2, double2 &x3, const GateMat<double> &U)
 {
     const double2 in[4] = {x0, x1, x2, x3};
     double2 out[4];
+#if QCB_F64_FORM == 0
 #pragma unroll
     for (int r = 0; r < 4; r++) {
-        double re = U.v[2 * r] * in[0].x;
-        double im = U.v[2 * r] * in[0].y;
-        re = fma(-U.v[2 * r + 1], in[0].y, re);
-        im = fma(U.v[2 * r + 1], in[0].x, im);
+        double re = gate_re(U, r, 0) * in[0].x;
+        double im = gate_re(U, r, 0) * in[0].y;
+        re = fma(-gate_im(U, r, 0), in[0].y, re);
+        im = fma(gate_im(U, r, 0), in[0].x, im);
 #pragma unroll
         for (int c = 1; c < 4; c++) {
-            const double ur = U.v[2 * (r + 4 * c)], ui = U.v[2 * (r + 4 * c) + 1];
+            const double ur = gate_re(U, r, c), ui = gate_im(U, r, c);
             re = fma(ur, in[c].x, re);
             im = fma(ur, in[c].y, im);
             re = fma(-ui, in[c].y, re);
@@ -144,6 +161,26 @@ QCB_HD void apply_quad(double2 &x0, double2 &x1, double2 &x2, double2 &x3, const
         out[r].x = re;
         out[r].y = im;
     }
+#else
+    double t[4];
+#pragma unroll
+    for (int c = 0; c < 4; c++) t[c] = in[c].x + in[c].y;
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const double *u = U.v + 12 * r; // A_r0..3, N_r0..3, M_r0..3
+        double s = u[0] * t[0];
+#pragma unroll
+        for (int c = 1; c < 4; c++) s = fma(u[c], t[c], s);
+        double re = s, im = s;
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            re = fma(u[4 + c], in[c].y, re);
+            im = fma(u[8 + c], in[c].x, im);
+        }
+        out[r].x = re;
+        out[r].y = im;
+    }
+#endif
     x0 = out[0]; x1 = out[1]; x2 = out[2]; x3 = out[3];
 }
 
@@ -192,16 +229,116 @@ QCB_HD void apply_quad(float2 &x0, float2 &x1, float2 &x2, float2 &x3, const Gat
 }
 
 // gate on register-window bits (LO, LO+1): 4 quads per thread
+template <int LO> QCB_HD constexpr int quad_other(int q)
+{
+    // spread the two bits of q over the window bits other than LO, LO+1
+    int other = 0, qq = q;
+    for (int b = 0; b < 4; b++)
+        if (b != LO && b != LO + 1) { other |= (qq & 1) << b; qq >>= 1; }
+    return other;
+}
+template <int LO> QCB_HD void apply_window_gate_f64(double2 (&a)[kRegAmps], const GateMat<double> *Ubase, const uint8_t *zq);
+template <int LO> QCB_HD void apply_window_gate_f64_rows(double2 (&a)[kRegAmps], const GateMat<double> *Ubase, const uint8_t *zq);
+template <int LO, typename R, typename V> QCB_HD void apply_window_gate(V (&a)[kRegAmps], const GateMat<R> *Ubase, const uint8_t *zq)
+{
+    if constexpr (sizeof(R) == 8 && QCB_F64_FORM == 2) {
+        apply_window_gate_f64<LO>(a, Ubase, zq);
+    } else if constexpr (sizeof(R) == 8 && QCB_F64_FORM == 3) {
+        apply_window_gate_f64_rows<LO>(a, Ubase, zq);
+    } else {
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int other = quad_other<LO>(q);
+            apply_quad(a[other], a[other | (1 << LO)], a[other | (2 << LO)], a[other | (3 << LO)],
+                       Ubase[(sizeof(R) == 8 && QCB_F64_FORM == 1) ? zq[q] : 0]);
+        }
+    }
+}
+// form 3: all four quads, two output rows at a time: every constant is fetched once per gate (as in form 0); the price is
+// t = p + q computed twice (once per row pair) because holding it for four quads does not fit the register file.
+template <int LO> QCB_HD void apply_window_gate_f64_rows(double2 (&a)[kRegAmps], const GateMat<double> *Ubase, const uint8_t *zq)
+{
+    double2 out01[4][2];
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const GateMat<double> &U = Ubase[zq[h]];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int o = quad_other<LO>(q);
+            double2 *x[4] = {&a[o], &a[o | (1 << LO)], &a[o | (2 << LO)], &a[o | (3 << LO)]};
+            double t[4];
+#pragma unroll
+            for (int c = 0; c < 4; c++) t[c] = x[c]->x + x[c]->y;
+            double2 out[2];
+#pragma unroll
+            for (int rr = 0; rr < 2; rr++) {
+                const double *u = U.v + 12 * (2 * h + rr);
+                double s = u[0] * t[0];
+#pragma unroll
+                for (int c = 1; c < 4; c++) s = fma(u[c], t[c], s);
+                double re = s, im = s;
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    re = fma(u[4 + c], x[c]->y, re);
+                    im = fma(u[8 + c], x[c]->x, im);
+                }
+                out[rr].x = re;
+                out[rr].y = im;
+            }
+            if (h == 0) { out01[q][0] = out[0]; out01[q][1] = out[1]; }
+            else { *x[0] = out01[q][0]; *x[1] = out01[q][1]; *x[2] = out[0]; *x[3] = out[1]; }
+        }
+    }
+}
 template <int LO, typename R, typename V> QCB_HD void apply_window_gate(V (&a)[kRegAmps], const GateMat<R> &U)
 {
+    const uint8_t z[4] = {0, 0, 0, 0};
+    apply_window_gate<LO, R, V>(a, &U, z);
+}
+// ComplexF64: two quads at a time, two output rows at a time -- the 24 constants of a row pair (48 uniform registers) are
+// fetched once for both quads (the whole 3M matrix, 96 uniform registers, does not fit the uniform register file, and
+// ptxas then moves the constants to vector registers and spills); zq[] are zeros the compiler cannot see through, so
+// that it does not try to share the fetches any further.
+template <int LO> QCB_HD void apply_window_gate_f64(double2 (&a)[kRegAmps], const GateMat<double> *Ubase, const uint8_t *zq)
+{
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
-        // spread the two bits of q over the window bits other than LO, LO+1
-        int other = 0, qq = q;
+    for (int qp = 0; qp < 2; qp++) {
+        const int o0 = quad_other<LO>(2 * qp), o1 = quad_other<LO>(2 * qp + 1);
+        double2 *x[2][4] = {{&a[o0], &a[o0 | (1 << LO)], &a[o0 | (2 << LO)], &a[o0 | (3 << LO)]},
+                            {&a[o1], &a[o1 | (1 << LO)], &a[o1 | (2 << LO)], &a[o1 | (3 << LO)]}};
+        double t[2][4];
 #pragma unroll
-        for (int b = 0; b < 4; b++)
-            if (b != LO && b != LO + 1) { other |= (qq & 1) << b; qq >>= 1; }
-        apply_quad(a[other], a[other | (1 << LO)], a[other | (2 << LO)], a[other | (3 << LO)], U);
+        for (int k = 0; k < 2; k++)
+#pragma unroll
+            for (int c = 0; c < 4; c++) t[k][c] = x[k][c]->x + x[k][c]->y;
+        double2 out[2][4];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const GateMat<double> &U = Ubase[zq[2 * qp + h]];
+#pragma unroll
+            for (int rr = 0; rr < 2; rr++) {
+                const int r = 2 * h + rr;
+                const double *u = U.v + 12 * r;
+#pragma unroll
+                for (int k = 0; k < 2; k++) {
+                    double s = u[0] * t[k][0];
+#pragma unroll
+                    for (int c = 1; c < 4; c++) s = fma(u[c], t[k][c], s);
+                    double re = s, im = s;
+#pragma unroll
+                    for (int c = 0; c < 4; c++) {
+                        re = fma(u[4 + c], x[k][c]->y, re);
+                        im = fma(u[8 + c], x[k][c]->x, im);
+                    }
+                    out[k][r].x = re;
+                    out[k][r].y = im;
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 2; k++)
+#pragma unroll
+            for (int c = 0; c < 4; c++) *x[k][c] = out[k][c];
     }
 }
 
@@ -312,10 +449,18 @@ QCB_HD void tile_stage(const PassParams<R> &P, int s, typename Vec2<R>::type *sm
 #pragma unroll
     for (int r = 0; r < kRegAmps; r++) a[r] = sm[e ^ S.roff[r]];
     const uint32_t mask = S.mask;
-    if (mask & 1u) apply_window_gate<1, R, V>(a, P.U[s * kSlots + 0]);
-    if (mask & 2u) apply_window_gate<0, R, V>(a, P.U[s * kSlots + 1]);
-    if (mask & 4u) apply_window_gate<2, R, V>(a, P.U[s * kSlots + 2]);
-    if (mask & 8u) apply_window_gate<1, R, V>(a, P.U[s * kSlots + 3]);
+    if (mask == 15u) {
+        // the full diamond as straight-line code: no register moves at the joins of four conditional gates
+        apply_window_gate<1, R, V>(a, &P.U[s * kSlots + 0], P.zq);
+        apply_window_gate<0, R, V>(a, &P.U[s * kSlots + 1], P.zq);
+        apply_window_gate<2, R, V>(a, &P.U[s * kSlots + 2], P.zq);
+        apply_window_gate<1, R, V>(a, &P.U[s * kSlots + 3], P.zq);
+    } else {
+        if (mask & 1u) apply_window_gate<1, R, V>(a, &P.U[s * kSlots + 0], P.zq);
+        if (mask & 2u) apply_window_gate<0, R, V>(a, &P.U[s * kSlots + 1], P.zq);
+        if (mask & 4u) apply_window_gate<2, R, V>(a, &P.U[s * kSlots + 2], P.zq);
+        if (mask & 8u) apply_window_gate<1, R, V>(a, &P.U[s * kSlots + 3], P.zq);
+    }
 #if defined(__CUDA_ARCH__)
     if (FORGET) asm volatile("" : "+r"(e));
 #endif
@@ -338,7 +483,7 @@ tile_pass_kernel(const typename Vec2<R>::type *src, typename Vec2<R>::type *dst,
     __syncthreads();
 #pragma unroll 1
     for (int s = 0; s < P.nstages; s++) {
-        tile_stage<R, TB>(P, s, sm, tid);
+        tile_stage<R, TB, Vec2<R>::SWB, true>(P, s, sm, tid);
         __syncthreads();
     }
     tile_store<R, TB>(dst, P, sm, tid, bid);
@@ -358,7 +503,7 @@ tile_pass_peer_kernel(const __grid_constant__ PeerSrc S, typename Vec2<R>::type 
     __syncthreads();
 #pragma unroll 1
     for (int s = 0; s < P.nstages; s++) {
-        tile_stage<R, TB>(P, s, sm, tid);
+        tile_stage<R, TB, Vec2<R>::SWB, true>(P, s, sm, tid);
         __syncthreads();
     }
     tile_store<R, TB>(dst, P, sm, tid, bid);
