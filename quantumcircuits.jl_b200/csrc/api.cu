@@ -752,6 +752,8 @@ int qcb_set_option(const char *key, long value)
         c.pass_tma = value;
     } else if (k == "pass_tma_max_stages") {
         c.pass_tma_max_stages = value;
+    } else if (k == "f64_3m_min_gates") {
+        c.f64_3m_min_gates = value; // ComplexF64 passes with at least this many gates use the 3M arithmetic (0: all, large: none)
     } else if (k == "tma_l2_promotion") {
         if (value < 0 || value > 2) return set_error(QCB_EINVAL, "tma_l2_promotion must be 0 (none), 1 (128 bytes) or 2 (256 bytes)");
         tma_strided_promotion() = (int)value;
@@ -813,7 +815,7 @@ int qcb_get_stat(const char *key, double *out)
                 if (cudaEventElapsedTime(&ms, c.pass_ev[i], c.pass_ev[i + 1]) == cudaSuccess) tot += ms;
                 if (f) {
                     const Ctx::PassMeta &m = c.pass_meta[i / 2];
-                    std::fprintf(f, "%zu %.4f stages=%d gates=%d window_bit=%d tma=%d\n", i / 2, ms, m.stages, m.gates, m.first_window_bit, m.tma);
+                    std::fprintf(f, "%zu %.4f stages=%d gates=%d window_bit=%d tma=%d masks=%llx\n", i / 2, ms, m.stages, m.gates, m.first_window_bit, m.tma, m.masks);
                 }
             }
             if (f) std::fclose(f);

@@ -18,14 +18,27 @@ namespace qcb {
 
 // src == nullptr: in place.  Otherwise the pass reads `src` (another state of the same size) and writes the state: every
 // amplitude is read and written exactly once per pass, so the first pass of a circuit can double as the copy of its input.
-template <typename R, int TB> static int launch_pass(qcb_state *s, const PassParams<R> &P, const void *src = nullptr)
+// ComplexF64 passes with at least `f64_3m_min_gates` gates run the 3M arithmetic (tile.cuh): below that the pass is bound
+// by HBM, not by the FP64 pipe, and the ordinary form is the faster one (fewer constants to fetch per gate).
+template <typename R> static bool pass_wants_3m(const PassParams<R> &P)
 {
+    if (sizeof(R) != 8) return false;
+    int gates = 0;
+    for (int i = 0; i < P.nstages; i++) gates += __builtin_popcount(P.stage[i].mask);
+    return gates >= ctx().f64_3m_min_gates;
+}
+
+template <typename R, int TB, bool M3 = false> static int launch_pass(qcb_state *s, const PassParams<R> &P, const void *src = nullptr)
+{
+    if constexpr (sizeof(R) == 8 && !M3) {
+        if (pass_wants_3m(P)) return launch_pass<R, TB, true>(s, P, src);
+    }
     using V = typename Vec2<R>::type;
     constexpr int NT = 1 << (TB - kRegBits);
     // resident threads per SM the register budget is sized for: 512 (ComplexF64, 128 registers) / 1024 (ComplexF32, 64)
     constexpr int RES = sizeof(R) == 8 ? 512 : 1024;
     constexpr int MINB = (RES / NT) > 0 ? ((RES / NT) > 32 ? 32 : (RES / NT)) : 1;
-    auto kern = tile_pass_kernel<R, TB, MINB>;
+    auto kern = tile_pass_kernel<R, TB, MINB, M3>;
     const size_t smem = sizeof(V) << TB;
     static bool attr_set = false;
     if (!attr_set) {
@@ -80,13 +93,16 @@ static bool use_tma_pass(const qcb_state *s, const PassPlan &pl, TmaPassGeom &g)
     return tma_pass_eligible(pl, s->nloc, g);
 }
 
-template <typename R, int TB> static int launch_pass_peer(qcb_state *s, const PeerSrc &src, void *dst, const PassParams<R> &P)
+template <typename R, int TB, bool M3 = false> static int launch_pass_peer(qcb_state *s, const PeerSrc &src, void *dst, const PassParams<R> &P)
 {
+    if constexpr (sizeof(R) == 8 && !M3) {
+        if (pass_wants_3m(P)) return launch_pass_peer<R, TB, true>(s, src, dst, P);
+    }
     using V = typename Vec2<R>::type;
     constexpr int NT = 1 << (TB - kRegBits);
     constexpr int RES = sizeof(R) == 8 ? 512 : 1024;
     constexpr int MINB = (RES / NT) > 0 ? ((RES / NT) > 32 ? 32 : (RES / NT)) : 1;
-    auto kern = tile_pass_peer_kernel<R, TB, MINB>;
+    auto kern = tile_pass_peer_kernel<R, TB, MINB, M3>;
     const size_t smem = sizeof(V) << TB;
     static bool attr_set = false;
     if (!attr_set) {
@@ -245,7 +261,11 @@ template <typename R> static int run_fused(qcb_state *s, const std::vector<GateO
         if (c.time_passes) {
             int fw = s->nloc;
             for (int b : pl.phys) if (b >= opt.low_bits) { fw = b; break; }
-            c.pass_meta.push_back(Ctx::PassMeta{(int)pl.stages.size(), pl.ngates, fw, tma_pass ? 1 : 0});
+            unsigned long long masks = 0;
+            for (size_t i = 0; i < pl.stages.size() && i < 16; i++)
+                for (int k = 0; k < kSlots; k++)
+                    if (pl.stages[i].gate[k] >= 0) masks |= 1ull << (4 * i + k);
+            c.pass_meta.push_back(Ctx::PassMeta{(int)pl.stages.size(), pl.ngates, fw, tma_pass ? 1 : 0, masks});
         }
         if constexpr (std::is_same<R, double>::value) {
             if (tma_pass) QCB_TRY(launch_pass_tma(s, P, g, first_src));

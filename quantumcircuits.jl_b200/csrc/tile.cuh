@@ -114,7 +114,6 @@ template <typename R> struct PassParams {
     GateMat<R> U[kMaxStages * kSlots];
     StageDesc stage[kMaxStages];
     int32_t nstages;
-    uint8_t zq[4];                     // zeros the compiler cannot see through (apply_window_gate)
     int32_t nseg;                      // the CTA index is deposited into the non-tile bits, segment by segment
     uint8_t seg_start[kMaxSeg], seg_len[kMaxSeg];
     uint8_t ld_phys[kMaxTB];           // memory-order bit k (thread bits first) -> physical index bit
@@ -128,22 +127,10 @@ template <typename R> struct PassParams {
 // ---------------------------------------------------------------------------------
 // one gate on one amplitude quad held in registers
 // ---------------------------------------------------------------------------------
-// ComplexF64: three real products per complex product (Gauss / "3M").  With u = A + iB and x = p + iq,
-//   Re(u x) = A (p + q) - (A + B) q,   Im(u x) = A (p + q) + (B - A) p,
-// the sum S_r = sum_c A_rc (p_c + q_c) is shared by both parts of output r and t_c = p_c + q_c by all four outputs:
-// 48 DFMA/DMUL + 4 DADD per quad instead of 64 on the FP64 pipe that bounds the deep passes.  Normwise error bound as
-// for the ordinary form (the component-wise one is lost: |err| <= c eps |u||x|, which is what a unitary needs).
-// QCB_F64_FORM selects the ComplexF64 arithmetic at compile time: 0 = four products per complex product (the form of
-// round 1), 1 = 3M, one quad at a time (all 48 constants fetched per quad), 2 = 3M, two quads x two output rows at a time
-// (apply_window_gate_f64 below), 3 = 3M, four quads x two output rows at a time (apply_window_gate_f64_rows; the default).
-#ifndef QCB_F64_FORM
-#define QCB_F64_FORM 3
-#endif
 QCB_HD void apply_quad(double2 &x0, double2 &x1, double2 &x2, double2 &x3, const GateMat<double> &U)
 {
     const double2 in[4] = {x0, x1, x2, x3};
     double2 out[4];
-#if QCB_F64_FORM == 0
 #pragma unroll
     for (int r = 0; r < 4; r++) {
         double re = gate_re(U, r, 0) * in[0].x;
@@ -161,26 +148,6 @@ QCB_HD void apply_quad(double2 &x0, double2 &x1, double2 &x2, double2 &x3, const
         out[r].x = re;
         out[r].y = im;
     }
-#else
-    double t[4];
-#pragma unroll
-    for (int c = 0; c < 4; c++) t[c] = in[c].x + in[c].y;
-#pragma unroll
-    for (int r = 0; r < 4; r++) {
-        const double *u = U.v + 12 * r; // A_r0..3, N_r0..3, M_r0..3
-        double s = u[0] * t[0];
-#pragma unroll
-        for (int c = 1; c < 4; c++) s = fma(u[c], t[c], s);
-        double re = s, im = s;
-#pragma unroll
-        for (int c = 0; c < 4; c++) {
-            re = fma(u[4 + c], in[c].y, re);
-            im = fma(u[8 + c], in[c].x, im);
-        }
-        out[r].x = re;
-        out[r].y = im;
-    }
-#endif
     x0 = out[0]; x1 = out[1]; x2 = out[2]; x3 = out[3];
 }
 
@@ -237,36 +204,26 @@ template <int LO> QCB_HD constexpr int quad_other(int q)
         if (b != LO && b != LO + 1) { other |= (qq & 1) << b; qq >>= 1; }
     return other;
 }
-template <int LO> QCB_HD void apply_window_gate_f64(double2 (&a)[kRegAmps], const GateMat<double> *Ubase, const uint8_t *zq);
-template <int LO> QCB_HD void apply_window_gate_f64_rows(double2 (&a)[kRegAmps], const GateMat<double> *Ubase, const uint8_t *zq);
-template <int LO, typename R, typename V> QCB_HD void apply_window_gate(V (&a)[kRegAmps], const GateMat<R> *Ubase, const uint8_t *zq)
-{
-    if constexpr (sizeof(R) == 8 && QCB_F64_FORM == 2) {
-        apply_window_gate_f64<LO>(a, Ubase, zq);
-    } else if constexpr (sizeof(R) == 8 && QCB_F64_FORM == 3) {
-        apply_window_gate_f64_rows<LO>(a, Ubase, zq);
-    } else {
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const int other = quad_other<LO>(q);
-            apply_quad(a[other], a[other | (1 << LO)], a[other | (2 << LO)], a[other | (3 << LO)],
-                       Ubase[(sizeof(R) == 8 && QCB_F64_FORM == 1) ? zq[q] : 0]);
-        }
-    }
-}
-// form 3: all four quads, two output rows at a time: every constant is fetched once per gate (as in form 0); the price is
-// t = p + q computed twice (once per row pair) because holding it for four quads does not fit the register file.
-template <int LO> QCB_HD void apply_window_gate_f64_rows(double2 (&a)[kRegAmps], const GateMat<double> *Ubase, const uint8_t *zq)
+
+// ComplexF64, three real products per complex product (Gauss / "3M").  With u = A + iB and x = p + iq,
+//   Re(u x) = A (p + q) - (A + B) q,   Im(u x) = A (p + q) + (B - A) p,
+// the sum S_r = sum_c A_rc (p_c + q_c) is shared by both parts of output r and t_c = p_c + q_c by all four outputs:
+// 48 DFMA/DMUL + 4 DADD per quad instead of 64 on the FP64 pipe that bounds the deep passes.  Normwise error bound as
+// for the ordinary form (the component-wise one is lost: |err| <= c eps |u||x|, which is what a unitary needs).
+// Order of evaluation: all four quads, two output rows at a time.  The 24 constants of a row pair are 48 uniform
+// registers and are fetched once per gate for all four quads, as the 32 constants of the ordinary form are; asking
+// ptxas for all 48 constants at once (one quad after the other) exceeds the 63 uniform registers, it then keeps the
+// constants in vector registers (LDC), spills, and the pass runs 35 % slower than the ordinary form (measured).
+template <int LO> QCB_HD void apply_window_gate_3m(double2 (&a)[kRegAmps], const GateMat<double> &U)
 {
     double2 out01[4][2];
 #pragma unroll
     for (int h = 0; h < 2; h++) {
-        const GateMat<double> &U = Ubase[zq[h]];
 #pragma unroll
         for (int q = 0; q < 4; q++) {
             const int o = quad_other<LO>(q);
             double2 *x[4] = {&a[o], &a[o | (1 << LO)], &a[o | (2 << LO)], &a[o | (3 << LO)]};
-            double t[4];
+            double t[4]; // (the compiler keeps t of the first row pair alive instead of adding twice)
 #pragma unroll
             for (int c = 0; c < 4; c++) t[c] = x[c]->x + x[c]->y;
             double2 out[2];
@@ -290,55 +247,18 @@ template <int LO> QCB_HD void apply_window_gate_f64_rows(double2 (&a)[kRegAmps],
         }
     }
 }
-template <int LO, typename R, typename V> QCB_HD void apply_window_gate(V (&a)[kRegAmps], const GateMat<R> &U)
+
+// M3 selects the 3M form for ComplexF64 (ignored for ComplexF32: FFMA2 does two real products per issue slot anyway)
+template <int LO, typename R, typename V, bool M3 = false> QCB_HD void apply_window_gate(V (&a)[kRegAmps], const GateMat<R> &U)
 {
-    const uint8_t z[4] = {0, 0, 0, 0};
-    apply_window_gate<LO, R, V>(a, &U, z);
-}
-// ComplexF64: two quads at a time, two output rows at a time -- the 24 constants of a row pair (48 uniform registers) are
-// fetched once for both quads (the whole 3M matrix, 96 uniform registers, does not fit the uniform register file, and
-// ptxas then moves the constants to vector registers and spills); zq[] are zeros the compiler cannot see through, so
-// that it does not try to share the fetches any further.
-template <int LO> QCB_HD void apply_window_gate_f64(double2 (&a)[kRegAmps], const GateMat<double> *Ubase, const uint8_t *zq)
-{
+    if constexpr (sizeof(R) == 8 && M3) {
+        apply_window_gate_3m<LO>(a, U);
+    } else {
 #pragma unroll
-    for (int qp = 0; qp < 2; qp++) {
-        const int o0 = quad_other<LO>(2 * qp), o1 = quad_other<LO>(2 * qp + 1);
-        double2 *x[2][4] = {{&a[o0], &a[o0 | (1 << LO)], &a[o0 | (2 << LO)], &a[o0 | (3 << LO)]},
-                            {&a[o1], &a[o1 | (1 << LO)], &a[o1 | (2 << LO)], &a[o1 | (3 << LO)]}};
-        double t[2][4];
-#pragma unroll
-        for (int k = 0; k < 2; k++)
-#pragma unroll
-            for (int c = 0; c < 4; c++) t[k][c] = x[k][c]->x + x[k][c]->y;
-        double2 out[2][4];
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-            const GateMat<double> &U = Ubase[zq[2 * qp + h]];
-#pragma unroll
-            for (int rr = 0; rr < 2; rr++) {
-                const int r = 2 * h + rr;
-                const double *u = U.v + 12 * r;
-#pragma unroll
-                for (int k = 0; k < 2; k++) {
-                    double s = u[0] * t[k][0];
-#pragma unroll
-                    for (int c = 1; c < 4; c++) s = fma(u[c], t[k][c], s);
-                    double re = s, im = s;
-#pragma unroll
-                    for (int c = 0; c < 4; c++) {
-                        re = fma(u[4 + c], x[k][c]->y, re);
-                        im = fma(u[8 + c], x[k][c]->x, im);
-                    }
-                    out[k][r].x = re;
-                    out[k][r].y = im;
-                }
-            }
+        for (int q = 0; q < 4; q++) {
+            const int other = quad_other<LO>(q);
+            apply_quad(a[other], a[other | (1 << LO)], a[other | (2 << LO)], a[other | (3 << LO)], U);
         }
-#pragma unroll
-        for (int k = 0; k < 2; k++)
-#pragma unroll
-            for (int c = 0; c < 4; c++) *x[k][c] = out[k][c];
     }
 }
 
@@ -434,8 +354,11 @@ QCB_HD void tile_store(typename Vec2<R>::type *__restrict__ dst, const PassParam
 }
 
 // FORGET: make the compiler forget the 16 element addresses between the loads and the stores (they are one XOR away from
-// `e`); the persistent kernels need those registers for their ring bookkeeping
-template <typename R, int TB, int SWB = Vec2<R>::SWB, bool FORGET = false>
+// `e`); the persistent kernels need those registers for their ring bookkeeping.
+// M3: ComplexF64 arithmetic in the 3M form, and the full diamond (all four slots) as straight-line code -- four
+// conditional gates cost ~43 register moves per gate at their joins (the window must sit in the same registers on both
+// sides), a quarter of the non-FP64 instructions of a deep pass.
+template <typename R, int TB, int SWB = Vec2<R>::SWB, bool FORGET = false, bool M3 = false>
 QCB_HD void tile_stage(const PassParams<R> &P, int s, typename Vec2<R>::type *sm, uint32_t tid)
 {
     using V = typename Vec2<R>::type;
@@ -449,17 +372,16 @@ QCB_HD void tile_stage(const PassParams<R> &P, int s, typename Vec2<R>::type *sm
 #pragma unroll
     for (int r = 0; r < kRegAmps; r++) a[r] = sm[e ^ S.roff[r]];
     const uint32_t mask = S.mask;
-    if (mask == 15u) {
-        // the full diamond as straight-line code: no register moves at the joins of four conditional gates
-        apply_window_gate<1, R, V>(a, &P.U[s * kSlots + 0], P.zq);
-        apply_window_gate<0, R, V>(a, &P.U[s * kSlots + 1], P.zq);
-        apply_window_gate<2, R, V>(a, &P.U[s * kSlots + 2], P.zq);
-        apply_window_gate<1, R, V>(a, &P.U[s * kSlots + 3], P.zq);
+    if (M3 && mask == 15u) {
+        apply_window_gate<1, R, V, M3>(a, P.U[s * kSlots + 0]);
+        apply_window_gate<0, R, V, M3>(a, P.U[s * kSlots + 1]);
+        apply_window_gate<2, R, V, M3>(a, P.U[s * kSlots + 2]);
+        apply_window_gate<1, R, V, M3>(a, P.U[s * kSlots + 3]);
     } else {
-        if (mask & 1u) apply_window_gate<1, R, V>(a, &P.U[s * kSlots + 0], P.zq);
-        if (mask & 2u) apply_window_gate<0, R, V>(a, &P.U[s * kSlots + 1], P.zq);
-        if (mask & 4u) apply_window_gate<2, R, V>(a, &P.U[s * kSlots + 2], P.zq);
-        if (mask & 8u) apply_window_gate<1, R, V>(a, &P.U[s * kSlots + 3], P.zq);
+        if (mask & 1u) apply_window_gate<1, R, V, M3>(a, P.U[s * kSlots + 0]);
+        if (mask & 2u) apply_window_gate<0, R, V, M3>(a, P.U[s * kSlots + 1]);
+        if (mask & 4u) apply_window_gate<2, R, V, M3>(a, P.U[s * kSlots + 2]);
+        if (mask & 8u) apply_window_gate<1, R, V, M3>(a, P.U[s * kSlots + 3]);
     }
 #if defined(__CUDA_ARCH__)
     if (FORGET) asm volatile("" : "+r"(e));
@@ -469,7 +391,7 @@ QCB_HD void tile_stage(const PassParams<R> &P, int s, typename Vec2<R>::type *sm
 }
 
 #if defined(__CUDACC__)
-template <typename R, int TB, int MINB>
+template <typename R, int TB, int MINB, bool M3>
 __global__ void __launch_bounds__(1 << (TB - kRegBits), MINB)
 tile_pass_kernel(const typename Vec2<R>::type *src, typename Vec2<R>::type *dst,
                  const __grid_constant__ PassParams<R> P)
@@ -483,14 +405,14 @@ tile_pass_kernel(const typename Vec2<R>::type *src, typename Vec2<R>::type *dst,
     __syncthreads();
 #pragma unroll 1
     for (int s = 0; s < P.nstages; s++) {
-        tile_stage<R, TB, Vec2<R>::SWB, true>(P, s, sm, tid);
+        tile_stage<R, TB, Vec2<R>::SWB, false, M3>(P, s, sm, tid);
         __syncthreads();
     }
     tile_store<R, TB>(dst, P, sm, tid, bid);
 }
 
 // the same pass with its loads taken from the peers' shards (fused qubit swap), always out of place
-template <typename R, int TB, int MINB>
+template <typename R, int TB, int MINB, bool M3>
 __global__ void __launch_bounds__(1 << (TB - kRegBits), MINB)
 tile_pass_peer_kernel(const __grid_constant__ PeerSrc S, typename Vec2<R>::type *dst, const __grid_constant__ PassParams<R> P)
 {
@@ -503,7 +425,7 @@ tile_pass_peer_kernel(const __grid_constant__ PeerSrc S, typename Vec2<R>::type 
     __syncthreads();
 #pragma unroll 1
     for (int s = 0; s < P.nstages; s++) {
-        tile_stage<R, TB, Vec2<R>::SWB, true>(P, s, sm, tid);
+        tile_stage<R, TB, Vec2<R>::SWB, false, M3>(P, s, sm, tid);
         __syncthreads();
     }
     tile_store<R, TB>(dst, P, sm, tid, bid);

@@ -8,6 +8,11 @@
 
 using namespace qcb;
 
+// ComplexF64 arithmetic of the replayed gate passes: 1 = the 3M form with straight-line full diamonds (what the GPU runs
+// for passes of >= 5 gates), 0 = the ordinary form
+static int g_emu_m3 = 1;
+extern "C" void emu_set_m3(int on) { g_emu_m3 = on; }
+
 template <typename R, int TB>
 static void run_pass(typename Vec2<R>::type *psi, int nloc, const PassParams<R> &P)
 {
@@ -18,7 +23,10 @@ static void run_pass(typename Vec2<R>::type *psi, int nloc, const PassParams<R> 
     for (unsigned long long b = 0; b < nblocks; b++) {
         for (uint32_t t = 0; t < NT; t++) tile_load<R, TB>(psi, P, sm.data(), t, b);
         for (int s = 0; s < P.nstages; s++)
-            for (uint32_t t = 0; t < NT; t++) tile_stage<R, TB>(P, s, sm.data(), t);
+            for (uint32_t t = 0; t < NT; t++) {
+                if (g_emu_m3) tile_stage<R, TB, Vec2<R>::SWB, false, true>(P, s, sm.data(), t);
+                else tile_stage<R, TB>(P, s, sm.data(), t);
+            }
         for (uint32_t t = 0; t < NT; t++) tile_store<R, TB>(psi, P, sm.data(), t, b);
     }
 }
@@ -104,7 +112,10 @@ template <typename R> struct EmuShards : ShardExecutor {
         for (unsigned long long b = 0; b < (1ull << (nloc - TB)); b++) {
             for (uint32_t t = 0; t < NT; t++) tile_load_peer<R, TB>(S, P, sm.data(), t, b);
             for (int s = 0; s < P.nstages; s++)
-                for (uint32_t t = 0; t < NT; t++) tile_stage<R, TB>(P, s, sm.data(), t);
+                for (uint32_t t = 0; t < NT; t++) {
+                    if (g_emu_m3) tile_stage<R, TB, Vec2<R>::SWB, false, true>(P, s, sm.data(), t);
+                    else tile_stage<R, TB>(P, s, sm.data(), t);
+                }
             for (uint32_t t = 0; t < NT; t++) tile_store<R, TB>(dst, P, sm.data(), t, b);
         }
     }

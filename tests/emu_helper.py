@@ -27,6 +27,11 @@ def lib():
     return _lib
 
 
+def set_m3(on):
+    """ComplexF64 arithmetic of the replayed gate passes: True = 3M form + straight-line full diamonds (default), False = ordinary."""
+    lib().emu_set_m3(C.c_int(1 if on else 0))
+
+
 def apply_gates(psi, q0, mats, tile_bits, low_bits, phys=None, nloc=None, max_gates=0, adjoint=False):
     """psi: flat complex array (modified copy returned); q0: 0-based logical low qubits; mats: (G,4,4)."""
     psi = np.ascontiguousarray(psi).copy()

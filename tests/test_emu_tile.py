@@ -42,6 +42,31 @@ def test_emu_brickwork_vs_oracle(emu, oracle, n, layers, tb, c):
     assert npass < G and nst < G  # fused: fewer sweeps than gates
 
 
+def test_emu_3m_form_equals_ordinary_form(emu, oracle):
+    """The 3M arithmetic of the deep ComplexF64 passes (tile.cuh: apply_window_gate_3m, 48 products + 4 sums per amplitude
+    quad) against the ordinary 64-product form and the oracle (src/apply.jl:62-84): same result up to rounding, and the
+    error of either form stays at the level of the other (normwise bound) over a deep circuit."""
+    rng = np.random.default_rng(3)
+    n, layers = 13, 24
+    G = onp.brickwork_num_gates(n, layers)
+    angles = rng.uniform(0, 2 * np.pi, (15, G))
+    q0 = np.array(onp.brickwork_gate_positions(n, layers)) - 1
+    mats = [oracle.build_general_unitary_gate(angles[:, g]) for g in range(G)]
+    psi0 = rand_state(rng, n)
+    ref = oracle.apply_brickwork(psi0, n, layers, angles)
+    try:
+        emu.set_m3(False)
+        out0, _ = emu.apply_gates(psi0, q0, mats, 11, 3)
+        emu.set_m3(True)
+        out3, _ = emu.apply_gates(psi0, q0, mats, 11, 3)
+    finally:
+        emu.set_m3(True)
+    assert not np.array_equal(out0, out3)  # two different instruction sequences ...
+    assert rel(out0, ref) < 1e-13 and rel(out3, ref) < 1e-13  # ... with the same accuracy
+    assert rel(out3, out0) < 1e-13
+    assert abs(np.linalg.norm(out3) - 1) < 1e-13
+
+
 def test_emu_c64(emu, oracle):
     rng = np.random.default_rng(64)
     n, layers = 13, 10
@@ -534,6 +559,11 @@ def test_emu_tma_gate_pass(emu, oracle, n, layers, maxg):
     out, (npass, ntma) = emu.apply_gates_tma(psi0, q0, mats, max_gates=maxg)
     assert ntma == npass and npass >= 1
     assert rel(out, ref) < 1e-12
-    # the LDG form of the same plan gives the same numbers bit for bit (same stage programs, same arithmetic order)
-    out2, _ = emu.apply_gates(psi0, q0, mats, 11, 3, max_gates=maxg)
+    # the LDG form of the same plan gives the same numbers bit for bit (same stage programs, same arithmetic order; the
+    # TMA kernel runs the ordinary ComplexF64 arithmetic, so the LDG form is replayed with it too)
+    try:
+        emu.set_m3(False)
+        out2, _ = emu.apply_gates(psi0, q0, mats, 11, 3, max_gates=maxg)
+    finally:
+        emu.set_m3(True)
     assert np.array_equal(out, out2)

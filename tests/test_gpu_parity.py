@@ -52,7 +52,8 @@ def _defaults():
     qc.set_option("adjoint_prog_host", 0)
     qc.set_option("contract_coop", 1)
     qc.set_option("measure_tma", 1)
-    qc.set_option("pass_tma", 1)
+    qc.set_option("pass_tma", 0)
+    qc.set_option("f64_3m_min_gates", 5)
     qc.set_option("adjoint_f32", 1)
     qc.set_option("adjoint_ctas", 5)
     qc.set_option("adjoint_defer", 1)
@@ -616,6 +617,7 @@ def test_tma_gate_pass_equals_ldg_pass(oracle, n, layers, cap):
     psi0 = rand_state(rng, n)
     if cap:
         qc.set_option("max_gates_per_pass", cap)
+    qc.set_option("f64_3m_min_gates", 1 << 30)  # the TMA kernel runs the ordinary arithmetic: compare like with like
     outs = {}
     for mode in (1, 0):
         qc.set_option("pass_tma", mode)
@@ -628,10 +630,28 @@ def test_tma_gate_pass_equals_ldg_pass(oracle, n, layers, cap):
         src = qc.B200State(psi0)
         qc.apply_(dst, src, c)
         assert np.array_equal(dst.to_numpy(), outs[mode]) and np.array_equal(src.to_numpy(), psi0)
-    qc.set_option("pass_tma", 1)
+    qc.set_option("pass_tma", 0)
     assert np.array_equal(outs[0], outs[1])
     if n <= 22:
         assert rel(outs[1], oracle.apply_brickwork(psi0, n, layers, c.gate_angles)) < 1e-12
+
+
+# ---- ComplexF64 arithmetic: the 3M form of the deep passes (tile.cuh: apply_window_gate_3m) == the ordinary form == oracle
+@pytest.mark.parametrize("n,layers", [(12, 20), (16, 12), (22, 10)])
+def test_3m_form_equals_ordinary_form(oracle, n, layers):
+    rng = np.random.default_rng(3300 + n)
+    c = circuit(n, layers, rng)
+    psi0 = rand_state(rng, n)
+    outs = {}
+    for min_gates in (0, 1 << 30):
+        qc.set_option("f64_3m_min_gates", min_gates)
+        st = qc.B200State(psi0)
+        qc.apply_(st, st, c)
+        outs[min_gates] = st.to_numpy()
+    qc.set_option("f64_3m_min_gates", 5)
+    ref = oracle.apply_brickwork(psi0, n, layers, c.gate_angles)
+    assert not np.array_equal(outs[0], outs[1 << 30])
+    assert rel(outs[0], ref) < 1e-12 and rel(outs[1 << 30], ref) < 1e-12 and rel(outs[0], outs[1 << 30]) < 1e-13
 
 
 # ---- size-independent properties at sizes the oracle cannot check in seconds
