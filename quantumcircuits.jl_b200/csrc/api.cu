@@ -792,6 +792,7 @@ int qcb_get_stat(const char *key, double *out)
     const std::string k(key ? key : "");
     if (k == "passes") *out = c.st_passes;
     else if (k == "stages") *out = c.st_stages;
+    else if (k == "gates_3m") *out = c.st_gates_3m;
     else if (k == "launches") *out = c.st_launches;
     else if (k == "gates") *out = c.st_gates;
     else if (k == "launches_total") *out = c.st_launches_total;

@@ -18,20 +18,29 @@ namespace qcb {
 
 // src == nullptr: in place.  Otherwise the pass reads `src` (another state of the same size) and writes the state: every
 // amplitude is read and written exactly once per pass, so the first pass of a circuit can double as the copy of its input.
-// ComplexF64 passes with at least `f64_3m_min_gates` gates run the 3M arithmetic (tile.cuh): below that the pass is bound
-// by HBM, not by the FP64 pipe, and the ordinary form is the faster one (fewer constants to fetch per gate).
-template <typename R> static bool pass_wants_3m(const PassParams<R> &P)
+// Arithmetic of a ComplexF64 pass (tile.cuh): passes with fewer than `f64_3m_min_gates` gates are bound by HBM, not by the
+// FP64 pipe, and keep the ordinary form (0: fewer constants to fetch per gate); deeper ones run the 3M form -- as
+// straight-line code when every stage is a full diamond (2), with conditional gates otherwise (1).
+template <typename R> static int pass_form(const PassParams<R> &P)
 {
-    if (sizeof(R) != 8) return false;
+    if (sizeof(R) != 8) return 0;
     int gates = 0;
-    for (int i = 0; i < P.nstages; i++) gates += __builtin_popcount(P.stage[i].mask);
-    return gates >= ctx().f64_3m_min_gates;
+    bool full = true;
+    for (int i = 0; i < P.nstages; i++) {
+        gates += __builtin_popcount(P.stage[i].mask);
+        full = full && P.stage[i].mask == 15;
+    }
+    if (gates < ctx().f64_3m_min_gates) return 0;
+    ctx().st_gates_3m += gates;
+    return full ? 2 : 1;
 }
 
-template <typename R, int TB, bool M3 = false> static int launch_pass(qcb_state *s, const PassParams<R> &P, const void *src = nullptr)
+template <typename R, int TB, int M3 = 0> static int launch_pass(qcb_state *s, const PassParams<R> &P, const void *src = nullptr)
 {
-    if constexpr (sizeof(R) == 8 && !M3) {
-        if (pass_wants_3m(P)) return launch_pass<R, TB, true>(s, P, src);
+    if constexpr (sizeof(R) == 8 && M3 == 0) {
+        const int form = pass_form(P);
+        if (form == 1) return launch_pass<R, TB, 1>(s, P, src);
+        if (form == 2) return launch_pass<R, TB, 2>(s, P, src);
     }
     using V = typename Vec2<R>::type;
     constexpr int NT = 1 << (TB - kRegBits);
@@ -93,10 +102,12 @@ static bool use_tma_pass(const qcb_state *s, const PassPlan &pl, TmaPassGeom &g)
     return tma_pass_eligible(pl, s->nloc, g);
 }
 
-template <typename R, int TB, bool M3 = false> static int launch_pass_peer(qcb_state *s, const PeerSrc &src, void *dst, const PassParams<R> &P)
+template <typename R, int TB, int M3 = 0> static int launch_pass_peer(qcb_state *s, const PeerSrc &src, void *dst, const PassParams<R> &P)
 {
-    if constexpr (sizeof(R) == 8 && !M3) {
-        if (pass_wants_3m(P)) return launch_pass_peer<R, TB, true>(s, src, dst, P);
+    if constexpr (sizeof(R) == 8 && M3 == 0) {
+        const int form = pass_form(P);
+        if (form == 1) return launch_pass_peer<R, TB, 1>(s, src, dst, P);
+        if (form == 2) return launch_pass_peer<R, TB, 2>(s, src, dst, P);
     }
     using V = typename Vec2<R>::type;
     constexpr int NT = 1 << (TB - kRegBits);

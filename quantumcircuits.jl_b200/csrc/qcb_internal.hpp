@@ -48,6 +48,7 @@ struct Ctx {
     struct PassMeta { int stages, gates, first_window_bit, tma; unsigned long long masks; }; // masks: 4 bits per stage, stage 0 lowest
     std::vector<PassMeta> pass_meta; // one per timed launch (diagnostics: env QCB_PASS_LOG=<file> dumps them with their times)
     double st_tma_passes = 0, st_fw_passes = 0, st_bw_passes = 0, st_ham_passes = 0;
+    double st_gates_3m = 0; // cumulative: gates applied in the 3M arithmetic (full diamonds of ComplexF64 passes), see tile.cuh
     int *d_barrier = nullptr; // 1 int for stream-ordered inter-rank barriers (NCCL all-reduce)
     // scratch
     // backward sweep of an unsharded gradient: the per-pass accumulator rows of ALL passes stay in d_partial (one area per

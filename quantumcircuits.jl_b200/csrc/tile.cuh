@@ -82,20 +82,19 @@ template <int SWB> QCB_HD uint32_t swz(uint32_t e)
 }
 
 // Gate matrix as the kernels consume it (r = output index, c = input index of the 4x4 form).
-//   double: with A = Re u, B = Im u: v[12r + c] = A_rc, v[12r + 4 + c] = -(A + B)_rc, v[12r + 8 + c] = (B - A)_rc -- the
-//           constants of the three-multiplication form of the complex product (apply_quad below), row by row in the
-//           order they are consumed; v[48 + r + 4c] = B_rc (A and B themselves are read by the tensor-core backward
-//           pass, adjoint_mma.cuh, through gate_re / gate_im).
+//   double: with A = Re u, B = Im u and k = 4r + c: v[k] = A_rc, v[16 + k] = B_rc (the ordinary form and the tensor-core
+//           backward pass read these two, 256 contiguous bytes), v[32 + k] = -(A + B)_rc, v[48 + k] = (B - A)_rc (with A:
+//           the constants of the three-multiplication form of the complex product, apply_window_gate_3m below).
 //   float : packed for FFMA2 (sm_100 fma.rn.f32x2): v[4k..4k+3] = (Re u, Re u, -Im u, Im u), so that
 //           (re, im) += (Re u, Re u) * (x.re, x.im) + (-Im u, Im u) * (x.im, x.re) is two packed FMAs.
 template <typename R> struct alignas(16) GateMat { R v[64]; };
 QCB_HD void gate_set(GateMat<double> &U, int r, int c, double re, double im)
 {
-    U.v[12 * r + c] = re; U.v[12 * r + 4 + c] = -(re + im); U.v[12 * r + 8 + c] = im - re;
-    U.v[48 + r + 4 * c] = im;
+    const int k = 4 * r + c;
+    U.v[k] = re; U.v[16 + k] = im; U.v[32 + k] = -(re + im); U.v[48 + k] = im - re;
 }
-QCB_HD double gate_re(const GateMat<double> &U, int r, int c) { return U.v[12 * r + c]; }
-QCB_HD double gate_im(const GateMat<double> &U, int r, int c) { return U.v[48 + r + 4 * c]; }
+QCB_HD double gate_re(const GateMat<double> &U, int r, int c) { return U.v[4 * r + c]; }
+QCB_HD double gate_im(const GateMat<double> &U, int r, int c) { return U.v[16 + 4 * r + c]; }
 QCB_HD void gate_set(GateMat<float> &U, int r, int c, double re, double im)
 {
     float *p = U.v + 4 * (r + 4 * c);
@@ -229,15 +228,15 @@ template <int LO> QCB_HD void apply_window_gate_3m(double2 (&a)[kRegAmps], const
             double2 out[2];
 #pragma unroll
             for (int rr = 0; rr < 2; rr++) {
-                const double *u = U.v + 12 * (2 * h + rr);
+                const double *u = U.v + 4 * (2 * h + rr);
                 double s = u[0] * t[0];
 #pragma unroll
                 for (int c = 1; c < 4; c++) s = fma(u[c], t[c], s);
                 double re = s, im = s;
 #pragma unroll
                 for (int c = 0; c < 4; c++) {
-                    re = fma(u[4 + c], x[c]->y, re);
-                    im = fma(u[8 + c], x[c]->x, im);
+                    re = fma(u[32 + c], x[c]->y, re);
+                    im = fma(u[48 + c], x[c]->x, im);
                 }
                 out[rr].x = re;
                 out[rr].y = im;
@@ -353,12 +352,32 @@ QCB_HD void tile_store(typename Vec2<R>::type *__restrict__ dst, const PassParam
     for (int i = 0; i < kRegAmps; i++) dst[g | P.ld_goff[i]] = sm[e ^ P.st_eoff[i]];
 }
 
+// the slots of MASK, 3M arithmetic, no conditionals
+template <uint32_t MASK, typename R, typename V> QCB_HD void apply_slots(V (&a)[kRegAmps], const GateMat<R> *U)
+{
+    if constexpr ((MASK & 1u) != 0) apply_window_gate<1, R, V, true>(a, U[0]);
+    if constexpr ((MASK & 2u) != 0) apply_window_gate<0, R, V, true>(a, U[1]);
+    if constexpr ((MASK & 4u) != 0) apply_window_gate<2, R, V, true>(a, U[2]);
+    if constexpr ((MASK & 8u) != 0) apply_window_gate<1, R, V, true>(a, U[3]);
+}
+template <bool FORGET, typename V> QCB_HD void stage_store(V *sm, uint32_t e, const StageDesc &S, const V (&a)[kRegAmps])
+{
+#if defined(__CUDA_ARCH__)
+    if (FORGET) asm volatile("" : "+r"(e));
+#endif
+#pragma unroll
+    for (int r = 0; r < kRegAmps; r++) sm[e ^ S.roff[r]] = a[r];
+}
+
 // FORGET: make the compiler forget the 16 element addresses between the loads and the stores (they are one XOR away from
 // `e`); the persistent kernels need those registers for their ring bookkeeping.
-// M3: ComplexF64 arithmetic in the 3M form, and the full diamond (all four slots) as straight-line code -- four
-// conditional gates cost ~43 register moves per gate at their joins (the window must sit in the same registers on both
-// sides), a quarter of the non-FP64 instructions of a deep pass.
-template <typename R, int TB, int SWB = Vec2<R>::SWB, bool FORGET = false, bool M3 = false>
+// M3 (ComplexF64 only): 0 = ordinary arithmetic; 1 = the 3M form, four conditional gates; 2 = the 3M form for passes
+// whose stages are all full diamonds, as straight-line code (four conditional gates cost ~43 register moves per gate at
+// their joins -- the window must sit in the same registers on both sides).  One code path per kernel: instruction fetch
+// is a limiter here.  A kernel holding the straight-line diamond AND a generic path (36 KB of stage code) ran the mixed
+// passes with `no_instruction` as the top stall (ncu) and 4 % slower overall than the one-path forms; straight-line code
+// for every partial mask the brickwork schedules produce (118 KB) was 5 % slower still (profiles/).
+template <typename R, int TB, int SWB = Vec2<R>::SWB, bool FORGET = false, int M3 = 0>
 QCB_HD void tile_stage(const PassParams<R> &P, int s, typename Vec2<R>::type *sm, uint32_t tid)
 {
     using V = typename Vec2<R>::type;
@@ -372,26 +391,29 @@ QCB_HD void tile_stage(const PassParams<R> &P, int s, typename Vec2<R>::type *sm
 #pragma unroll
     for (int r = 0; r < kRegAmps; r++) a[r] = sm[e ^ S.roff[r]];
     const uint32_t mask = S.mask;
-    if (M3 && mask == 15u) {
-        apply_window_gate<1, R, V, M3>(a, P.U[s * kSlots + 0]);
-        apply_window_gate<0, R, V, M3>(a, P.U[s * kSlots + 1]);
-        apply_window_gate<2, R, V, M3>(a, P.U[s * kSlots + 2]);
-        apply_window_gate<1, R, V, M3>(a, P.U[s * kSlots + 3]);
-    } else {
-        if (mask & 1u) apply_window_gate<1, R, V, M3>(a, P.U[s * kSlots + 0]);
-        if (mask & 2u) apply_window_gate<0, R, V, M3>(a, P.U[s * kSlots + 1]);
-        if (mask & 4u) apply_window_gate<2, R, V, M3>(a, P.U[s * kSlots + 2]);
-        if (mask & 8u) apply_window_gate<1, R, V, M3>(a, P.U[s * kSlots + 3]);
+    if (M3 == 2) {
+        // a pass of full diamonds only (the host checks every mask): straight-line code, no joins with the window live
+        apply_slots<15, R, V>(a, &P.U[s * kSlots]);
+        stage_store<FORGET>(sm, e, S, a);
+        return;
     }
-#if defined(__CUDA_ARCH__)
-    if (FORGET) asm volatile("" : "+r"(e));
-#endif
-#pragma unroll
-    for (int r = 0; r < kRegAmps; r++) sm[e ^ S.roff[r]] = a[r];
+    if (M3 == 1) {
+        if (mask & 1u) apply_window_gate<1, R, V, true>(a, P.U[s * kSlots + 0]);
+        if (mask & 2u) apply_window_gate<0, R, V, true>(a, P.U[s * kSlots + 1]);
+        if (mask & 4u) apply_window_gate<2, R, V, true>(a, P.U[s * kSlots + 2]);
+        if (mask & 8u) apply_window_gate<1, R, V, true>(a, P.U[s * kSlots + 3]);
+        stage_store<FORGET>(sm, e, S, a);
+        return;
+    }
+    if (mask & 1u) apply_window_gate<1, R, V>(a, P.U[s * kSlots + 0]);
+    if (mask & 2u) apply_window_gate<0, R, V>(a, P.U[s * kSlots + 1]);
+    if (mask & 4u) apply_window_gate<2, R, V>(a, P.U[s * kSlots + 2]);
+    if (mask & 8u) apply_window_gate<1, R, V>(a, P.U[s * kSlots + 3]);
+    stage_store<FORGET>(sm, e, S, a);
 }
 
 #if defined(__CUDACC__)
-template <typename R, int TB, int MINB, bool M3>
+template <typename R, int TB, int MINB, int M3>
 __global__ void __launch_bounds__(1 << (TB - kRegBits), MINB)
 tile_pass_kernel(const typename Vec2<R>::type *src, typename Vec2<R>::type *dst,
                  const __grid_constant__ PassParams<R> P)
@@ -412,7 +434,7 @@ tile_pass_kernel(const typename Vec2<R>::type *src, typename Vec2<R>::type *dst,
 }
 
 // the same pass with its loads taken from the peers' shards (fused qubit swap), always out of place
-template <typename R, int TB, int MINB, bool M3>
+template <typename R, int TB, int MINB, int M3>
 __global__ void __launch_bounds__(1 << (TB - kRegBits), MINB)
 tile_pass_peer_kernel(const __grid_constant__ PeerSrc S, typename Vec2<R>::type *dst, const __grid_constant__ PassParams<R> P)
 {

@@ -8,10 +8,23 @@
 
 using namespace qcb;
 
-// ComplexF64 arithmetic of the replayed gate passes: 1 = the 3M form with straight-line full diamonds (what the GPU runs
-// for passes of >= 5 gates), 0 = the ordinary form
+// ComplexF64 arithmetic of the replayed gate passes: 1 = the 3M form (what the GPU runs for passes of >= 5 gates: the
+// straight-line kernel when every stage of the pass is a full diamond, the conditional one otherwise), 0 = the ordinary form
 static int g_emu_m3 = 1;
 extern "C" void emu_set_m3(int on) { g_emu_m3 = on; }
+template <typename R> static int emu_pass_form(const PassParams<R> &P)
+{
+    if (!g_emu_m3) return 0;
+    for (int i = 0; i < P.nstages; i++)
+        if (P.stage[i].mask != 15) return 1;
+    return 2;
+}
+template <typename R, int TB> static void emu_stage(const PassParams<R> &P, int form, int s, typename Vec2<R>::type *sm, uint32_t t)
+{
+    if (form == 2) tile_stage<R, TB, Vec2<R>::SWB, false, 2>(P, s, sm, t);
+    else if (form == 1) tile_stage<R, TB, Vec2<R>::SWB, false, 1>(P, s, sm, t);
+    else tile_stage<R, TB>(P, s, sm, t);
+}
 
 template <typename R, int TB>
 static void run_pass(typename Vec2<R>::type *psi, int nloc, const PassParams<R> &P)
@@ -22,11 +35,9 @@ static void run_pass(typename Vec2<R>::type *psi, int nloc, const PassParams<R> 
     std::vector<V> sm(1u << TB);
     for (unsigned long long b = 0; b < nblocks; b++) {
         for (uint32_t t = 0; t < NT; t++) tile_load<R, TB>(psi, P, sm.data(), t, b);
+        const int form = emu_pass_form(P);
         for (int s = 0; s < P.nstages; s++)
-            for (uint32_t t = 0; t < NT; t++) {
-                if (g_emu_m3) tile_stage<R, TB, Vec2<R>::SWB, false, true>(P, s, sm.data(), t);
-                else tile_stage<R, TB>(P, s, sm.data(), t);
-            }
+            for (uint32_t t = 0; t < NT; t++) emu_stage<R, TB>(P, form, s, sm.data(), t);
         for (uint32_t t = 0; t < NT; t++) tile_store<R, TB>(psi, P, sm.data(), t, b);
     }
 }
@@ -111,11 +122,9 @@ template <typename R> struct EmuShards : ShardExecutor {
         std::vector<V> sm(1u << TB);
         for (unsigned long long b = 0; b < (1ull << (nloc - TB)); b++) {
             for (uint32_t t = 0; t < NT; t++) tile_load_peer<R, TB>(S, P, sm.data(), t, b);
+            const int form = emu_pass_form(P);
             for (int s = 0; s < P.nstages; s++)
-                for (uint32_t t = 0; t < NT; t++) {
-                    if (g_emu_m3) tile_stage<R, TB, Vec2<R>::SWB, false, true>(P, s, sm.data(), t);
-                    else tile_stage<R, TB>(P, s, sm.data(), t);
-                }
+                for (uint32_t t = 0; t < NT; t++) emu_stage<R, TB>(P, form, s, sm.data(), t);
             for (uint32_t t = 0; t < NT; t++) tile_store<R, TB>(dst, P, sm.data(), t, b);
         }
     }
