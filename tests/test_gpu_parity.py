@@ -53,7 +53,7 @@ def _defaults():
     qc.set_option("contract_coop", 1)
     qc.set_option("measure_tma", 1)
     qc.set_option("pass_tma", 0)
-    qc.set_option("f64_3m_min_gates", 5)
+    qc.set_option("f64_3m_min_gates", 4)
     qc.set_option("adjoint_f32", 1)
     qc.set_option("adjoint_ctas", 5)
     qc.set_option("adjoint_defer", 1)
@@ -648,7 +648,7 @@ def test_3m_form_equals_ordinary_form(oracle, n, layers):
         st = qc.B200State(psi0)
         qc.apply_(st, st, c)
         outs[min_gates] = st.to_numpy()
-    qc.set_option("f64_3m_min_gates", 5)
+    qc.set_option("f64_3m_min_gates", 4)
     ref = oracle.apply_brickwork(psi0, n, layers, c.gate_angles)
     assert not np.array_equal(outs[0], outs[1 << 30])
     assert rel(outs[0], ref) < 1e-12 and rel(outs[1 << 30], ref) < 1e-12 and rel(outs[0], outs[1 << 30]) < 1e-13
