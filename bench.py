@@ -452,6 +452,21 @@ def run_ours(args):
         roofline["hbm_bound_regime"] = {"max_gates_per_pass": 3, "launches_per_circuit": p3, "avg_launch_ms": kms3 / max(k3, 1.0), "achieved": ach3,
                                         "peak": peak, "unit": "GB/s", "frac": ach3 / peak, "gate_apps_per_sec": G / (ms3 * 1e-3),
                                         "circuit_ms": ms3, "share_of_circuit": kms3 / ms3}
+        # ... and with one gate per pass (one register stage: what the reference's one-launch-per-gate structure would cost
+        # on this kernel), one timed circuit
+        qc.set_option("max_gates_per_pass", 1)
+        qc.set_option("time_passes", 1)
+        h0.record()
+        step()
+        h1.record()
+        torch.cuda.synchronize()
+        ms1 = h0.elapsed_time(h1)
+        k1, kms1 = qc.get_stat("pass_count"), qc.get_stat("pass_ms")
+        qc.set_option("time_passes", 0)
+        launches += k1
+        ach1 = bytes_pass / (kms1 / max(k1, 1.0) * 1e-3) / 1e9
+        roofline["one_gate_per_pass"] = {"launches_per_circuit": k1, "avg_launch_ms": kms1 / max(k1, 1.0), "achieved": ach1, "peak": peak, "unit": "GB/s",
+                                         "frac": ach1 / peak, "gate_apps_per_sec": G / (ms1 * 1e-3), "circuit_ms": ms1}
         qc.set_option("max_gates_per_pass", 1 << 30)
 
     # ---- end to end through the host-buffer API

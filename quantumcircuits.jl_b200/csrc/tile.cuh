@@ -15,7 +15,8 @@
 //   stage: every thread pulls the 16 amplitudes spanned by 4 consecutive local bits
 //          [p0, p0+4) into registers and applies up to 4 gates on the bit pairs
 //          C=(1,2), A=(0,1), B=(2,3), C=(1,2) of that window (a brickwork diamond),
-//          64 real FMAs per amplitude quad per gate; gate matrices are kernel
+//          64 real FMAs per amplitude quad per gate (48 products + 4 sums in the 3M form the
+//          deep ComplexF64 passes run, apply_window_gate_3m); gate matrices are kernel
 //          parameters, so ptxas feeds them to DFMA/FFMA from uniform registers.
 //
 // Shared memory is XOR-swizzled (low SWB bits of the 16 B / 8 B chunk index ^= xor of
