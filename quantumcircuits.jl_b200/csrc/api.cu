@@ -752,6 +752,8 @@ int qcb_set_option(const char *key, long value)
         c.pass_tma = value;
     } else if (k == "pass_tma_max_stages") {
         c.pass_tma_max_stages = value;
+    } else if (k == "pass_async") {
+        c.pass_async = value ? 1 : 0; // gate passes on the persistent kernel with asynchronous tile loads (tile_async.cuh)
     } else if (k == "f64_3m_min_gates") {
         c.f64_3m_min_gates = value; // ComplexF64 passes with at least this many gates use the 3M arithmetic (0: all, large: none)
     } else if (k == "tma_l2_promotion") {
@@ -793,6 +795,7 @@ int qcb_get_stat(const char *key, double *out)
     if (k == "passes") *out = c.st_passes;
     else if (k == "stages") *out = c.st_stages;
     else if (k == "gates_3m") *out = c.st_gates_3m;
+    else if (k == "async_passes") *out = c.st_async_passes;
     else if (k == "launches") *out = c.st_launches;
     else if (k == "gates") *out = c.st_gates;
     else if (k == "launches_total") *out = c.st_launches_total;

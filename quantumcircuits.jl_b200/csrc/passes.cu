@@ -12,6 +12,7 @@
 #include "kernels.cuh"
 #include "qcb_internal.hpp"
 #include "tile_tma.cuh"
+#include "tile_async.cuh"
 
 namespace qcb {
 
@@ -47,6 +48,29 @@ template <typename R, int TB, int M3 = 0> static int launch_pass(qcb_state *s, c
     // resident threads per SM the register budget is sized for: 512 (ComplexF64, 128 registers) / 1024 (ComplexF32, 64)
     constexpr int RES = sizeof(R) == 8 ? 512 : 1024;
     constexpr int MINB = (RES / NT) > 0 ? ((RES / NT) > 32 ? 32 : (RES / NT)) : 1;
+    const unsigned long long nblocks = 1ull << (s->nloc - TB);
+    // persistent form with asynchronous tile loads (tile_async.cuh): two tile buffers per CTA
+    if constexpr ((sizeof(V) << (TB + 1)) <= (size_t)(64 << 10)) {
+        if (ctx().pass_async) {
+            constexpr int ARES = sizeof(R) == 8 ? 384 : 1024; // ComplexF64: 3 x 128 threads per SM, up to 168 registers
+            constexpr int AMINB = (ARES / NT) > 0 ? ((ARES / NT) > 32 ? 32 : (ARES / NT)) : 1;
+            auto akern = tile_pass_async_kernel<R, TB, AMINB, M3>;
+            const size_t asmem = sizeof(V) << (TB + 1);
+            static int ctas_per_sm = 0;
+            if (!ctas_per_sm) {
+                QCB_CUDA(cudaFuncSetAttribute(akern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)asmem));
+                QCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, akern, NT, asmem));
+                if (ctas_per_sm < 1) ctas_per_sm = 1;
+            }
+            const unsigned grid = (unsigned)std::min<unsigned long long>(nblocks, (unsigned long long)ctx().sm_count * ctas_per_sm);
+            PassTimerScope timer;
+            akern<<<grid, NT, asmem, ctx().stream>>>((const V *)(src ? src : s->d), (V *)s->d, P, nblocks);
+            QCB_CUDA(cudaGetLastError());
+            count_launch();
+            ctx().st_async_passes += 1;
+            return QCB_OK;
+        }
+    }
     auto kern = tile_pass_kernel<R, TB, MINB, M3>;
     const size_t smem = sizeof(V) << TB;
     static bool attr_set = false;
@@ -54,7 +78,6 @@ template <typename R, int TB, int M3 = 0> static int launch_pass(qcb_state *s, c
         QCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
-    const unsigned long long nblocks = 1ull << (s->nloc - TB);
     PassTimerScope timer;
     kern<<<(unsigned)nblocks, NT, smem, ctx().stream>>>((const V *)(src ? src : s->d), (V *)s->d, P);
     QCB_CUDA(cudaGetLastError());

@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <vector>
 #include "../../quantumcircuits.jl_b200/csrc/dist_plan.hpp"
+#include "../../quantumcircuits.jl_b200/csrc/tile_async.cuh"
 
 using namespace qcb;
 
@@ -26,12 +27,36 @@ template <typename R, int TB> static void emu_stage(const PassParams<R> &P, int 
     else tile_stage<R, TB>(P, s, sm, t);
 }
 
+// > 0: replay the persistent form with asynchronous tile loads (tile_async.cuh) on a grid of that many CTAs: two tile
+// buffers per CTA, the copies of tile k + 1 issued (here: done) before the stages of tile k
+static int g_emu_async_grid = 0;
+extern "C" void emu_set_async(int grid) { g_emu_async_grid = grid; }
+
 template <typename R, int TB>
 static void run_pass(typename Vec2<R>::type *psi, int nloc, const PassParams<R> &P)
 {
     using V = typename Vec2<R>::type;
     const uint32_t NT = 1u << (TB - kRegBits);
     const unsigned long long nblocks = 1ull << (nloc - TB);
+    if (g_emu_async_grid > 0) {
+        const unsigned long long stride = (unsigned long long)g_emu_async_grid;
+        const int form = emu_pass_form(P);
+        std::vector<V> ring(2u << TB);
+        for (unsigned long long cta = 0; cta < stride && cta < nblocks; cta++) {
+            unsigned long long t = cta;
+            for (uint32_t tid = 0; tid < NT; tid++) tile_load_async<R, TB>(psi, P, ring.data(), tid, t);
+            uint32_t k = 0;
+            for (; t < nblocks; t += stride, k ^= 1u) {
+                V *sm = ring.data() + ((size_t)k << TB);
+                if (t + stride < nblocks)
+                    for (uint32_t tid = 0; tid < NT; tid++) tile_load_async<R, TB>(psi, P, ring.data() + ((size_t)(k ^ 1u) << TB), tid, t + stride);
+                for (int s = 0; s < P.nstages; s++)
+                    for (uint32_t tid = 0; tid < NT; tid++) emu_stage<R, TB>(P, form, s, sm, tid);
+                for (uint32_t tid = 0; tid < NT; tid++) tile_store<R, TB>(psi, P, sm, tid, t);
+            }
+        }
+        return;
+    }
     std::vector<V> sm(1u << TB);
     for (unsigned long long b = 0; b < nblocks; b++) {
         for (uint32_t t = 0; t < NT; t++) tile_load<R, TB>(psi, P, sm.data(), t, b);

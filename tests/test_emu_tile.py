@@ -67,6 +67,26 @@ def test_emu_3m_form_equals_ordinary_form(emu, oracle):
     assert abs(np.linalg.norm(out3) - 1) < 1e-13
 
 
+@pytest.mark.parametrize("n,layers,tb,grid,dt", [(13, 9, 9, 3, np.complex128), (14, 8, 11, 5, np.complex128), (15, 6, 11, 1, np.complex64), (12, 10, 11, 7, np.complex128)])
+def test_emu_async_gate_pass(emu, oracle, n, layers, tb, grid, dt):
+    """Persistent gate pass with asynchronous tile loads (tile_async.cuh): the same numbers as the one-tile-per-CTA form,
+    bit for bit, on any grid size (a grid that does not divide the tile count, more CTAs than tiles)."""
+    rng = np.random.default_rng(7700 + n)
+    G = onp.brickwork_num_gates(n, layers)
+    angles = rng.uniform(0, 2 * np.pi, (15, G))
+    q0 = np.array(onp.brickwork_gate_positions(n, layers)) - 1
+    mats = [oracle.build_general_unitary_gate(angles[:, g]) for g in range(G)]
+    psi0 = rand_state(rng, n, dt)
+    ref, _ = emu.apply_gates(psi0, q0, mats, tb, 3)
+    try:
+        emu.set_async(grid)
+        out, _ = emu.apply_gates(psi0, q0, mats, tb, 3)
+    finally:
+        emu.set_async(0)
+    assert np.array_equal(out, ref)
+    assert rel(out.astype(np.complex128), oracle.apply_brickwork(psi0.astype(np.complex128), n, layers, angles)) < (1e-13 if dt == np.complex128 else 1e-5)
+
+
 def test_emu_c64(emu, oracle):
     rng = np.random.default_rng(64)
     n, layers = 13, 10

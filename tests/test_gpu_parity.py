@@ -40,6 +40,9 @@ def circuit(n, layers, rng, scale=None):
     return c
 
 
+PASS_ASYNC_DEFAULT = 0
+
+
 @pytest.fixture(autouse=True)
 def _defaults():
     qc.init()
@@ -54,6 +57,7 @@ def _defaults():
     qc.set_option("measure_tma", 1)
     qc.set_option("pass_tma", 0)
     qc.set_option("f64_3m_min_gates", 4)
+    qc.set_option("pass_async", PASS_ASYNC_DEFAULT)
     qc.set_option("adjoint_f32", 1)
     qc.set_option("adjoint_ctas", 5)
     qc.set_option("adjoint_defer", 1)
@@ -634,6 +638,33 @@ def test_tma_gate_pass_equals_ldg_pass(oracle, n, layers, cap):
     assert np.array_equal(outs[0], outs[1])
     if n <= 22:
         assert rel(outs[1], oracle.apply_brickwork(psi0, n, layers, c.gate_angles)) < 1e-12
+
+
+# ---- persistent gate pass with asynchronous tile loads (tile_async.cuh) == one tile per CTA (tile.cuh), bit for bit
+@pytest.mark.parametrize("dtype", [np.complex128, np.complex64])
+@pytest.mark.parametrize("n,layers,cap", [(11, 8, 0), (13, 20, 0), (17, 12, 3), (22, 10, 0), (24, 5, 1)])
+def test_async_gate_pass_equals_sync_pass(oracle, n, layers, cap, dtype):
+    rng = np.random.default_rng(1200 + 7 * n + layers)
+    c = circuit(n, layers, rng)
+    psi0 = rand_state(rng, n, dtype)
+    if cap:
+        qc.set_option("max_gates_per_pass", cap)
+    outs = {}
+    for mode in (1, 0):
+        qc.set_option("pass_async", mode)
+        a0 = qc.get_stat("async_passes")
+        st = qc.B200State(psi0)
+        qc.apply_(st, st, c)
+        assert (qc.get_stat("async_passes") - a0 == qc.get_stat("passes")) if mode else (qc.get_stat("async_passes") == a0)
+        outs[mode] = st.to_numpy()
+        dst = st.similar()  # out of place: the first pass reads psi and writes psi'
+        src = qc.B200State(psi0)
+        qc.apply_(dst, src, c)
+        assert np.array_equal(dst.to_numpy(), outs[mode]) and np.array_equal(src.to_numpy(), psi0)
+    qc.set_option("pass_async", PASS_ASYNC_DEFAULT)
+    assert np.array_equal(outs[0], outs[1])
+    if n <= 22:
+        assert rel(outs[1].astype(np.complex128), oracle.apply_brickwork(psi0.astype(np.complex128), n, layers, c.gate_angles)) < TOL[dtype]
 
 
 # ---- ComplexF64 arithmetic: the 3M form of the deep passes (tile.cuh: apply_window_gate_3m) == the ordinary form == oracle
