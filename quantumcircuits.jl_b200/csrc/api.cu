@@ -752,6 +752,12 @@ int qcb_set_option(const char *key, long value)
         c.pass_tma = value;
     } else if (k == "pass_tma_max_stages") {
         c.pass_tma_max_stages = value;
+    } else if (k == "small_cluster") {
+        // gate lists on states of at most this many qubits run in one launch on a thread-block cluster (small_circuit.cuh);
+        // 0 = never, 1 = up to the kernel's maximum (15 qubits ComplexF64 / 16 ComplexF32).  Default 12: above that the
+        // distributed-shared-memory traffic of the gates on the CTA-rank bits makes it slower than the tile passes (measured)
+        if (value < 0 || value > 16) return set_error(QCB_EINVAL, "small_cluster must be 0 (off), 1 (kernel maximum) or a qubit count <= 16");
+        c.small_cluster = value;
     } else if (k == "pass_async") {
         c.pass_async = value ? 1 : 0; // gate passes on the persistent kernel with asynchronous tile loads (tile_async.cuh)
     } else if (k == "f64_3m_min_gates") {
@@ -796,6 +802,7 @@ int qcb_get_stat(const char *key, double *out)
     else if (k == "stages") *out = c.st_stages;
     else if (k == "gates_3m") *out = c.st_gates_3m;
     else if (k == "async_passes") *out = c.st_async_passes;
+    else if (k == "cluster_circuits") *out = c.st_cluster_circuits;
     else if (k == "launches") *out = c.st_launches;
     else if (k == "gates") *out = c.st_gates;
     else if (k == "launches_total") *out = c.st_launches_total;

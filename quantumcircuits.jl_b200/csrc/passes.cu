@@ -13,6 +13,7 @@
 #include "qcb_internal.hpp"
 #include "tile_tma.cuh"
 #include "tile_async.cuh"
+#include "small_circuit.cuh"
 
 namespace qcb {
 
@@ -752,6 +753,79 @@ int run_adjoint_fused(qcb_state *psi, qcb_state *lam, const std::vector<GateOp> 
     return run_adjoint_fused_t<float>(psi, lam, rev, mats, d_env, false);
 }
 
+// ---- small states: the whole gate list in one launch on a thread-block cluster (small_circuit.cuh) ------------------------
+static bool small_cluster_eligible(const qcb_state *s, const std::vector<GateOp> &gates)
+{
+    const Ctx &c = ctx();
+    if (!c.small_cluster || c.force_simple || s->sharded || gates.size() < 2) return false;
+    const int kmax = small_circuit_max_qubits((int)amp_bytes(s->dtype));
+    if (s->nloc < 2 || s->nloc > (c.small_cluster == 1 ? kmax : std::min<long>(kmax, c.small_cluster))) return false;
+    for (int q = 0; q < s->n; q++)
+        if (s->phys[q] != q) return false;
+    return true;
+}
+
+template <typename R> static int run_small_cluster(qcb_state *s, const std::vector<GateOp> &gates, const double *mats, bool adjoint, const void *first_src)
+{
+    using V = typename Vec2<R>::type;
+    Ctx &c = ctx();
+    const int G = (int)gates.size();
+    const size_t table = (size_t)G * sizeof(GateMat<R>), bytes = table + (size_t)G * sizeof(int);
+    if (bytes > c.gates_cap) {
+        if (c.gates_ev) cudaEventSynchronize(c.gates_ev);
+        if (c.h_gates) cudaFreeHost(c.h_gates);
+        if (c.d_gates) cudaFree(c.d_gates);
+        c.h_gates = c.d_gates = nullptr; c.gates_cap = 0;
+        const size_t cap = std::max<size_t>(bytes * 2, (size_t)256 << 10);
+        QCB_CUDA(cudaMallocHost(&c.h_gates, cap));
+        QCB_CUDA(cudaMalloc(&c.d_gates, cap));
+        c.gates_cap = cap;
+    }
+    if (!c.gates_ev) QCB_CUDA(cudaEventCreateWithFlags(&c.gates_ev, cudaEventDisableTiming));
+    else QCB_CUDA(cudaEventSynchronize(c.gates_ev)); // the previous upload has left the pinned buffer
+    GateMat<R> *hg = static_cast<GateMat<R> *>(c.h_gates);
+    int *hk = reinterpret_cast<int *>(static_cast<char *>(c.h_gates) + table);
+    for (int g = 0; g < G; g++) {
+        const double *m = mats + 32 * (size_t)gates[g].mat;
+        for (int r = 0; r < 4; r++)
+            for (int cc = 0; cc < 4; cc++) {
+                const int src = adjoint ? (cc + 4 * r) : (r + 4 * cc);
+                gate_set(hg[g], r, cc, m[2 * src], adjoint ? -m[2 * src + 1] : m[2 * src + 1]);
+            }
+        hk[g] = gates[g].q;
+    }
+    QCB_CUDA(cudaMemcpyAsync(c.d_gates, c.h_gates, bytes, cudaMemcpyHostToDevice, c.stream));
+    QCB_CUDA(cudaEventRecord(c.gates_ev, c.stream));
+    const int n = s->nloc, gbits = small_circuit_gbits(n);
+    const size_t smem = small_circuit_smem<R>(n);
+    auto kern = cluster_circuit_kernel<R>;
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+        QCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set = smem;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(1u << gbits);
+    cfg.blockDim = dim3(kSmallThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = c.stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1u << gbits; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const V *src = (const V *)(first_src ? first_src : s->d);
+    V *dst = (V *)s->d;
+    const GateMat<R> *dg = static_cast<const GateMat<R> *>(c.d_gates);
+    const int *dk = reinterpret_cast<const int *>(static_cast<const char *>(c.d_gates) + table);
+    PassTimerScope timer;
+    QCB_CUDA(cudaLaunchKernelEx(&cfg, kern, src, dst, dg, dk, n, gbits, G));
+    count_launch();
+    c.st_passes += 1;
+    c.st_cluster_circuits += 1;
+    return QCB_OK;
+}
+
 // first_src != nullptr: the state's storage is uninitialised and the circuit's input is the device buffer `first_src`
 // (same size and type): the first fused pass reads it directly; paths without such a pass copy it first.
 int run_gate_list(qcb_state *s, const std::vector<GateOp> &gates, const double *mats, bool adjoint, const void *first_src)
@@ -769,6 +843,8 @@ int run_gate_list(qcb_state *s, const std::vector<GateOp> &gates, const double *
     }
     if (gates.empty()) return QCB_OK;
     if (s->sharded) return dist_run_gate_list(s, gates, mats, adjoint);
+    if (small_cluster_eligible(s, gates))
+        return s->dtype == QCB_C128 ? run_small_cluster<double>(s, gates, mats, adjoint, first_src) : run_small_cluster<float>(s, gates, mats, adjoint, first_src);
     if (s->dtype == QCB_C128)
         return simple ? run_simple<double>(s, gates, mats, adjoint) : run_fused<double>(s, gates, mats, adjoint, first_src);
     return simple ? run_simple<float>(s, gates, mats, adjoint) : run_fused<float>(s, gates, mats, adjoint, first_src);

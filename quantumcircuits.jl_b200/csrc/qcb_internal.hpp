@@ -37,7 +37,7 @@ struct Ctx {
     cudaEvent_t chunk_ev[2][16] = {};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // options
-    long tile_bits = 11, low_bits = 3, max_gates_per_pass = 1 << 30, force_simple = 0, adjoint_tile_bits = 0, adjoint_mma = 1, adjoint_warps = 0, adjoint_prog_host = 0, measure_ctas = 0, contract_coop = 1, measure_persistent = 0, measure_tma = 1, pass_tma = 0, pass_tma_max_stages = 3, adjoint_f32 = 1, adjoint_ctas = 5, adjoint_defer = 1, f64_3m_min_gates = 4, pass_async = 0;
+    long tile_bits = 11, low_bits = 3, max_gates_per_pass = 1 << 30, force_simple = 0, adjoint_tile_bits = 0, adjoint_mma = 1, adjoint_warps = 0, adjoint_prog_host = 0, measure_ctas = 0, contract_coop = 1, measure_persistent = 0, measure_tma = 1, pass_tma = 0, pass_tma_max_stages = 3, adjoint_f32 = 1, adjoint_ctas = 5, adjoint_defer = 1, f64_3m_min_gates = 4, pass_async = 0, small_cluster = 12;
     // stats
     double st_passes = 0, st_stages = 0, st_launches = 0, st_gates = 0, st_launches_total = 0, st_swaps = 0, st_fused_swaps = 0;
     long fuse_swaps = 1;
@@ -48,6 +48,11 @@ struct Ctx {
     struct PassMeta { int stages, gates, first_window_bit, tma; unsigned long long masks; }; // masks: 4 bits per stage, stage 0 lowest
     std::vector<PassMeta> pass_meta; // one per timed launch (diagnostics: env QCB_PASS_LOG=<file> dumps them with their times)
     double st_tma_passes = 0, st_fw_passes = 0, st_bw_passes = 0, st_ham_passes = 0;
+    double st_cluster_circuits = 0; // cumulative: gate lists run by the cluster-resident kernel (small_circuit.cuh)
+    // gate table of the cluster-resident kernel: pinned host staging + device copy, and the event of the last upload
+    void *h_gates = nullptr, *d_gates = nullptr;
+    size_t gates_cap = 0;
+    cudaEvent_t gates_ev = nullptr;
     double st_async_passes = 0; // cumulative: gate passes launched on the persistent cp.async kernel (tile_async.cuh)
     double st_gates_3m = 0; // cumulative: gates applied in the 3M arithmetic (full diamonds of ComplexF64 passes), see tile.cuh
     int *d_barrier = nullptr; // 1 int for stream-ordered inter-rank barriers (NCCL all-reduce)

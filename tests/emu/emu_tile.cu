@@ -6,6 +6,7 @@
 #include <vector>
 #include "../../quantumcircuits.jl_b200/csrc/dist_plan.hpp"
 #include "../../quantumcircuits.jl_b200/csrc/tile_async.cuh"
+#include "../../quantumcircuits.jl_b200/csrc/small_circuit.cuh"
 
 using namespace qcb;
 
@@ -1055,4 +1056,57 @@ extern "C" int emu_apply_gates_tma(int nloc, void *psi_, int ngates, const int *
         std::fprintf(stderr, "emu tma: %s\n", e.what());
         return 1;
     }
+}
+
+// ---- cluster-resident small-circuit kernel (small_circuit.cuh): replay with simulated CTAs, same index algebra and arithmetic
+template <typename R>
+static int emu_small_circuit_impl(void *psi_, int n, int gbits, int ngates, const int *q, const double *mats, int adjoint)
+{
+    using V = typename Vec2<R>::type;
+    const int L = n - gbits;
+    if (L < 2) return 2;
+    const unsigned nloc = 1u << L, NR = 1u << gbits;
+    V *psi = (V *)psi_;
+    std::vector<std::vector<V>> A(NR, std::vector<V>(nloc)), B(NR, std::vector<V>(nloc));
+    for (unsigned r = 0; r < NR; r++)
+        for (unsigned i = 0; i < nloc; i++) A[r][i] = psi[((size_t)r << L) + i];
+    for (int g = 0; g < ngates; g++) {
+        GateMat<R> U;
+        const double *m = mats + 32 * (size_t)g;
+        for (int r = 0; r < 4; r++)
+            for (int c = 0; c < 4; c++) {
+                const int src = adjoint ? (c + 4 * r) : (r + 4 * c);
+                gate_set(U, r, c, m[2 * src], adjoint ? -m[2 * src + 1] : m[2 * src + 1]);
+            }
+        const int k = q[g];
+        if (k + 1 < L) {
+            for (unsigned rank = 0; rank < NR; rank++)
+                for (unsigned qd = 0; qd < (nloc >> 2); qd++) {
+                    const unsigned base = small_quad_base(qd, k);
+                    V *a = A[rank].data();
+                    apply_quad(a[base], a[base | (1u << k)], a[base | (2u << k)], a[base | (3u << k)], U);
+                }
+        } else {
+            for (unsigned rank = 0; rank < NR; rank++)
+                for (unsigned a = 0; a < nloc; a++) {
+                    unsigned owner[4], loc[4];
+                    const int r = small_remote_item(rank, L, a, k, owner, loc);
+                    V x[4];
+                    for (int c = 0; c < 4; c++) {
+                        if (owner[c] >= NR) return 3;
+                        x[c] = A[owner[c]][loc[c]];
+                    }
+                    B[rank][a] = small_row<R, V>(U, r, x);
+                }
+            A.swap(B);
+        }
+    }
+    for (unsigned r = 0; r < NR; r++)
+        for (unsigned i = 0; i < nloc; i++) psi[((size_t)r << L) + i] = A[r][i];
+    return 0;
+}
+extern "C" int emu_small_circuit(int dtype, int n, int gbits, void *psi, int ngates, const int *q, const double *mats, int adjoint)
+{
+    if (gbits < 0) gbits = small_circuit_gbits(n);
+    return dtype ? emu_small_circuit_impl<double>(psi, n, gbits, ngates, q, mats, adjoint) : emu_small_circuit_impl<float>(psi, n, gbits, ngates, q, mats, adjoint);
 }

@@ -12,7 +12,7 @@ _lib = None
 
 
 def build(force=False):
-    srcs = [os.path.join(_HERE, "emu_tile.cu"), os.path.join(_CSRC, "tile.cuh"), os.path.join(_CSRC, "schedule.hpp"), os.path.join(_CSRC, "dist_plan.hpp"), os.path.join(_CSRC, "adjoint.cuh"), os.path.join(_CSRC, "adjoint_mma.cuh"), os.path.join(_CSRC, "adjoint_f32.cuh"), os.path.join(_CSRC, "gates_hd.cuh"), os.path.join(_CSRC, "measure_tile.cuh"), os.path.join(_CSRC, "measure_plan.hpp"), os.path.join(_CSRC, "kernels.cuh"), os.path.join(_CSRC, "flip_tile.cuh"), os.path.join(_CSRC, "tma.cuh"), os.path.join(_CSRC, "tile_tma.cuh"), os.path.join(_CSRC, "tile_async.cuh")]
+    srcs = [os.path.join(_HERE, "emu_tile.cu"), os.path.join(_CSRC, "tile.cuh"), os.path.join(_CSRC, "schedule.hpp"), os.path.join(_CSRC, "dist_plan.hpp"), os.path.join(_CSRC, "adjoint.cuh"), os.path.join(_CSRC, "adjoint_mma.cuh"), os.path.join(_CSRC, "adjoint_f32.cuh"), os.path.join(_CSRC, "gates_hd.cuh"), os.path.join(_CSRC, "measure_tile.cuh"), os.path.join(_CSRC, "measure_plan.hpp"), os.path.join(_CSRC, "kernels.cuh"), os.path.join(_CSRC, "flip_tile.cuh"), os.path.join(_CSRC, "tma.cuh"), os.path.join(_CSRC, "tile_tma.cuh"), os.path.join(_CSRC, "tile_async.cuh"), os.path.join(_CSRC, "small_circuit.cuh")]
     if force or not os.path.exists(_SO) or any(os.path.getmtime(_SO) < os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["nvcc", "-O2", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler",
                                "-fPIC", "-shared", "-o", _SO, srcs[0]], cwd=_HERE)
@@ -243,3 +243,16 @@ def contract_env_gate(angles15, env, post):
     if rc:
         raise RuntimeError("per-layer and whole-gate contraction differ")
     return out, u.reshape(4, 4, order="F")
+
+
+def small_circuit(psi, q0, mats, gbits=-1, adjoint=False):
+    """Replay of the cluster-resident small-circuit kernel (small_circuit.cuh) with 2^gbits simulated CTAs (-1: the host's choice)."""
+    psi = np.ascontiguousarray(psi).copy()
+    n = int(psi.size).bit_length() - 1
+    q0 = np.ascontiguousarray(q0, dtype=np.int32)
+    m = np.ascontiguousarray(np.stack([np.asarray(M, dtype=np.complex128).reshape(-1, order="F") for M in mats]))
+    rc = lib().emu_small_circuit(C.c_int(1 if psi.dtype == np.complex128 else 0), C.c_int(n), C.c_int(gbits), psi.ctypes.data_as(C.c_void_p),
+                                 C.c_int(len(q0)), q0.ctypes.data_as(C.c_void_p), m.ctypes.data_as(C.c_void_p), C.c_int(1 if adjoint else 0))
+    if rc:
+        raise RuntimeError(f"emu_small_circuit rc={rc}")
+    return psi

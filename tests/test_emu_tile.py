@@ -87,6 +87,24 @@ def test_emu_async_gate_pass(emu, oracle, n, layers, tb, grid, dt):
     assert rel(out.astype(np.complex128), oracle.apply_brickwork(psi0.astype(np.complex128), n, layers, angles)) < (1e-13 if dt == np.complex128 else 1e-5)
 
 
+@pytest.mark.parametrize("n,layers,gbits,dt", [(4, 6, 0, np.complex128), (9, 8, 0, np.complex128), (10, 7, 1, np.complex128), (11, 6, 2, np.complex64),
+                                               (12, 20, 3, np.complex128), (12, 5, -1, np.complex64), (8, 9, 3, np.complex128), (6, 5, 2, np.complex128)])
+def test_emu_small_circuit(emu, oracle, n, layers, gbits, dt):
+    """Cluster-resident small-circuit kernel (small_circuit.cuh), replayed with simulated CTAs: local gates in place, gates on the
+    CTA-rank bits owner-computes through the other CTAs' buffers; vs the oracle (src/apply.jl:62-84), and U^dagger undoes U."""
+    rng = np.random.default_rng(5100 + 13 * n + layers)
+    G = onp.brickwork_num_gates(n, layers)
+    angles = rng.uniform(0, 2 * np.pi, (15, G))
+    q0 = np.array(onp.brickwork_gate_positions(n, layers)) - 1
+    mats = [oracle.build_general_unitary_gate(angles[:, g]) for g in range(G)]
+    psi0 = rand_state(rng, n, dt)
+    tol = 1e-13 if dt == np.complex128 else 1e-5
+    out = emu.small_circuit(psi0, q0, mats, gbits)
+    assert rel(out.astype(np.complex128), oracle.apply_brickwork(psi0.astype(np.complex128), n, layers, angles)) < tol
+    back = emu.small_circuit(out, q0[::-1], mats[::-1], gbits, adjoint=True)
+    assert rel(back.astype(np.complex128), psi0.astype(np.complex128)) < 10 * tol
+
+
 def test_emu_c64(emu, oracle):
     rng = np.random.default_rng(64)
     n, layers = 13, 10

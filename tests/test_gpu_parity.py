@@ -58,6 +58,7 @@ def _defaults():
     qc.set_option("pass_tma", 0)
     qc.set_option("f64_3m_min_gates", 4)
     qc.set_option("pass_async", PASS_ASYNC_DEFAULT)
+    qc.set_option("small_cluster", 0)  # the tests below exercise the tile passes also on small states; the cluster kernel has its own tests
     qc.set_option("adjoint_f32", 1)
     qc.set_option("adjoint_ctas", 5)
     qc.set_option("adjoint_defer", 1)
@@ -638,6 +639,46 @@ def test_tma_gate_pass_equals_ldg_pass(oracle, n, layers, cap):
     assert np.array_equal(outs[0], outs[1])
     if n <= 22:
         assert rel(outs[1], oracle.apply_brickwork(psi0, n, layers, c.gate_angles)) < 1e-12
+
+
+# ---- small states: the whole gate list in one launch on a thread-block cluster (small_circuit.cuh) == tile passes == oracle
+@pytest.mark.parametrize("dtype", [np.complex128, np.complex64])
+@pytest.mark.parametrize("n,layers", [(2, 3), (3, 4), (5, 7), (8, 6), (9, 12), (10, 9), (11, 8), (12, 20), (13, 11), (14, 6), (15, 5), (16, 4)])
+def test_cluster_circuit_kernel(oracle, n, layers, dtype):
+    if n > (15 if dtype == np.complex128 else 16):
+        pytest.skip("two 2^n-amplitude buffers do not fit the shared memory of 8 CTAs")
+    rng = np.random.default_rng(4400 + 17 * n + layers)
+    c = circuit(n, layers, rng)
+    psi0 = rand_state(rng, n, dtype)
+    ref = oracle.apply_brickwork(psi0.astype(np.complex128), n, layers, c.gate_angles)
+    qc.set_option("small_cluster", 1)
+    try:
+        k0 = qc.get_stat("cluster_circuits")
+        st = qc.B200State(psi0)
+        qc.apply_(st, st, c)
+        assert qc.get_stat("cluster_circuits") == k0 + 1 and qc.get_stat("launches") == 1
+        out = st.to_numpy()
+        dst = st.similar()  # out of place: reads psi, writes psi'
+        src = qc.B200State(psi0)
+        qc.apply_(dst, src, c)
+        assert np.array_equal(dst.to_numpy(), out) and np.array_equal(src.to_numpy(), psi0)
+        # a gate list in random positions, some repeated (non-unitary matrices, test/correctness_tests.jl:86-124 style)
+        ks = [int(k) for k in rng.integers(1, n, size=9)]
+        us = [rand_nonunitary(rng, 4) for _ in ks]
+        gl = [qc.Localised2SpinAdjGate(qc.Generic2SpinGate(u.reshape(2, 2, 2, 2, order="F")), k) for u, k in zip(us, ks)]
+        k1 = qc.get_stat("cluster_circuits")
+        got = qc.apply(psi0, gl)
+        assert qc.get_stat("cluster_circuits") == k1 + 1
+        want = psi0.astype(np.complex128)
+        for u, k in zip(us, ks):
+            want = oracle.apply_2q(want, u, k)
+        assert rel(np.asarray(got).reshape(-1, order="F").astype(np.complex128), want) < 20 * TOL[dtype]
+    finally:
+        qc.set_option("small_cluster", 0)
+    assert rel(out.astype(np.complex128), ref) < TOL[dtype]
+    st2 = qc.B200State(psi0)
+    qc.apply_(st2, st2, c)  # tile passes
+    assert rel(out.astype(np.complex128), st2.to_numpy().astype(np.complex128)) < (1e-13 if dtype == np.complex128 else 1e-5)
 
 
 # ---- persistent gate pass with asynchronous tile loads (tile_async.cuh) == one tile per CTA (tile.cuh), bit for bit
