@@ -741,7 +741,12 @@ def extra_configs(qc, peak, args):
         # a backward pass reads and writes both states
         alg = (2 * fw + 2 + 4 * bw) * S
         ta, tm = cpu_costs(n, dtype, H)
-        e = {"config": name, "ms": ms, "ms_min": ms_min, "kernel": "forward tile_pass x%d + H psi + adjoint_pass x%d + contraction" % (fw, bw),
+        one_launch = bw == 0 and G > 0  # states of <= 12 qubits: circuit, H psi, backward sweep and environments in one cluster launch
+        if one_launch:
+            alg = 2 * S  # the state is read once and stays in shared memory; what leaves the kernel is 32 doubles per gate
+        e = {"config": name, "ms": ms, "ms_min": ms_min,
+             "kernel": ("cluster_gradient_kernel (state in distributed shared memory, one launch) + finish + contraction" if one_launch else
+                        "forward tile_pass x%d + H psi + adjoint_pass x%d + contraction" % (fw, bw)),
              "launches_per_call": per_call, "algorithmic_bytes": alg, "achieved_gbs": alg / (ms * 1e-3) / 1e9, "frac": alg / (ms * 1e-3) / 1e9 / peak,
              "energy": res["E"], "grad_max": float(np.max(np.abs(res["g"]))),
              "cpu_estimate_s": None if ta is None else (2 * G + 15 * G * (G + 1)) * ta + 30 * G * tm,

@@ -530,6 +530,18 @@ static int gradients_impl(const qcb_state *psi0, int nbits, int nlayers, const d
     std::vector<GateOp> gates;
     std::vector<double> mats;
     QCB_TRY(brickwork_gates(nbits, nlayers, angles, 0, G, false, gates, mats));
+    if (!csr && small_gradient_eligible(psi0, G)) {
+        // small states: forward circuit, lambda = H psi, backward sweep and the environments in ONE cluster launch
+        // (small_circuit.cuh), then the contraction with dU/dtheta
+        const GradArea ar{(size_t)G};
+        QCB_TRY(grad_area_begin(ar, angles));
+        c.st_launches = 0;
+        HamEval H{ham_kind, nbits, hp[0], hp[1], hp[2]};
+        QCB_TRY(run_small_gradient(psi0, gates, mats.data(), H, c.d_out + ar.env(), c.d_out + ar.energy()));
+        QCB_TRY(grad_area_finish(ar, false, want_energy, out_E, out_grads));
+        c.st_passes = 1; c.st_stages = 0; c.st_gates = 4.0 * G; c.st_fw_passes = 1; c.st_bw_passes = 0;
+        return QCB_OK;
+    }
     // psi .= psi0 (gradients.jl:90) and the forward pass (:92-101) in one: the first fused pass reads psi0 and writes psi
     QCB_TRY(run_gate_list(&A, gates, mats.data(), false, psi0->d));
     const double fw_passes = c.st_passes, fw_stages = c.st_stages, fw_launches = c.st_launches;
@@ -758,6 +770,8 @@ int qcb_set_option(const char *key, long value)
         // distributed-shared-memory traffic of the gates on the CTA-rank bits makes it slower than the tile passes (measured)
         if (value < 0 || value > 16) return set_error(QCB_EINVAL, "small_cluster must be 0 (off), 1 (kernel maximum) or a qubit count <= 16");
         c.small_cluster = value;
+    } else if (k == "small_gbits") {
+        c.small_gbits = value; // cluster size of the small-state kernels: at most 2^value CTAs (-1: by state size)
     } else if (k == "pass_async") {
         c.pass_async = value ? 1 : 0; // gate passes on the persistent kernel with asynchronous tile loads (tile_async.cuh)
     } else if (k == "f64_3m_min_gates") {

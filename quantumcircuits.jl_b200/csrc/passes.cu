@@ -754,6 +754,14 @@ int run_adjoint_fused(qcb_state *psi, qcb_state *lam, const std::vector<GateOp> 
 }
 
 // ---- small states: the whole gate list in one launch on a thread-block cluster (small_circuit.cuh) ------------------------
+// index bits that go to the CTA rank (option small_gbits: -1 = by size, else at most that many)
+static int small_gbits_for(int n)
+{
+    const int g = small_circuit_gbits(n);
+    const long o = ctx().small_gbits;
+    return o < 0 ? g : (int)std::min<long>(g, o);
+}
+
 static bool small_cluster_eligible(const qcb_state *s, const std::vector<GateOp> &gates)
 {
     const Ctx &c = ctx();
@@ -796,8 +804,8 @@ template <typename R> static int run_small_cluster(qcb_state *s, const std::vect
     }
     QCB_CUDA(cudaMemcpyAsync(c.d_gates, c.h_gates, bytes, cudaMemcpyHostToDevice, c.stream));
     QCB_CUDA(cudaEventRecord(c.gates_ev, c.stream));
-    const int n = s->nloc, gbits = small_circuit_gbits(n);
-    const size_t smem = small_circuit_smem<R>(n);
+    const int n = s->nloc, gbits = small_gbits_for(n);
+    const size_t smem = small_circuit_smem<R>(n, gbits);
     auto kern = cluster_circuit_kernel<R>;
     static size_t smem_set = 0;
     if (smem > smem_set) {
@@ -824,6 +832,86 @@ template <typename R> static int run_small_cluster(qcb_state *s, const std::vect
     c.st_passes += 1;
     c.st_cluster_circuits += 1;
     return QCB_OK;
+}
+
+// energy + environments of a brickwork circuit in one cluster launch (small_circuit.cuh: cluster_gradient_kernel) + the warp-per-gate
+// finish; d_env: 32 doubles per gate (convention of k_adjoint_step), d_energy2: 2 doubles
+bool small_gradient_eligible(const qcb_state *s, int ngates)
+{
+    const Ctx &c = ctx();
+    if (!c.small_cluster || c.force_simple || s->sharded || ngates < 1) return false;
+    if (s->nloc < 2 || s->nloc > kSmallGradMaxQubits || (c.small_cluster != 1 && s->nloc > c.small_cluster)) return false;
+    for (int q = 0; q < s->n; q++)
+        if (s->phys[q] != q) return false;
+    return true;
+}
+
+template <typename R> static int run_small_gradient_t(const qcb_state *s, const std::vector<GateOp> &gates, const double *mats, const HamEval &H,
+                                                      double *d_env, double *d_energy2)
+{
+    using V = typename Vec2<R>::type;
+    Ctx &c = ctx();
+    const int G = (int)gates.size(), n = s->nloc, gbits = small_gbits_for(n), NR = 1 << gbits;
+    const size_t table = (size_t)G * sizeof(GateMat<R>);
+    const size_t up = 2 * table + (((size_t)G * sizeof(int) + 15) / 16) * 16;            // U | U^dagger | k
+    const size_t bytes = up + ((size_t)NR * G * 32 + (size_t)NR * 32) * sizeof(double);  // + Mpart | Epart (device only)
+    if (bytes > c.gates_cap) {
+        if (c.gates_ev) cudaEventSynchronize(c.gates_ev);
+        if (c.h_gates) cudaFreeHost(c.h_gates);
+        if (c.d_gates) cudaFree(c.d_gates);
+        c.h_gates = c.d_gates = nullptr; c.gates_cap = 0;
+        const size_t cap = std::max<size_t>(bytes * 2, (size_t)256 << 10);
+        QCB_CUDA(cudaMallocHost(&c.h_gates, cap));
+        QCB_CUDA(cudaMalloc(&c.d_gates, cap));
+        c.gates_cap = cap;
+    }
+    if (!c.gates_ev) QCB_CUDA(cudaEventCreateWithFlags(&c.gates_ev, cudaEventDisableTiming));
+    else QCB_CUDA(cudaEventSynchronize(c.gates_ev));
+    GateMat<R> *hu = static_cast<GateMat<R> *>(c.h_gates), *hd = hu + G;
+    int *hk = reinterpret_cast<int *>(static_cast<char *>(c.h_gates) + 2 * table);
+    for (int g = 0; g < G; g++) {
+        const double *m = mats + 32 * (size_t)gates[g].mat;
+        for (int r = 0; r < 4; r++)
+            for (int cc = 0; cc < 4; cc++) {
+                gate_set(hu[g], r, cc, m[2 * (r + 4 * cc)], m[2 * (r + 4 * cc) + 1]);
+                gate_set(hd[g], r, cc, m[2 * (cc + 4 * r)], -m[2 * (cc + 4 * r) + 1]); // conjugate transpose, src/gradients.jl:27-32
+            }
+        hk[g] = gates[g].q;
+    }
+    QCB_CUDA(cudaMemcpyAsync(c.d_gates, c.h_gates, up, cudaMemcpyHostToDevice, c.stream));
+    QCB_CUDA(cudaEventRecord(c.gates_ev, c.stream));
+    const GateMat<R> *du = static_cast<const GateMat<R> *>(c.d_gates), *dd = du + G;
+    const int *dk = reinterpret_cast<const int *>(static_cast<const char *>(c.d_gates) + 2 * table);
+    double *Mpart = reinterpret_cast<double *>(static_cast<char *>(c.d_gates) + up), *Epart = Mpart + (size_t)NR * G * 32;
+    const size_t smem = small_gradient_smem<R>(n, gbits);
+    auto kern = cluster_gradient_kernel<R>;
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+        QCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set = smem;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)NR);
+    cfg.blockDim = dim3(kSmallThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = c.stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)NR; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    QCB_CUDA(cudaLaunchKernelEx(&cfg, kern, (const V *)s->d, du, dd, dk, n, gbits, G, H, Mpart, Epart));
+    k_small_env_finish<R><<<(unsigned)G, 32, 0, c.stream>>>(Mpart, Epart, du, G, NR, d_env, d_energy2);
+    QCB_CUDA(cudaGetLastError());
+    count_launch(2);
+    c.st_cluster_circuits += 1;
+    return QCB_OK;
+}
+
+int run_small_gradient(const qcb_state *s, const std::vector<GateOp> &gates, const double *mats, const HamEval &H, double *d_env, double *d_energy2)
+{
+    return s->dtype == QCB_C128 ? run_small_gradient_t<double>(s, gates, mats, H, d_env, d_energy2)
+                                : run_small_gradient_t<float>(s, gates, mats, H, d_env, d_energy2);
 }
 
 // first_src != nullptr: the state's storage is uninitialised and the circuit's input is the device buffer `first_src`

@@ -423,6 +423,38 @@ def test_gradients_vs_reference_algorithm(oracle, n, layers, scale, ham):
     assert np.max(np.abs(g32 - g_ref)) < 1e-5 * max(scale_g, 1.0)
 
 
+# ---- the same on the cluster-resident kernel (small_circuit.cuh: forward circuit, H psi, backward sweep and environments in one
+# launch) == the reference's shift sweep == the pass-based adjoint sweep
+@pytest.mark.parametrize("n,layers,scale", [(2, 3, None), (3, 5, None), (4, 3, 0.1), (6, 7, None), (8, 4, 0.01), (9, 6, None), (10, 4, None), (11, 5, None), (12, 3, None)])
+@pytest.mark.parametrize("ham", ["tfim", "east"])
+def test_cluster_gradient_kernel(oracle, n, layers, scale, ham):
+    rng = np.random.default_rng(99 * n + layers)
+    c = circuit(n, layers, rng, scale)
+    if ham == "tfim":
+        H, kind = qc.TFIMHamiltonian(1.0, 0.1, 0.5), 0
+    else:
+        H, kind = qc.EastModelHamiltonian(0.1, -0.1), 1
+    psi0 = rand_state(rng, n) if n % 2 else onp.zero_state(n)
+    E_ref, g_ref = oracle.gradients_brickwork(psi0, n, layers, c.gate_angles, kind, H.params())
+    E_p, g_p = qc.gradients(H, psi0, c, calculate_energy=True)  # pass-based sweep (fixture: small_cluster = 0)
+    qc.set_option("small_cluster", 12)
+    try:
+        k0 = qc.get_stat("cluster_circuits")
+        E, g = qc.gradients(H, psi0, c, calculate_energy=True)
+        assert qc.get_stat("cluster_circuits") == k0 + 1 and qc.get_stat("launches") == 3  # gradient kernel, finish, contraction
+        g_only = qc.gradients(H, qc.B200State(psi0), c)
+        E32, g32 = qc.gradients(H, psi0.astype(np.complex64), c, calculate_energy=True)
+    finally:
+        qc.set_option("small_cluster", 0)
+    scale_g = max(np.max(np.abs(g_ref)), 1e-6)
+    assert abs(E - E_ref) < 1e-12 * max(1.0, abs(E_ref)) and abs(E - E_p) < 1e-12 * max(1.0, abs(E_ref))
+    assert np.max(np.abs(g - g_ref)) < 1e-12 * max(scale_g, 1.0) + 1e-12 * scale_g
+    assert np.max(np.abs(g - g_p)) < 1e-12 * max(scale_g, 1.0) + 1e-12 * scale_g
+    np.testing.assert_allclose(g_only, g, atol=1e-15)
+    assert abs(E32 - E_ref) < 1e-5 * max(1.0, abs(E_ref))
+    assert np.max(np.abs(g32 - g_ref)) < 1e-5 * max(scale_g, 1.0)
+
+
 @pytest.mark.parametrize("n,layers,atb", [(9, 3, 0), (12, 4, 0), (13, 5, 9), (16, 6, 10), (18, 4, 11), (19, 7, 12), (22, 4, 0)])
 def test_gradients_f32_tensor_core_pass(oracle, n, layers, atb):
     """ComplexF32 backward pass with both register windows resident, FFMA2 outer products and a warp transpose-reduction

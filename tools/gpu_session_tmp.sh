@@ -1,10 +1,16 @@
 #!/bin/bash
-# session Z: kernel-only durations of the cluster circuit kernel (ncu launch list)
+# session AE: 128 vs 256 threads per CTA in the small-state kernels
 mkdir -p gpurun_out
 O=gpurun_out
-for n in 9 10 12 14 15; do
-timeout -k 10 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:cluster_circuit -c 4 --csv --log-file $O/r02z_ncu_n$n.csv python tools/prof_case.py pass $n layers=20 reps=2 small_cluster=1 > /dev/null 2>&1
-tail -n 2 $O/r02z_ncu_n$n.csv | cut -c1-260
+V=quantumcircuits.jl_b200/variants
+{
+for lib in "" $V/libqcb200_t128.so; do
+echo "# lib=$lib"
+QCB200_LIB=$lib timeout -k 10 200 python tools/prof_case.py grad 12 layers=20 reps=30
+QCB200_LIB=$lib timeout -k 10 200 python tools/prof_case.py pass 12 layers=20 reps=50
+QCB200_LIB=$lib timeout -k 10 200 python tools/prof_case.py grad 10 layers=20 reps=30
+QCB200_LIB=$lib timeout -k 10 200 python tools/prof_case.py grad 8 layers=8 reps=30
 done
-timeout -k 10 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 40 --csv --log-file $O/r02z_ncu_tile12.csv python tools/prof_case.py pass 12 layers=20 reps=2 small_cluster=0 > /dev/null 2>&1
-tail -n 6 $O/r02z_ncu_tile12.csv | cut -c1-260
+} > $O/r02ae_cases.jsonl 2> $O/r02ae_cases.err
+cut -c1-200 $O/r02ae_cases.jsonl; tail -n 3 $O/r02ae_cases.err
+QCB200_LIB=$V/libqcb200_t128.so timeout -k 10 300 python -m pytest tests/test_gpu_parity.py -q -x -m gpu -k "cluster" 2>&1 | tail -n 2
