@@ -349,6 +349,8 @@ def run_ours(args):
         qdist.init_from_torch()
         if os.environ.get("QCB_FUSE_SWAPS") == "0":
             qc.set_option("fuse_swaps", 0)
+        if os.environ.get("QCB_PEER_SWAP") == "0":  # A/B: staged NCCL exchange instead of the in-place peer swap
+            qc.set_option("peer_swap", 0)
         state = qdist.ShardedState(n, npdt)
         step = lambda: state.apply_circuit(circuit)  # noqa: E731
         nloc = state.local_qubits
@@ -604,7 +606,10 @@ def run_ours(args):
             "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f64" if args.dtype == "c128" else "f32", "data": "synthetic",
             "config": config_of(n, layers, G, args.dtype, world),
             "details": {"swaps": None if world == 1 else ("qubit swaps fused into gate passes as NVLink peer loads (CUDA IPC)"
-                                                          if getattr(state, "peers_mapped", False) else "qubit swaps via NCCL all-to-all"),
+                                                          if getattr(state, "peers_mapped", False) else
+                                                          "in-place qubit swaps over NVLink peer memory (k_swap_peer: no second buffer fits)"
+                                                          if getattr(state, "peer_swap_mapped", False) else "qubit swaps via NCCL all-to-all"),
+                        "peer_swaps_total": None if world == 1 else qc.get_stat("peer_swaps"),
                         "swaps_per_circuit": None if world == 1 else qc.get_stat("swaps"),
                         "gate_apps_per_sec_raw": gate_apps, "tile_bits": int(qc_opt("tile_bits", 11)), "low_bits": int(qc_opt("low_bits", 3))},
             "gpu_launches": int(launches), "clocks": clocks,

@@ -800,6 +800,10 @@ int qcb_set_option(const char *key, long value)
         return QCB_OK; // (no effect on plans)
     } else if (k == "fuse_swaps") {
         c.fuse_swaps = value ? 1 : 0;
+    } else if (k == "peer_swap") {
+        c.peer_swap = value ? 1 : 0; // in-place qubit swaps over NVLink peer memory when a shard has no second buffer (else: staged NCCL)
+    } else if (k == "dist_second_buffer") {
+        c.dist_second_buffer = value ? 1 : 0; // 0: sharded states created from now on get no second buffer (tests of the in-place swap paths)
     } else if (k == "force_simple") {
         c.force_simple = value ? 1 : 0;
     } else
@@ -817,6 +821,7 @@ int qcb_get_stat(const char *key, double *out)
     else if (k == "gates_3m") *out = c.st_gates_3m;
     else if (k == "async_passes") *out = c.st_async_passes;
     else if (k == "cluster_circuits") *out = c.st_cluster_circuits;
+    else if (k == "peer_swaps") *out = c.st_peer_swaps;
     else if (k == "launches") *out = c.st_launches;
     else if (k == "gates") *out = c.st_gates;
     else if (k == "launches_total") *out = c.st_launches_total;

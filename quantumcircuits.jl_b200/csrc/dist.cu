@@ -19,11 +19,43 @@ namespace qcb {
 
 int dist_alloc_alt(qcb_state *s)
 {
+    if (!ctx().dist_second_buffer) return QCB_OK; // (option: exercise the paths of shards too large for a second buffer)
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return QCB_OK;
     if (free_b < s->bytes + ((size_t)6 << 30)) return QCB_OK; // keep headroom for scratch and NCCL buffers
     if (cudaMalloc(&s->alt, s->bytes) != cudaSuccess) { s->alt = nullptr; cudaGetLastError(); }
     return QCB_OK;
+}
+
+int stream_barrier();
+
+// In-place exchange over NVLink peer memory, for shards too large for a second buffer (34 qubits on 2 GPUs): block j of this
+// rank <-> block `me` of rank j, element by element, no staging.  Each pair of ranks splits its exchange: the lower rank
+// swaps the first half of the block pair, the higher rank the second half, so both directions of every link carry loads and
+// stores at the same time and every element is touched by exactly one thread.  Ordering across ranks: a stream barrier
+// before (every shard is final) and after (nobody still reads or writes a peer's shard).
+struct PeerPtrs { uint4 *p[8]; };
+static __global__ void __launch_bounds__(256) k_swap_peer(uint4 *__restrict__ mine, PeerPtrs peers, int P, int me, unsigned long long blk16)
+{
+    const unsigned long long half = blk16 >> 1, stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (int j = 0; j < P; j++) {
+        if (j == me) continue;
+        const unsigned long long off = me < j ? 0ull : half;
+        uint4 *a = mine + (unsigned long long)j * blk16 + off;
+        uint4 *b = peers.p[j] + (unsigned long long)me * blk16 + off;
+        unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+        for (; i + 3 * stride < half; i += 4 * stride) { // four independent remote loads in flight per thread
+            const uint4 b0 = b[i], b1 = b[i + stride], b2 = b[i + 2 * stride], b3 = b[i + 3 * stride];
+            const uint4 a0 = a[i], a1 = a[i + stride], a2 = a[i + 2 * stride], a3 = a[i + 3 * stride];
+            a[i] = b0; a[i + stride] = b1; a[i + 2 * stride] = b2; a[i + 3 * stride] = b3;
+            b[i] = a0; b[i + stride] = a1; b[i + 2 * stride] = a2; b[i + 3 * stride] = a3;
+        }
+        for (; i < half; i += stride) {
+            const uint4 bv = b[i], av = a[i];
+            a[i] = bv;
+            b[i] = av;
+        }
+    }
 }
 
 // exchange rank bit k with local bit nloc-g+k: block j of this rank <-> block `rank` of rank j
@@ -48,6 +80,15 @@ static int swap_top_device(qcb_state *s)
         QCB_CUDA(cudaMemcpyAsync(o + (size_t)me * blk, d + (size_t)me * blk, blk, cudaMemcpyDeviceToDevice, c.stream));
         std::swap(s->d, s->alt);
         count_launch(2);
+    } else if (c.peer_swap && (int)s->peer_d.size() == P && blk % 32 == 0) {
+        PeerPtrs pp;
+        for (int r = 0; r < 8; r++) pp.p[r] = r < P ? static_cast<uint4 *>(s->peer_d[r]) : nullptr;
+        QCB_TRY(stream_barrier());
+        k_swap_peer<<<(unsigned)c.sm_count * 8u, 256, 0, c.stream>>>(reinterpret_cast<uint4 *>(d), pp, P, me, (unsigned long long)(blk / 16));
+        QCB_CUDA(cudaGetLastError());
+        QCB_TRY(stream_barrier());
+        count_launch(3);
+        c.st_peer_swaps += 1;
     } else {
         // in place through a bounded staging buffer: (P-1) chunks
         const size_t CH = std::min(blk, (size_t)256 << 20);
@@ -78,7 +119,7 @@ static int swap_top_device(qcb_state *s)
 }
 
 // stream-ordered barrier across the ranks: a 1-int all-reduce on the work stream
-static int stream_barrier()
+int stream_barrier()
 {
     Ctx &c = ctx();
     if (!c.d_barrier) {
@@ -333,19 +374,25 @@ int qcb_state_ipc_import(qcb_state *s, const void *all_handles /* nranks x 128 b
     if (!s->sharded || c.nranks > 8) return set_error(QCB_EINVAL, "peer mapping needs a sharded state and at most 8 ranks");
     if (!s->peer_d.empty()) qcb_state_ipc_close(s);
     const char zero[64] = {0};
-    // some rank has no second buffer: stay on NCCL (decided before anything is mapped)
-    for (int r = 0; r < c.nranks; r++)
-        if (!s->alt || !memcmp((const char *)all_handles + 128 * (size_t)r + 64, zero, 64)) return QCB_OK;
+    // some rank has no second buffer: map the first buffers only (in-place peer swaps, k_swap_peer); the swaps fused into
+    // gate passes need both
+    bool both = s->alt != nullptr, none = s->alt == nullptr;
+    for (int r = 0; r < c.nranks; r++) {
+        const bool has = memcmp((const char *)all_handles + 128 * (size_t)r + 64, zero, 64) != 0;
+        both = both && has;
+        none = none && !has;
+    }
+    if (!both && !none) return QCB_OK; // mixed: no mapping at all, every swap stays on NCCL
     s->peer_d.assign(c.nranks, nullptr);
-    s->peer_alt.assign(c.nranks, nullptr);
+    if (both) s->peer_alt.assign(c.nranks, nullptr);
     for (int r = 0; r < c.nranks; r++) {
         const char *h = (const char *)all_handles + 128 * (size_t)r;
-        if (r == c.rank) { s->peer_d[r] = s->d; s->peer_alt[r] = s->alt; continue; }
+        if (r == c.rank) { s->peer_d[r] = s->d; if (both) s->peer_alt[r] = s->alt; continue; }
         cudaIpcMemHandle_t hd, ha;
         memcpy(&hd, h, 64);
         memcpy(&ha, h + 64, 64);
         cudaError_t e1 = cudaIpcOpenMemHandle(&s->peer_d[r], hd, cudaIpcMemLazyEnablePeerAccess);
-        cudaError_t e2 = e1 == cudaSuccess ? cudaIpcOpenMemHandle(&s->peer_alt[r], ha, cudaIpcMemLazyEnablePeerAccess) : e1;
+        cudaError_t e2 = (e1 == cudaSuccess && both) ? cudaIpcOpenMemHandle(&s->peer_alt[r], ha, cudaIpcMemLazyEnablePeerAccess) : e1;
         if (e1 != cudaSuccess || e2 != cudaSuccess) {
             cudaGetLastError();
             qcb_state_ipc_close(s); // unmaps what the lower ranks already opened

@@ -56,6 +56,7 @@ class ShardedState:
         nloc = C.c_int(0)
         _lib.check(_lib.lib().qcb_state_local_qubits(self._handle, C.byref(nloc)))
         self.local_qubits = nloc.value
+        self.peer_swap_mapped = False
         self.peers_mapped = self._map_peers()
         self.set_zero_state()
 
@@ -67,8 +68,8 @@ class ShardedState:
         rc = _lib.lib().qcb_state_ipc_export(self._handle, mine.ctypes.data_as(C.c_void_p))
         table = [None] * dist.get_world_size()
         dist.all_gather_object(table, mine.tobytes() if rc == 0 else bytes(128))
-        if rc != 0 or any(t[64:] == bytes(64) for t in table):
-            return False  # some rank has no second buffer (or export failed): swaps stay on NCCL
+        if rc != 0 or any(t[:64] == bytes(64) for t in table):
+            return False  # export failed somewhere: swaps stay on NCCL
         blob = np.frombuffer(b"".join(table), dtype=np.uint8).copy()
         ok = _lib.lib().qcb_state_ipc_import(self._handle, blob.ctypes.data_as(C.c_void_p)) == 0
         flags = [None] * dist.get_world_size()
@@ -76,7 +77,10 @@ class ShardedState:
         if not all(flags):
             _lib.lib().qcb_state_ipc_close(self._handle)
             return False
-        return True
+        # second buffers everywhere: swaps ride on gate passes (peer loads); nowhere: in-place peer swaps (k_swap_peer);
+        # mixed: nothing was mapped
+        self.peer_swap_mapped = all(t[64:] == bytes(64) for t in table)
+        return all(t[64:] != bytes(64) for t in table)
 
     def close(self):
         """Collective: unmap peers on every rank, synchronise, free."""

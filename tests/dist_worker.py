@@ -93,6 +93,41 @@ def main():
         if rank == 0:
             print(f"{'PASS' if good else 'FAIL'} round-trip n={n} err={rt:.2e}", flush=True)
         st.close()
+    # ---- shards without a second buffer (what 34 qubits on 2 GPUs look like): in-place qubit swaps over NVLink peer memory
+    # (k_swap_peer) == the staged NCCL exchange == oracle
+    qc.set_option("dist_second_buffer", 0)
+    for n, layers, dt in [(20, 12, np.complex128), (22, 9, np.complex64)]:
+        rng = np.random.default_rng(n * 100 + layers + 7)
+        c = qc.GenericBrickworkCircuit(n, layers)
+        c.gate_angles[...] = rng.uniform(0, 2 * np.pi, c.gate_angles.shape)
+        v = rng.standard_normal(2 ** n) + 1j * rng.standard_normal(2 ** n)
+        psi0 = (v / np.linalg.norm(v)).astype(dt)
+        st = qdist.ShardedState(n, dt)
+        per = 1 << st.local_qubits
+        outs = {}
+        for mode in (1, 0):
+            qc.set_option("peer_swap", mode)
+            p0 = qc.get_stat("peer_swaps")
+            st.upload_shard(psi0[rank * per:(rank + 1) * per])
+            st.apply_circuit(c)
+            swaps, pswaps = qc.get_stat("swaps"), qc.get_stat("peer_swaps") - p0
+            outs[mode] = st.download_shard()
+            want = swaps >= 1 and (pswaps >= 1 if (mode and st.peer_swap_mapped) else pswaps == 0)
+            ok = ok and want
+            if rank == 0 and not want:
+                print(f"FAIL no-second-buffer n={n}: swaps={swaps} peer_swaps={pswaps} mode={mode} mapped={st.peer_swap_mapped}", flush=True)
+        qc.set_option("peer_swap", 1)
+        ref = oracle.apply_brickwork(psi0.astype(np.complex128), n, layers, c.gate_angles)[rank * per:(rank + 1) * per]
+        err2 = torch.tensor([np.linalg.norm(outs[1] - ref) ** 2, np.linalg.norm(ref) ** 2, np.linalg.norm(outs[1] - outs[0]) ** 2], dtype=torch.float64, device="cuda")
+        dist.all_reduce(err2)
+        relerr, same = float(torch.sqrt(err2[0] / err2[1]).item()), float(torch.sqrt(err2[2]).item())
+        good = relerr < (1e-12 if dt == np.complex128 else 1e-5) and same == 0.0 and not st.peers_mapped
+        ok = ok and good
+        if rank == 0:
+            print(f"{'PASS' if good else 'FAIL'} no second buffer n={n} {np.dtype(dt).name} P={world}: peer swap rel={relerr:.2e}, "
+                  f"peer swap == staged NCCL diff={same:.1e}, peer_swap_mapped={st.peer_swap_mapped}", flush=True)
+        st.close()
+    qc.set_option("dist_second_buffer", 1)
     # ---- adjoint gradients on the sharded state vs the single-GPU gradient of the same circuit (both Hamiltonians, both
     # dtypes; the ComplexF64 backward pass runs on the tensor cores, the scalar pass is checked with adjoint_mma = 0) and,
     # at a size the oracle handles, vs the oracle's restatement of the reference's shift sweep ----------------------------
