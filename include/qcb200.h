@@ -180,7 +180,9 @@ int qcb_state_local_qubits(const qcb_state *s, int *out);
 /* Optional: let the ranks read each other's shards directly (CUDA IPC over NVLink).  Every rank exports 128 bytes, the
  * host gathers them in rank order and every rank imports the whole table.  With peers mapped, a qubit swap is no longer
  * a separate all-to-all: it is fused into the next gate pass, whose tile loads come straight from the peers' memory.
- * Option "fuse_swaps" (default 1) switches the fusion off without unmapping. */
+ * Option "fuse_swaps" (default 1) switches the fusion off without unmapping.  When no rank could allocate a second buffer
+ * (34 qubits on 2 GPUs) only the first buffers are mapped and a qubit swap is an in-place exchange over peer memory (one kernel,
+ * no staging; option "peer_swap", default 1); when some ranks have a second buffer and others do not, nothing is mapped. */
 int qcb_state_ipc_export(const qcb_state *s, void *out_128_bytes);
 int qcb_state_ipc_import(qcb_state *s, const void *all_handles);
 int qcb_state_ipc_close(qcb_state *s); /* unmap the peers' buffers; then synchronise the ranks before qcb_state_destroy */

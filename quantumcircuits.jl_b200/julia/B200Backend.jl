@@ -326,7 +326,8 @@ end
 #     id = rank == 0 ? dist_unique_id() : nothing;  id = MPI.bcast(id, 0, comm)        # any host channel
 #     dist_init(rank, nranks, id)
 #     psi = B200ShardedState{Float64}(34)                    # 2^(34 - log2 nranks) amplitudes on this rank's GPU
-#     map_peers!(psi, h -> MPI.Allgather(h, comm))           # optional: swaps fused into gate passes over NVLink
+#     map_peers!(psi, h -> MPI.Allgather(h, comm))           # optional: swaps fused into gate passes over NVLink (or, without
+#                                                            # second buffers, in-place swaps over peer memory)
 #     apply!(psi, circuit);  E = measure(H, psi);  E, g = gradients(H, psi, circuit; calculate_energy=true)
 # ------------------------------------------------------------------------------------------------
 dist_unique_id() = (id = zeros(UInt8, 128); check(ccall((:qcb_dist_unique_id, LIB), Cint, (Ptr{UInt8},), id)); id)
