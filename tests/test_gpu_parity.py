@@ -455,6 +455,26 @@ def test_cluster_gradient_kernel(oracle, n, layers, scale, ham):
     assert np.max(np.abs(g32 - g_ref)) < 1e-5 * max(scale_g, 1.0)
 
 
+# (compute-sanitizer is closed on the GPU pool: a race in the cluster kernels' barrier / buffer-swap protocol would show up as run-to-run
+# differences -- every sum is taken in a fixed order, so the results must repeat bit for bit)
+@pytest.mark.parametrize("n,layers", [(12, 20), (11, 9), (10, 12)])
+def test_cluster_kernels_repeat_bit_for_bit(n, layers):
+    rng = np.random.default_rng(7 * n + layers)
+    c = circuit(n, layers, rng)
+    H = qc.TFIMHamiltonian(1.0, 0.1, 0.5)
+    psi0 = qc.B200State(rand_state(rng, n))
+    qc.set_option("small_cluster", 12)
+    try:
+        E0, g0 = qc.gradients(H, psi0, c, calculate_energy=True)
+        out0 = qc.apply(psi0, c).to_numpy()
+        for _ in range(40):
+            E, g = qc.gradients(H, psi0, c, calculate_energy=True)
+            assert E == E0 and np.array_equal(g, g0)
+            assert np.array_equal(qc.apply(psi0, c).to_numpy(), out0)
+    finally:
+        qc.set_option("small_cluster", 0)
+
+
 @pytest.mark.parametrize("n,layers,atb", [(9, 3, 0), (12, 4, 0), (13, 5, 9), (16, 6, 10), (18, 4, 11), (19, 7, 12), (22, 4, 0)])
 def test_gradients_f32_tensor_core_pass(oracle, n, layers, atb):
     """ComplexF32 backward pass with both register windows resident, FFMA2 outer products and a warp transpose-reduction

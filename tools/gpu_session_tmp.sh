@@ -1,16 +1,11 @@
 #!/bin/bash
-# session AE: 128 vs 256 threads per CTA in the small-state kernels
+# session AH: compute-sanitizer (memcheck + racecheck) on the kernels of session 3: cluster-resident circuit / gradient kernels, 3M gate passes,
+# cp.async persistent pass
 mkdir -p gpurun_out
 O=gpurun_out
-V=quantumcircuits.jl_b200/variants
-{
-for lib in "" $V/libqcb200_t128.so; do
-echo "# lib=$lib"
-QCB200_LIB=$lib timeout -k 10 200 python tools/prof_case.py grad 12 layers=20 reps=30
-QCB200_LIB=$lib timeout -k 10 200 python tools/prof_case.py pass 12 layers=20 reps=50
-QCB200_LIB=$lib timeout -k 10 200 python tools/prof_case.py grad 10 layers=20 reps=30
-QCB200_LIB=$lib timeout -k 10 200 python tools/prof_case.py grad 8 layers=8 reps=30
+for tool in memcheck racecheck; do
+timeout -k 10 500 compute-sanitizer --tool $tool --error-exitcode 7 python tools/prof_case.py grad 12 layers=6 reps=1 > $O/r02ah_${tool}_cluster_grad.log 2>&1; echo "$tool cluster grad rc=$?"; tail -n 3 $O/r02ah_${tool}_cluster_grad.log | cut -c1-200
+timeout -k 10 500 compute-sanitizer --tool $tool --error-exitcode 7 python tools/prof_case.py pass 13 layers=8 reps=1 small_cluster=1 > $O/r02ah_${tool}_cluster_circuit.log 2>&1; echo "$tool cluster circuit rc=$?"; tail -n 3 $O/r02ah_${tool}_cluster_circuit.log | cut -c1-200
+timeout -k 10 500 compute-sanitizer --tool $tool --error-exitcode 7 python tools/prof_case.py pass 16 layers=12 reps=1 > $O/r02ah_${tool}_pass3m.log 2>&1; echo "$tool 3M pass rc=$?"; tail -n 3 $O/r02ah_${tool}_pass3m.log | cut -c1-200
+timeout -k 10 500 compute-sanitizer --tool $tool --error-exitcode 7 python tools/prof_case.py pass 16 layers=12 reps=1 pass_async=1 > $O/r02ah_${tool}_async.log 2>&1; echo "$tool async pass rc=$?"; tail -n 3 $O/r02ah_${tool}_async.log | cut -c1-200
 done
-} > $O/r02ae_cases.jsonl 2> $O/r02ae_cases.err
-cut -c1-200 $O/r02ae_cases.jsonl; tail -n 3 $O/r02ae_cases.err
-QCB200_LIB=$V/libqcb200_t128.so timeout -k 10 300 python -m pytest tests/test_gpu_parity.py -q -x -m gpu -k "cluster" 2>&1 | tail -n 2
