@@ -127,21 +127,31 @@ __device__ __forceinline__ void small_apply_gates(cg::cluster_group &cluster, Sm
                 __syncthreads();
                 dirty = true;
             } else {
-                if (dirty) cluster.sync(); // every CTA's buffer is complete before anybody reads it remotely
-                for (unsigned a = tid; a < nloc; a += kSmallThreads) {
-                    unsigned owner[4], loc[4];
-                    const int r = small_remote_item(rank, L, a, k, owner, loc);
-                    V x[4];
+                // One cluster barrier per gate: every CTA's buffer A is complete before anybody reads it remotely.  The results
+                // go to B, which nobody reads remotely before the NEXT cluster barrier -- and A is not written again before
+                // that barrier either (gates in between work on B in place), by which time every CTA has finished reading it.
+                cluster.sync();
+                for (unsigned a0 = tid; a0 < nloc; a0 += 2 * kSmallThreads) {
+                    // two amplitudes per thread and iteration: all remote loads in flight before the first use
+                    const unsigned a1 = a0 + kSmallThreads;
+                    const bool two = a1 < nloc;
+                    unsigned owner0[4], loc0[4], owner1[4], loc1[4];
+                    const int r0 = small_remote_item(rank, L, a0, k, owner0, loc0);
+                    const int r1 = small_remote_item(rank, L, two ? a1 : a0, k, owner1, loc1);
+                    V x0[4], x1[4];
 #pragma unroll
                     for (int c = 0; c < 4; c++) {
-                        const V *p = owner[c] == rank ? A : cluster.map_shared_rank(A, owner[c]);
-                        x[c] = p[loc[c]];
+                        const V *p0 = owner0[c] == rank ? A : cluster.map_shared_rank(A, owner0[c]);
+                        const V *p1 = owner1[c] == rank ? A : cluster.map_shared_rank(A, owner1[c]);
+                        x0[c] = p0[loc0[c]];
+                        x1[c] = p1[loc1[c]];
                     }
-                    B[a] = small_row<R, V>(U, r, x);
+                    B[a0] = small_row<R, V>(U, r0, x0);
+                    if (two) B[a1] = small_row<R, V>(U, r1, x1);
                 }
-                cluster.sync(); // all remote reads of A are done; B is complete everywhere
+                __syncthreads(); // B is complete in this CTA (local gates may follow)
                 S.A = B; S.B = A;
-                dirty = false;
+                dirty = true;
             }
         }
     }
@@ -168,6 +178,7 @@ cluster_circuit_kernel(const typename Vec2<R>::type *__restrict__ src, typename 
     small_apply_gates<R>(cluster, S, dirty, gsm, ksm, gates, gate_k, ngates, rank, L);
     __syncthreads();
     for (unsigned i = tid; i < nloc; i += kSmallThreads) dst[((size_t)rank << L) + i] = S.A[i];
+    if (gbits) cluster.sync(); // no CTA leaves while another one may still read its buffers
 }
 
 // ---- energy + all environments of a brickwork circuit in the same launch (the adjoint sweep of src/gradients.jl:88-152 as in
@@ -237,8 +248,15 @@ cluster_gradient_kernel(const typename Vec2<R>::type *__restrict__ src, const Ga
     int *ksm = reinterpret_cast<int *>(gsm + kSmallChunk);
     for (unsigned i = tid; i < nloc; i += kSmallThreads) P.A[i] = src[((size_t)rank << L) + i];
     bool dirty = true;
+#ifdef QCB_SMALL_TIMING
+    long long tq[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tq0 = clock64();
+#define QCB_TICK(i) { const long long now = clock64(); tq[i] += now - tq0; tq0 = now; }
+#else
+#define QCB_TICK(i)
+#endif
     // forward circuit
     small_apply_gates<R>(cluster, P, dirty, gsm, ksm, gates, gate_k, ngates, rank, L);
+    QCB_TICK(0)
     // lambda = H psi, E = <psi|lambda>   (kernels.cuh: k_apply_ham)
     if (dirty) cluster.sync();
     {
@@ -272,6 +290,7 @@ cluster_gradient_kernel(const typename Vec2<R>::type *__restrict__ src, const Ga
     }
     cluster.sync(); // lambda is complete everywhere and nobody reads psi remotely any more
     dirty = false;
+    QCB_TICK(1)
     small_flush_part(part, Epart + 32 * rank, tid);
     unsigned cur = 1;      // part buffer of the gate being processed
     double *pending = nullptr; // where the sums in part[cur ^ 1] go (the previous gate's), once a barrier has passed
@@ -285,6 +304,7 @@ cluster_gradient_kernel(const typename Vec2<R>::type *__restrict__ src, const Ga
             double acc[32];
 #pragma unroll
             for (int v = 0; v < 32; v++) acc[v] = 0.0;
+            QCB_TICK(2)
             if (k + 1 < L) {
                 for (unsigned q = tid; q < (nloc >> 2); q += kSmallThreads) {
                     const unsigned base = small_quad_base(q, k);
@@ -299,8 +319,10 @@ cluster_gradient_kernel(const typename Vec2<R>::type *__restrict__ src, const Ga
                     for (int c = 0; c < 4; c++) { P.A[base | ((unsigned)c << k)] = x[c]; Q.A[base | ((unsigned)c << k)] = l[c]; }
                 }
                 dirty = true;
+                QCB_TICK(3)
             } else {
-                if (dirty) cluster.sync();
+                cluster.sync(); // (one barrier per gate, as in small_apply_gates)
+                QCB_TICK(4)
                 for (unsigned a = tid; a < nloc; a += kSmallThreads) {
                     unsigned owner[4], loc[4];
                     const int r = small_remote_item(rank, L, a, k, owner, loc);
@@ -316,21 +338,29 @@ cluster_gradient_kernel(const typename Vec2<R>::type *__restrict__ src, const Ga
                     P.B[a] = small_row<R, V>(Ud, r, x);
                     Q.B[a] = small_row<R, V>(Ud, r, l);
                 }
-                cluster.sync();
                 V *t = P.A; P.A = P.B; P.B = t;
                 t = Q.A; Q.A = Q.B; Q.B = t;
-                dirty = false;
+                dirty = true;
+                QCB_TICK(5)
             }
-            // this gate's sums: per warp now, across the warps one barrier later (under the next gate's arithmetic)
-            const double ws = small_warp_reduce32(acc, tid & 31u);
+            // this gate's sums: per warp now, across the warps one barrier later (under the next gate's arithmetic).  Warps
+            // without work in this gate (a local gate has 2^(L-2) quads) skip the 62 shuffles: the shuffle unit is shared
+            const unsigned nwork = k + 1 < L ? (nloc >> 2) : nloc;
+            const double ws = (tid & ~31u) < nwork ? small_warp_reduce32(acc, tid & 31u) : 0.0;
             part[(cur * kSmallWarps + (tid >> 5)) * 32 + (tid & 31u)] = ws;
             if (pending) small_flush_part(part + (cur ^ 1u) * kSmallWarps * 32, pending, tid);
             __syncthreads(); // the gate's writes to the state, its part[] rows; the flush has read the other buffer
             pending = Mpart + ((size_t)rank * ngates + (g0 + j)) * 32;
             cur ^= 1u;
+            QCB_TICK(6)
         }
     }
     if (pending) small_flush_part(part + (cur ^ 1u) * kSmallWarps * 32, pending, tid);
+    if (gbits) cluster.sync(); // no CTA leaves while another one may still read its buffers
+#ifdef QCB_SMALL_TIMING
+    if (tid == 0 && rank == 0)
+        printf("cycles: forward %lld  Hpsi %lld  loop-top %lld  bwd-local %lld  bwd-remote-sync %lld  bwd-remote %lld  reduce+barrier %lld\n", tq[0], tq[1], tq[2], tq[3], tq[4], tq[5], tq[6]);
+#endif
 }
 
 // env_g = (sum over the CTAs of M_g) conj(U_g)  -- the environment in the convention of k_adjoint_step (kernels.cuh): psi after,
