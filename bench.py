@@ -778,7 +778,7 @@ def extra_configs(qc, peak, args):
     out.append({"config": "C1: 12 q x 20 half-layers forward circuit (110 gates), ComplexF64, resident state", "ms": ms, "ms_min": ms_min,
                 "kernel": "small-state circuit kernel" if qc.get_stat("passes") <= 1 else "tile_pass_kernel", "launches_per_call": (qc.get_stat("launches_total") - l0) / 23.0,
                 "algorithmic_bytes": 2 * S, "achieved_gbs": 2 * S / (ms * 1e-3) / 1e9, "frac": 2 * S / (ms * 1e-3) / 1e9 / peak,
-                "gate_apps_per_sec": 110 / (ms * 1e-3), "note": "launch-latency bound: a 64 KiB state", "_launches": qc.get_stat("launches_total") - l0})
+                "gate_apps_per_sec": 110 / (ms * 1e-3), "note": "a 64 KiB state: one cluster launch, the state stays in distributed shared memory; bound by per-gate latency (barriers, DSMEM reads), ms includes the host's table build and the launch", "_launches": qc.get_stat("launches_total") - l0})
     # expectation value at 30 qubits (one read of the state is the algorithmic traffic)
     for dtype, nm in ((np.complex128, "ComplexF64"), (np.complex64, "ComplexF32")):
         st = qc.B200State(30, dtype)
