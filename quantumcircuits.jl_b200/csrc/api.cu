@@ -675,6 +675,10 @@ int qcb_finalize(void)
     if (c.h_out) cudaFreeHost(c.h_out);
     c.d_partial = c.d_out = c.h_out = nullptr;
     c.partial_cap = c.out_cap = 0;
+    if (c.h_gates) cudaFreeHost(c.h_gates);
+    if (c.d_gates) cudaFree(c.d_gates);
+    if (c.gates_ev) cudaEventDestroy(c.gates_ev);
+    c.h_gates = c.d_gates = nullptr; c.gates_cap = 0; c.gates_ev = nullptr;
     cudaEventDestroy(c.ev0); cudaEventDestroy(c.ev1);
     for (int i = 0; i < 2; i++)
         for (int k = 0; k < 16; k++) if (c.chunk_ev[i][k]) { cudaEventDestroy(c.chunk_ev[i][k]); c.chunk_ev[i][k] = nullptr; }
