@@ -301,26 +301,52 @@ cluster_gradient_kernel(const typename Vec2<R>::type *__restrict__ src, const Ga
         for (int j = cnt - 1; j >= 0; j--) {
             const int k = ksm[j];
             const GateMat<R> &Ud = gsm[j];
-            double acc[32];
-#pragma unroll
-            for (int v = 0; v < 32; v++) acc[v] = 0.0;
             QCB_TICK(2)
+            double *prow = part + (cur * kSmallWarps + (tid >> 5)) * 32; // this warp's sums for this gate
             if (k + 1 < L) {
-                for (unsigned q = tid; q < (nloc >> 2); q += kSmallThreads) {
-                    const unsigned base = small_quad_base(q, k);
-                    V x[4], l[4];
+                // Local gate.  The outer products M = sum_quads conj(lambda) psi^T over the warp's quads run on the FP64 tensor
+                // cores with operands fetched from shared memory (states BEFORE the un-application): A[m][q] = real component m of
+                // lambda of quad q, B[q][n] = component n of psi of quad q (mma.sync m8n8k4, as in adjoint.cuh) -- two accumulators
+                // per lane and one lane exchange instead of 64 DFMA and a 31-step shuffle reduction per thread.
+                const unsigned lane = tid & 31u, g = lane >> 2, t4 = lane & 3u, jj = g >> 1, pt = g & 1u, nq = nloc >> 2;
+                const R *pL = reinterpret_cast<const R *>(Q.A) + pt, *pP = reinterpret_cast<const R *>(P.A) + pt;
+                double d0[2] = {0.0, 0.0}, d1[2] = {0.0, 0.0};
+                for (unsigned q0 = tid & ~31u; q0 < nq; q0 += kSmallThreads) { // (warp-uniform bounds: mma.sync needs the whole warp)
 #pragma unroll
-                    for (int c = 0; c < 4; c++) { x[c] = P.A[base | ((unsigned)c << k)]; l[c] = Q.A[base | ((unsigned)c << k)]; }
+                    for (int m = 0; m < 8; m++) {
+                        const unsigned quad = q0 + 4u * (unsigned)m + t4;
+                        const unsigned idx = small_quad_base(quad < nq ? quad : 0u, k) | (jj << k);
+                        const double a = quad < nq ? (double)pL[2 * idx] : 0.0, b = quad < nq ? (double)pP[2 * idx] : 0.0;
+                        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                                     : "+d"(d0[m & 1]), "+d"(d1[m & 1]) : "d"(a), "d"(b));
+                    }
+                    __syncwarp(); // every operand of the warp's quads is read before a lane rewrites its quad
+                    const unsigned q = q0 + lane;
+                    if (q < nq) {
+                        const unsigned base = small_quad_base(q, k);
+                        V x[4], l[4];
 #pragma unroll
-                    for (int r = 0; r < 4; r++) small_outer_row(acc, r, l[r], x);
-                    apply_quad(x[0], x[1], x[2], x[3], Ud);
-                    apply_quad(l[0], l[1], l[2], l[3], Ud);
+                        for (int c = 0; c < 4; c++) { x[c] = P.A[base | ((unsigned)c << k)]; l[c] = Q.A[base | ((unsigned)c << k)]; }
+                        apply_quad(x[0], x[1], x[2], x[3], Ud);
+                        apply_quad(l[0], l[1], l[2], l[3], Ud);
 #pragma unroll
-                    for (int c = 0; c < 4; c++) { P.A[base | ((unsigned)c << k)] = x[c]; Q.A[base | ((unsigned)c << k)] = l[c]; }
+                        for (int c = 0; c < 4; c++) { P.A[base | ((unsigned)c << k)] = x[c]; Q.A[base | ((unsigned)c << k)] = l[c]; }
+                    }
+                    __syncwarp();
+                }
+                const double s0 = d0[0] + d0[1], s1 = d1[0] + d1[1];
+                const double o0 = __shfl_xor_sync(0xffffffffu, s0, 4), o1 = __shfl_xor_sync(0xffffffffu, s1, 4);
+                if (!pt) { // the lane of Re(lambda_jj) assembles M[jj][t4]
+                    const unsigned kk = jj + 4u * t4;
+                    prow[2 * kk] = s0 + o1;
+                    prow[2 * kk + 1] = s1 - o0;
                 }
                 dirty = true;
                 QCB_TICK(3)
             } else {
+                double acc[32];
+#pragma unroll
+                for (int v = 0; v < 32; v++) acc[v] = 0.0;
                 cluster.sync(); // (one barrier per gate, as in small_apply_gates)
                 QCB_TICK(4)
                 for (unsigned a = tid; a < nloc; a += kSmallThreads) {
@@ -342,12 +368,9 @@ cluster_gradient_kernel(const typename Vec2<R>::type *__restrict__ src, const Ga
                 t = Q.A; Q.A = Q.B; Q.B = t;
                 dirty = true;
                 QCB_TICK(5)
+                // per-warp sums by a transpose-reduction (31 shuffles per lane); across the warps one barrier later
+                prow[tid & 31u] = small_warp_reduce32(acc, tid & 31u);
             }
-            // this gate's sums: per warp now, across the warps one barrier later (under the next gate's arithmetic).  Warps
-            // without work in this gate (a local gate has 2^(L-2) quads) skip the 62 shuffles: the shuffle unit is shared
-            const unsigned nwork = k + 1 < L ? (nloc >> 2) : nloc;
-            const double ws = (tid & ~31u) < nwork ? small_warp_reduce32(acc, tid & 31u) : 0.0;
-            part[(cur * kSmallWarps + (tid >> 5)) * 32 + (tid & 31u)] = ws;
             if (pending) small_flush_part(part + (cur ^ 1u) * kSmallWarps * 32, pending, tid);
             __syncthreads(); // the gate's writes to the state, its part[] rows; the flush has read the other buffer
             pending = Mpart + ((size_t)rank * ngates + (g0 + j)) * 32;
