@@ -616,14 +616,21 @@ def test_gradients_c2_shape_against_shift_subset(oracle):
         assert abs((ep - em) / 2 - g.reshape(-1, order="F")[idx]) < 1e-11
 
 
-def test_optimise_trajectory(oracle):
+@pytest.mark.parametrize("small_cluster", [0, 12])  # pass-based sweep / cluster-resident kernels (small_circuit.cuh)
+def test_optimise_trajectory(oracle, small_cluster):
     rng = np.random.default_rng(7)
     n, layers, epochs, lr = 8, 3, 6, 0.01
     c = circuit(n, layers, rng, 0.01)
     a0 = c.gate_angles.copy()
     H = qc.TFIMHamiltonian(1.0, 0.2, 0.5)
     e_ref, a_ref = oracle.optimise_brickwork(onp.zero_state(n), n, layers, a0, 0, H.params(), epochs, lr)
-    energies = qc.optimise_(c, H, qc.zero_state_tensor(n), epochs, lr)
+    qc.set_option("small_cluster", small_cluster)
+    try:
+        k0 = qc.get_stat("cluster_circuits")
+        energies = qc.optimise_(c, H, qc.zero_state_tensor(n), epochs, lr)
+        assert (qc.get_stat("cluster_circuits") > k0) == bool(small_cluster)
+    finally:
+        qc.set_option("small_cluster", 0)
     np.testing.assert_allclose(energies, e_ref, atol=1e-10)
     np.testing.assert_allclose(c.gate_angles, a_ref, atol=1e-10)
 
