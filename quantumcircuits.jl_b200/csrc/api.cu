@@ -560,12 +560,19 @@ static int gradients_impl(const qcb_state *psi0, int nbits, int nlayers, const d
     const unsigned long long namps = 1ull << nbits;
     HamEval H{ham_kind, nbits, csr ? 0.0 : hp[0], csr ? 0.0 : hp[1], csr ? 0.0 : hp[2]};
     {
-        const unsigned blocks = grid_for(namps, kRedThreads, 8);
+        // ham_tile: 0 = plain gather, 1 = low-bit tile in shared memory for ComplexF32 (default), 2 = for both types (measured slower)
+        const bool f64 = psi0->dtype == QCB_C128;
+        const bool tiled = !csr && nbits >= 13 && c.ham_tile >= (f64 ? 2 : 1);
+        const unsigned blocks = tiled ? grid_for((namps >> (f64 ? 11 : 12)) * kRedThreads, kRedThreads, 6) : grid_for(namps, kRedThreads, 8);
         QCB_TRY(ensure_partial((size_t)blocks * 2));
         if (csr && psi0->dtype == QCB_C128)
             k_apply_csr<double><<<blocks, kRedThreads, 0, c.stream>>>((double2 *)B.d, (const double2 *)A.d, csr->nrows, csr->rowptr, csr->colidx, csr->vals, (double2 *)c.d_partial);
         else if (csr)
             k_apply_csr<float><<<blocks, kRedThreads, 0, c.stream>>>((float2 *)B.d, (const float2 *)A.d, csr->nrows, csr->rowptr, csr->colidx, csr->vals, (double2 *)c.d_partial);
+        else if (tiled && f64)
+            k_apply_ham_tiled<double, 11><<<blocks, kRedThreads, 0, c.stream>>>((double2 *)B.d, (const double2 *)A.d, namps >> 11, H, (double2 *)c.d_partial);
+        else if (tiled)
+            k_apply_ham_tiled<float, 12><<<blocks, kRedThreads, 0, c.stream>>>((float2 *)B.d, (const float2 *)A.d, namps >> 12, H, (double2 *)c.d_partial);
         else if (psi0->dtype == QCB_C128)
             k_apply_ham<double><<<blocks, kRedThreads, 0, c.stream>>>((double2 *)B.d, (const double2 *)A.d, namps, H, (double2 *)c.d_partial);
         else
@@ -761,6 +768,10 @@ int qcb_set_option(const char *key, long value)
         c.adjoint_ctas = value;
     } else if (k == "adjoint_f32") {
         c.adjoint_f32 = value ? 1 : 0;
+    } else if (k == "ham_tile") {
+        // lambda = H psi of the gradient: flips of the low index bits from shared memory (k_apply_ham_tiled) or the plain gather
+        if (value < 0 || value > 2) return set_error(QCB_EINVAL, "ham_tile must be 0 (gather), 1 (low-bit tile for ComplexF32) or 2 (for both types)");
+        c.ham_tile = value;
     } else if (k == "adjoint_mma") {
         c.adjoint_mma = value ? 1 : 0;
     } else if (k == "pass_tma") {

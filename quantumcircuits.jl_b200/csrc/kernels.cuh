@@ -195,6 +195,66 @@ __global__ void __launch_bounds__(kRedThreads) k_apply_ham(typename Vec2<R>::typ
     }
 }
 
+#if defined(__CUDACC__)
+// The same sweep with the flips of the low TBL index bits served from shared memory: a CTA stages 2^TBL consecutive amplitudes
+// (32 KiB) and only the flips of bits >= TBL go to L1 / L2.  Chunks are taken in index order by the whole grid.  The sums run in
+// the same order as in k_apply_ham: lambda is bit-identical to it.  Default for ComplexF32, where the gather form is bound by
+// load instructions (28 q: 9.1 -> 6.5 ms); the ComplexF64 gather is bound by DRAM (its high-bit partner streams miss L2:
+// 9.5 state-sized reads) and gets slower with tiles (more CTAs' partner streams compete for L2: 12-13 reads) -- DESIGN 2.2.
+template <typename R, int TBL>
+__global__ void __launch_bounds__(kRedThreads) k_apply_ham_tiled(typename Vec2<R>::type *__restrict__ lam,
+                                                                 const typename Vec2<R>::type *__restrict__ psi, unsigned long long nchunks,
+                                                                 HamEval H, double2 *partial)
+{
+    using V = typename Vec2<R>::type;
+    constexpr int kPer = (1 << TBL) / kRedThreads;
+    __shared__ V sm[1 << TBL];
+    const double oc = H.offdiag_coef();
+    double acc[2] = {0.0, 0.0};
+    for (unsigned long long ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+        const unsigned long long base = ch << TBL;
+#pragma unroll
+        for (int j = 0; j < kPer; j++) sm[threadIdx.x + j * kRedThreads] = psi[base + threadIdx.x + j * kRedThreads];
+        __syncthreads();
+#pragma unroll 2
+        for (int j = 0; j < kPer; j++) {
+            const uint32_t e = threadIdx.x + j * kRedThreads;
+            const unsigned long long C = base + e;
+            const V p = sm[e];
+            double xr = 0, xi = 0;
+#pragma unroll
+            for (int i = 0; i < TBL; i++) { // (H.n >= TBL)
+                if (!H.flip_on(C, i)) continue;
+                const V o = sm[e ^ (1u << i)];
+                xr += (double)o.x;
+                xi += (double)o.y;
+            }
+#pragma unroll 4
+            for (int i = TBL; i < H.n; i++) {
+                if (!H.flip_on(C, i)) continue;
+                const V o = psi[C ^ (1ull << i)];
+                xr += (double)o.x;
+                xi += (double)o.y;
+            }
+            const double d = H.diag(C);
+            const double lr = d * (double)p.x + oc * xr, li = d * (double)p.y + oc * xi;
+            V r;
+            r.x = (R)lr;
+            r.y = (R)li;
+            lam[C] = r;
+            acc[0] += (double)p.x * lr + (double)p.y * li;
+            acc[1] += (double)p.x * li - (double)p.y * lr;
+        }
+        __syncthreads();
+    }
+    if (partial) {
+        __shared__ double out[2];
+        block_sum<2>(acc, out);
+        if (threadIdx.x == 0) partial[blockIdx.x] = make_double2(out[0], out[1]);
+    }
+}
+#endif
+
 // E = <psi| H |psi> for an explicit (sparse) Hamiltonian in CSR form: src/circuits.jl:49-55, real(dot(psi, H, psi)).
 // One row per thread (the reference's matrices have n+1 entries per row), accumulated in double.
 template <typename R>

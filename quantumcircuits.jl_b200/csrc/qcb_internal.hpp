@@ -37,7 +37,7 @@ struct Ctx {
     cudaEvent_t chunk_ev[2][16] = {};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // options
-    long tile_bits = 11, low_bits = 3, max_gates_per_pass = 1 << 30, force_simple = 0, adjoint_tile_bits = 0, adjoint_mma = 1, adjoint_warps = 0, adjoint_prog_host = 0, measure_ctas = 0, contract_coop = 1, measure_persistent = 0, measure_tma = 1, pass_tma = 0, pass_tma_max_stages = 3, adjoint_f32 = 1, adjoint_ctas = 5, adjoint_defer = 1, f64_3m_min_gates = 4, pass_async = 0, small_cluster = 12, small_gbits = -1;
+    long tile_bits = 11, low_bits = 3, max_gates_per_pass = 1 << 30, force_simple = 0, adjoint_tile_bits = 0, adjoint_mma = 1, adjoint_warps = 0, adjoint_prog_host = 0, measure_ctas = 0, contract_coop = 1, measure_persistent = 0, measure_tma = 1, pass_tma = 0, pass_tma_max_stages = 3, adjoint_f32 = 1, adjoint_ctas = 5, adjoint_defer = 1, f64_3m_min_gates = 4, pass_async = 0, small_cluster = 12, small_gbits = -1, ham_tile = 1;
     // stats
     double st_passes = 0, st_stages = 0, st_launches = 0, st_gates = 0, st_launches_total = 0, st_swaps = 0, st_fused_swaps = 0;
     long fuse_swaps = 1, peer_swap = 1, dist_second_buffer = 1;

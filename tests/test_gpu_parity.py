@@ -14,6 +14,9 @@ GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 TOL = {np.complex128: 1e-12, np.complex64: 1e-5}
 
 
+HAM_TILE_DEFAULT = 1
+
+
 def rand_state(rng, n, dtype=np.complex128):
     v = rng.standard_normal(2 ** n) + 1j * rng.standard_normal(2 ** n)
     return (v / np.linalg.norm(v)).astype(dtype)
@@ -501,6 +504,34 @@ def test_gradients_f32_tensor_core_pass(oracle, n, layers, atb):
         _, g_ref = oracle.gradients_brickwork(v, n, layers, c.gate_angles, 0 if n % 2 else 1, H.params())
         assert np.max(np.abs(g1 - g_ref)) < 1e-5 * scale_g
     qc.set_option("adjoint_f32", 1)
+
+
+@pytest.mark.parametrize("n,layers", [(13, 3), (14, 2), (17, 3), (21, 2), (24, 2)])
+@pytest.mark.parametrize("dtype", [np.complex128, np.complex64])
+def test_gradients_tiled_hamiltonian_sweep(oracle, n, layers, dtype):
+    """lambda = H psi with the low-bit flips served from shared memory (k_apply_ham_tiled; default for ComplexF32) vs the plain
+    gather (option ham_tile = 0): the same sums in the same order, so the gradient is bit-identical and the energy agrees to the
+    rounding of its partial sums; TFIM and East; at n <= 14 also against the oracle's restatement of the reference's sweep
+    (src/gradients.jl:104 measure!, src/hamiltonians/tfim.jl:17-54, east_model.jl:30-52)."""
+    rng = np.random.default_rng(4000 + 17 * n + layers)
+    c = circuit(n, layers, rng)
+    H = qc.EastModelHamiltonian(0.1, -0.1) if n % 2 else qc.TFIMHamiltonian(1.0, 0.9045, 1.4)
+    v = rand_state(rng, n, dtype)
+    psi0 = qc.B200State(v)
+    try:
+        qc.set_option("ham_tile", 0)
+        E0, g0 = qc.gradients(H, psi0, c, calculate_energy=True)
+        for mode in (1, 2):  # tiles for ComplexF32 only (default); for both types
+            qc.set_option("ham_tile", mode)
+            E1, g1 = qc.gradients(H, psi0, c, calculate_energy=True)
+            assert np.array_equal(g1, g0), mode
+            assert abs(E1 - E0) < 1e-13 * max(1.0, abs(E0)), mode
+    finally:
+        qc.set_option("ham_tile", HAM_TILE_DEFAULT)
+    if n <= 14:
+        tol = 1e-12 if dtype == np.complex128 else 1e-5
+        E_ref, g_ref = oracle.gradients_brickwork(v.astype(np.complex128), n, layers, c.gate_angles, 1 if n % 2 else 0, H.params())
+        assert np.max(np.abs(g1 - g_ref)) < tol * max(1.0, np.max(np.abs(g_ref)))
 
 
 @pytest.mark.parametrize("n,layers", [(9, 2), (12, 20), (14, 9), (17, 5), (20, 4), (23, 3)])
