@@ -195,56 +195,66 @@ __global__ void __launch_bounds__(kRedThreads) k_apply_ham(typename Vec2<R>::typ
     }
 }
 
-#if defined(__CUDACC__)
 // The same sweep with the flips of the low TBL index bits served from shared memory: a CTA stages 2^TBL consecutive amplitudes
 // (32 KiB) and only the flips of bits >= TBL go to L1 / L2.  Chunks are taken in index order by the whole grid.  The sums run in
 // the same order as in k_apply_ham: lambda is bit-identical to it.  Default for ComplexF32, where the gather form is bound by
 // load instructions (28 q: 9.1 -> 6.5 ms); the ComplexF64 gather is bound by DRAM (its high-bit partner streams miss L2:
 // 9.5 state-sized reads) and gets slower with tiles (more CTAs' partner streams compete for L2: 12-13 reads) -- DESIGN 2.2.
+// The two per-thread phases are __host__ __device__ so that the CPU suite replays them (tests/emu).
+template <typename R, int TBL>
+QCB_HD void ham_tile_load(typename Vec2<R>::type *sm, const typename Vec2<R>::type *__restrict__ psi, unsigned long long base, uint32_t t)
+{
+#pragma unroll
+    for (int j = 0; j < (1 << TBL) / kRedThreads; j++) sm[t + j * kRedThreads] = psi[base + t + j * kRedThreads];
+}
+template <typename R, int TBL>
+QCB_HD void ham_tile_rows(typename Vec2<R>::type *__restrict__ lam, const typename Vec2<R>::type *__restrict__ psi,
+                          const typename Vec2<R>::type *sm, unsigned long long base, uint32_t t, const HamEval &H, double oc, double &er, double &ei)
+{
+    using V = typename Vec2<R>::type;
+#pragma unroll 2
+    for (int j = 0; j < (1 << TBL) / kRedThreads; j++) {
+        const uint32_t e = t + j * kRedThreads;
+        const unsigned long long C = base + e;
+        const V p = sm[e];
+        double xr = 0, xi = 0;
+#pragma unroll
+        for (int i = 0; i < TBL; i++) { // (H.n >= TBL)
+            if (!H.flip_on(C, i)) continue;
+            const V o = sm[e ^ (1u << i)];
+            xr += (double)o.x;
+            xi += (double)o.y;
+        }
+#pragma unroll 4
+        for (int i = TBL; i < H.n; i++) {
+            if (!H.flip_on(C, i)) continue;
+            const V o = psi[C ^ (1ull << i)];
+            xr += (double)o.x;
+            xi += (double)o.y;
+        }
+        const double d = H.diag(C);
+        const double lr = d * (double)p.x + oc * xr, li = d * (double)p.y + oc * xi;
+        V r;
+        r.x = (R)lr;
+        r.y = (R)li;
+        lam[C] = r;
+        er += (double)p.x * lr + (double)p.y * li;
+        ei += (double)p.x * li - (double)p.y * lr;
+    }
+}
+#if defined(__CUDACC__)
 template <typename R, int TBL>
 __global__ void __launch_bounds__(kRedThreads) k_apply_ham_tiled(typename Vec2<R>::type *__restrict__ lam,
                                                                  const typename Vec2<R>::type *__restrict__ psi, unsigned long long nchunks,
                                                                  HamEval H, double2 *partial)
 {
-    using V = typename Vec2<R>::type;
-    constexpr int kPer = (1 << TBL) / kRedThreads;
-    __shared__ V sm[1 << TBL];
+    __shared__ typename Vec2<R>::type sm[1 << TBL];
     const double oc = H.offdiag_coef();
     double acc[2] = {0.0, 0.0};
     for (unsigned long long ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
-        const unsigned long long base = ch << TBL;
-#pragma unroll
-        for (int j = 0; j < kPer; j++) sm[threadIdx.x + j * kRedThreads] = psi[base + threadIdx.x + j * kRedThreads];
+        ham_tile_load<R, TBL>(sm, psi, ch << TBL, threadIdx.x);
         __syncthreads();
-#pragma unroll 2
-        for (int j = 0; j < kPer; j++) {
-            const uint32_t e = threadIdx.x + j * kRedThreads;
-            const unsigned long long C = base + e;
-            const V p = sm[e];
-            double xr = 0, xi = 0;
-#pragma unroll
-            for (int i = 0; i < TBL; i++) { // (H.n >= TBL)
-                if (!H.flip_on(C, i)) continue;
-                const V o = sm[e ^ (1u << i)];
-                xr += (double)o.x;
-                xi += (double)o.y;
-            }
-#pragma unroll 4
-            for (int i = TBL; i < H.n; i++) {
-                if (!H.flip_on(C, i)) continue;
-                const V o = psi[C ^ (1ull << i)];
-                xr += (double)o.x;
-                xi += (double)o.y;
-            }
-            const double d = H.diag(C);
-            const double lr = d * (double)p.x + oc * xr, li = d * (double)p.y + oc * xi;
-            V r;
-            r.x = (R)lr;
-            r.y = (R)li;
-            lam[C] = r;
-            acc[0] += (double)p.x * lr + (double)p.y * li;
-            acc[1] += (double)p.x * li - (double)p.y * lr;
-        }
+        ham_tile_rows<R, TBL>(lam, psi, sm, ch << TBL, threadIdx.x, H, oc, acc[0], acc[1]);
         __syncthreads();
     }
     if (partial) {

@@ -602,6 +602,34 @@ extern "C" int emu_measure(int dtype, int n, const void *psi, int kind, double p
     return 0;
 }
 
+// ---- lambda = H psi with the low-bit flips from a staged tile (kernels.cuh: ham_tile_load / ham_tile_rows, k_apply_ham_tiled) ----
+template <typename R, int TBL>
+static void emu_ham_tiled_run(typename Vec2<R>::type *lam, const typename Vec2<R>::type *psi, const HamEval &H, int grid, double *E2)
+{
+    using V = typename Vec2<R>::type;
+    std::vector<V> sm((size_t)1 << TBL);
+    const unsigned long long nchunks = 1ull << (H.n - TBL);
+    const double oc = H.offdiag_coef();
+    for (int cta = 0; cta < grid; cta++)
+        for (unsigned long long ch = (unsigned long long)cta; ch < nchunks; ch += (unsigned long long)grid) {
+            for (uint32_t t = 0; t < (uint32_t)kRedThreads; t++) ham_tile_load<R, TBL>(sm.data(), psi, ch << TBL, t);
+            for (uint32_t t = 0; t < (uint32_t)kRedThreads; t++) ham_tile_rows<R, TBL>(lam, psi, sm.data(), ch << TBL, t, H, oc, E2[0], E2[1]);
+        }
+}
+extern "C" int emu_apply_ham_tiled(int dtype, int n, const void *psi, int kind, double p0, double p1, double p2, int grid, void *lam, double *E2)
+{
+    HamEval H{kind, n, p0, p1, p2};
+    E2[0] = E2[1] = 0.0;
+    if (dtype) {
+        if (n < 11) return 3;
+        emu_ham_tiled_run<double, 11>((double2 *)lam, (const double2 *)psi, H, grid, E2);
+    } else {
+        if (n < 12) return 3;
+        emu_ham_tiled_run<float, 12>((float2 *)lam, (const float2 *)psi, H, grid, E2);
+    }
+    return 0;
+}
+
 // ---- sharded expectation value with simulated ranks: local passes (rank bits via c_hi), one swap_top, top pass ----------
 template <int TBX> static void emu_meas_dispatch(const double2 *psi, int nloc, const MeasParams<double> &P, double *acc)
 {

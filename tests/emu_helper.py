@@ -192,6 +192,21 @@ def measure(psi, kind, params, tile_bits, low_bits):
     return E.value, npass.value
 
 
+def apply_ham_tiled(psi, kind, params, grid=3):
+    """lambda = H psi with the flips of the low index bits served from a staged tile (kernels.cuh: k_apply_ham_tiled, the tile
+    sizes the library launches: 2^11 ComplexF64 / 2^12 ComplexF32) on `grid` emulated CTAs.  Returns (lambda, <psi|lambda>)."""
+    psi = np.ascontiguousarray(psi)
+    n = int(psi.size).bit_length() - 1
+    lam = np.zeros_like(psi)
+    E2 = np.zeros(2)
+    rc = lib().emu_apply_ham_tiled(C.c_int(1 if psi.dtype == np.complex128 else 0), C.c_int(n), psi.ctypes.data_as(C.c_void_p), C.c_int(kind),
+                                   C.c_double(params[0]), C.c_double(params[1]), C.c_double(params[2]), C.c_int(grid),
+                                   lam.ctypes.data_as(C.c_void_p), E2.ctypes.data_as(C.c_void_p))
+    if rc:
+        raise RuntimeError(f"emu_apply_ham_tiled rc={rc}")
+    return lam, complex(E2[0], E2[1])
+
+
 def flip_measure(psi, kind, params, grid=3, n_total=None, c_hi=0):
     """TMA-fed persistent expectation value (flip_tile.cuh) with emulated tile loads.  psi: the local amplitudes; for a
     simulated shard pass n_total and c_hi = rank << nloc.  Returns (diagonal sum, flip sum, levels); E = diag + coef * flips."""

@@ -375,6 +375,55 @@ def test_emu_tiled_measure(emu, oracle, n, tb, c):
     assert abs(E32 - oracle.measure_tfim(psi, 1.0, 0.1, 0.5).real) < 1e-5 * n
 
 
+# ---- lambda = H psi with the low-bit flips from a staged tile -----------------------------------------------
+def _ham_apply_np(psi, kind, hp):
+    """H psi by index arithmetic: TFIM -J (sum ZZ + h sum Z + g sum X) (src/hamiltonians/tfim.jl:17-54), East model
+    (east_model.jl:30-52); qubit i + 1 is index bit i.  Checked against the oracle's dense matrices in the test below."""
+    v = np.asarray(psi, dtype=np.complex128).reshape(-1)
+    n = int(v.size).bit_length() - 1
+    idx = np.arange(v.size, dtype=np.int64)
+    bits = [(idx >> i) & 1 for i in range(n)]
+    if kind == 0:
+        J, h, g = hp
+        z = [1 - 2 * b for b in bits]
+        diag = -J * (sum(z[i] * z[i + 1] for i in range(n - 1)) + h * sum(z))
+        return diag * v - J * g * sum(v[idx ^ (1 << i)] for i in range(n))
+    c, A, B = hp
+    nn = [1 - b for b in bits]  # the projector N = |0><0|
+    diag = B * (nn[0] + sum(nn[i - 1] * nn[i] + c * nn[i - 1] for i in range(1, n))) + c
+    x = v[idx ^ 1] + sum(nn[i - 1] * v[idx ^ (1 << i)] for i in range(1, n))
+    return diag * v + A * x
+
+
+def test_ham_apply_np_matches_dense_hamiltonians():
+    rng = np.random.default_rng(77)
+    n = 8
+    psi = rand_state(rng, n)
+    A, B = onp.east_params(0.1, -0.1)
+    assert np.max(np.abs(_ham_apply_np(psi, 0, (0.7, -0.3, 1.4)) - onp.dense_tfim(n, 0.7, -0.3, 1.4) @ psi)) < 1e-13
+    assert np.max(np.abs(_ham_apply_np(psi, 1, (0.1, A, B)) - onp.dense_east(n, 0.1, -0.1) @ psi)) < 1e-13
+
+
+@pytest.mark.parametrize("n,grid", [(12, 1), (13, 3), (15, 5)])
+def test_emu_apply_ham_tiled(emu, oracle, n, grid):
+    """k_apply_ham_tiled replayed thread by thread (tile load, LDS flips of the low bits, gathers of the rest): lambda against
+    the index-arithmetic H psi, E = <psi|lambda> against the oracle's expectation kernels; both dtypes, TFIM and East."""
+    rng = np.random.default_rng(500 + n)
+    psi = rand_state(rng, n)
+    A, B = onp.east_params(0.1, -0.1)
+    for kind, hp, ref in [(0, (0.7, -0.3, 1.4), oracle.measure_tfim(psi, 0.7, -0.3, 1.4)),
+                          (1, (0.1, A, B), oracle.measure_east(psi, 0.1, A, B))]:
+        want = _ham_apply_np(psi, kind, hp)
+        lam, E = emu.apply_ham_tiled(psi, kind, hp, grid)
+        assert np.max(np.abs(lam - want)) < 1e-14 * n
+        assert abs(E - ref) < 1e-12 * max(1.0, abs(ref))
+        p32 = psi.astype(np.complex64)
+        lam32, E32 = emu.apply_ham_tiled(p32, kind, hp, grid)
+        assert lam32.dtype == np.complex64
+        assert np.max(np.abs(lam32 - _ham_apply_np(p32, kind, hp))) < 2e-7 * np.max(np.abs(want))  # one FP32 rounding
+        assert abs(E32 - ref) < 1e-5 * max(1.0, abs(ref))
+
+
 # ---- scheduler / tile-shape corner cases ------------------------------------------------------------------
 @pytest.mark.parametrize("n,tb,c,maxg", [(9, 13, 3, 0), (10, 10, 0, 0), (11, 9, 5, 0), (12, 12, 3, 1), (12, 9, 3, 2), (13, 11, 4, 5), (10, 9, 3, 3)])
 def test_emu_tile_shape_corner_cases(emu, oracle, n, tb, c, maxg):
