@@ -12,14 +12,12 @@ timeout -k 10 200 python tools/prof_case.py grad32 28
 timeout -k 10 200 python tools/prof_case.py grad 28
 timeout -k 10 200 python tools/prof_case.py grad 20 reps=20
 timeout -k 10 200 python tools/prof_case.py grad 12 layers=20 reps=20
-} > $O/r02ar_cases.jsonl 2> $O/r02ar_cases.err
-cut -c1-330 $O/r02ar_cases.jsonl; tail -n 3 $O/r02ar_cases.err
-timeout -k 10 1200 python -m pytest tests -q -m gpu > $O/r02ar_pytest_gpu.log 2>&1; echo "rc=$?" >> $O/r02ar_pytest_gpu.log
-tail -n 4 $O/r02ar_pytest_gpu.log
-timeout -k 10 600 python -c "import __graft_entry__ as g; g.smoke()" > $O/r02ar_smoke.log 2>&1; echo "rc=$?" >> $O/r02ar_smoke.log; tail -n 2 $O/r02ar_smoke.log
-timeout -k 10 1500 python bench.py --steps 5 --warmup 3 > $O/r02ar_bench.json 2> $O/r02ar_bench.err; echo "bench rc=$?"; cut -c1-400 $O/r02ar_bench.json; tail -n 3 $O/r02ar_bench.err
-timeout -k 10 600 python bench.py --impl reference --steps 2 --warmup 1 > $O/r02ar_bench_reference.json 2> $O/r02ar_bench_reference.err; cut -c1-300 $O/r02ar_bench_reference.json
-timeout -k 10 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/r02ar_launches_bench.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $O/r02ar_ncu_bench.log 2>&1; echo "ncu launches rc=$?"
-timeout -k 10 600 ncu --set full --clock-control none --import-source on -k regex:tile_pass_kernel -s 20 -c 2 -o $O/r02ar_prof_tile_pass_30q -f python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --no-extra > $O/r02ar_ncu_tile.log 2>&1; echo "ncu full rc=$?"
-ls -la $O | grep r02ar
-timeout -k 10 300 ncu --set full --clock-control none --import-source on -k regex:k_apply_ham_tiled -c 1 -o $O/r02ar_prof_apply_ham_tiled_f32_28q -f python tools/prof_case.py grad32 28 reps=1 > $O/r02ar_ncu_ham.log 2>&1; echo "ncu ham rc=$?"
+} > $O/r02at_cases.jsonl 2> $O/r02at_cases.err
+cut -c1-330 $O/r02at_cases.jsonl; tail -n 3 $O/r02at_cases.err
+timeout -k 10 1200 python -m pytest tests -q -m gpu > $O/r02at_pytest_gpu.log 2>&1; echo "rc=$?" >> $O/r02at_pytest_gpu.log
+tail -n 4 $O/r02at_pytest_gpu.log
+timeout -k 10 600 python -c "import __graft_entry__ as g; g.smoke()" > $O/r02at_smoke.log 2>&1; echo "rc=$?" >> $O/r02at_smoke.log; tail -n 2 $O/r02at_smoke.log
+timeout -k 10 1500 python bench.py --steps 5 --warmup 3 > $O/r02at_bench.json 2> $O/r02at_bench.err; echo "bench rc=$?"; cut -c1-400 $O/r02at_bench.json; tail -n 3 $O/r02at_bench.err
+timeout -k 10 600 python bench.py --impl reference --steps 2 --warmup 1 > $O/r02at_bench_reference.json 2> $O/r02at_bench_reference.err; cut -c1-300 $O/r02at_bench_reference.json
+timeout -k 10 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/r02at_launches_bench.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $O/r02at_ncu_bench.log 2>&1; echo "ncu launches rc=$?"
+ls -la $O | grep r02at
