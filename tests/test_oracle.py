@@ -186,6 +186,23 @@ def test_tfim_kernel_vs_dense(oracle, nbits, params):
     assert abs(E32.real - E_dense) < 1e-5 * max(1, abs(E_dense))
 
 
+# ---- an answer from outside the code base: the open transverse-field Ising chain is a free-fermion model
+@pytest.mark.parametrize("nbits,J,g", [(6, 1.0, 0.5), (9, 1.0, 1.4), (10, 0.7, 1.0)])
+def test_tfim_ground_energy_equals_free_fermion_solution(oracle, nbits, J, g):
+    """-J (sum ZZ + g sum X) (h = 0; src/hamiltonians/tfim.jl:17-54, examples/matrix_tfim.jl:7-32) is, after X <-> Z, the chain
+    -J sum XX - Jg sum Z, which the Jordan-Wigner map turns into free fermions (Lieb-Schultz-Mattis): with A the symmetric and B
+    the antisymmetric hopping / pairing matrices, A + B = 2 (Jg I - J S), S the upper shift of the open chain, and
+    E0 = -1/2 sum of the singular values of A + B.  The lowest eigenvalue of the oracle's dense TFIM and the kernel
+    expectation value of its ground vector must both equal that number."""
+    sv = np.linalg.svd(J * g * np.eye(nbits) - J * np.eye(nbits, k=1), compute_uv=False)
+    E0 = -float(np.sum(sv))
+    w, v = np.linalg.eigh(onp.dense_tfim(nbits, J, 0.0, g))
+    assert abs(w[0] - E0) < 1e-11 * nbits
+    gs = v[:, 0].astype(np.complex128)
+    assert abs(oracle.measure_tfim(gs, J, 0.0, g).real - E0) < 1e-11 * nbits
+    assert abs(onp.measure_tfim(gs, J, 0.0, g).real - E0) < 1e-11 * nbits
+
+
 # ---- examples/test_gradient_accuracy.jl:25-57 : gradients! == naive per-angle shift
 @pytest.mark.parametrize("ham", ["tfim", "east"])
 def test_gradients_vs_naive_shift(oracle, ham):
