@@ -308,6 +308,31 @@ def test_measure_tma_vs_oracle(oracle, n, dtype):
         assert levels == (1 + -(-(n - tba) // 9) if n >= tba + 2 else levels)
 
 
+@pytest.mark.parametrize("n,J,g", [(11, 1.0, 0.5), (16, 1.0, 1.4), (18, 0.7, 1.0)])
+def test_tfim_ground_state_against_free_fermion_solution(n, J, g):
+    """A known answer from outside the code base (no oracle involved): the ground energy of the open chain
+    -J (sum ZZ + g sum X) (src/hamiltonians/tfim.jl:17-54 with h = 0) is E0 = -sum of the singular values of Jg I - J S
+    (Jordan-Wigner / Lieb-Schultz-Mattis, S = upper shift).  The ground vector comes from a Lanczos run on an index-arithmetic
+    H psi; the GPU's expectation value of it (gather kernel at 11 q, TMA-fed kernel above) must be E0 in both dtypes."""
+    from scipy.sparse.linalg import LinearOperator, eigsh
+
+    E0 = -float(np.sum(np.linalg.svd(J * g * np.eye(n) - J * np.eye(n, k=1), compute_uv=False)))
+    idx = np.arange(2 ** n, dtype=np.int64)
+    z = [1 - 2 * ((idx >> i) & 1) for i in range(n)]
+    diag = -J * sum(z[i] * z[i + 1] for i in range(n - 1)).astype(np.float64)
+
+    def matvec(v):
+        v = np.asarray(v).reshape(-1)
+        return diag * v - J * g * sum(v[idx ^ (1 << i)] for i in range(n))
+
+    w, v = eigsh(LinearOperator((2 ** n, 2 ** n), matvec=matvec, dtype=np.float64), k=1, which="SA", tol=1e-12)
+    assert abs(w[0] - E0) < 1e-9 * n  # the Lanczos run found the free-fermion ground energy
+    gs = (v[:, 0] / np.linalg.norm(v[:, 0])).astype(np.complex128)
+    H = qc.TFIMHamiltonian(J, 0.0, g)
+    assert abs(qc.measure_(None, H, qc.B200State(gs)) - E0) < 1e-10 * n
+    assert abs(qc.measure_(None, H, qc.B200State(gs.astype(np.complex64))) - E0) < 1e-5 * n
+
+
 @pytest.mark.parametrize("n,dtype", [(13, np.complex128), (17, np.complex64), (21, np.complex128)])
 def test_measure_persistent_option(oracle, n, dtype):
     """Persistent form of the tiled expectation value (option measure_persistent) == the default one-tile-per-CTA form."""
