@@ -531,6 +531,29 @@ def test_gradients_f32_tensor_core_pass(oracle, n, layers, atb):
     qc.set_option("adjoint_f32", 1)
 
 
+@pytest.mark.parametrize("n,layers,ham", [(11, 4, "tfim"), (16, 3, "east"), (20, 2, "tfim")])
+def test_gradients_against_central_differences(n, layers, ham):
+    """The definition of the derivative, no oracle involved: dE/dtheta of the adjoint sweep (cluster kernel at 11 q; fused
+    tensor-core backward passes above) against (E(theta + eps) - E(theta - eps)) / 2 eps of the GPU's own forward circuit +
+    expectation value, for angles of the first, a middle and the last gate (src/gradients.jl:88-152 computes the same
+    numbers by the exact shift rule)."""
+    rng = np.random.default_rng(9000 + n)
+    c = circuit(n, layers, rng)
+    H = qc.TFIMHamiltonian(1.0, 0.9045, 1.4) if ham == "tfim" else qc.EastModelHamiltonian(0.1, -0.1)
+    psi0 = qc.B200State(rand_state(rng, n))
+    g = qc.gradients(H, psi0, c)
+    G = c.gate_angles.shape[1]
+    eps = 1e-5
+    for k, gate in [(0, 0), (7, G // 2), (14, G - 1), (3, 1), (11, G - 2)]:
+        keep = c.gate_angles[k, gate]
+        c.gate_angles[k, gate] = keep + eps
+        ep = qc.measure(H, psi0, c)
+        c.gate_angles[k, gate] = keep - eps
+        em = qc.measure(H, psi0, c)
+        c.gate_angles[k, gate] = keep
+        assert abs((ep - em) / (2 * eps) - g[k, gate]) < 2e-8 * max(1.0, np.max(np.abs(g))), (k, gate)
+
+
 @pytest.mark.parametrize("n,layers", [(13, 3), (14, 2), (17, 3), (21, 2), (24, 2)])
 @pytest.mark.parametrize("dtype", [np.complex128, np.complex64])
 def test_gradients_tiled_hamiltonian_sweep(oracle, n, layers, dtype):
