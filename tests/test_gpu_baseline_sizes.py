@@ -81,6 +81,39 @@ def test_c3_30q_prefix_vs_oracle(oracle):
     assert abs(E - E_ref) < 1e-12 * max(1.0, abs(E_ref))
 
 
+# ---- C3 size, a known answer that involves neither the oracle nor the device code: with the entangling angles at zero every
+# gate is a product gate after a swap (tests/product_circuit.py), so circuit(|0..0>) is a product state whose amplitude at any
+# index is a product of 30 numbers.  30 qubits x 12 half-layers (174 gates, fused passes incl. the top qubit pairs), 2^20
+# random indices + the corners + the norm; ComplexF32 at 28 qubits.
+@pytest.mark.parametrize("n,layers,dtype", [(30, 12, np.complex128), (28, 9, np.complex64), (17, 30, np.complex128)])
+def test_non_entangling_circuit_gives_the_analytic_product_state(n, layers, dtype):
+    import torch
+
+    from product_circuit import product_amplitudes, product_circuit_vectors
+
+    free, _ = torch.cuda.mem_get_info()
+    if free < (20 if n == 30 else 6) * 2 ** 30:
+        pytest.skip("not enough free HBM")
+    rng = np.random.default_rng(77 + n)
+    c = circuit(n, layers, rng)
+    c.gate_angles[12:15] = 0
+    st = qc.B200State(n, dtype)
+    from qcb200.apply import _apply_circuit_inplace
+
+    _apply_circuit_inplace(st, c)
+    assert qc.get_stat("passes") < c.gate_angles.shape[1] / 3  # fused passes
+    tol = 1e-12 if dtype == np.complex128 else 2e-5
+    assert abs(st.norm2() - 1) < tol
+    idx = np.concatenate([rng.integers(0, 1 << n, size=1 << 20), [0, 1, (1 << n) - 1, 1 << (n - 1), (1 << n) - 2]])
+    want = product_amplitudes(product_circuit_vectors(n, layers, c.gate_angles), idx)
+    got = st.tensor[torch.from_numpy(idx).to(st.tensor.device)].cpu().numpy()
+    # amplitudes of a 30-qubit product state are ~ 2^-15: compare relative to the largest sampled magnitude
+    assert np.max(np.abs(got - want)) < tol * np.max(np.abs(want))
+    big = np.abs(want) > 0.01 * np.max(np.abs(want))
+    assert np.count_nonzero(big) > 100
+    assert np.max(np.abs(got[big] - want[big]) / np.abs(want[big])) < (1e-10 if dtype == np.complex128 else 2e-3)
+
+
 # ---- C5: 28 qubits x 4 half-layers (54 gates, 810 angles), TFIM(J=1, h=0.9045, g=1.4), ComplexF64 and ComplexF32
 # (examples/test_optimise.jl:9-16 shape; src/gradients.jl:1-17,88-152)
 def test_c5_28q_gradient_and_optimise(oracle):

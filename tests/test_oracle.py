@@ -186,6 +186,25 @@ def test_tfim_kernel_vs_dense(oracle, nbits, params):
     assert abs(E32.real - E_dense) < 1e-5 * max(1, abs(E_dense))
 
 
+# ---- an answer from outside the code base: gates without entangling angles are product gates after a swap
+@pytest.mark.parametrize("nbits,nlayers", [(2, 1), (5, 3), (9, 6), (12, 9)])
+def test_non_entangling_brickwork_gives_the_analytic_product_state(oracle, nbits, nlayers):
+    """src/gates.jl:80-109 with the three entangling angles at zero is (r2 x r1 rz) SWAP (rz r4 x r3); a brickwork circuit
+    (src/circuits.jl:9-31) of such gates maps |0..0> to a product state that tests/product_circuit.py tracks as n 2-vectors.
+    Pins gate builder, qubit order, layer geometry and the application kernel (src/apply.jl:62-84) at once."""
+    from product_circuit import product_amplitudes, product_circuit_vectors
+
+    rng = np.random.default_rng(40 + nbits)
+    G = onp.brickwork_num_gates(nbits, nlayers)
+    angles = rng.uniform(0, 2 * np.pi, (15, G))
+    angles[12:15] = 0
+    want = product_amplitudes(product_circuit_vectors(nbits, nlayers, angles), np.arange(2 ** nbits))
+    psi0 = onp.zero_state(nbits).reshape(-1)
+    assert np.max(np.abs(oracle.apply_brickwork(psi0, nbits, nlayers, angles).reshape(-1) - want)) < 1e-14
+    if nbits <= 9:
+        assert np.max(np.abs(np.asarray(onp.apply_brickwork(psi0, nbits, nlayers, angles)).reshape(-1, order="F") - want)) < 1e-14
+
+
 # ---- an answer from outside the code base: the open transverse-field Ising chain is a free-fermion model
 @pytest.mark.parametrize("nbits,J,g", [(6, 1.0, 0.5), (9, 1.0, 1.4), (10, 0.7, 1.0)])
 def test_tfim_ground_energy_equals_free_fermion_solution(oracle, nbits, J, g):
