@@ -41,6 +41,32 @@ def test_general_unitary_gate_matches_oracle(oracle):
         np.testing.assert_allclose(u, onp.build_general_unitary_gate(a), atol=1e-15)
 
 
+def test_general_unitary_gate_is_the_canonical_two_qubit_gate(oracle):
+    """A published answer from outside the code base: src/gates.jl:80-109 is the three-CNOT circuit of Vatan & Williams for a
+    general two-qubit gate, so its local invariants (Makhlin: G1 = tr^2 m / 16 det U, G2 = (tr^2 m - tr m^2) / 4 det U with
+    m = (Q'UQ)^T (Q'UQ), Q the magic basis) depend on the three entangling angles alone and equal those of
+    exp(i (a XX + b YY + c ZZ)) with (a, b, c) = (theta, phi, lambda) / 2 + pi / 4, whatever the twelve local angles are:
+    G1 = cos^2 2a cos^2 2b cos^2 2c - sin^2 2a sin^2 2b sin^2 2c + (i / 4) sin 4a sin 4b sin 4c, G2 = cos 4a + cos 4b + cos 4c.
+    Checked for the library's host gate builder (qcb_general_unitary_gate) and both oracles; the matrix is unitary."""
+    Q = np.array([[1, 0, 0, 1j], [0, 1j, 1, 0], [0, 1j, -1, 0], [1, 0, 0, -1j]]) / np.sqrt(2)
+    rng = np.random.default_rng(11)
+    for _ in range(20):
+        ang = rng.uniform(-np.pi, 2 * np.pi, 15)
+        a, b, c = ang[12:15] / 2 + np.pi / 4
+        G1 = (np.cos(2 * a) * np.cos(2 * b) * np.cos(2 * c)) ** 2 - (np.sin(2 * a) * np.sin(2 * b) * np.sin(2 * c)) ** 2 \
+            + 0.25j * np.sin(4 * a) * np.sin(4 * b) * np.sin(4 * c)
+        G2 = np.cos(4 * a) + np.cos(4 * b) + np.cos(4 * c)
+        for U in (qcb200.build_general_unitary_gate(ang).mat().reshape(4, 4, order="F"), oracle.build_general_unitary_gate(ang),
+                  onp.build_general_unitary_gate(ang)):
+            np.testing.assert_allclose(U.conj().T @ U, np.eye(4), atol=1e-14)
+            Ub = Q.conj().T @ U @ Q
+            m = Ub.T @ Ub
+            d = np.linalg.det(U)
+            t = np.trace(m)
+            assert abs(t * t / (16 * d) - G1) < 1e-12
+            assert abs((t * t - np.trace(m @ m)) / (4 * d) - G2) < 1e-12
+
+
 def test_general_unitary_gate_derivative():
     L = _lib.lib()
     rng = np.random.default_rng(1)
