@@ -42,6 +42,26 @@ def test_emu_brickwork_vs_oracle(emu, oracle, n, layers, tb, c):
     assert npass < G and nst < G  # fused: fewer sweeps than gates
 
 
+@pytest.mark.parametrize("n,layers,tb,c", [(12, 7, 11, 3), (15, 9, 11, 3), (16, 6, 12, 4)])
+def test_emu_non_entangling_circuit_gives_the_analytic_product_state(emu, n, layers, tb, c):
+    """No oracle involved: the device code of the fused gate pass (tile.cuh) and the pass scheduler, replayed on the CPU with
+    matrices from the library's host gate builder (qcb_general_unitary_gate), against the analytic product state of a
+    brickwork circuit without entangling angles (tests/product_circuit.py)."""
+    import qcb200
+    from product_circuit import product_amplitudes, product_circuit_vectors
+
+    rng = np.random.default_rng(n * 7 + layers)
+    G = onp.brickwork_num_gates(n, layers)
+    angles = rng.uniform(0, 2 * np.pi, (15, G))
+    angles[12:15] = 0
+    q0 = np.array(onp.brickwork_gate_positions(n, layers)) - 1
+    mats = [qcb200.build_general_unitary_gate(angles[:, g]).mat().reshape(4, 4, order="F") for g in range(G)]
+    out, (npass, _) = emu.apply_gates(onp.zero_state(n).reshape(-1), q0, mats, tb, c)
+    want = product_amplitudes(product_circuit_vectors(n, layers, angles), np.arange(2 ** n))
+    assert np.max(np.abs(out - want)) < 1e-14
+    assert npass < G
+
+
 def test_emu_3m_form_equals_ordinary_form(emu, oracle):
     """The 3M arithmetic of the deep ComplexF64 passes (tile.cuh: apply_window_gate_3m, 48 products + 4 sums per amplitude
     quad) against the ordinary 64-product form and the oracle (src/apply.jl:62-84): same result up to rounding, and the
