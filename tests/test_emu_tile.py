@@ -62,6 +62,40 @@ def test_emu_non_entangling_circuit_gives_the_analytic_product_state(emu, n, lay
     assert npass < G
 
 
+def _product_case(n, layers, seed):
+    import qcb200
+    from product_circuit import product_amplitudes, product_circuit_vectors
+
+    rng = np.random.default_rng(seed)
+    G = onp.brickwork_num_gates(n, layers)
+    angles = rng.uniform(0, 2 * np.pi, (15, G))
+    angles[12:15] = 0
+    q0 = np.array(onp.brickwork_gate_positions(n, layers)) - 1
+    mats = [qcb200.build_general_unitary_gate(angles[:, g]).mat().reshape(4, 4, order="F") for g in range(G)]
+    want = product_amplitudes(product_circuit_vectors(n, layers, angles), np.arange(2 ** n))
+    return q0, mats, want
+
+
+@pytest.mark.parametrize("n,g,layers,tb,fuse", [(13, 1, 14, 9, False), (14, 2, 21, 9, True), (15, 3, 18, 9, False), (16, 3, 17, 11, True)])
+def test_emu_sharded_non_entangling_circuit_gives_the_analytic_product_state(emu, n, g, layers, tb, fuse):
+    """No oracle involved: sharded planner (dist_plan.hpp: qubit swaps, bit-permuting passes, swaps fused into gate passes)
+    with 2^g simulated ranks against the analytic product state (tests/product_circuit.py)."""
+    q0, mats, want = _product_case(n, layers, 50 * n + g)
+    out, phys, st = emu.sharded_apply_gates(onp.zero_state(n).reshape(-1), g, q0, mats, tb, 3, fuse_swaps=fuse)
+    assert list(phys) == list(range(n))
+    assert st["swaps"] >= 1
+    assert np.max(np.abs(out - want)) < 1e-14
+
+
+@pytest.mark.parametrize("n,layers,gbits,dtype", [(8, 9, -1, np.complex128), (11, 12, 2, np.complex128), (12, 20, 3, np.complex128), (12, 7, 3, np.complex64)])
+def test_emu_cluster_kernel_non_entangling_circuit_gives_the_analytic_product_state(emu, n, layers, gbits, dtype):
+    """No oracle involved: the cluster-resident small-circuit kernel (small_circuit.cuh, state in the distributed shared
+    memory of 2^gbits CTAs) replayed on the CPU against the analytic product state."""
+    q0, mats, want = _product_case(n, layers, 90 * n + layers)
+    out = emu.small_circuit(onp.zero_state(n).reshape(-1).astype(dtype), q0, mats, gbits)
+    assert np.max(np.abs(out - want)) < (1e-14 if dtype == np.complex128 else 2e-6)
+
+
 def test_emu_3m_form_equals_ordinary_form(emu, oracle):
     """The 3M arithmetic of the deep ComplexF64 passes (tile.cuh: apply_window_gate_3m, 48 products + 4 sums per amplitude
     quad) against the ordinary 64-product form and the oracle (src/apply.jl:62-84): same result up to rounding, and the
