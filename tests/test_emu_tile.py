@@ -661,6 +661,41 @@ def test_emu_flip_measure(emu, oracle, n, dt):
         assert nl == 1 + -(-(n - tba) // 9)
 
 
+def _tfim_ground_state(n, J, g):
+    """(E0, ground vector) of -J (sum ZZ + g sum X) on an open chain: E0 from the free-fermion solution (minus the sum of the
+    singular values of Jg I - J S), the vector from a Lanczos run on an index-arithmetic H psi -- no oracle involved."""
+    from scipy.sparse.linalg import LinearOperator, eigsh
+
+    E0 = -float(np.sum(np.linalg.svd(J * g * np.eye(n) - J * np.eye(n, k=1), compute_uv=False)))
+    idx = np.arange(2 ** n, dtype=np.int64)
+    z = [1 - 2 * ((idx >> i) & 1) for i in range(n)]
+    diag = -J * sum(z[i] * z[i + 1] for i in range(n - 1)).astype(np.float64)
+    mv = lambda v: diag * np.asarray(v).reshape(-1) - J * g * sum(np.asarray(v).reshape(-1)[idx ^ (1 << i)] for i in range(n))
+    w, v = eigsh(LinearOperator((2 ** n, 2 ** n), matvec=mv, dtype=np.float64), k=1, which="SA", tol=1e-12)
+    assert abs(w[0] - E0) < 1e-9 * n
+    return E0, (v[:, 0] / np.linalg.norm(v[:, 0])).astype(np.complex128)
+
+
+@pytest.mark.parametrize("n,J,g", [(15, 1.0, 1.4), (16, 0.7, 1.0)])
+def test_emu_expectation_kernels_reproduce_the_free_fermion_ground_energy(emu, n, J, g):
+    """No oracle involved: every expectation-value kernel replayed on the CPU (round-1 tiles, their persistent form, the
+    TMA-fed flip tiles, the sharded form with 4 simulated ranks, and <psi|H psi> of the tiled H psi sweep) returns the
+    free-fermion ground energy of the open transverse-field chain for its ground vector."""
+    E0, gs = _tfim_ground_state(n, J, g)
+    hp = (J, 0.0, g)
+    tol = 1e-10 * n
+    assert abs(emu.measure(gs, 0, hp, 11, 3)[0] - E0) < tol
+    assert abs(emu.measure_persistent(gs, 0, hp, 10, 3, 5) - E0) < tol
+    d, f, _ = emu.flip_measure(gs, 0, hp, grid=3)
+    assert abs(d - J * g * f - E0) < tol
+    assert abs(emu.sharded_measure(gs, 2, 0, hp, 9, 3) - E0) < tol
+    lam, E = emu.apply_ham_tiled(gs, 0, hp, 3)
+    assert abs(E.real - E0) < tol and abs(E.imag) < tol
+    assert np.max(np.abs(lam - E0 * gs)) < 1e-7  # H psi = E0 psi up to the Lanczos residual
+    E32 = emu.flip_measure(gs.astype(np.complex64), 0, hp, grid=2)
+    assert abs(E32[0] - J * g * E32[1] - E0) < 1e-5 * n
+
+
 def test_emu_flip_measure_simulated_shards(emu, oracle):
     """local part of a sharded expectation value: every simulated rank sweeps its shard with c_hi = rank << nloc; the sum of
     the diagonal parts and of the local-qubit flips equals the oracle's value minus the flips of the rank-bit qubits."""
