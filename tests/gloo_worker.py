@@ -101,11 +101,29 @@ def main():
     gerr = float(np.max(np.abs(grads - g_ref)))
     ok2 = rc2 == 0 and abs(tot[-2] - E_ref) < 1e-12 * max(1.0, abs(E_ref)) and abs(tot[-1]) < 1e-12 and gerr < 1e-12 and nswaps[0] - swaps_before >= 3
     ok = ok and ok2
+    # ---- a known answer without the oracle: a circuit without entangling angles maps |0..0> to an analytic product state
+    # (tests/product_circuit.py); matrices from the library's host gate builder ------------------------------------------
+    import qcb200
+    from product_circuit import product_amplitudes, product_circuit_vectors
+
+    angles3 = rng.uniform(0, 2 * np.pi, (15, G))
+    angles3[12:15] = 0
+    mats3 = np.ascontiguousarray(np.stack([qcb200.build_general_unitary_gate(angles3[:, i]).mat().reshape(-1, order="F") for i in range(G)]))
+    shard3 = np.zeros(per, dtype=np.complex128)
+    if rank == 0:
+        shard3[0] = 1
+    phys3 = np.zeros(n, dtype=np.int32)
+    rc3 = emu_helper.lib().emu_rank_apply_gates(C.c_int(n), C.c_int(g), shard3.ctypes.data_as(C.c_void_p), C.c_int(G),
+                                                q0.ctypes.data_as(C.c_void_p), mats3.ctypes.data_as(C.c_void_p), C.c_int(9), C.c_int(3),
+                                                C.c_int(1), swap_cb, phys3.ctypes.data_as(C.c_void_p))
+    want3 = product_amplitudes(product_circuit_vectors(n, layers, angles3), np.arange(rank * per, (rank + 1) * per))
+    perr = float(np.max(np.abs(shard3 - want3)))
+    ok = ok and rc3 == 0 and perr < 1e-14 and list(phys3) == list(range(n))
     flags = [None] * world
     dist.all_gather_object(flags, ok)
     if rank == 0:
         print(("PASS" if all(flags) else "FAIL"), f"gloo sharded world={world} rc={rc} err={err:.2e} swaps={nswaps[0]}; "
-              f"gradients rc={rc2} dE={abs(tot[-2] - E_ref):.2e} dgrad={gerr:.2e}", flush=True)
+              f"gradients rc={rc2} dE={abs(tot[-2] - E_ref):.2e} dgrad={gerr:.2e}; product state rc={rc3} err={perr:.2e}", flush=True)
     dist.destroy_process_group()
     sys.exit(0 if all(flags) else 1)
 
