@@ -413,6 +413,42 @@ def test_emu_sharded_gradients(emu, oracle, n, layers, g, tb, ham):
     assert st["swaps"] >= 1  # the top qubits' gates needed at least one more exchange after the Hamiltonian's
 
 
+@pytest.mark.parametrize("n,layers,g,ham", [(12, 3, 1, "tfim"), (13, 2, 2, "east")])
+def test_emu_gradients_against_central_differences(emu, n, layers, g, ham):
+    """No oracle involved: the adjoint sweep replayed on the CPU (sharded planner on 2^g simulated ranks, environments
+    contracted with the library's dU/dtheta) against central differences of the replayed forward circuit + expectation value,
+    gate matrices from the library's host builder (src/gradients.jl:88-152 computes the same numbers by the shift rule)."""
+    import ctypes as C
+
+    import qcb200
+    from qcb200 import _lib
+
+    rng = np.random.default_rng(n * 17 + layers)
+    G = onp.brickwork_num_gates(n, layers)
+    angles = rng.uniform(0, 2 * np.pi, (15, G))
+    q0 = np.array(onp.brickwork_gate_positions(n, layers)) - 1
+    build = lambda a: [qcb200.build_general_unitary_gate(a[:, k]).mat().reshape(4, 4, order="F") for k in range(G)]
+    psi0 = rand_state(rng, n)
+    kind, hp = (0, (1.0, 0.9045, 1.4)) if ham == "tfim" else (1, (0.1,) + tuple(onp.east_params(0.1, -0.1)))
+    env, E, _ = emu.sharded_gradient_env(psi0, g, kind, hp, q0, build(angles), 9, 3)
+
+    def energy(a):
+        out, _ = emu.apply_gates(psi0, q0, build(a), 10, 3)
+        return emu.measure(out, kind, hp, 9, 3)[0]
+
+    assert abs(E.real - energy(angles)) < 1e-12
+    eps = 1e-5
+    for j, k in [(0, 0), (7, G // 2), (14, G - 1), (12, 1), (13, G - 2), (5, 2)]:
+        a = np.ascontiguousarray(angles[:, k])
+        d = np.empty(16, dtype=np.complex128)
+        _lib.check(_lib.lib().qcb_general_unitary_gate_derivative(a.ctypes.data_as(C.c_void_p), C.c_int(j), d.ctypes.data_as(C.c_void_p)))
+        grad = 2 * np.real(np.sum(env[k] * d.reshape(4, 4, order="F")))
+        ap, am = angles.copy(), angles.copy()
+        ap[j, k] += eps
+        am[j, k] -= eps
+        assert abs((energy(ap) - energy(am)) / (2 * eps) - grad) < 2e-8, (j, k)
+
+
 # ---- tiled expectation value -----------------------------------------------------------------------------
 @pytest.mark.parametrize("n,tb,c", [(10, 8, 3), (13, 9, 3), (14, 12, 3), (15, 13, 3), (16, 10, 4), (17, 12, 3)])
 def test_emu_tiled_measure(emu, oracle, n, tb, c):
