@@ -14,6 +14,15 @@
  * (test/correctness_tests.jl:3-150), kernel-TFIM == dense TFIM
  * (examples/test_gradients.jl:10-28, examples/matrix_tfim.jl:7-32) and
  * gradients! == naive per-angle shift (examples/test_gradient_accuracy.jl:25-57).
+ * In the task statement's terms this is "PARITY UNPINNED": there is neither a golden
+ * vector of the reference nor an output of the reference itself behind this file.
+ * What stands in for them, besides the reference's own equivalence tests, are answers
+ * that come from outside any code base (tests/test_oracle.py, tests/test_abi.py):
+ * the analytic product state of a brickwork circuit without entangling angles
+ * (tests/product_circuit.py: gate builder, qubit order, layer geometry, application),
+ * the free-fermion ground energy of the open transverse-field Ising chain (TFIM
+ * matrix and kernel), the Makhlin invariants of the general two-qubit gate, and
+ * central differences for the gradients.
  *
  * Every function cites the reference lines it follows (paths relative to
  * /root/reference).  Layout conventions:
